@@ -1,0 +1,59 @@
+// TEST INFRASTRUCTURE: compiles the product's __host__ __device__ field / curve formulas
+// (zksnark-rs_b200/csrc/ff.cuh, ec.cuh) with g++ so their algebra can be checked against Oracle A
+// on a machine without a GPU.  Never linked into libzkb200.so and never used by the product path.
+#include <cstring>
+#include "ec.cuh"
+using namespace zkb;
+
+template <class F> static F ld(const uint64_t* p) { F r; memcpy(r.v, p, 32); return to_mont(r); }
+template <class F> static void st(uint64_t* p, const F& m) { F c = from_mont(m); memcpy(p, c.v, 32); }
+static Fq2 ld2(const uint64_t* p) { Fq2 r; r.c0 = ld<Fq>(p); r.c1 = ld<Fq>(p + 4); return r; }
+static void st2(uint64_t* p, const Fq2& a) { st(p, a.c0); st(p + 4, a.c1); }
+static G1Affine ldg1(const uint64_t* p) { G1Affine r; r.x = ld<Fq>(p); r.y = ld<Fq>(p + 4); return r; }
+static void stg1(uint64_t* p, const G1Affine& a) { st(p, a.x); st(p + 4, a.y); }
+static G2Affine ldg2(const uint64_t* p) { G2Affine r; r.x = ld2(p); r.y = ld2(p + 8); return r; }
+static void stg2(uint64_t* p, const G2Affine& a) { st2(p, a.x); st2(p + 8, a.y); }
+
+extern "C" {
+// op: 0 mul 1 add 2 sub 3 inverse(a) ; field: 0 Fr 1 Fq
+void hc_field(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+  if (field == 0) {
+    Fr x = ld<Fr>(a), y = ld<Fr>(b), r;
+    r = op == 0 ? x * y : op == 1 ? x + y : op == 2 ? x - y : inverse(x);
+    st(out, r);
+  } else {
+    Fq x = ld<Fq>(a), y = ld<Fq>(b), r;
+    r = op == 0 ? x * y : op == 1 ? x + y : op == 2 ? x - y : inverse(x);
+    st(out, r);
+  }
+}
+void hc_fq2(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+  Fq2 x = ld2(a), y = ld2(b);
+  Fq2 r = op == 0 ? x * y : op == 1 ? x + y : op == 2 ? x - y : op == 3 ? inverse(x) : sqr(x);
+  st2(out, r);
+}
+// out = a + b (both affine, through XYZZ: to_xyzz(a) madd b), out2 = to_affine(add(xyzz(a), xyzz(b)))
+void hc_g1_add(const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t* out2) {
+  G1Affine A = ldg1(a), B = ldg1(b);
+  stg1(out, to_affine(madd(to_xyzz(A), B)));
+  // exercise the general add with non-trivial zz on both sides: (2A - A) + (2B - B)
+  G1XYZZ a2 = add(dbl(to_xyzz(A)), neg(to_xyzz(A)));
+  G1XYZZ b2 = add(dbl_affine(B), to_xyzz(neg(B)));
+  stg1(out2, to_affine(add(a2, b2)));
+}
+void hc_g1_mul(const uint64_t* a, const uint64_t* k, uint64_t* out) {
+  uint32_t kk[8]; memcpy(kk, k, 32);
+  stg1(out, to_affine(scalar_mul(ldg1(a), kk)));
+}
+void hc_g2_add(const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t* out2) {
+  G2Affine A = ldg2(a), B = ldg2(b);
+  stg2(out, to_affine(madd(to_xyzz(A), B)));
+  G2XYZZ a2 = add(dbl(to_xyzz(A)), neg(to_xyzz(A)));
+  G2XYZZ b2 = add(dbl_affine(B), to_xyzz(neg(B)));
+  stg2(out2, to_affine(add(a2, b2)));
+}
+void hc_g2_mul(const uint64_t* a, const uint64_t* k, uint64_t* out) {
+  uint32_t kk[8]; memcpy(kk, k, 32);
+  stg2(out, to_affine(scalar_mul(ldg2(a), kk)));
+}
+}

@@ -1,0 +1,154 @@
+// Short-Weierstrass (a = 0) group arithmetic for BN254 G1 (over Fq) and G2 (over Fq2).
+//
+// Replaces crate `bn`'s G1/G2 `+`, `-`, `* Fr` as reached through
+// /root/reference/src/groth16/fr.rs:114-119 (exp_encrypted_g1/g2) and :175-223 (Add/Sub/Sum).
+// The reference folds Jacobian points one scalar-mul at a time; here accumulators are kept in
+// extended-Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2), the cheapest mixed
+// addition for bucket accumulation (8M+2S).  Results are only ever compared in AFFINE form, so the
+// internal coordinate system is free.  All special cases (identity operands, P+P, P+(-P)) are
+// handled: identity points are legal CRS entries (groth16/mod.rs:407).
+#pragma once
+#include "ff.cuh"
+
+namespace zkb {
+
+// Affine point.  Identity is encoded as (0, 0), which is not on either curve (b != 0).
+template <class F>
+struct alignas(16) Affine {
+  F x, y;
+  ZKB_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+  ZKB_HD static Affine inf() { Affine r; r.x = F::zero(); r.y = F::zero(); return r; }
+};
+
+// Extended Jacobian.  Identity <=> zz == 0.
+template <class F>
+struct alignas(16) XYZZ {
+  F x, y, zz, zzz;
+  ZKB_HD bool is_inf() const { return zz.is_zero(); }
+  ZKB_HD static XYZZ inf() { XYZZ r; r.x = F::zero(); r.y = F::zero(); r.zz = F::zero(); r.zzz = F::zero(); return r; }
+};
+
+typedef Affine<Fq> G1Affine;
+typedef Affine<Fq2> G2Affine;
+typedef XYZZ<Fq> G1XYZZ;
+typedef XYZZ<Fq2> G2XYZZ;
+
+template <class F> ZKB_HD XYZZ<F> to_xyzz(const Affine<F>& p) {
+  XYZZ<F> r;
+  if (p.is_inf()) return XYZZ<F>::inf();
+  r.x = p.x; r.y = p.y; r.zz = F::one(); r.zzz = F::one();
+  return r;
+}
+
+template <class F> ZKB_HD Affine<F> neg(const Affine<F>& p) {
+  Affine<F> r; r.x = p.x; r.y = neg(p.y); return r;  // -(0,0) = (0,0): identity stays identity
+}
+template <class F> ZKB_HD XYZZ<F> neg(const XYZZ<F>& p) {
+  XYZZ<F> r = p; r.y = neg(p.y); return r;
+}
+
+// 2*P for affine P (mdbl-2008-s-1): 3M... in fact 2M + 4S here
+template <class F> ZKB_HD XYZZ<F> dbl_affine(const Affine<F>& p) {
+  if (p.is_inf()) return XYZZ<F>::inf();
+  XYZZ<F> r;
+  F u = dbl(p.y);
+  F v = sqr(u);
+  F w = u * v;
+  F s = p.x * v;
+  F xx = sqr(p.x);
+  F m = dbl(xx) + xx;
+  r.x = sqr(m) - dbl(s);
+  r.y = m * (s - r.x) - w * p.y;
+  r.zz = v;
+  r.zzz = w;
+  return r;  // y == 0 cannot happen on a prime-order curve (no 2-torsion); would give zz = 0 = identity anyway
+}
+
+// 2*P (dbl-2008-s-1)
+template <class F> ZKB_HD XYZZ<F> dbl(const XYZZ<F>& p) {
+  if (p.is_inf()) return p;
+  XYZZ<F> r;
+  F u = dbl(p.y);
+  F v = sqr(u);
+  F w = u * v;
+  F s = p.x * v;
+  F xx = sqr(p.x);
+  F m = dbl(xx) + xx;
+  r.x = sqr(m) - dbl(s);
+  r.y = m * (s - r.x) - w * p.y;
+  r.zz = v * p.zz;
+  r.zzz = w * p.zzz;
+  return r;
+}
+
+// acc + P, P affine (madd-2008-s), complete
+template <class F> ZKB_HD XYZZ<F> madd(const XYZZ<F>& a, const Affine<F>& p) {
+  if (p.is_inf()) return a;
+  if (a.is_inf()) return to_xyzz(p);
+  F u2 = p.x * a.zz;
+  F s2 = p.y * a.zzz;
+  F pp_ = u2 - a.x;
+  F rr = s2 - a.y;
+  if (pp_.is_zero()) {
+    if (rr.is_zero()) return dbl_affine(p);
+    return XYZZ<F>::inf();
+  }
+  XYZZ<F> r;
+  F pp = sqr(pp_);
+  F ppp = pp_ * pp;
+  F q = a.x * pp;
+  r.x = sqr(rr) - ppp - dbl(q);
+  r.y = rr * (q - r.x) - a.y * ppp;
+  r.zz = a.zz * pp;
+  r.zzz = a.zzz * ppp;
+  return r;
+}
+
+// a + b (add-2008-s), complete
+template <class F> ZKB_HD XYZZ<F> add(const XYZZ<F>& a, const XYZZ<F>& b) {
+  if (b.is_inf()) return a;
+  if (a.is_inf()) return b;
+  F u1 = a.x * b.zz;
+  F u2 = b.x * a.zz;
+  F s1 = a.y * b.zzz;
+  F s2 = b.y * a.zzz;
+  F pp_ = u2 - u1;
+  F rr = s2 - s1;
+  if (pp_.is_zero()) {
+    if (rr.is_zero()) return dbl(a);
+    return XYZZ<F>::inf();
+  }
+  XYZZ<F> r;
+  F pp = sqr(pp_);
+  F ppp = pp_ * pp;
+  F q = u1 * pp;
+  r.x = sqr(rr) - ppp - dbl(q);
+  r.y = rr * (q - r.x) - s1 * ppp;
+  r.zz = a.zz * b.zz * pp;
+  r.zzz = a.zzz * b.zzz * ppp;
+  return r;
+}
+
+template <class F> ZKB_HD Affine<F> to_affine(const XYZZ<F>& p) {
+  if (p.is_inf()) return Affine<F>::inf();
+  // x = X/ZZ, y = Y/ZZZ; one inversion: i = 1/(ZZ*ZZZ)
+  F i = inverse(p.zz * p.zzz);
+  Affine<F> r;
+  r.x = p.x * (i * p.zzz);
+  r.y = p.y * (i * p.zz);
+  return r;
+}
+
+// k*P by MSB-first double-and-add; k is a plain 256-bit integer (8 u32 limbs, canonical Fr residue)
+template <class F> ZKB_HD XYZZ<F> scalar_mul(const Affine<F>& p, const uint32_t k[8]) {
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int i = 7; i >= 0; i--) {
+    for (int b = 31; b >= 0; b--) {
+      acc = dbl(acc);
+      if ((k[i] >> b) & 1u) acc = madd(acc, p);
+    }
+  }
+  return acc;
+}
+
+}  // namespace zkb

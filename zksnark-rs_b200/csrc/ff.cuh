@@ -1,0 +1,432 @@
+// 256-bit prime-field arithmetic for BN254 Fr / Fq on sm_100a.
+//
+// Replaces the arithmetic of crate `bn` 0.4.3 (Fr, Fq, Fq2) that the reference reaches through
+// /root/reference/src/groth16/fr.rs:18-71 (FrLocal + - * / neg) and, via G1/G2, fr.rs:101-123.
+//
+// Representation: 8 x 32-bit little-endian limbs in Montgomery form (R = 2^256), fully reduced
+// (< p) between operations.  The device multiplier is an interleaved (CIOS) Montgomery product on
+// two staggered accumulators ("even" / "odd" 64-bit columns) so that every partial product is one
+// 32x32+64 wide multiply-add (IMAD.WIDE.U32 with carry) -- no tensor cores, this is integer work.
+// The carry-chain bookkeeping is validated bit-for-bit on the CPU by tools/emul_montmul.py.
+//
+// The same header compiles for the host (portable unsigned __int128 path) so the host side of the
+// library (constant setup, twiddle generation) shares one implementation; the host path is never
+// used to produce a result the GPU path is supposed to produce.
+#pragma once
+#include <stdint.h>
+#include "constants.h"
+
+#if defined(__CUDACC__)
+#define ZKB_HD __host__ __device__ __forceinline__
+#define ZKB_D __device__ __forceinline__
+#else
+#define ZKB_HD inline
+#define ZKB_D inline
+#endif
+
+namespace zkb {
+
+template <class P>
+struct alignas(16) Fp {
+  uint32_t v[8];
+
+  ZKB_HD static Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+    return r;
+  }
+  ZKB_HD static Fp one() {
+    Fp r;
+    r.v[0] = P::ONE0; r.v[1] = P::ONE1; r.v[2] = P::ONE2; r.v[3] = P::ONE3;
+    r.v[4] = P::ONE4; r.v[5] = P::ONE5; r.v[6] = P::ONE6; r.v[7] = P::ONE7;
+    return r;
+  }
+  ZKB_HD static Fp r2() {
+    Fp r;
+    r.v[0] = P::R20; r.v[1] = P::R21; r.v[2] = P::R22; r.v[3] = P::R23;
+    r.v[4] = P::R24; r.v[5] = P::R25; r.v[6] = P::R26; r.v[7] = P::R27;
+    return r;
+  }
+  ZKB_HD static Fp modulus() {
+    Fp r;
+    r.v[0] = P::P0; r.v[1] = P::P1; r.v[2] = P::P2; r.v[3] = P::P3;
+    r.v[4] = P::P4; r.v[5] = P::P5; r.v[6] = P::P6; r.v[7] = P::P7;
+    return r;
+  }
+  ZKB_HD bool is_zero() const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i];
+    return o == 0;
+  }
+  ZKB_HD bool operator==(const Fp& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i];
+    return o == 0;
+  }
+  ZKB_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// host (portable) primitives
+// ------------------------------------------------------------------------------------------------
+namespace host_impl {
+typedef unsigned __int128 u128;
+
+template <class P>
+inline void load64(const Fp<P>& a, uint64_t o[4]) {
+  for (int i = 0; i < 4; i++) o[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+}
+template <class P>
+inline Fp<P> store64(const uint64_t o[4]) {
+  Fp<P> r;
+  for (int i = 0; i < 4; i++) { r.v[2 * i] = (uint32_t)o[i]; r.v[2 * i + 1] = (uint32_t)(o[i] >> 32); }
+  return r;
+}
+template <class P>
+inline void mod64(uint64_t p[4]) { Fp<P> m = Fp<P>::modulus(); load64(m, p); }
+
+// returns borrow of a - b
+inline uint64_t sub4(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {
+  u128 br = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 t = (u128)a[i] - b[i] - br;
+    r[i] = (uint64_t)t;
+    br = (t >> 64) & 1;
+  }
+  return (uint64_t)br;
+}
+inline uint64_t add4(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 t = (u128)a[i] + b[i] + c;
+    r[i] = (uint64_t)t;
+    c = t >> 64;
+  }
+  return (uint64_t)c;
+}
+template <class P>
+inline Fp<P> add(const Fp<P>& x, const Fp<P>& y) {
+  uint64_t a[4], b[4], p[4], s[4], d[4];
+  load64(x, a); load64(y, b); mod64<P>(p);
+  add4(s, a, b);  // no overflow: a,b < p < 2^254
+  uint64_t br = sub4(d, s, p);
+  return store64<P>(br ? s : d);
+}
+template <class P>
+inline Fp<P> sub(const Fp<P>& x, const Fp<P>& y) {
+  uint64_t a[4], b[4], p[4], d[4], e[4];
+  load64(x, a); load64(y, b); mod64<P>(p);
+  uint64_t br = sub4(d, a, b);
+  add4(e, d, p);
+  return store64<P>(br ? e : d);
+}
+template <class P>
+inline Fp<P> mul(const Fp<P>& x, const Fp<P>& y) {
+  uint64_t a[4], b[4], p[4];
+  load64(x, a); load64(y, b); mod64<P>(p);
+  // -p^-1 mod 2^64 from the 32-bit constant by one Newton step
+  uint64_t inv = P::INV;            // -p^-1 mod 2^32
+  uint64_t pinv = (uint64_t)0 - inv;  // p^-1 mod 2^32 (as 64-bit: valid mod 2^32)
+  pinv = pinv * (2 - p[0] * pinv);    // now valid mod 2^64
+  uint64_t ninv = (uint64_t)0 - pinv;
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      u128 s = (u128)a[j] * b[i] + t[j] + c;
+      t[j] = (uint64_t)s; c = s >> 64;
+    }
+    u128 s = (u128)t[4] + c; t[4] = (uint64_t)s; t[5] = (uint64_t)(s >> 64);
+    uint64_t m = t[0] * ninv;
+    c = ((u128)m * p[0] + t[0]) >> 64;
+    for (int j = 1; j < 4; j++) {
+      u128 s2 = (u128)m * p[j] + t[j] + c;
+      t[j - 1] = (uint64_t)s2; c = s2 >> 64;
+    }
+    s = (u128)t[4] + c; t[3] = (uint64_t)s; t[4] = t[5] + (uint64_t)(s >> 64);
+  }
+  uint64_t d[4];
+  uint64_t br = sub4(d, t, p);
+  return store64<P>((t[4] == 0 && br) ? t : d);
+}
+}  // namespace host_impl
+
+// ------------------------------------------------------------------------------------------------
+// device primitives (PTX carry chains)
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+namespace dev_impl {
+
+// acc[0..7] += {s0,s2,s4,s6} * m on 64-bit columns (0,1),(2,3),(4,5),(6,7); carry-out added to *top
+#define ZKB_CMAD_TOP(acc, top, s0, s2, s4, s6, m)                                                  \
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"                                                         \
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"                                                        \
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"                                                       \
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"                                                       \
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"                                                       \
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"                                                       \
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"                                                       \
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"                                                       \
+      "addc.u32 %8, %8, 0;"                                                                        \
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),        \
+        "+r"(acc[6]), "+r"(acc[7]), "+r"(top)                                                      \
+      : "r"(s0), "r"(s2), "r"(s4), "r"(s6), "r"(m))
+
+// same without a carry-out (the caller guarantees none: top limb has >= 2 spare bits)
+#define ZKB_CMAD(acc, s0, s2, s4, s6, m)                                                           \
+  asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"                                                         \
+      "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"                                                        \
+      "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"                                                        \
+      "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"                                                        \
+      "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"                                                       \
+      "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"                                                       \
+      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"                                                       \
+      "madc.hi.u32 %7, %11, %12, %7;"                                                              \
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),        \
+        "+r"(acc[6]), "+r"(acc[7])                                                                 \
+      : "r"(s0), "r"(s2), "r"(s4), "r"(s6), "r"(m))
+
+// X[0] += Y[1] (carry c); Y = (Y >> 64) + {s1,s3,s5,s7} * m + c
+#define ZKB_SHIFT_MAD(X0, Y, s1, s3, s5, s7, m)                                                    \
+  asm("add.cc.u32 %0, %0, %2;\n\t"                                                                 \
+      "madc.lo.cc.u32 %1, %9, %13, %3;\n\t"                                                        \
+      "madc.hi.cc.u32 %2, %9, %13, %4;\n\t"                                                        \
+      "madc.lo.cc.u32 %3, %10, %13, %5;\n\t"                                                       \
+      "madc.hi.cc.u32 %4, %10, %13, %6;\n\t"                                                       \
+      "madc.lo.cc.u32 %5, %11, %13, %7;\n\t"                                                       \
+      "madc.hi.cc.u32 %6, %11, %13, %8;\n\t"                                                       \
+      "madc.lo.cc.u32 %7, %12, %13, 0;\n\t"                                                        \
+      "madc.hi.u32 %8, %12, %13, 0;"                                                               \
+      : "+r"(X0), "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]),          \
+        "+r"(Y[6]), "+r"(Y[7])                                                                     \
+      : "r"(s1), "r"(s3), "r"(s5), "r"(s7), "r"(m))
+
+template <class P>
+__device__ __forceinline__ void mont_round(uint32_t (&X)[8], uint32_t (&Y)[8], const uint32_t* a,
+                                           uint32_t bi, bool first) {
+  if (first) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=&r"(X[j]), "=&r"(X[j + 1]) : "r"(a[j]), "r"(bi));
+      asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=&r"(Y[j]), "=&r"(Y[j + 1]) : "r"(a[j + 1]), "r"(bi));
+    }
+  } else {
+    ZKB_SHIFT_MAD(X[0], Y, a[1], a[3], a[5], a[7], bi);
+    ZKB_CMAD_TOP(X, Y[7], a[0], a[2], a[4], a[6], bi);
+  }
+  uint32_t mi = X[0] * P::INV;
+  const uint32_t p0 = P::P0, p1 = P::P1, p2 = P::P2, p3 = P::P3, p4 = P::P4, p5 = P::P5, p6 = P::P6, p7 = P::P7;
+  ZKB_CMAD(Y, p1, p3, p5, p7, mi);
+  ZKB_CMAD_TOP(X, Y[7], p0, p2, p4, p6, mi);
+}
+
+// r = r - p if r >= p   (r < 2p)
+template <class P>
+__device__ __forceinline__ void final_sub(uint32_t (&r)[8]) {
+  uint32_t t[8], br;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(br)
+      : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(P::P0), "r"(P::P1), "r"(P::P2), "r"(P::P3), "r"(P::P4), "r"(P::P5), "r"(P::P6), "r"(P::P7));
+  // br == 0xffffffff when r < p (keep r), 0 when r >= p (take t)
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = br ? r[i] : t[i];
+}
+
+template <class P>
+__device__ __forceinline__ Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t X[8], Y[8];
+  mont_round<P>(X, Y, a.v, b.v[0], true);
+  mont_round<P>(Y, X, a.v, b.v[1], false);
+  mont_round<P>(X, Y, a.v, b.v[2], false);
+  mont_round<P>(Y, X, a.v, b.v[3], false);
+  mont_round<P>(X, Y, a.v, b.v[4], false);
+  mont_round<P>(Y, X, a.v, b.v[5], false);
+  mont_round<P>(X, Y, a.v, b.v[6], false);
+  mont_round<P>(Y, X, a.v, b.v[7], false);
+  // after the last round Y[0] == 0 and the value is X + (Y >> 32)
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7])
+      : "r"(Y[1]), "r"(Y[2]), "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]));
+  final_sub<P>(X);
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = X[i];
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ Fp<P> add(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t s[8];
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=&r"(s[0]), "=&r"(s[1]), "=&r"(s[2]), "=&r"(s[3]), "=&r"(s[4]), "=&r"(s[5]), "=&r"(s[6]), "=&r"(s[7])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  final_sub<P>(s);
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = s[i];
+  return r;
+}
+
+template <class P>
+__device__ __forceinline__ Fp<P> sub(const Fp<P>& a, const Fp<P>& b) {
+  uint32_t d[8], br;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=&r"(d[0]), "=&r"(d[1]), "=&r"(d[2]), "=&r"(d[3]), "=&r"(d[4]), "=&r"(d[5]), "=&r"(d[6]), "=&r"(d[7]), "=&r"(br)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  // br = 0xffffffff on borrow: add p back
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, %15;"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7])
+      : "r"(P::P0 & br), "r"(P::P1 & br), "r"(P::P2 & br), "r"(P::P3 & br), "r"(P::P4 & br), "r"(P::P5 & br),
+        "r"(P::P6 & br), "r"(P::P7 & br));
+  Fp<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = d[i];
+  return r;
+}
+}  // namespace dev_impl
+#endif  // __CUDA_ARCH__
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+template <class P> ZKB_HD Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__)
+  return dev_impl::mul(a, b);
+#else
+  return host_impl::mul(a, b);
+#endif
+}
+template <class P> ZKB_HD Fp<P> operator+(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__)
+  return dev_impl::add(a, b);
+#else
+  return host_impl::add(a, b);
+#endif
+}
+template <class P> ZKB_HD Fp<P> operator-(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__)
+  return dev_impl::sub(a, b);
+#else
+  return host_impl::sub(a, b);
+#endif
+}
+template <class P> ZKB_HD Fp<P> neg(const Fp<P>& a) { return Fp<P>::zero() - a; }
+template <class P> ZKB_HD Fp<P> sqr(const Fp<P>& a) { return a * a; }
+template <class P> ZKB_HD Fp<P> dbl(const Fp<P>& a) { return a + a; }
+
+// canonical residue (4x u64 LE at the C ABI == 8x u32 LE) <-> Montgomery form
+template <class P> ZKB_HD Fp<P> to_mont(const Fp<P>& canon) { return canon * Fp<P>::r2(); }
+template <class P> ZKB_HD Fp<P> from_mont(const Fp<P>& m) {
+  Fp<P> one_raw = Fp<P>::zero();
+  one_raw.v[0] = 1;
+  return m * one_raw;
+}
+
+// a^e for a 256-bit exponent given as 8 u32 limbs (plain integer, not Montgomery)
+template <class P> ZKB_HD Fp<P> pow_limbs(const Fp<P>& a, const uint32_t e[8]) {
+  Fp<P> acc = Fp<P>::one();
+  bool started = false;
+  for (int i = 7; i >= 0; i--) {
+    for (int b = 31; b >= 0; b--) {
+      if (started) acc = sqr(acc);
+      if ((e[i] >> b) & 1u) { acc = started ? acc * a : a; started = true; }
+    }
+  }
+  return acc;
+}
+template <class P> ZKB_HD Fp<P> pow_u64(const Fp<P>& a, uint64_t e) {
+  uint32_t l[8] = {(uint32_t)e, (uint32_t)(e >> 32), 0, 0, 0, 0, 0, 0};
+  return pow_limbs(a, l);
+}
+// Fermat inverse a^(p-2); inverse(0) = 0 (callers check for zero where the reference would panic)
+template <class P> ZKB_HD Fp<P> inverse(const Fp<P>& a) {
+  uint32_t e[8] = {P::P0 - 2u, P::P1, P::P2, P::P3, P::P4, P::P5, P::P6, P::P7};  // P0 >= 2 for both primes
+  return pow_limbs(a, e);
+}
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+// ------------------------------------------------------------------------------------------------
+// Fq2 = Fq[u]/(u^2 + 1)   (crate bn: Fq2, non-residue -1)
+// ------------------------------------------------------------------------------------------------
+struct alignas(16) Fq2 {
+  Fq c0, c1;
+  ZKB_HD static Fq2 zero() { Fq2 r; r.c0 = Fq::zero(); r.c1 = Fq::zero(); return r; }
+  ZKB_HD static Fq2 one() { Fq2 r; r.c0 = Fq::one(); r.c1 = Fq::zero(); return r; }
+  ZKB_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  ZKB_HD bool operator==(const Fq2& b) const { return c0 == b.c0 && c1 == b.c1; }
+  ZKB_HD bool operator!=(const Fq2& b) const { return !(*this == b); }
+};
+ZKB_HD Fq2 operator+(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
+ZKB_HD Fq2 operator-(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
+ZKB_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
+  // Karatsuba: 3 base multiplications
+  Fq v0 = a.c0 * b.c0, v1 = a.c1 * b.c1;
+  Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
+  Fq2 r;
+  r.c0 = v0 - v1;
+  r.c1 = s - v0 - v1;
+  return r;
+}
+ZKB_HD Fq2 sqr(const Fq2& a) {
+  Fq t = a.c0 * a.c1;
+  Fq2 r;
+  r.c0 = (a.c0 + a.c1) * (a.c0 - a.c1);
+  r.c1 = t + t;
+  return r;
+}
+ZKB_HD Fq2 neg(const Fq2& a) { Fq2 r; r.c0 = neg(a.c0); r.c1 = neg(a.c1); return r; }
+ZKB_HD Fq2 dbl(const Fq2& a) { return a + a; }
+ZKB_HD Fq2 inverse(const Fq2& a) {
+  Fq n = inverse(sqr(a.c0) + sqr(a.c1));
+  Fq2 r;
+  r.c0 = a.c0 * n;
+  r.c1 = neg(a.c1 * n);
+  return r;
+}
+
+}  // namespace zkb
