@@ -1,0 +1,174 @@
+/* zkb200.h -- C ABI of libzkb200.so: the B200 (sm_100a) accelerator for the groth16::prove() hot path
+ * of republicprotocol/zksnark-rs.
+ *
+ * The reference is a pure-Rust crate with NO FFI boundary: its extension seams are the generic
+ * bounds of `prove<P,T,U,V>` (src/groth16/mod.rs:213-229).  This header is the boundary a Rust
+ * `extern "C"` block (rust/zkb200_sys.rs) binds; each entry point cites the
+ * reference code it replaces.
+ *
+ * Conventions
+ *  - Field elements (Fr scalars, Fq coordinates) cross the ABI as 4 x uint64_t little-endian limbs
+ *    of the CANONICAL residue (never Montgomery form).
+ *  - G1 points: affine (x, y) = 8 x uint64_t.  G2 points: affine (x.c0, x.c1, y.c0, y.c1) =
+ *    16 x uint64_t.  The identity is all-zero (it is a legal CRS entry, src/groth16/mod.rs:407).
+ *  - Every function returns 0 (ZKB_OK) or a negative error code; nothing throws or aborts.  The
+ *    Rust shim turns non-zero into panic!() to mirror the reference's panics
+ *    (src/groth16/fr.rs:54, src/field/mod.rs:440).
+ *  - Caller owns all host buffers.  The library owns device objects until the matching *_free.
+ *  - Calls are synchronous on return.  A zkb_ctx is bound to one CUDA device and is not
+ *    thread-safe; distinct contexts are independent.
+ *  - There is NO CPU fallback: every entry point that computes fails with ZKB_ERR_CUDA when no
+ *    sm_100-class device is present.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKB_OK 0
+#define ZKB_ERR_CUDA (-1)        /* CUDA runtime error / no device */
+#define ZKB_ERR_ARG (-2)         /* invalid argument (null pointer, size mismatch, non power of two ...) */
+#define ZKB_ERR_ALLOC (-3)       /* device or host allocation failed */
+#define ZKB_ERR_UNSUPPORTED (-4) /* valid request this build does not implement */
+#define ZKB_ERR_DIV_ZERO (-5)    /* the reference would panic: inverse of zero (fr.rs:54,69) */
+
+typedef struct zkb_ctx zkb_ctx;
+typedef struct zkb_qap zkb_qap;     /* device-resident QAP<CoefficientPoly<FrLocal>> (sparse evaluation rows) */
+typedef struct zkb_crs zkb_crs;     /* device-resident (SigmaG1<G1Local>, SigmaG2<G2Local>) */
+typedef struct zkb_bases zkb_bases; /* device-resident vector of G1 or G2 affine points */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int zkb_ctx_create(zkb_ctx** out, int device_id);
+void zkb_ctx_destroy(zkb_ctx* ctx);
+/* Message of the last error on this context ("" if none).  ctx may be NULL (-> global message). */
+const char* zkb_last_error(const zkb_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t zkb_launch_count(const zkb_ctx* ctx);
+/* Pinned host memory for buffers that are copied every proof (weights).  Optional. */
+int zkb_host_alloc(void** out, size_t bytes);
+void zkb_host_free(void* p);
+/* Raw device memory (so a torch-free caller can keep inputs resident in HBM). */
+int zkb_dev_alloc(zkb_ctx* ctx, void** out, size_t bytes);
+void zkb_dev_free(zkb_ctx* ctx, void* p);
+int zkb_memcpy_h2d(zkb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int zkb_memcpy_d2h(zkb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int zkb_sync(zkb_ctx* ctx);
+/* The stream every kernel of this context is launched on (a cudaStream_t), for event timing. */
+void* zkb_stream(zkb_ctx* ctx);
+
+/* ---- QAP: replaces `QAP<CoefficientPoly<FrLocal>>` (groth16/mod.rs:60-67) and its constructor
+ * `From<RootRepresentation>` (groth16/fr.rs:140-173).  The reference stores every u_i, v_i, w_i as
+ * a dense coefficient vector (3*M*n field elements); this type stores the same polynomials by
+ * their non-zero evaluations on the root domain -- exactly the `DummyRep` data model
+ * (circuit/dummy_rep.rs:7-13).  Rows are CSR by wire: row i of u holds (gate index k, value) for
+ * every root_k where u_i(root_k) != 0.  Domain: the n-th roots of unity, gate k <-> omega^k
+ * (omega = 5^((r-1)/n)); n must be a power of two, 2 <= n <= 2^27. */
+typedef struct {
+  uint64_t n;         /* number of gates = qap.degree                                   */
+  uint64_t m;         /* number of rows (wires incl. the unity wire) = qap.u.len()      */
+  uint64_t n_input;   /* qap.input (number of verifier-visible wires, excl. unity)      */
+  const uint64_t* row_ptr[3];  /* u, v, w: m+1 offsets into gate/coeff                  */
+  const uint32_t* gate[3];     /* nnz gate indices (0-based)                            */
+  const uint64_t* coeff[3];    /* nnz x 4 limbs, canonical                              */
+} zkb_qap_host;
+int zkb_qap_upload(zkb_ctx* ctx, const zkb_qap_host* qap, zkb_qap** out);
+void zkb_qap_free(zkb_ctx* ctx, zkb_qap* qap);
+
+/* ---- CRS: replaces `SigmaG1<G1Local>` / `SigmaG2<G2Local>` (groth16/mod.rs:105-121). ---------- */
+typedef struct {
+  uint64_t n;            /* xi1 / xi2 length = qap.degree; xi_t has n-1 entries (mod.rs:168) */
+  uint64_t n_sum_gamma;  /* input+1 (mod.rs:154)  */
+  uint64_t n_sum_delta;  /* m-input-1 (mod.rs:163) */
+  const uint64_t* alpha1; const uint64_t* beta1; const uint64_t* delta1;  /* 8 limbs each */
+  const uint64_t* xi1;        /* n x 8       */
+  const uint64_t* xi_t;       /* (n-1) x 8   */
+  const uint64_t* sum_gamma;  /* n_sum_gamma x 8 */
+  const uint64_t* sum_delta;  /* n_sum_delta x 8 */
+  const uint64_t* beta2; const uint64_t* gamma2; const uint64_t* delta2;  /* 16 limbs each */
+  const uint64_t* xi2;        /* n x 16      */
+} zkb_crs_host;
+/* Upload a CRS computed elsewhere (e.g. by the reference's setup()).  rank/world shard the MSM
+ * base vectors by contiguous index ranges across `world` processes (one GPU each); pass 0,1 for a
+ * single GPU. */
+int zkb_crs_upload(zkb_ctx* ctx, const zkb_crs_host* crs, int rank, int world, zkb_crs** out);
+/* groth16::setup (groth16/mod.rs:134-197) on the device with the five secrets injected
+ * (toxic = alpha, beta, gamma, delta, x; 5 x 4 limbs, all non-zero as random_elem guarantees,
+ * fr.rs:90-99).  Base points are (G1::one()*69) and (G2::one()*96), fr.rs:106-113. */
+int zkb_setup(zkb_ctx* ctx, const zkb_qap* qap, const uint64_t* toxic, int rank, int world, zkb_crs** out);
+/* Copy the (full, unsharded; requires world == 1) CRS back in the zkb_crs_host layout.  The caller
+ * provides every buffer of `dst` sized from dst->n / n_sum_gamma / n_sum_delta (query with
+ * zkb_crs_dims first). */
+int zkb_crs_dims(const zkb_crs* crs, uint64_t* n, uint64_t* n_sum_gamma, uint64_t* n_sum_delta);
+int zkb_crs_download(zkb_ctx* ctx, const zkb_crs* crs, zkb_crs_host* dst);
+void zkb_crs_free(zkb_ctx* ctx, zkb_crs* crs);
+
+/* ---- the hot path: groth16::prove (groth16/mod.rs:213-296) --------------------------------- */
+typedef struct {
+  uint64_t a[8];   /* Proof.a: G1 affine */
+  uint64_t b[16];  /* Proof.b: G2 affine */
+  uint64_t c[8];   /* Proof.c: G1 affine */
+} zkb_proof;
+/* weights: m x 4 limbs (host memory; copied to the device inside the call).  r, s: the two
+ * scalars the reference draws at mod.rs:231, injected so results are reproducible. */
+int zkb_prove(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const uint64_t* weights,
+              const uint64_t r[4], const uint64_t s[4], zkb_proof* out);
+/* Same with the weights already resident in device memory (m x 4 limbs, canonical). */
+int zkb_prove_dev(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const uint64_t* d_weights,
+                  const uint64_t r[4], const uint64_t s[4], zkb_proof* out);
+/* Multi-GPU: each rank runs the polynomial stage and the MSMs over ITS shard of the CRS and
+ * returns four partial sums (affine, canonical): a_g1 (8), b_g1 (8), c_g1 = h-term + witness-term
+ * (8), b_g2 (16) = 40 limbs.  The caller all-gathers the 40-limb records (NCCL) and every rank --
+ * or rank 0 -- folds them with zkb_prove_combine. */
+#define ZKB_PARTIAL_LIMBS 40
+int zkb_prove_partial(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const uint64_t* weights,
+                      int weights_on_device, uint64_t* out_partial /* 40 limbs, host */);
+int zkb_prove_combine(zkb_ctx* ctx, const zkb_crs* crs, const uint64_t* partials /* world x 40, host */,
+                      int world, const uint64_t r[4], const uint64_t s[4], zkb_proof* out);
+/* h(x) alone: h = (u_sum * v_sum - w_sum) / t  (mod.rs:277; coefficient_poly.rs:93-157;
+ * field/mod.rs:428-469).  Outputs (host, canonical, n x 4 limbs each; any may be NULL):
+ * u_sum, v_sum coefficient vectors and h (n-1 meaningful coefficients, h[n-1] = 0). */
+int zkb_qap_h(zkb_ctx* ctx, const zkb_qap* qap, const uint64_t* weights, uint64_t* u_sum,
+              uint64_t* v_sum, uint64_t* h);
+
+/* ---- the two kernels standalone ------------------------------------------------------------- */
+/* In-place size-2^log_n transform of a DEVICE vector of canonical Fr residues with the reference's
+ * convention (field/mod.rs:508-537): out[i] = sum_j in[j] * root^(i*j), natural order in and out,
+ * root = omega_{2^log_n} (forward) or its inverse with the 1/n scaling (inverse != 0).
+ * coset_shift (host, 4 limbs, may be NULL): forward evaluates on shift*omega^i; inverse undoes it. */
+int zkb_ntt_fr(zkb_ctx* ctx, uint64_t* d_data, uint32_t log_n, int inverse, const uint64_t* coset_shift);
+/* Kernel-only variant for measurement: data already in Montgomery form, natural order in,
+ * bit-reversed order out (forward DIF) -- the form the prove pipeline uses internally. */
+int zkb_ntt_fr_raw(zkb_ctx* ctx, uint64_t* d_data_mont, uint32_t log_n, int inverse);
+/* Element-wise conversion of a device vector between canonical and Montgomery form. */
+int zkb_fr_to_mont(zkb_ctx* ctx, uint64_t* d_data, size_t n, int to_mont);
+
+/* Resident base-point vectors.  group: 1 = G1 (8 limbs / point), 2 = G2 (16 limbs / point). */
+int zkb_bases_upload(zkb_ctx* ctx, int group, const uint64_t* h_points, size_t n, zkb_bases** out);
+/* P_i = k_i * base (base = 69*G1::one() or 96*G2::one(), i.e. encrypt_g1 / encrypt_g2 of k_i,
+ * fr.rs:106-113), computed on the device from n host scalars. */
+int zkb_bases_generate(zkb_ctx* ctx, int group, const uint64_t* h_scalars, size_t n, zkb_bases** out);
+int zkb_bases_download(zkb_ctx* ctx, const zkb_bases* b, uint64_t* h_points);
+void zkb_bases_free(zkb_ctx* ctx, zkb_bases* b);
+/* sum_i scalars[i] * bases[i]  (the `.zip().map(exp_encrypted_g*).sum()` pattern, groth16/mod.rs:
+ * 255-272, 279-290; fr.rs:114-119, 191-223).  scalars: n x 4 limbs canonical, host or device.
+ * n may be smaller than the base vector (zip truncation).  out: 8 (G1) or 16 (G2) limbs, host.
+ * window_bits = 0 lets the library choose. */
+int zkb_msm(zkb_ctx* ctx, const zkb_bases* bases, const uint64_t* scalars, int scalars_on_device,
+            size_t n, int window_bits, uint64_t* out);
+/* Partial MSM over bases[first, first+n) (multi-GPU point sharding): result in affine form;
+ * the caller gathers and folds with zkb_points_sum. */
+int zkb_points_sum(zkb_ctx* ctx, int group, const uint64_t* h_points, size_t n, uint64_t* out);
+
+/* Peak-rate micro-benchmark: every thread runs `iters` dependent-chain pairs of Fq Montgomery
+ * multiplications (ILP 4); returns measured modmul/s in *rate (denominator of the point-add
+ * roofline) and the launch duration in *ms. */
+int zkb_bench_modmul(zkb_ctx* ctx, int field /*0 Fr, 1 Fq*/, int iters, double* rate, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */

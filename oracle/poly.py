@@ -196,3 +196,31 @@ def root_poly(F: Field, roots: list) -> list:
     for r in roots:
         acc = poly_mul(F, acc, [F.neg(r), F.from_usize(1)])
     return acc
+
+
+def ntt_fast(F: Field, seq: list, root: int) -> list:
+    """O(n log n) evaluation with the SAME convention as ``dft`` (field/mod.rs:508-520), for
+    power-of-two lengths: out[i] = sum_j seq[j]*root^(i*j).  Test infrastructure: lets parity tests
+    reach sizes the naive dft cannot; pinned against ``dft`` in tests/test_oracle_kats.py."""
+    n = len(seq)
+    if n == 1:
+        return list(seq)
+    assert n % 2 == 0
+    r2 = F.mul(root, root)
+    even = ntt_fast(F, seq[0::2], r2)
+    odd = ntt_fast(F, seq[1::2], r2)
+    out = [0] * n
+    w = F.one()
+    h = n // 2
+    for i in range(h):
+        t = F.mul(w, odd[i])
+        out[i] = F.add(even[i], t)
+        out[i + h] = F.sub(even[i], t)
+        w = F.mul(w, root)
+    return out
+
+
+def intt_fast(F: Field, seq: list, root: int) -> list:
+    """Inverse of ``ntt_fast`` with idft's 1/n scaling (field/mod.rs:524-537)."""
+    ninv = F.mul_inv(F.from_usize(len(seq)))
+    return [F.mul(x, ninv) for x in ntt_fast(F, seq, F.mul_inv(root))]

@@ -1,0 +1,348 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libzkb200.so) against the CPU oracle.
+
+Bit-exact comparisons on canonical residues and affine coordinates (integer arithmetic: no
+tolerance anywhere).  Small sizes are compared with the literal restatement of the reference
+(oracle.groth16 / oracle.poly / oracle.bn254); full sizes use size-independent properties
+(closed-form proof from the toxic waste, sum_i s_i k_i collapse for MSMs, transform round trips).
+"""
+
+import importlib
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bn254 as bn
+from oracle import closed_form as cf
+from oracle import groth16 as og
+from oracle import poly, synthetic
+from oracle.fields import FR
+
+pytestmark = pytest.mark.gpu
+zk = importlib.import_module("zksnark-rs_b200")
+zg = importlib.import_module("zksnark-rs_b200.groth16")
+P = FR.p
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = zk.Context(0)
+    yield c
+    c.close()
+
+
+def rand_fr(rng, nonzero=False):
+    return rng.randrange(1 if nonzero else 0, P)
+
+
+# ------------------------------------------------------------------------------------------------
+# NTT  (reference convention: field/mod.rs:508-537)
+@pytest.mark.parametrize("log_n", [1, 2, 3, 5, 6])
+def test_ntt_matches_naive_dft(ctx, log_n):
+    rng = random.Random(100 + log_n)
+    n = 1 << log_n
+    x = [rand_fr(rng) for _ in range(n)]
+    w = synthetic.omega(log_n)
+    assert zk.ntt(ctx, x) == poly.dft(FR, x, w)
+    assert zk.ntt(ctx, x, inverse=True) == poly.idft(FR, x, w)
+
+
+@pytest.mark.parametrize("log_n", [9, 10, 11, 13, 15, 16])
+def test_ntt_matches_fast_oracle(ctx, log_n):
+    rng = random.Random(200 + log_n)
+    n = 1 << log_n
+    x = [rand_fr(rng) for _ in range(n)]
+    w = synthetic.omega(log_n)
+    y = zk.ntt(ctx, x)
+    assert y == poly.ntt_fast(FR, x, w)
+    assert zk.ntt(ctx, y, inverse=True) == x
+
+
+def test_ntt_coset_and_edge_sizes(ctx):
+    rng = random.Random(3)
+    assert zk.ntt(ctx, [5]) == [5] and zk.ntt(ctx, [5], inverse=True) == [5]
+    n, g = 64, 7
+    x = [rand_fr(rng) for _ in range(n)]
+    shifted = [a * pow(g, i, P) % P for i, a in enumerate(x)]
+    y = zk.ntt(ctx, x, coset_shift=g)
+    assert y == poly.dft(FR, shifted, synthetic.omega(6))
+    assert zk.ntt(ctx, y, inverse=True, coset_shift=g) == x
+    # all-zero and all-(r-1) vectors
+    assert zk.ntt(ctx, [0] * 16) == [0] * 16
+    top = [P - 1] * 16
+    assert zk.ntt(ctx, top) == poly.dft(FR, top, synthetic.omega(4))
+
+
+@pytest.mark.parametrize("log_n", [20, 22])
+def test_ntt_roundtrip_and_linearity_full_size(ctx, log_n):
+    """BASELINE configs 2^20 / 2^22: iNTT(NTT(x)) == x and NTT(x)[0] == sum(x), NTT(delta_1) == powers."""
+    n = 1 << log_n
+    rng = np.random.default_rng(log_n)
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 60) - 1)  # < 2^252 < r: canonical residues
+    d = ctx.dev_alloc(a.nbytes)
+    try:
+        ctx.h2d(d, a)
+        lib = ctx.lib
+        import ctypes as C
+        ctx.check(lib.zkb_ntt_fr(ctx.h, C.c_void_p(d), log_n, 0, None), "ntt")
+        y = np.empty_like(a)
+        ctx.d2h(y, d)
+        # X[0] = sum of inputs (column sums of 32-bit halves stay below 2^64)
+        lo = (a & np.uint64(0xFFFFFFFF)).sum(axis=0, dtype=np.uint64)
+        hi = (a >> np.uint64(32)).sum(axis=0, dtype=np.uint64)
+        tot = sum((int(lo[j]) + (int(hi[j]) << 32)) << (64 * j) for j in range(4)) % P
+        assert zg.limbs_to_ints(y[:1])[0] == tot
+        ctx.check(lib.zkb_ntt_fr(ctx.h, C.c_void_p(d), log_n, 1, None), "intt")
+        ctx.d2h(y, d)
+        assert np.array_equal(y, a)
+        # delta at index 1 -> out[i] = omega^i
+        e = np.zeros_like(a)
+        e[1, 0] = 1
+        ctx.h2d(d, e)
+        ctx.check(lib.zkb_ntt_fr(ctx.h, C.c_void_p(d), log_n, 0, None), "ntt")
+        ctx.d2h(y, d)
+        w = synthetic.omega(log_n)
+        for i in [0, 1, 2, 3, 1000, n // 2, n - 1]:
+            assert zg.limbs_to_ints(y[i:i + 1])[0] == pow(w, i, P)
+    finally:
+        ctx.dev_free(d)
+
+
+# ------------------------------------------------------------------------------------------------
+# fixed-base generation + MSM
+def test_bases_generate_matches_oracle(ctx):
+    rng = random.Random(5)
+    ks = [0, 1, 2, P - 1, 69] + [rand_fr(rng) for _ in range(6)]
+    g1 = zk.Bases.generate(ctx, 1, ks).download()
+    g2 = zk.Bases.generate(ctx, 2, ks).download()
+    assert g1 == [bn.g1_mul(bn.BASE_G1, k) for k in ks]
+    assert g2 == [bn.g2_mul(bn.BASE_G2, k) for k in ks]
+    assert g1[0] is None and g2[0] is None  # encrypt_g1(0) is the identity (mod.rs:407)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_msm_small_adversarial(ctx, group):
+    """Zero scalars, 1, r-1, repeated points, P and -P, identity among the bases."""
+    rng = random.Random(40 + group)
+    base = bn.BASE_G1 if group == 1 else bn.BASE_G2
+    mul = bn.g1_mul if group == 1 else bn.g2_mul
+    neg = bn.g1_neg if group == 1 else bn.g2_neg
+    ora = bn.msm_g1 if group == 1 else bn.msm_g2
+    Pt = mul(base, 12345)
+    pts = [Pt, Pt, neg(Pt), None, mul(base, 7), mul(base, 7), base, mul(base, P - 1)]
+    pts += [mul(base, rand_fr(rng)) for _ in range(8)]
+    scal = [5, 5, 10, 999, 0, 1, P - 1, P - 1] + [rand_fr(rng) for _ in range(8)]
+    b = zk.Bases.upload(ctx, group, pts)
+    for c in (0, 2, 3, 5, 8, 13):
+        assert zk.msm(ctx, b, scal, window_bits=c) == ora(scal, pts), f"window {c}"
+    # everything cancels -> identity
+    assert zk.msm(ctx, b, [3, 4, 7] + [0] * 13) is None
+    # zip truncation: fewer scalars than bases; and the empty sum is the identity (fr.rs:196)
+    assert zk.msm(ctx, b, scal[:3]) == ora(scal[:3], pts[:3])
+    assert zk.msm(ctx, b, []) is None
+    # same scalar everywhere (one bucket per window takes all points)
+    assert zk.msm(ctx, b, [scal[9]] * 16) == ora([scal[9]] * 16, pts)
+
+
+@pytest.mark.parametrize("group,log_n", [(1, 8), (1, 12), (2, 10), (1, 16), (2, 14)])
+def test_msm_collapse_property(ctx, group, log_n):
+    """bases P_i = k_i * BASE  =>  sum s_i P_i = (sum s_i k_i) * BASE.  Size independent."""
+    n = 1 << log_n
+    rng = random.Random(log_n * 10 + group)
+    ks = [rand_fr(rng) for _ in range(n)]
+    ss = [rand_fr(rng) for _ in range(n)]
+    # witness-like skew: a block of zeros and ones
+    for i in range(0, n, 5):
+        ss[i] = i % 2
+    b = zk.Bases.generate(ctx, group, ks)
+    e = sum(s * k for s, k in zip(ss, ks)) % P
+    want = bn.g1_mul(bn.BASE_G1, e) if group == 1 else bn.g2_mul(bn.BASE_G2, e)
+    assert zk.msm(ctx, b, ss) == want
+
+
+def test_msm_2pow20_collapse(ctx):
+    """BASELINE config 4 size (2^20 points), same collapse property, numpy-generated inputs."""
+    n = 1 << 20
+    rng = np.random.default_rng(20)
+    k = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    s = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    k[:, 3] &= np.uint64((1 << 60) - 1)
+    s[:, 3] &= np.uint64((1 << 60) - 1)
+    b = zk.Bases.generate(ctx, 1, k)
+    ki, si = zg.limbs_to_ints(k), zg.limbs_to_ints(s)
+    e = sum(x * y for x, y in zip(ki, si)) % P
+    assert zk.msm(ctx, b, s) == bn.g1_mul(bn.BASE_G1, e)
+
+
+def test_points_sum(ctx):
+    pts = [bn.g1_mul(bn.BASE_G1, k) for k in (3, 5, 7)] + [None]
+    assert zg.points_sum(ctx, 1, pts) == bn.g1_mul(bn.BASE_G1, 15)
+    q = [bn.g2_mul(bn.BASE_G2, k) for k in (3, P - 3)]
+    assert zg.points_sum(ctx, 2, q) is None
+
+
+# ------------------------------------------------------------------------------------------------
+# QAP / setup / prove against the literal restatement
+def _horner_case(n, seed, valid=True):
+    rng = random.Random(seed)
+    log_n = n.bit_length() - 1
+    w = synthetic.omega(log_n)
+    roots = [pow(w, k, P) for k in range(n)]
+    rep = synthetic.horner_rep(FR, n, roots)
+    x, cs = rand_fr(rng, True), [rand_fr(rng) for _ in range(n)]
+    wit = synthetic.horner_witness(FR, n, x, cs)
+    if not valid:
+        wit[3] = (wit[3] + 1) % P
+        wit[-1] = rand_fr(rng)
+    toxic = tuple(rand_fr(rng, True) for _ in range(5))
+    r, s = rand_fr(rng, True), rand_fr(rng, True)
+    return rep, wit, toxic, r, s
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16])
+@pytest.mark.parametrize("valid", [True, False])
+def test_h_matches_reference_quotient(ctx, n, valid):
+    """u_sum, v_sum (mod.rs:233-246) and h = (u*v - w)/t (mod.rs:277) vs schoolbook Mul + long division,
+    for satisfying AND non-satisfying witnesses (the reference discards the remainder)."""
+    rep, wit, *_ = _horner_case(n, 7 * n + valid, valid)
+    dense = og.qap_from_root_rep(FR, rep)
+    u, v, w = og.weighted_sums(FR, dense, wit)
+    h = og.quotient_h(FR, dense, u, v, w)
+    q = zk.QAP.from_root_representation(ctx, rep)
+    gu, gv, gh = zk.qap_h(ctx, q, wit)
+    pad = lambda p, k: (list(p) + [0] * k)[:k]
+    assert gu == pad(u, n) and gv == pad(v, n)
+    assert gh == pad(h, n - 1)
+
+
+def test_horner_rows_match_oracle_rep(ctx):
+    n = 8
+    rep, wit, toxic, r, s = _horner_case(n, 1)
+    q1 = zk.QAP.from_root_representation(ctx, rep)
+    q2 = zk.QAP.horner(ctx, n)
+    assert zk.qap_h(ctx, q1, wit) == zk.qap_h(ctx, q2, wit)
+    assert zg.horner_witness(n, wit[1], [wit[4], wit[6], wit[8], wit[10], wit[12], wit[14], wit[16], wit[17]]) == wit
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_setup_matches_reference(ctx, n):
+    rep, wit, toxic, r, s = _horner_case(n, 50 + n)
+    dense = og.qap_from_root_rep(FR, rep)
+    s1, s2 = og.setup(og.BN254Backend(), dense, toxic)
+    q = zk.QAP.from_root_representation(ctx, rep)
+    crs = zk.setup(ctx, q, toxic).download()
+    assert crs["alpha1"] == s1.alpha and crs["beta1"] == s1.beta and crs["delta1"] == s1.delta
+    assert crs["xi1"] == s1.xi and crs["xi_t"] == s1.xi_t
+    assert crs["sum_gamma"] == s1.sum_gamma and crs["sum_delta"] == s1.sum_delta
+    assert crs["beta2"] == s2.beta and crs["gamma2"] == s2.gamma and crs["delta2"] == s2.delta
+    assert crs["xi2"] == s2.xi
+    assert len(crs["xi_t"]) == n - 1 and len(crs["sum_gamma"]) == rep.input + 1  # mod.rs:154,168
+
+
+@pytest.mark.parametrize("n,valid", [(2, True), (4, True), (8, True), (8, False), (16, True)])
+def test_prove_matches_reference(ctx, n, valid):
+    """Bit-exact Proof{a,b,c} vs the literal restatement of groth16::prove, CRS uploaded from the
+    oracle's setup() (so prove is tested independently of the device setup)."""
+    rep, wit, toxic, r, s = _horner_case(n, 90 + n, valid)
+    B = og.BN254Backend()
+    dense = og.qap_from_root_rep(FR, rep)
+    sig = og.setup(B, dense, toxic)
+    want = og.prove(B, dense, sig, wit, r, s)
+    q = zk.QAP.from_root_representation(ctx, rep)
+    crs = zk.CRS.upload(ctx, sig[0], sig[1])
+    got = zk.prove(ctx, q, crs, wit, r, s)
+    assert (got.a, got.b, got.c) == (want.a, want.b, want.c)
+    if valid:
+        assert og.verify(B, sig, wit[1:rep.input + 1], og.Proof(got.a, got.b, got.c))
+    # zip truncation of the weights (mod.rs:237..288): a short witness == zero-padded witness
+    short = wit[: len(wit) - 2]
+    want2 = og.prove(B, dense, sig, short, r, s)
+    got2 = zk.prove(ctx, q, crs, short, r, s)
+    assert (got2.a, got2.b, got2.c) == (want2.a, want2.b, want2.c)
+
+
+def test_prove_with_identity_in_crs(ctx):
+    """encrypt_g1(0) entries (identity points) are legal CRS members (mod.rs:407)."""
+    n = 4
+    rep, wit, toxic, r, s = _horner_case(n, 5)
+    B = og.BN254Backend()
+    dense = og.qap_from_root_rep(FR, rep)
+    s1, s2 = og.setup(B, dense, toxic)
+    s1.sum_delta[1] = None
+    s1.xi[2] = None
+    s2.xi[1] = None
+    want = og.prove(B, dense, (s1, s2), wit, r, s)
+    q = zk.QAP.from_root_representation(ctx, rep)
+    got = zk.prove(ctx, q, zk.CRS.upload(ctx, s1, s2), wit, r, s)
+    assert (got.a, got.b, got.c) == (want.a, want.b, want.c)
+
+
+def _rows_from_csr(rows):
+    out = []
+    for ptr, gate, coeff in rows:
+        cs = zg.limbs_to_ints(coeff)
+        out.append([[(int(gate[e]), cs[e]) for e in range(int(ptr[i]), int(ptr[i + 1]))] for i in range(len(ptr) - 1)])
+    return out
+
+
+@pytest.mark.parametrize("log_n", [6, 10, 12, 16])
+def test_prove_closed_form_and_pairing(ctx, log_n):
+    """Device setup + prove on the synthetic Horner QAP (BASELINE config 2 at 2^16) against the
+    closed-form proof from the toxic waste (bit-exact) and, for 2^6, the reference's own
+    acceptance criterion verify(...) == true (lib.rs:156-190) through the oracle pairing."""
+    n = 1 << log_n
+    rng = random.Random(log_n)
+    m, n_input, rows = zg.horner_qap_rows(n)
+    x, cs = rand_fr(rng, True), [rand_fr(rng) for _ in range(n)]
+    wit = zg.horner_witness(n, x, cs)
+    toxic = tuple(rand_fr(rng, True) for _ in range(5))
+    r, s = rand_fr(rng, True), rand_fr(rng, True)
+    q = zk.QAP(ctx, n, m, n_input, rows)
+    crs = zk.setup(ctx, q, toxic)
+    got = zk.prove(ctx, q, crs, wit, r, s)
+    ru, rv, rw = _rows_from_csr(rows)
+    want = cf.expected_proof(n, synthetic.omega(log_n), ru, rv, rw, n_input, wit, toxic, r, s)
+    assert (got.a, got.b, got.c) == want
+    if log_n == 6:
+        d = crs.download()
+        s1 = og.SigmaG1(d["alpha1"], d["beta1"], d["delta1"], d["xi1"], d["sum_gamma"], d["sum_delta"], d["xi_t"])
+        s2 = og.SigmaG2(d["beta2"], d["gamma2"], d["delta2"], d["xi2"])
+        assert og.verify(og.BN254Backend(), (s1, s2), wit[1:3], og.Proof(got.a, got.b, got.c))
+        bad = list(wit)
+        bad[2] = (bad[2] + 1) % P  # wrong public output -> reject (lib.rs:182-189)
+        assert not og.verify(og.BN254Backend(), (s1, s2), bad[1:3], og.Proof(got.a, got.b, got.c))
+
+
+def test_prove_sharded_equals_single(ctx):
+    """Multi-GPU decomposition on one device: world-2 and world-3 shards, partial sums folded by
+    zkb_prove_combine, must equal the unsharded proof bit for bit."""
+    n = 64
+    rng = random.Random(77)
+    m, n_input, rows = zg.horner_qap_rows(n)
+    wit = zg.horner_witness(n, rand_fr(rng, True), [rand_fr(rng) for _ in range(n)])
+    toxic = tuple(rand_fr(rng, True) for _ in range(5))
+    r, s = rand_fr(rng, True), rand_fr(rng, True)
+    q = zk.QAP(ctx, n, m, n_input, rows)
+    full = zk.prove(ctx, q, zk.setup(ctx, q, toxic), wit, r, s)
+    for world in (2, 3):
+        parts = []
+        shards = [zk.setup(ctx, q, toxic, rank=k, world=world) for k in range(world)]
+        for k in range(world):
+            parts.append(zk.prove_partial(ctx, q, shards[k], wit))
+        got = zk.prove_combine(ctx, shards[0], np.stack(parts), r, s)
+        assert (got.a, got.b, got.c) == (full.a, full.b, full.c)
+
+
+def test_error_paths(ctx):
+    with pytest.raises(zk.ZkbError):
+        zk.QAP(ctx, 6, 4, 1, [(np.zeros(5, dtype=np.uint64), np.zeros(0, dtype=np.uint32), np.zeros((0, 4), dtype=np.uint64))] * 3)
+    n = 4
+    m, n_input, rows = zg.horner_qap_rows(n)
+    q = zk.QAP(ctx, n, m, n_input, rows)
+    with pytest.raises(zk.ZkbError):
+        zk.setup(ctx, q, (1, 2, 0, 4, 5))  # zero secret: the reference's random_elem never yields 0
+    q8 = zk.QAP.horner(ctx, 8)
+    crs4 = zk.setup(ctx, q, (1, 2, 3, 4, 5))
+    with pytest.raises(zk.ZkbError):
+        zk.prove(ctx, q8, crs4, [1] * 18, 1, 1)  # CRS of another QAP

@@ -1,0 +1,143 @@
+// Internal definitions shared by the translation units of libzkb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/zkb200.h"
+#include "ec.cuh"
+
+namespace zkb {
+
+struct Ctx;
+
+// device scratch arena entry
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace zkb
+
+struct zkb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second queue: the G2 MSM runs beside the G1 MSMs
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int sm_count = 148;
+  uint64_t launches = 0;
+  std::string err;
+  // twiddle tables tw[log_n][inverse]: omega^k (k < n/2) in Montgomery form, built lazily
+  zkb::Fr* tw[28][2] = {};
+  // reusable scratch (grown on demand, never shrunk)
+  zkb::DevBuf scratch[16];
+};
+
+namespace zkb {
+
+extern thread_local std::string g_err;
+
+int set_err(zkb_ctx* ctx, int code, const char* fmt, ...);
+
+#define ZKB_CUDA(ctx, expr)                                                                     \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return ::zkb::set_err(ctx, ZKB_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,    \
+                            cudaGetErrorString(e__));                                           \
+  } while (0)
+
+#define ZKB_TRY(expr)          \
+  do {                         \
+    int rc__ = (expr);         \
+    if (rc__ != ZKB_OK) return rc__; \
+  } while (0)
+
+// kernel launch bookkeeping: count + check
+#define ZKB_LAUNCH(ctx, kernel, grid, block, smem, strm, ...)                                   \
+  do {                                                                                          \
+    kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                                   \
+    (ctx)->launches++;                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess)                                                                     \
+      return ::zkb::set_err(ctx, ZKB_ERR_CUDA, "%s:%d: launch %s -> %s", __FILE__, __LINE__,    \
+                            #kernel, cudaGetErrorString(e__));                                  \
+  } while (0)
+
+// grow-only scratch slot
+int scratch_get(zkb_ctx* ctx, int slot, size_t bytes, void** out);
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- ntt.cu -------------------------------------------------------------------------------------
+// In-place transform, Montgomery form.  DIF: natural in -> bit-reversed out.
+int ntt_dif(zkb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, cudaStream_t st);
+// DIT: bit-reversed in -> natural out.
+int ntt_dit(zkb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, cudaStream_t st);
+// out[bitrev(i)] = in[i] * scale (scale may be null), out != in
+int bitrev_permute(zkb_ctx* ctx, Fr* out, const Fr* in, uint32_t log_n, const Fr* h_scale, cudaStream_t st);
+// d[i] *= base^i  (Montgomery form); if bitrev, position i holds logical index bitrev(i)
+int scale_powers(zkb_ctx* ctx, Fr* d, uint32_t log_n, const Fr& base, const Fr& first, bool bitrev, cudaStream_t st);
+int vec_to_mont(zkb_ctx* ctx, Fr* d, size_t n, bool to, cudaStream_t st);
+int vec_mul(zkb_ctx* ctx, Fr* out, const Fr* a, const Fr* b, size_t n, cudaStream_t st);
+// out[i] = first * base^i
+int fill_powers(zkb_ctx* ctx, Fr* out, const Fr& base, const Fr& first, size_t n, cudaStream_t st);
+Fr host_omega(uint32_t log_n, bool inverse);  // Montgomery form
+int get_twiddles(zkb_ctx* ctx, uint32_t log_n, bool inverse, Fr** out);
+
+// ---- msm.cu -------------------------------------------------------------------------------------
+// result (XYZZ, Montgomery, device) = sum scalars[i] * points[i], i < n.
+// scalars: device, 8 x u32 each; `mont` says whether they are in Montgomery form.
+int msm_g1(zkb_ctx* ctx, const G1Affine* pts, const Fr* scalars, bool mont, size_t n, int c, G1XYZZ* d_out,
+           int slot_base, cudaStream_t st);
+int msm_g2(zkb_ctx* ctx, const G2Affine* pts, const Fr* scalars, bool mont, size_t n, int c, G2XYZZ* d_out,
+           int slot_base, cudaStream_t st);
+int fixed_base_g1(zkb_ctx* ctx, G1Affine* out, const Fr* scalars_mont, size_t n, cudaStream_t st);
+int fixed_base_g2(zkb_ctx* ctx, G2Affine* out, const Fr* scalars_mont, size_t n, cudaStream_t st);
+// canonical <-> Montgomery for arrays of Fq (point coordinates)
+int fq_to_mont(zkb_ctx* ctx, Fq* d, size_t n, bool to, cudaStream_t st);
+int xyzz_to_affine_g1(zkb_ctx* ctx, G1Affine* out, const G1XYZZ* in, size_t n, cudaStream_t st);
+int xyzz_to_affine_g2(zkb_ctx* ctx, G2Affine* out, const G2XYZZ* in, size_t n, cudaStream_t st);
+int sum_affine_g1(zkb_ctx* ctx, const G1Affine* pts, size_t n, G1XYZZ* d_out, cudaStream_t st);
+int sum_affine_g2(zkb_ctx* ctx, const G2Affine* pts, size_t n, G2XYZZ* d_out, cudaStream_t st);
+
+}  // namespace zkb
+
+struct zkb_bases {
+  int group = 1;
+  size_t n = 0;
+  void* d = nullptr;  // G1Affine* or G2Affine*, Montgomery form
+};
+
+struct zkb_qap {
+  uint64_t n = 0, m = 0, n_input = 0;
+  uint32_t log_n = 0;
+  // by-gate CSR (transposed from the by-wire rows at upload): for gate k, entries [gptr[k], gptr[k+1])
+  uint32_t* d_gptr[3] = {};
+  uint32_t* d_wire[3] = {};
+  zkb::Fr* d_coeff[3] = {};  // Montgomery
+  // by-wire CSR as uploaded (setup evaluates rows at x)
+  uint32_t* d_rptr[3] = {};
+  uint32_t* d_gate[3] = {};
+  zkb::Fr* d_rcoeff[3] = {};  // Montgomery, in row order
+  uint64_t nnz[3] = {};
+  // coset tables in bit-reversed position order: P[i] = g^br(i) / n, Q[i] = g^-br(i) / (2n), g = omega_2n
+  zkb::Fr* d_cosP = nullptr;
+  zkb::Fr* d_cosQ = nullptr;
+  // per-QAP workspace: 8 vectors of n Fr, and the witness in canonical + Montgomery form (m Fr each)
+  zkb::Fr* d_ws = nullptr;
+  zkb::Fr* d_wcanon = nullptr;
+  zkb::Fr* d_wmont = nullptr;
+};
+
+struct zkb_crs {
+  uint64_t n = 0, n_sum_gamma = 0, n_sum_delta = 0;
+  int rank = 0, world = 1;
+  // shard ranges [lo, hi) into the logical vectors
+  uint64_t xi_lo = 0, xi_hi = 0, xit_lo = 0, xit_hi = 0, sd_lo = 0, sd_hi = 0;
+  zkb::G1Affine *alpha1 = nullptr, *beta1 = nullptr, *delta1 = nullptr;  // one block of 3 points
+  zkb::G1Affine *xi1 = nullptr, *xi_t = nullptr, *sum_gamma = nullptr, *sum_delta = nullptr;
+  zkb::G2Affine *beta2 = nullptr, *gamma2 = nullptr, *delta2 = nullptr;
+  zkb::G2Affine* xi2 = nullptr;
+};

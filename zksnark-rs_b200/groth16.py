@@ -1,0 +1,590 @@
+"""Host-side mirror of the reference's Groth16 interface for the prove() path, over libzkb200.so.
+
+Names follow /root/reference/src/groth16/mod.rs: ``QAP`` (:60-67), ``SigmaG1``/``SigmaG2`` (:105-121,
+held together here as one device-resident ``CRS``), ``Proof`` (:124-128), ``setup`` (:134-197),
+``prove`` (:213-296).  Field elements are Python ints (canonical residues); G1 points are ``None``
+(identity) or ``(x, y)``; G2 points are ``None`` or ``((x0, x1), (y0, y1))``.
+
+Everything that computes goes through the CUDA library; nothing here does field or curve
+arithmetic on the CPU (packing ints into limbs and building index arrays is all the host does).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import secrets
+from dataclasses import dataclass
+
+import numpy as np
+
+FR_MODULUS = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+TWO_ADICITY = 28
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class ZkbError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (the reference panics instead)."""
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libzkb200.so")
+
+
+class _QapHost(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("m", C.c_uint64), ("n_input", C.c_uint64),
+                ("row_ptr", C.c_void_p * 3), ("gate", C.c_void_p * 3), ("coeff", C.c_void_p * 3)]
+
+
+class _CrsHost(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("n_sum_gamma", C.c_uint64), ("n_sum_delta", C.c_uint64),
+                ("alpha1", C.c_void_p), ("beta1", C.c_void_p), ("delta1", C.c_void_p),
+                ("xi1", C.c_void_p), ("xi_t", C.c_void_p), ("sum_gamma", C.c_void_p), ("sum_delta", C.c_void_p),
+                ("beta2", C.c_void_p), ("gamma2", C.c_void_p), ("delta2", C.c_void_p), ("xi2", C.c_void_p)]
+
+
+class _ProofC(C.Structure):
+    _fields_ = [("a", C.c_uint64 * 8), ("b", C.c_uint64 * 16), ("c", C.c_uint64 * 8)]
+
+
+# every symbol include/zkb200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+ABI = {
+    "zkb_ctx_create": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "zkb_ctx_destroy": (None, [_P]),
+    "zkb_last_error": (C.c_char_p, [_P]),
+    "zkb_launch_count": (C.c_uint64, [_P]),
+    "zkb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "zkb_host_free": (None, [_P]),
+    "zkb_dev_alloc": (C.c_int, [_P, C.POINTER(_P), C.c_size_t]),
+    "zkb_dev_free": (None, [_P, _P]),
+    "zkb_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "zkb_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "zkb_sync": (C.c_int, [_P]),
+    "zkb_stream": (_P, [_P]),
+    "zkb_qap_upload": (C.c_int, [_P, C.POINTER(_QapHost), C.POINTER(_P)]),
+    "zkb_qap_free": (None, [_P, _P]),
+    "zkb_crs_upload": (C.c_int, [_P, C.POINTER(_CrsHost), C.c_int, C.c_int, C.POINTER(_P)]),
+    "zkb_setup": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "zkb_crs_dims": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "zkb_crs_download": (C.c_int, [_P, _P, C.POINTER(_CrsHost)]),
+    "zkb_crs_free": (None, [_P, _P]),
+    "zkb_prove": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(_ProofC)]),
+    "zkb_prove_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(_ProofC)]),
+    "zkb_prove_partial": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
+    "zkb_prove_combine": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.POINTER(_ProofC)]),
+    "zkb_qap_h": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "zkb_ntt_fr": (C.c_int, [_P, _P, C.c_uint32, C.c_int, _P]),
+    "zkb_ntt_fr_raw": (C.c_int, [_P, _P, C.c_uint32, C.c_int]),
+    "zkb_fr_to_mont": (C.c_int, [_P, _P, C.c_size_t, C.c_int]),
+    "zkb_bases_upload": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.POINTER(_P)]),
+    "zkb_bases_generate": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.POINTER(_P)]),
+    "zkb_bases_download": (C.c_int, [_P, _P, _P]),
+    "zkb_bases_free": (None, [_P, _P]),
+    "zkb_msm": (C.c_int, [_P, _P, _P, C.c_int, C.c_size_t, C.c_int, _P]),
+    "zkb_points_sum": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P]),
+    "zkb_bench_modmul": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen libzkb200.so and bind every symbol of include/zkb200.h.  Fails loudly when the CUDA
+    library has not been built -- there is no fallback implementation."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ZkbError(f"{path} not found: build it with `python zksnark-rs_b200/build.py` "
+                           "(nvcc, sm_100a); this package has no CPU fallback")
+        lib = C.CDLL(path)
+        for name, (res, args) in ABI.items():
+            fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+# ------------------------------------------------------------------------------------------------
+# limb packing
+def fr_limbs(values) -> np.ndarray:
+    """ints -> (len, 4) uint64 little-endian limbs."""
+    vals = list(values)
+    buf = b"".join(int(v).to_bytes(32, "little") for v in vals)
+    return np.frombuffer(buf, dtype="<u8").reshape(len(vals), 4).copy()
+
+
+def limbs_to_ints(arr: np.ndarray) -> list:
+    a = np.ascontiguousarray(arr, dtype="<u8").reshape(-1, 4)
+    raw = a.tobytes()
+    return [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(a.shape[0])]
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def g1_pack(points) -> np.ndarray:
+    flat = []
+    for P in points:
+        flat += [0, 0] if P is None else [P[0], P[1]]
+    return fr_limbs(flat).reshape(-1, 8)
+
+
+def g2_pack(points) -> np.ndarray:
+    flat = []
+    for P in points:
+        flat += [0, 0, 0, 0] if P is None else [P[0][0], P[0][1], P[1][0], P[1][1]]
+    return fr_limbs(flat).reshape(-1, 16)
+
+
+def g1_unpack(arr) -> list:
+    v = limbs_to_ints(np.asarray(arr).reshape(-1, 4))
+    out = []
+    for i in range(0, len(v), 2):
+        out.append(None if v[i] == 0 and v[i + 1] == 0 else (v[i], v[i + 1]))
+    return out
+
+
+def g2_unpack(arr) -> list:
+    v = limbs_to_ints(np.asarray(arr).reshape(-1, 4))
+    out = []
+    for i in range(0, len(v), 4):
+        q = v[i:i + 4]
+        out.append(None if not any(q) else ((q[0], q[1]), (q[2], q[3])))
+    return out
+
+
+def omega(log_n: int) -> int:
+    """Primitive 2^log_n-th root of unity of Fr used for the gate domain: 5^((r-1)/2^log_n)."""
+    return pow(5, (FR_MODULUS - 1) >> log_n, FR_MODULUS)
+
+
+def random_elem() -> int:
+    """`Random::random_elem` for FrLocal (fr.rs:90-99): uniform and never zero."""
+    return secrets.randbelow(FR_MODULUS - 1) + 1
+
+
+# ------------------------------------------------------------------------------------------------
+class Context:
+    """One CUDA device (zkb_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.zkb_ctx_create(C.byref(h), device)
+        if rc != 0:
+            raise ZkbError(f"zkb_ctx_create({device}) = {rc}: {self.lib.zkb_last_error(None).decode()}")
+        self.h = h
+        self.device = device
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            raise ZkbError(f"{what} = {rc}: {self.lib.zkb_last_error(self.h).decode()}")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.zkb_launch_count(self.h))
+
+    def sync(self):
+        self.check(self.lib.zkb_sync(self.h), "zkb_sync")
+
+    def stream(self) -> int:
+        return int(self.lib.zkb_stream(self.h) or 0)
+
+    # raw device memory for resident inputs
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self.check(self.lib.zkb_dev_alloc(self.h, C.byref(p), nbytes), "zkb_dev_alloc")
+        return p.value
+
+    def dev_free(self, p: int):
+        self.lib.zkb_dev_free(self.h, C.c_void_p(p))
+
+    def h2d(self, dptr: int, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        self.check(self.lib.zkb_memcpy_h2d(self.h, C.c_void_p(dptr), _ptr(arr), arr.nbytes), "zkb_memcpy_h2d")
+
+    def d2h(self, arr: np.ndarray, dptr: int):
+        self.check(self.lib.zkb_memcpy_d2h(self.h, _ptr(arr), C.c_void_p(dptr), arr.nbytes), "zkb_memcpy_d2h")
+
+    def pinned(self, shape, dtype="<u8") -> np.ndarray:
+        """numpy array backed by pinned host memory (for per-proof witness uploads)."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self.check(self.lib.zkb_host_alloc(C.byref(p), nbytes), "zkb_host_alloc")
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        return arr
+
+    def bench_modmul(self, field: int = 1, iters: int = 2000):
+        rate, ms = C.c_double(), C.c_double()
+        self.check(self.lib.zkb_bench_modmul(self.h, field, iters, C.byref(rate), C.byref(ms)), "zkb_bench_modmul")
+        return rate.value, ms.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            for p in getattr(self, "_pinned", []):
+                self.lib.zkb_host_free(p)
+            self._pinned = []
+            self.lib.zkb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+def _csr(rows_of_pairs, n_rows):
+    """list (per wire) of [(gate, coeff int)] -> row_ptr u64, gate u32, coeff limbs."""
+    ptr = np.zeros(n_rows + 1, dtype=np.uint64)
+    gates, coeffs = [], []
+    for i, row in enumerate(rows_of_pairs):
+        for g, c in row:
+            gates.append(g)
+            coeffs.append(c)
+        ptr[i + 1] = len(gates)
+    return ptr, np.asarray(gates, dtype=np.uint32), fr_limbs(coeffs).reshape(-1, 4)
+
+
+def horner_qap_rows(n: int):
+    """CSR rows (by wire) of the synthetic n-gate Horner circuit deg_{n-1} (generalises
+    test_programs/deg_15.zk).  Row order as ASTParser produces it (circuit/mod.rs:230-526): 0 unity,
+    1 x, 2 y, t_k -> 2k+1, c_k -> 2k+2 (k<n), c_n -> 2n+1.  Gate k (1-based) is gate index k-1.
+    Returns (m, n_input, [(row_ptr, gate, coeff)] for u, v, w)."""
+    assert n >= 2
+    m = 2 * n + 2
+    one = np.zeros((1, 4), dtype=np.uint64)
+    one[0, 0] = 1
+    k = np.arange(1, n, dtype=np.uint64)  # 1..n-1
+    # u: row 0 -> gate n-1 ; row 1 -> gates 0..n-2
+    pu = np.zeros(m + 1, dtype=np.uint64)
+    pu[1] = 1
+    pu[2:] = n
+    gu = np.concatenate([[n - 1], np.arange(0, n - 1)]).astype(np.uint32)
+    # v: rows 3..2n one entry each: row 2k+1 (t_k) -> gate k ; row 2k+2 (c_k) -> gate k-1 ; row 2n+1 (c_n) -> gate n-1
+    pv = np.zeros(m + 1, dtype=np.uint64)
+    pv[4:] = np.arange(1, m - 2, dtype=np.uint64)  # rows 3.. have one entry each
+    gv = np.empty(m - 3, dtype=np.uint32)
+    gv[0:2 * (n - 1):2] = k            # rows 3,5,.. = t_k
+    gv[1:2 * (n - 1):2] = k - 1        # rows 4,6,.. = c_k
+    gv[2 * (n - 1)] = n - 1            # row 2n+1 = c_n
+    # w: row 2 (y) -> gate n-1 ; row 2k+1 (t_k) -> gate k-1
+    cnt = np.zeros(m, dtype=np.uint64)
+    cnt[2] = 1
+    cnt[3:2 * n:2] = 1
+    pw = np.zeros(m + 1, dtype=np.uint64)
+    pw[1:] = np.cumsum(cnt)
+    gw = np.concatenate([[n - 1], np.arange(0, n - 1)]).astype(np.uint32)
+    rows = []
+    for p, g in ((pu, gu), (pv, gv), (pw, gw)):
+        rows.append((p, g, np.repeat(one, len(g), axis=0)))
+    return m, 2, rows
+
+
+def horner_witness(n: int, x: int, cs) -> list:
+    """Wire assignment (row order of horner_qap_rows) for inputs x, c_1..c_n."""
+    p = FR_MODULUS
+    a = [0] * (2 * n + 2)
+    a[0], a[1] = 1, x % p
+    acc = x * cs[0] % p
+    a[3], a[4] = acc, cs[0] % p
+    for k in range(2, n):
+        acc = x * (acc + cs[k - 1]) % p
+        a[2 * k + 1], a[2 * k + 2] = acc, cs[k - 1] % p
+    a[2 * n + 1] = cs[n - 1] % p
+    a[2] = (acc + cs[n - 1]) % p
+    return a
+
+
+class QAP:
+    """Device-resident `QAP<CoefficientPoly<FrLocal>>` (groth16/mod.rs:60-67), stored as sparse
+    evaluation rows on the roots-of-unity domain instead of 3*m dense coefficient vectors."""
+
+    def __init__(self, ctx: Context, n: int, m: int, n_input: int, rows):
+        self.ctx, self.n, self.m, self.input = ctx, n, m, n_input
+        self.degree = n
+        host = _QapHost()
+        host.n, host.m, host.n_input = n, m, n_input
+        keep = []
+        for t, (ptr, gate, coeff) in enumerate(rows):
+            ptr = np.ascontiguousarray(ptr, dtype=np.uint64)
+            gate = np.ascontiguousarray(gate, dtype=np.uint32)
+            coeff = np.ascontiguousarray(coeff, dtype=np.uint64)
+            assert ptr.shape == (m + 1,) and coeff.size == gate.size * 4
+            keep += [ptr, gate, coeff]
+            host.row_ptr[t], host.gate[t], host.coeff[t] = ptr.ctypes.data, gate.ctypes.data, coeff.ctypes.data
+        h = C.c_void_p()
+        ctx.check(ctx.lib.zkb_qap_upload(ctx.h, C.byref(host), C.byref(h)), "zkb_qap_upload")
+        self.h = h
+
+    @classmethod
+    def from_root_representation(cls, ctx: Context, rep) -> "QAP":
+        """`From<RootRepresentation> for QAP` (fr.rs:140-173).  ``rep`` has u, v, w (per wire: list of
+        (root, value)), roots, input -- the DummyRep data model (circuit/dummy_rep.rs:7-13).  The roots
+        must be the powers of omega_n in order (the only domain this build accelerates)."""
+        n = len(rep.roots)
+        if n < 2 or n & (n - 1):
+            raise ZkbError("QAP: the number of roots must be a power of two >= 2")
+        w = omega(n.bit_length() - 1)
+        index, acc = {}, 1
+        for k in range(n):
+            index[acc] = k
+            acc = acc * w % FR_MODULUS
+        if [index.get(r % FR_MODULUS) for r in rep.roots] != list(range(n)):
+            raise ZkbError("QAP: roots must be omega^0 .. omega^(n-1) (roots-of-unity domain)")
+        if not (len(rep.u) == len(rep.v) == len(rep.w)):
+            raise ZkbError("QAP: u, v, w must have the same number of rows")  # assert at fr.rs:157-158
+        m = len(rep.u)
+        rows = []
+        for mat in (rep.u, rep.v, rep.w):
+            rows.append(_csr([[(index[r % FR_MODULUS], c % FR_MODULUS) for r, c in row] for row in mat], m))
+        return cls(ctx, n, m, rep.input, rows)
+
+    @classmethod
+    def horner(cls, ctx: Context, n: int) -> "QAP":
+        m, n_input, rows = horner_qap_rows(n)
+        return cls(ctx, n, m, n_input, rows)
+
+    def free(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.zkb_qap_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CRS:
+    """Device-resident (SigmaG1, SigmaG2) (groth16/mod.rs:105-121)."""
+
+    def __init__(self, ctx: Context, h, rank=0, world=1):
+        self.ctx, self.h, self.rank, self.world = ctx, h, rank, world
+
+    @classmethod
+    def upload(cls, ctx: Context, sigma_g1, sigma_g2, rank=0, world=1) -> "CRS":
+        """From the reference-shaped objects (attributes alpha, beta, delta, xi, sum_gamma, sum_delta,
+        xi_t / beta, gamma, delta, xi)."""
+        host = _CrsHost()
+        host.n, host.n_sum_gamma, host.n_sum_delta = len(sigma_g1.xi), len(sigma_g1.sum_gamma), len(sigma_g1.sum_delta)
+        arrs = {
+            "alpha1": g1_pack([sigma_g1.alpha]), "beta1": g1_pack([sigma_g1.beta]), "delta1": g1_pack([sigma_g1.delta]),
+            "xi1": g1_pack(sigma_g1.xi), "xi_t": g1_pack(sigma_g1.xi_t), "sum_gamma": g1_pack(sigma_g1.sum_gamma),
+            "sum_delta": g1_pack(sigma_g1.sum_delta),
+            "beta2": g2_pack([sigma_g2.beta]), "gamma2": g2_pack([sigma_g2.gamma]), "delta2": g2_pack([sigma_g2.delta]),
+            "xi2": g2_pack(sigma_g2.xi),
+        }
+        for k, a in arrs.items():
+            setattr(host, k, a.ctypes.data if a.size else None)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.zkb_crs_upload(ctx.h, C.byref(host), rank, world, C.byref(h)), "zkb_crs_upload")
+        return cls(ctx, h, rank, world)
+
+    def dims(self):
+        n, g, d = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.ctx.lib.zkb_crs_dims(self.h, C.byref(n), C.byref(g), C.byref(d)), "zkb_crs_dims")
+        return n.value, g.value, d.value
+
+    def download(self) -> dict:
+        n, ng, nd = self.dims()
+        host = _CrsHost()
+        host.n, host.n_sum_gamma, host.n_sum_delta = n, ng, nd
+        shapes = {"alpha1": (1, 8), "beta1": (1, 8), "delta1": (1, 8), "xi1": (n, 8), "xi_t": (n - 1, 8),
+                  "sum_gamma": (ng, 8), "sum_delta": (nd, 8), "beta2": (1, 16), "gamma2": (1, 16), "delta2": (1, 16),
+                  "xi2": (n, 16)}
+        arrs = {k: np.zeros(s, dtype=np.uint64) for k, s in shapes.items()}
+        for k, a in arrs.items():
+            setattr(host, k, a.ctypes.data if a.size else None)
+        self.ctx.check(self.ctx.lib.zkb_crs_download(self.ctx.h, self.h, C.byref(host)), "zkb_crs_download")
+        out = {}
+        for k, a in arrs.items():
+            pts = g2_unpack(a) if a.shape[1] == 16 else g1_unpack(a)
+            out[k] = pts[0] if k in ("alpha1", "beta1", "delta1", "beta2", "gamma2", "delta2") else pts
+        return out
+
+    def free(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.zkb_crs_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+@dataclass
+class Proof:
+    """groth16/mod.rs:124-128."""
+
+    a: object
+    b: object
+    c: object
+
+
+def _proof(pc: _ProofC) -> Proof:
+    return Proof(a=g1_unpack(np.array(pc.a[:], dtype=np.uint64))[0],
+                 b=g2_unpack(np.array(pc.b[:], dtype=np.uint64))[0],
+                 c=g1_unpack(np.array(pc.c[:], dtype=np.uint64))[0])
+
+
+def setup(ctx: Context, qap: QAP, toxic=None, rank=0, world=1) -> CRS:
+    """groth16::setup (mod.rs:134-197).  ``toxic`` = (alpha, beta, gamma, delta, x); drawn with
+    random_elem() when omitted, as the reference does (:139-145)."""
+    if toxic is None:
+        toxic = tuple(random_elem() for _ in range(5))
+    t = fr_limbs(toxic)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.zkb_setup(ctx.h, qap.h, _ptr(t), rank, world, C.byref(h)), "zkb_setup")
+    return CRS(ctx, h, rank, world)
+
+
+def _weights_array(qap: QAP, weights) -> np.ndarray:
+    if isinstance(weights, np.ndarray):
+        w = np.ascontiguousarray(weights, dtype=np.uint64).reshape(-1, 4)
+    else:
+        w = fr_limbs(weights)
+    if w.shape[0] != qap.m:  # every zip in prove() truncates to the shorter side (mod.rs:237..288)
+        full = np.zeros((qap.m, 4), dtype=np.uint64)
+        k = min(qap.m, w.shape[0])
+        full[:k] = w[:k]
+        w = full
+    return w
+
+
+def prove(ctx: Context, qap: QAP, crs: CRS, weights, r=None, s=None) -> Proof:
+    """groth16::prove (mod.rs:213-296).  r, s are drawn with random_elem() (mod.rs:231) unless given."""
+    r = random_elem() if r is None else r
+    s = random_elem() if s is None else s
+    w = _weights_array(qap, weights)
+    rl, sl = fr_limbs([r]), fr_limbs([s])
+    out = _ProofC()
+    ctx.check(ctx.lib.zkb_prove(ctx.h, qap.h, crs.h, _ptr(w), _ptr(rl), _ptr(sl), C.byref(out)), "zkb_prove")
+    return _proof(out)
+
+
+def prove_dev(ctx: Context, qap: QAP, crs: CRS, d_weights: int, r: int, s: int) -> Proof:
+    rl, sl = fr_limbs([r]), fr_limbs([s])
+    out = _ProofC()
+    ctx.check(ctx.lib.zkb_prove_dev(ctx.h, qap.h, crs.h, C.c_void_p(d_weights), _ptr(rl), _ptr(sl), C.byref(out)),
+              "zkb_prove_dev")
+    return _proof(out)
+
+
+def prove_partial(ctx: Context, qap: QAP, crs: CRS, weights, on_device=False) -> np.ndarray:
+    """This rank's four partial sums over its CRS shard: 40 limbs (a_g1, b_g1, c_g1, b_g2)."""
+    out = np.zeros(40, dtype=np.uint64)
+    if on_device:
+        wp = C.c_void_p(weights)
+    else:
+        w = _weights_array(qap, weights)
+        wp = _ptr(w)
+    ctx.check(ctx.lib.zkb_prove_partial(ctx.h, qap.h, crs.h, wp, 1 if on_device else 0, _ptr(out)), "zkb_prove_partial")
+    return out
+
+
+def prove_combine(ctx: Context, crs: CRS, partials: np.ndarray, r: int, s: int) -> Proof:
+    p = np.ascontiguousarray(partials, dtype=np.uint64).reshape(-1, 40)
+    rl, sl = fr_limbs([r]), fr_limbs([s])
+    out = _ProofC()
+    ctx.check(ctx.lib.zkb_prove_combine(ctx.h, crs.h, _ptr(p), p.shape[0], _ptr(rl), _ptr(sl), C.byref(out)),
+              "zkb_prove_combine")
+    return _proof(out)
+
+
+def qap_h(ctx: Context, qap: QAP, weights):
+    """(u_sum, v_sum, h) coefficient lists: mod.rs:233-246 and :277."""
+    w = _weights_array(qap, weights)
+    outs = [np.zeros((qap.n, 4), dtype=np.uint64) for _ in range(3)]
+    ctx.check(ctx.lib.zkb_qap_h(ctx.h, qap.h, _ptr(w), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2])), "zkb_qap_h")
+    u, v, h = (limbs_to_ints(o) for o in outs)
+    return u, v, h[: qap.n - 1]
+
+
+def ntt(ctx: Context, values, inverse=False, coset_shift=None) -> list:
+    """dft / idft (field/mod.rs:508-537) of a power-of-two-length list at root omega_n."""
+    n = len(values)
+    if n == 0 or n & (n - 1):
+        raise ZkbError("ntt: length must be a power of two")
+    a = fr_limbs(values)
+    d = ctx.dev_alloc(a.nbytes)
+    try:
+        ctx.h2d(d, a)
+        sh = fr_limbs([coset_shift]) if coset_shift is not None else None
+        ctx.check(ctx.lib.zkb_ntt_fr(ctx.h, C.c_void_p(d), n.bit_length() - 1, 1 if inverse else 0,
+                                     _ptr(sh) if sh is not None else None), "zkb_ntt_fr")
+        ctx.d2h(a, d)
+    finally:
+        ctx.dev_free(d)
+    return limbs_to_ints(a)
+
+
+class Bases:
+    """Device-resident vector of G1 (group=1) or G2 (group=2) points."""
+
+    def __init__(self, ctx: Context, h, group: int, n: int):
+        self.ctx, self.h, self.group, self.n = ctx, h, group, n
+
+    @classmethod
+    def upload(cls, ctx: Context, group: int, points) -> "Bases":
+        arr = g1_pack(points) if group == 1 else g2_pack(points)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.zkb_bases_upload(ctx.h, group, _ptr(arr) if arr.size else None, len(points), C.byref(h)),
+                  "zkb_bases_upload")
+        return cls(ctx, h, group, len(points))
+
+    @classmethod
+    def generate(cls, ctx: Context, group: int, scalars) -> "Bases":
+        """P_i = encrypt_g1(k_i) / encrypt_g2(k_i) (fr.rs:106-113) on the device."""
+        arr = scalars if isinstance(scalars, np.ndarray) else fr_limbs(scalars)
+        arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.zkb_bases_generate(ctx.h, group, _ptr(arr), arr.shape[0], C.byref(h)), "zkb_bases_generate")
+        return cls(ctx, h, group, arr.shape[0])
+
+    def download(self) -> list:
+        arr = np.zeros((self.n, 8 if self.group == 1 else 16), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.zkb_bases_download(self.ctx.h, self.h, _ptr(arr)), "zkb_bases_download")
+        return g1_unpack(arr) if self.group == 1 else g2_unpack(arr)
+
+    def free(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.zkb_bases_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def msm(ctx: Context, bases: Bases, scalars, window_bits: int = 0, on_device=False, n=None):
+    """sum_i scalars[i] * bases[i] -- the `.zip().map(exp_encrypted_g*).sum()` pattern (mod.rs:255-272)."""
+    out = np.zeros(8 if bases.group == 1 else 16, dtype=np.uint64)
+    if on_device:
+        sp, cnt = C.c_void_p(scalars), n
+    else:
+        arr = scalars if isinstance(scalars, np.ndarray) else fr_limbs(scalars)
+        arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+        sp, cnt = (_ptr(arr) if arr.size else None), arr.shape[0]
+    ctx.check(ctx.lib.zkb_msm(ctx.h, bases.h, sp, 1 if on_device else 0, cnt, window_bits, _ptr(out)), "zkb_msm")
+    return (g1_unpack(out) if bases.group == 1 else g2_unpack(out))[0]
+
+
+def points_sum(ctx: Context, group: int, points):
+    arr = g1_pack(points) if group == 1 else g2_pack(points)
+    out = np.zeros(8 if group == 1 else 16, dtype=np.uint64)
+    ctx.check(ctx.lib.zkb_points_sum(ctx.h, group, _ptr(arr) if arr.size else None, len(points), _ptr(out)),
+              "zkb_points_sum")
+    return (g1_unpack(out) if group == 1 else g2_unpack(out))[0]
