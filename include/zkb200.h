@@ -48,6 +48,13 @@ void zkb_ctx_destroy(zkb_ctx* ctx);
 const char* zkb_last_error(const zkb_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t zkb_launch_count(const zkb_ctx* ctx);
+/* Per-kernel-class timing with CUDA events on the launching stream.  zkb_profile(ctx, 1) clears and
+ * starts recording, zkb_profile(ctx, 0) stops; zkb_profile_read sums the recorded launch durations
+ * of one class: 1 NTT butterfly passes, 2 G1 bucket accumulation, 3 G2 bucket accumulation; *units is
+ * the work those launches covered (NTT: elements x passes; accumulation: point records = points x
+ * windows, an upper bound that counts the ~2^-c fraction of zero digits). */
+int zkb_profile(zkb_ctx* ctx, int enable);
+int zkb_profile_read(zkb_ctx* ctx, int kind, double* total_ms, uint64_t* count, uint64_t* units);
 /* Pinned host memory for buffers that are copied every proof (weights).  Optional. */
 int zkb_host_alloc(void** out, size_t bytes);
 void zkb_host_free(void* p);

@@ -1,0 +1,131 @@
+"""CPU-side checks of the product's host logic and of the C ABI surface (no compute calls: there
+is no GPU here and the library has no CPU fallback)."""
+
+import ctypes
+import importlib
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import synthetic
+from oracle.fields import FR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+zk = importlib.import_module("zksnark-rs_b200")
+zg = importlib.import_module("zksnark-rs_b200.groth16")
+zd = importlib.import_module("zksnark-rs_b200.dist")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(zk.lib_path()):
+        importlib.import_module("zksnark-rs_b200.build").build()
+    return zk.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "zkb200.h")).read()
+    declared = set(re.findall(r"\b(zkb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(zg.ABI), declared ^ set(zg.ABI)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_no_cpu_fallback(lib):
+    """Without a device every computing entry point must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    assert lib.zkb_ctx_create(ctypes.byref(h), 0) == -1
+    assert b"no CPU fallback" in lib.zkb_last_error(None)
+    with pytest.raises(zk.ZkbError):
+        zk.Context(0)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "zksnark-rs_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle_b" not in src, f
+
+
+def test_limb_packing_roundtrip():
+    vals = [0, 1, FR.p - 1, 2**64, 2**200 + 12345]
+    arr = zg.fr_limbs(vals)
+    assert arr.shape == (5, 4) and arr.dtype == np.uint64
+    assert zg.limbs_to_ints(arr) == vals
+    pts = [None, (3, 4)]
+    assert zg.g1_unpack(zg.g1_pack(pts)) == pts
+    q = [None, ((1, 2), (3, 4))]
+    assert zg.g2_unpack(zg.g2_pack(q)) == q
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 64])
+def test_horner_rows_equal_oracle_rep(n):
+    """The numpy CSR generator of the synthetic circuit == the oracle's DummyRep (parser row order)."""
+    log_n = n.bit_length() - 1
+    w = synthetic.omega(log_n)
+    roots = [pow(w, k, FR.p) for k in range(n)]
+    rep = synthetic.horner_rep(FR, n, roots)
+    idx = {r: k for k, r in enumerate(roots)}
+    m, n_input, rows = zg.horner_qap_rows(n)
+    assert m == len(rep.u) and n_input == rep.input
+    for (ptr, gate, coeff), mat in zip(rows, (rep.u, rep.v, rep.w)):
+        cs = zg.limbs_to_ints(coeff)
+        for i in range(m):
+            got = sorted((int(gate[e]), cs[e]) for e in range(int(ptr[i]), int(ptr[i + 1])))
+            assert got == sorted((idx[r], c) for r, c in mat[i])
+    x, cs_ = 12345, list(range(7, 7 + n))
+    assert zg.horner_witness(n, x, cs_) == synthetic.horner_witness(FR, n, x, cs_)
+    assert zg.omega(log_n) == w
+
+
+def test_shard_ranges_partition():
+    for length in (0, 1, 7, 1024, (1 << 20) - 1):
+        for world in (1, 2, 3, 8):
+            spans = [zd.shard_range(length, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == length
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_bench_mirrors_of_library_plans():
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    assert bench.ntt_plan(20) == [(0, 10), (10, 15), (15, 20)]
+    assert bench.ntt_plan(8) == [(0, 8)]
+    assert bench.msm_window(1 << 20) in (15, 16)
+
+
+_GLOO_WORKER = r"""
+import importlib, os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+zd = importlib.import_module("zksnark-rs_b200.dist")
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+part = (np.arange(40, dtype=np.uint64) + np.uint64(1000 * rank)) | np.uint64(1 << 63)  # exercise the sign bit
+allp = zd.all_gather_partials(part)
+assert allp.shape == (world, 40)
+for r in range(world):
+    assert np.array_equal(allp[r], (np.arange(40, dtype=np.uint64) + np.uint64(1000 * r)) | np.uint64(1 << 63))
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_all_gather_partials_world2_gloo(tmp_path):
+    """N>1 host path on CPU: world_size 2, gloo backend, rendezvous on 127.0.0.1."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29611", str(script), ROOT]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

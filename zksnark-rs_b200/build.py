@@ -4,6 +4,7 @@ file so it travels to the GPU box with the repository snapshot."""
 from __future__ import annotations
 
 import concurrent.futures
+import hashlib
 import os
 import subprocess
 import sys
@@ -25,23 +26,39 @@ def _nvcc() -> str:
     return "nvcc"
 
 
-def _stale(target: str, deps: list) -> bool:
-    if not os.path.exists(target):
-        return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+def _digest(paths: list, extra: str = "") -> str:
+    h = hashlib.sha256(extra.encode())
+    for p in paths:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _fresh(target: str, digest: str) -> bool:
+    """Content-hash stamps instead of mtimes: the snapshot that travels to the GPU box does not
+    preserve modification-time order, and a needless rebuild there costs minutes of GPU time."""
+    stamp = target + ".sha256"
+    return os.path.exists(target) and os.path.exists(stamp) and open(stamp).read().strip() == digest
+
+
+def _stamp(target: str, digest: str) -> None:
+    with open(target + ".sha256", "w") as f:
+        f.write(digest)
 
 
 def _compile(src: str) -> str:
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
     deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS]
-    if _stale(obj, deps):
+    digest = _digest(deps, " ".join(NVCC_FLAGS))
+    if not _fresh(obj, digest):
         cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if _digest(deps, " ".join(NVCC_FLAGS)) == digest:  # sources unchanged while nvcc ran
+            _stamp(obj, digest)
     return obj
 
 
@@ -52,9 +69,11 @@ def build(force: bool = False) -> str:
             os.remove(os.path.join(OBJ, f))
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(_compile, SOURCES))
-    if _stale(LIB, objs):
+    digest = _digest(objs)
+    if not _fresh(LIB, digest):
         cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         subprocess.check_call(cmd)
+        _stamp(LIB, digest)
     return LIB
 
 

@@ -32,6 +32,11 @@ struct zkb_ctx {
   zkb::Fr* tw[28][2] = {};
   // reusable scratch (grown on demand, never shrunk)
   zkb::DevBuf scratch[16];
+  // optional per-kernel-class CUDA-event timing (zkb_profile): pairs recorded around tracked launches
+  bool profile = false;
+  struct ProfRec { cudaEvent_t a, b; int kind; };
+  uint64_t prof_units[16] = {};  // work units per tracked class (NTT: elements x passes; ACC: records)
+  std::vector<ProfRec> prof;
 };
 
 namespace zkb {
@@ -58,6 +63,24 @@ int set_err(zkb_ctx* ctx, int code, const char* fmt, ...);
 #define ZKB_LAUNCH(ctx, kernel, grid, block, smem, strm, ...)                                   \
   do {                                                                                          \
     kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                                   \
+    (ctx)->launches++;                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess)                                                                     \
+      return ::zkb::set_err(ctx, ZKB_ERR_CUDA, "%s:%d: launch %s -> %s", __FILE__, __LINE__,    \
+                            #kernel, cudaGetErrorString(e__));                                  \
+  } while (0)
+
+// tracked kernel classes for zkb_profile
+enum ProfKind { PK_NTT = 1, PK_ACC_G1 = 2, PK_ACC_G2 = 3, PK_SORT = 4, PK_REDUCE = 5, PK_POINTWISE = 6, PK_ASSEMBLE = 7, PK_MAX = 8 };
+void prof_begin(zkb_ctx* ctx, int kind, cudaStream_t st);
+void prof_end(zkb_ctx* ctx, cudaStream_t st);
+
+// tracked launch: CUDA events on the launching stream around the kernel when profiling is on
+#define ZKB_LAUNCH_K(ctx, kind, kernel, grid, block, smem, strm, ...)                           \
+  do {                                                                                          \
+    if ((ctx)->profile) ::zkb::prof_begin(ctx, kind, strm);                                     \
+    kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                                   \
+    if ((ctx)->profile) ::zkb::prof_end(ctx, strm);                                             \
     (ctx)->launches++;                                                                          \
     cudaError_t e__ = cudaGetLastError();                                                       \
     if (e__ != cudaSuccess)                                                                     \

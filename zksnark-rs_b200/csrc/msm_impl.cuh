@@ -10,7 +10,8 @@
 //                       (digits in [-2^(c-1), 2^(c-1)]), histogram of bucket sizes
 //   2. scan             exclusive prefix sum of the W * 2^(c-1) bucket sizes
 //   3. k_digits_scatter counting-sort the (point index, sign) records by bucket
-//   4. k_accumulate     one thread per bucket: XYZZ mixed additions over its sorted run
+//   4. k_accumulate_chunks  one thread per 32 sorted records: XYZZ mixed additions, flush at bucket
+//                       boundaries; k_fix_heads: per-warp fold of buckets that span chunks (shuffle tree)
 //   5. k_reduce_chunks  per window, running-sum reduction of L-bucket chunks
 //   6. k_window_finish  per window: sum_t (T_t + v0_t * S_t) with a shared-memory tree
 //   7. k_combine        Horner over the windows (c doublings per window)
@@ -150,21 +151,84 @@ static __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-template <class F>
-__global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
-                                                    const uint32_t* __restrict__ sorted, size_t nbuckets,
-                                                    XYZZ<F>* __restrict__ buckets) {
-  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nbuckets) return;
-  uint32_t p = offs[g], e = offs[g + 1];
+// Bucket accumulation, load-balanced: the sorted record array is cut into chunks of S records and
+// every thread sums exactly one chunk with XYZZ mixed additions, flushing at bucket boundaries.
+// A bucket that begins inside the chunk is written to buckets[g]; the leading piece of a bucket
+// that began in an earlier chunk goes to heads[t] (head_id[t] = g) and is folded in by
+// k_fix_heads.  buckets[] is zero-filled (= identity) beforehand, empty buckets are never touched.
+static const uint32_t NO_HEAD = 0xffffffffu;
+
+template <class F, int S>
+__global__ void __launch_bounds__(128) k_accumulate_chunks(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
+                                                           const uint32_t* __restrict__ sorted, uint32_t nbk, size_t nchunks,
+                                                           XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads,
+                                                           uint32_t* __restrict__ head_id) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  const uint32_t total = offs[nbk];
+  const size_t start64 = t * (size_t)S;
+  if (start64 >= total) { head_id[t] = NO_HEAD; return; }
+  const uint32_t start = (uint32_t)start64;
+  const uint32_t end = (total - start > (uint32_t)S) ? start + S : total;
+  // g: offs[g] <= start < offs[g+1]
+  uint32_t lo = 0, hi = nbk;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (offs[mid] <= start) lo = mid + 1; else hi = mid;
+  }
+  uint32_t g = lo - 1;
+  bool is_head = offs[g] < start;
+  head_id[t] = is_head ? g : NO_HEAD;
+  uint32_t bend = offs[g + 1];
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (; p < e; p++) {
+  for (uint32_t p = start; p < end; p++) {
+    if (p == bend) {
+      if (is_head) { heads[t] = acc; is_head = false; } else buckets[g] = acc;
+      acc = XYZZ<F>::inf();
+      do { g++; bend = offs[g + 1]; } while (bend <= p);
+    }
     uint32_t rec = sorted[p];
     Affine<F> P = pts[rec & 0x7fffffffu];
     if (rec >> 31) P = neg(P);
     acc = madd(acc, P);
   }
-  buckets[g] = acc;
+  if (is_head) heads[t] = acc; else buckets[g] = acc;
+}
+
+template <class F>
+__device__ __forceinline__ XYZZ<F> shfl_down_xyzz(const XYZZ<F>& p, int off) {
+  XYZZ<F> r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], off);
+  return r;
+}
+
+// one warp per chunk; only the warp of the first chunk of a run of heads for the same bucket works:
+// lanes stride over the run, then a warp-shuffle reduction tree, then the fold into buckets[g].
+template <class F>
+__global__ void __launch_bounds__(128) k_fix_heads(size_t nchunks, XYZZ<F>* __restrict__ buckets,
+                                                   const XYZZ<F>* __restrict__ heads, const uint32_t* __restrict__ head_id) {
+  size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= nchunks) return;
+  const uint32_t g = head_id[t];
+  if (g == NO_HEAD) return;
+  if (t > 0 && head_id[t - 1] == g) return;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (size_t base = t;; base += 32) {
+    size_t idx = base + lane;
+    bool in = idx < nchunks && head_id[idx] == g;
+    unsigned m = __ballot_sync(0xffffffffu, in);
+    if (in) acc = add(acc, heads[idx]);
+    if (m != 0xffffffffu) break;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    XYZZ<F> o = shfl_down_xyzz(acc, off);
+    acc = add(acc, o);
+  }
+  if (lane == 0) buckets[g] = add(buckets[g], acc);
 }
 
 // chunk t of window j covers bucket values v0+1 .. v0+L (v0 = t*L).  S = sum B_v, T = sum (v - v0) B_v.
@@ -238,12 +302,16 @@ __global__ void k_set_inf(XYZZ<F>* out) {
 }
 
 static int pick_c(size_t n) {
-  int lg = 0;
-  while (((size_t)1 << (lg + 1)) <= n) lg++;
-  int c = lg - 4;
-  if (c < 4) c = 4;
-  if (c > 16) c = 16;
-  return c;
+  // minimise W * (10 n + 2 * 14 * 2 * 2^(c-1)) modmuls: N*W mixed adds (10M) + bucket reduction
+  // (2 full adds of 14M per bucket, weighted x2 for its lower parallelism)
+  int best = 4;
+  double best_cost = 1e300;
+  for (int c = 4; c <= 18; c++) {
+    double W = 254 / c + 1;
+    double cost = W * (10.0 * (double)n + 56.0 * (double)((size_t)1 << (c - 1)));
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
 }
 
 template <class F>
@@ -275,11 +343,15 @@ static int msm_impl(zkb_ctx* ctx, const Affine<F>* pts, const Fr* scalars, bool 
   sums = cursor + nbk;
   ZKB_TRY(scratch_get(ctx, slot + 1, (size_t)pl.W * n * 4, &p));
   sorted = (uint32_t*)p;
-  ZKB_TRY(scratch_get(ctx, slot + 2, (nbk + 2 * nchunks + pl.W) * sizeof(XYZZ<F>), &p));
+  const int ACC_S = 32;  // records per accumulation chunk
+  size_t nacc = ((size_t)pl.W * n + ACC_S - 1) / ACC_S;
+  ZKB_TRY(scratch_get(ctx, slot + 2, (nbk + 2 * nchunks + pl.W + nacc) * sizeof(XYZZ<F>) + nacc * 4, &p));
   buckets = (XYZZ<F>*)p;
   S = buckets + nbk;
   T = S + nchunks;
   wsum = T + nchunks;
+  XYZZ<F>* heads = wsum + pl.W;
+  uint32_t* head_id = (uint32_t*)(heads + nacc);
 
   ZKB_CUDA(ctx, cudaMemsetAsync(hist, 0, nbk * 4, st));
   ZKB_LAUNCH(ctx, k_digits_count, cdiv(n, 256), 256, 0, st, scalars, mont ? 1 : 0, n, pl, hist);
@@ -287,7 +359,11 @@ static int msm_impl(zkb_ctx* ctx, const Affine<F>* pts, const Fr* scalars, bool 
   ZKB_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, st, sums, nscan_blocks, sums + nscan_blocks);
   ZKB_LAUNCH(ctx, k_scan_add, cdiv(nbk + 1, 256), 256, 0, st, offs, cursor, sums, nbk, sums + nscan_blocks);
   ZKB_LAUNCH(ctx, k_digits_scatter, cdiv(n, 256), 256, 0, st, scalars, mont ? 1 : 0, n, pl, cursor, sorted);
-  ZKB_LAUNCH(ctx, k_accumulate<F>, cdiv(nbk, 128), 128, 0, st, pts, offs, sorted, nbk, buckets);
+  ZKB_CUDA(ctx, cudaMemsetAsync(buckets, 0, nbk * sizeof(XYZZ<F>), st));  // all-zero XYZZ = identity
+  ZKB_LAUNCH_K(ctx, sizeof(F) == sizeof(Fq) ? PK_ACC_G1 : PK_ACC_G2, (k_accumulate_chunks<F, ACC_S>), cdiv(nacc, 128), 128, 0, st,
+               pts, offs, sorted, (uint32_t)nbk, nacc, buckets, heads, head_id);
+  if (ctx->profile) ctx->prof_units[sizeof(F) == sizeof(Fq) ? PK_ACC_G1 : PK_ACC_G2] += (uint64_t)pl.W * n;
+  ZKB_LAUNCH(ctx, k_fix_heads<F>, cdiv(nacc * 32, 128), 128, 0, st, nacc, buckets, heads, head_id);
   ZKB_LAUNCH(ctx, k_reduce_chunks<F>, cdiv(nchunks, 128), 128, 0, st, buckets, pl.nb, L, nchunks, S, T);
   unsigned fin_threads = per_win >= 128 ? 128 : (per_win >= 32 ? 32 : 1);
   // round per_win down to a power of two thread count (per_win is a power of two)

@@ -184,7 +184,8 @@ static int run_ntt(zkb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, cudaStream
     unsigned grid = (unsigned)(((size_t)1 << log_n) >> logT);
     unsigned block = T / 2;
     size_t smem = (size_t)T * 32;
-    ZKB_LAUNCH(ctx, k_ntt_pass<DIT>, grid, block, smem, st, d, tw, log_n, p.hi, p.lo, p.logC);
+    if (ctx->profile) ctx->prof_units[PK_NTT] += (uint64_t)1 << log_n;
+    ZKB_LAUNCH_K(ctx, PK_NTT, k_ntt_pass<DIT>, grid, block, smem, st, d, tw, log_n, p.hi, p.lo, p.logC);
   }
   return ZKB_OK;
 }

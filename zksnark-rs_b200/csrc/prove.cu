@@ -53,6 +53,20 @@ int scratch_get(zkb_ctx* ctx, int slot, size_t bytes, void** out) {
   return ZKB_OK;
 }
 
+void prof_begin(zkb_ctx* ctx, int kind, cudaStream_t st) {
+  zkb_ctx::ProfRec r;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  r.kind = kind;
+  cudaEventRecord(r.a, st);
+  ctx->prof.push_back(r);
+}
+void prof_end(zkb_ctx* ctx, cudaStream_t st) { cudaEventRecord(ctx->prof.back().b, st); }
+static void prof_clear(zkb_ctx* ctx) {
+  for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  ctx->prof.clear();
+}
+
 static Fr fr_from_limbs(const uint64_t* l) {  // canonical limbs -> Montgomery (host)
   Fr c;
   memcpy(c.v, l, 32);
@@ -266,6 +280,7 @@ void zkb_ctx_destroy(zkb_ctx* ctx) {
       if (p) cudaFree(p);
   for (auto& b : ctx->scratch)
     if (b.p) cudaFree(b.p);
+  prof_clear(ctx);
   cudaEventDestroy(ctx->ev_fork);
   cudaEventDestroy(ctx->ev_join);
   cudaStreamDestroy(ctx->stream);
@@ -275,6 +290,32 @@ void zkb_ctx_destroy(zkb_ctx* ctx) {
 
 const char* zkb_last_error(const zkb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 uint64_t zkb_launch_count(const zkb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zkb_profile(zkb_ctx* ctx, int enable) {
+  if (!ctx) return ZKB_ERR_ARG;
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZKB_CUDA(ctx, cudaDeviceSynchronize());
+  prof_clear(ctx);
+  for (auto& u : ctx->prof_units) u = 0;
+  ctx->profile = enable != 0;
+  return ZKB_OK;
+}
+int zkb_profile_read(zkb_ctx* ctx, int kind, double* total_ms, uint64_t* count, uint64_t* units) {
+  if (!ctx || kind < 1 || kind >= PK_MAX) return set_err(ctx, ZKB_ERR_ARG, "zkb_profile_read: bad kind");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZKB_CUDA(ctx, cudaDeviceSynchronize());
+  double tot = 0;
+  uint64_t cnt = 0;
+  for (auto& r : ctx->prof) {
+    if (r.kind != kind) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { tot += ms; cnt++; }
+  }
+  if (total_ms) *total_ms = tot;
+  if (count) *count = cnt;
+  if (units) *units = ctx->prof_units[kind];
+  return ZKB_OK;
+}
 
 int zkb_host_alloc(void** out, size_t bytes) {
   if (!out) return ZKB_ERR_ARG;

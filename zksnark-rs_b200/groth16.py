@@ -54,6 +54,8 @@ ABI = {
     "zkb_ctx_destroy": (None, [_P]),
     "zkb_last_error": (C.c_char_p, [_P]),
     "zkb_launch_count": (C.c_uint64, [_P]),
+    "zkb_profile": (C.c_int, [_P, C.c_int]),
+    "zkb_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "zkb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "zkb_host_free": (None, [_P]),
     "zkb_dev_alloc": (C.c_int, [_P, C.POINTER(_P), C.c_size_t]),
@@ -219,6 +221,15 @@ class Context:
         arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
         self._pinned = getattr(self, "_pinned", []) + [p]
         return arr
+
+    def profile(self, enable: bool):
+        self.check(self.lib.zkb_profile(self.h, 1 if enable else 0), "zkb_profile")
+
+    def profile_read(self, kind: int):
+        """(total ms, launches, work units) of one tracked kernel class: 1 NTT passes, 2 G1 / 3 G2 bucket accumulation."""
+        ms, cnt, units = C.c_double(), C.c_uint64(), C.c_uint64()
+        self.check(self.lib.zkb_profile_read(self.h, kind, C.byref(ms), C.byref(cnt), C.byref(units)), "zkb_profile_read")
+        return ms.value, cnt.value, units.value
 
     def bench_modmul(self, field: int = 1, iters: int = 2000):
         rate, ms = C.c_double(), C.c_double()
