@@ -154,20 +154,18 @@ static __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restri
 // Bucket accumulation, load-balanced: the sorted record array is cut into chunks of S records and
 // every thread sums exactly one chunk with XYZZ mixed additions, flushing at bucket boundaries.
 // A bucket that begins inside the chunk is written to buckets[g]; the leading piece of a bucket
-// that began in an earlier chunk goes to heads[t] (head_id[t] = g) and is folded in by
+// that began in an earlier chunk goes to heads[t] and is folded in by
 // k_fix_heads.  buckets[] is zero-filled (= identity) beforehand, empty buckets are never touched.
-static const uint32_t NO_HEAD = 0xffffffffu;
 
 template <class F, int S>
 __global__ void __launch_bounds__(128) k_accumulate_chunks(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
                                                            const uint32_t* __restrict__ sorted, uint32_t nbk, size_t nchunks,
-                                                           XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads,
-                                                           uint32_t* __restrict__ head_id) {
+                                                           XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nchunks) return;
   const uint32_t total = offs[nbk];
   const size_t start64 = t * (size_t)S;
-  if (start64 >= total) { head_id[t] = NO_HEAD; return; }
+  if (start64 >= total) return;
   const uint32_t start = (uint32_t)start64;
   const uint32_t end = (total - start > (uint32_t)S) ? start + S : total;
   // g: offs[g] <= start < offs[g+1]
@@ -178,7 +176,6 @@ __global__ void __launch_bounds__(128) k_accumulate_chunks(const Affine<F>* __re
   }
   uint32_t g = lo - 1;
   bool is_head = offs[g] < start;
-  head_id[t] = is_head ? g : NO_HEAD;
   uint32_t bend = offs[g + 1];
   XYZZ<F> acc = XYZZ<F>::inf();
   for (uint32_t p = start; p < end; p++) {
@@ -205,30 +202,51 @@ __device__ __forceinline__ XYZZ<F> shfl_down_xyzz(const XYZZ<F>& p, int off) {
   return r;
 }
 
-// one warp per chunk; only the warp of the first chunk of a run of heads for the same bucket works:
-// lanes stride over the run, then a warp-shuffle reduction tree, then the fold into buckets[g].
 template <class F>
-__global__ void __launch_bounds__(128) k_fix_heads(size_t nchunks, XYZZ<F>* __restrict__ buckets,
-                                                   const XYZZ<F>* __restrict__ heads, const uint32_t* __restrict__ head_id) {
-  size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__device__ __forceinline__ XYZZ<F> shfl_xyzz(const XYZZ<F>& p, int src) {
+  XYZZ<F> r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) d[i] = __shfl_sync(0xffffffffu, s[i], src);
+  return r;
+}
+
+// Fold the head pieces into their buckets.  One thread per bucket g: the chunks whose first record
+// lies strictly inside bucket g are t with offs[g] < t*S < offs[g+1] (computed from the offsets, so
+// no search).  Short runs (the common case: ~1 head per bucket when the mean bucket size is about
+// S) are summed by the owning thread; long runs (skewed scalars: one huge bucket) are summed by
+// the whole warp, lanes striding over the run followed by a shuffle tree.
+template <class F, int S>
+__global__ void __launch_bounds__(128) k_fix_heads(const uint32_t* __restrict__ offs, uint32_t nbk,
+                                                   XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ heads) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  if (t >= nchunks) return;
-  const uint32_t g = head_id[t];
-  if (g == NO_HEAD) return;
-  if (t > 0 && head_id[t - 1] == g) return;
+  uint32_t t0 = 1, t1 = 0;
+  if (g < nbk) {
+    const uint32_t lo = offs[g], hi = offs[g + 1];
+    if (hi > lo) { t0 = lo / S + 1; t1 = (hi - 1) / S; }
+  }
+  const uint32_t cnt = t1 >= t0 ? t1 - t0 + 1 : 0;
+  const bool big = cnt > 8;
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (size_t base = t;; base += 32) {
-    size_t idx = base + lane;
-    bool in = idx < nchunks && head_id[idx] == g;
-    unsigned m = __ballot_sync(0xffffffffu, in);
-    if (in) acc = add(acc, heads[idx]);
-    if (m != 0xffffffffu) break;
+  if (!big)
+    for (uint32_t t = t0; t <= t1; t++) acc = add(acc, heads[t]);
+  unsigned todo = __ballot_sync(0xffffffffu, big);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint32_t b0 = __shfl_sync(0xffffffffu, t0, src), b1 = __shfl_sync(0xffffffffu, t1, src);
+    XYZZ<F> part = XYZZ<F>::inf();
+    for (uint32_t t = b0 + lane; t <= b1; t += 32) part = add(part, heads[t]);
+    for (int off = 16; off > 0; off >>= 1) {
+      XYZZ<F> o = shfl_down_xyzz(part, off);
+      part = add(part, o);
+    }
+    XYZZ<F> tot = shfl_xyzz(part, 0);
+    if (lane == src) acc = tot;
   }
-  for (int off = 16; off > 0; off >>= 1) {
-    XYZZ<F> o = shfl_down_xyzz(acc, off);
-    acc = add(acc, o);
-  }
-  if (lane == 0) buckets[g] = add(buckets[g], acc);
+  if (cnt) buckets[g] = add(buckets[g], acc);
 }
 
 // chunk t of window j covers bucket values v0+1 .. v0+L (v0 = t*L).  S = sum B_v, T = sum (v - v0) B_v.
@@ -345,13 +363,12 @@ static int msm_impl(zkb_ctx* ctx, const Affine<F>* pts, const Fr* scalars, bool 
   sorted = (uint32_t*)p;
   const int ACC_S = 32;  // records per accumulation chunk
   size_t nacc = ((size_t)pl.W * n + ACC_S - 1) / ACC_S;
-  ZKB_TRY(scratch_get(ctx, slot + 2, (nbk + 2 * nchunks + pl.W + nacc) * sizeof(XYZZ<F>) + nacc * 4, &p));
+  ZKB_TRY(scratch_get(ctx, slot + 2, (nbk + 2 * nchunks + pl.W + nacc) * sizeof(XYZZ<F>), &p));
   buckets = (XYZZ<F>*)p;
   S = buckets + nbk;
   T = S + nchunks;
   wsum = T + nchunks;
   XYZZ<F>* heads = wsum + pl.W;
-  uint32_t* head_id = (uint32_t*)(heads + nacc);
 
   ZKB_CUDA(ctx, cudaMemsetAsync(hist, 0, nbk * 4, st));
   ZKB_LAUNCH(ctx, k_digits_count, cdiv(n, 256), 256, 0, st, scalars, mont ? 1 : 0, n, pl, hist);
@@ -361,9 +378,9 @@ static int msm_impl(zkb_ctx* ctx, const Affine<F>* pts, const Fr* scalars, bool 
   ZKB_LAUNCH(ctx, k_digits_scatter, cdiv(n, 256), 256, 0, st, scalars, mont ? 1 : 0, n, pl, cursor, sorted);
   ZKB_CUDA(ctx, cudaMemsetAsync(buckets, 0, nbk * sizeof(XYZZ<F>), st));  // all-zero XYZZ = identity
   ZKB_LAUNCH_K(ctx, sizeof(F) == sizeof(Fq) ? PK_ACC_G1 : PK_ACC_G2, (k_accumulate_chunks<F, ACC_S>), cdiv(nacc, 128), 128, 0, st,
-               pts, offs, sorted, (uint32_t)nbk, nacc, buckets, heads, head_id);
+               pts, offs, sorted, (uint32_t)nbk, nacc, buckets, heads);
   if (ctx->profile) ctx->prof_units[sizeof(F) == sizeof(Fq) ? PK_ACC_G1 : PK_ACC_G2] += (uint64_t)pl.W * n;
-  ZKB_LAUNCH(ctx, k_fix_heads<F>, cdiv(nacc * 32, 128), 128, 0, st, nacc, buckets, heads, head_id);
+  ZKB_LAUNCH(ctx, (k_fix_heads<F, ACC_S>), cdiv(nbk, 128), 128, 0, st, offs, (uint32_t)nbk, buckets, heads);
   ZKB_LAUNCH(ctx, k_reduce_chunks<F>, cdiv(nchunks, 128), 128, 0, st, buckets, pl.nb, L, nchunks, S, T);
   unsigned fin_threads = per_win >= 128 ? 128 : (per_win >= 32 ? 32 : 1);
   // round per_win down to a power of two thread count (per_win is a power of two)
