@@ -5,7 +5,7 @@
 
 A step is ONE groth16::prove() (src/groth16/mod.rs:213-296): witness -> u_sum, v_sum, h (6 NTTs) ->
 5 MSMs (4 over G1, 1 over G2) -> Proof{a,b,c}.  N > 1 (torchrun, one rank per GPU): the MSM base
-vectors are sharded by points, every rank proves over its shard, the 40-limb partial sums are
+vectors are sharded by points, every rank proves over its shard, the 32-limb partial sums are
 all-gathered over NCCL and folded -- one proof, strong scaling.
 
 `value`  : proofs/s with the witness already resident in HBM (device-timed with CUDA events on the
@@ -182,19 +182,19 @@ def run_ours(args):
     d_w = ctx.dev_alloc(w_np.nbytes)
     ctx.h2d(d_w, w_np)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    gather_in = torch.empty(40, dtype=torch.int64, device="cuda")
-    gather_out = torch.empty(40 * world, dtype=torch.int64, device="cuda")
+    gather_in = torch.empty(32, dtype=torch.int64, device="cuda")
+    gather_out = torch.empty(32 * world, dtype=torch.int64, device="cuda")
 
     def step(on_device):
         if world == 1:
             if on_device:
                 return zg.prove_dev(ctx, qap, crs, d_w, r, s)
             return zk.prove(ctx, qap, crs, w_pin, r, s)
-        part = zk.prove_partial(ctx, qap, crs, d_w if on_device else w_pin, on_device=on_device)
+        part = zk.prove_partial(ctx, qap, crs, d_w if on_device else w_pin, r, s, on_device=on_device)
         gather_in.copy_(torch.from_numpy(part.view(np.int64)))
         dist.all_gather_into_tensor(gather_out, gather_in)
-        allp = gather_out.cpu().numpy().view(np.uint64).reshape(world, 40)
-        return zk.prove_combine(ctx, crs, allp, r, s)
+        allp = gather_out.cpu().numpy().view(np.uint64).reshape(world, 32)
+        return zk.prove_combine(ctx, allp)
 
     def barrier():
         torch.cuda.synchronize()
@@ -283,7 +283,7 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (CRS 384 MiB + witness 64 MiB streamed every proof)",
                        "timing": "CUDA events on the library stream, max over ranks"},
             "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(w_np.nbytes),
-                    "d2h_bytes_per_step": 256 if world == 1 else 256 + 320, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 256 if world == 1 else 256 + 256, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_ntt": roofline_ntt,
             "msm_g2": {"kernel": "k_accumulate_chunks<Fq2,32>", "total_ms": g2_ms, "launches": g2_cnt, "records": g2_recs,

@@ -126,15 +126,16 @@ int zkb_prove(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const uint64
 /* Same with the weights already resident in device memory (m x 4 limbs, canonical). */
 int zkb_prove_dev(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const uint64_t* d_weights,
                   const uint64_t r[4], const uint64_t s[4], zkb_proof* out);
-/* Multi-GPU: each rank runs the polynomial stage and the MSMs over ITS shard of the CRS and
- * returns four partial sums (affine, canonical): a_g1 (8), b_g1 (8), c_g1 = h-term + witness-term
- * (8), b_g2 (16) = 40 limbs.  The caller all-gathers the 40-limb records (NCCL) and every rank --
- * or rank 0 -- folds them with zkb_prove_combine. */
-#define ZKB_PARTIAL_LIMBS 40
+/* Multi-GPU: each rank runs the polynomial stage and the MSMs over ITS shard of the CRS (rank 0 also
+ * carries the fixed-point terms alpha1 + r delta1 etc.) and returns its partial sums of A, B, C in the
+ * zkb_proof layout (affine, canonical: a 8 | b 16 | c 8 = 32 limbs).  The caller all-gathers the
+ * 32-limb records (NCCL; EC addition is not an NCCL reduction op) and every rank -- or rank 0 --
+ * folds them with zkb_prove_combine. */
+#define ZKB_PARTIAL_LIMBS 32
 int zkb_prove_partial(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const uint64_t* weights,
-                      int weights_on_device, uint64_t* out_partial /* 40 limbs, host */);
-int zkb_prove_combine(zkb_ctx* ctx, const zkb_crs* crs, const uint64_t* partials /* world x 40, host */,
-                      int world, const uint64_t r[4], const uint64_t s[4], zkb_proof* out);
+                      int weights_on_device, const uint64_t r[4], const uint64_t s[4],
+                      uint64_t* out_partial /* 32 limbs, host */);
+int zkb_prove_combine(zkb_ctx* ctx, const uint64_t* partials /* world x 32, host */, int world, zkb_proof* out);
 /* h(x) alone: h = (u_sum * v_sum - w_sum) / t  (mod.rs:277; coefficient_poly.rs:93-157;
  * field/mod.rs:428-469).  Outputs (host, canonical, n x 4 limbs each; any may be NULL):
  * u_sum, v_sum coefficient vectors and h (n-1 meaningful coefficients, h[n-1] = 0). */
@@ -153,7 +154,9 @@ int zkb_ntt_fr_raw(zkb_ctx* ctx, uint64_t* d_data_mont, uint32_t log_n, int inve
 /* Element-wise conversion of a device vector between canonical and Montgomery form. */
 int zkb_fr_to_mont(zkb_ctx* ctx, uint64_t* d_data, size_t n, int to_mont);
 
-/* Resident base-point vectors.  group: 1 = G1 (8 limbs / point), 2 = G2 (16 limbs / point). */
+/* Resident base-point vectors.  group: 1 = G1 (8 limbs / point), 2 = G2 (16 limbs / point).  The
+ * points are expanded on the device into the fixed-base window table the MSM reads
+ * (W = 254/c + 1 rows of 2^(c*j) multiples; c chosen from n). */
 int zkb_bases_upload(zkb_ctx* ctx, int group, const uint64_t* h_points, size_t n, zkb_bases** out);
 /* P_i = k_i * base (base = 69*G1::one() or 96*G2::one(), i.e. encrypt_g1 / encrypt_g2 of k_i,
  * fr.rs:106-113), computed on the device from n host scalars. */
@@ -163,11 +166,11 @@ void zkb_bases_free(zkb_ctx* ctx, zkb_bases* b);
 /* sum_i scalars[i] * bases[i]  (the `.zip().map(exp_encrypted_g*).sum()` pattern, groth16/mod.rs:
  * 255-272, 279-290; fr.rs:114-119, 191-223).  scalars: n x 4 limbs canonical, host or device.
  * n may be smaller than the base vector (zip truncation).  out: 8 (G1) or 16 (G2) limbs, host.
- * window_bits = 0 lets the library choose. */
-int zkb_msm(zkb_ctx* ctx, const zkb_bases* bases, const uint64_t* scalars, int scalars_on_device,
+ * window_bits = 0 uses the table as built; another value rebuilds the table of `bases` for that
+ * window size first (slow; meant for tests and tuning). */
+int zkb_msm(zkb_ctx* ctx, zkb_bases* bases, const uint64_t* scalars, int scalars_on_device,
             size_t n, int window_bits, uint64_t* out);
-/* Partial MSM over bases[first, first+n) (multi-GPU point sharding): result in affine form;
- * the caller gathers and folds with zkb_points_sum. */
+/* Sum of n affine points (fold of per-GPU partial results; `Sum for G1Local`, fr.rs:191-198). */
 int zkb_points_sum(zkb_ctx* ctx, int group, const uint64_t* h_points, size_t n, uint64_t* out);
 
 /* Peak-rate micro-benchmark: every thread runs `iters` dependent-chain pairs of Fq Montgomery

@@ -329,8 +329,8 @@ def test_prove_sharded_equals_single(ctx):
         parts = []
         shards = [zk.setup(ctx, q, toxic, rank=k, world=world) for k in range(world)]
         for k in range(world):
-            parts.append(zk.prove_partial(ctx, q, shards[k], wit))
-        got = zk.prove_combine(ctx, shards[0], np.stack(parts), r, s)
+            parts.append(zk.prove_partial(ctx, q, shards[k], wit, r, s))
+        got = zk.prove_combine(ctx, np.stack(parts))
         assert (got.a, got.b, got.c) == (full.a, full.b, full.c)
 
 

@@ -110,11 +110,11 @@ sys.path.insert(0, sys.argv[1])
 zd = importlib.import_module("zksnark-rs_b200.dist")
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-part = (np.arange(40, dtype=np.uint64) + np.uint64(1000 * rank)) | np.uint64(1 << 63)  # exercise the sign bit
+part = (np.arange(32, dtype=np.uint64) + np.uint64(1000 * rank)) | np.uint64(1 << 63)  # exercise the sign bit
 allp = zd.all_gather_partials(part)
-assert allp.shape == (world, 40)
+assert allp.shape == (world, 32)
 for r in range(world):
-    assert np.array_equal(allp[r], (np.arange(40, dtype=np.uint64) + np.uint64(1000 * r)) | np.uint64(1 << 63))
+    assert np.array_equal(allp[r], (np.arange(32, dtype=np.uint64) + np.uint64(1000 * r)) | np.uint64(1 << 63))
 dist.destroy_process_group()
 print("ok", rank)
 """

@@ -90,6 +90,11 @@ void prof_end(zkb_ctx* ctx, cudaStream_t st);
 
 // grow-only scratch slot
 int scratch_get(zkb_ctx* ctx, int slot, size_t bytes, void** out);
+void prof_clear(zkb_ctx* ctx);
+// host helpers (api.cu): canonical limbs / small integers -> Montgomery Fr; device Fq array -> canonical host limbs
+Fr fr_from_limbs(const uint64_t* l);
+Fr fr_from_u64(uint64_t x);
+int download_fq(zkb_ctx* ctx, uint64_t* dst, const void* d_src, size_t n_fq);
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
@@ -109,13 +114,23 @@ int fill_powers(zkb_ctx* ctx, Fr* out, const Fr& base, const Fr& first, size_t n
 Fr host_omega(uint32_t log_n, bool inverse);  // Montgomery form
 int get_twiddles(zkb_ctx* ctx, uint32_t log_n, bool inverse, Fr** out);
 
-// ---- msm.cu -------------------------------------------------------------------------------------
-// result (XYZZ, Montgomery, device) = sum scalars[i] * points[i], i < n.
-// scalars: device, 8 x u32 each; `mont` says whether they are in Montgomery form.
-int msm_g1(zkb_ctx* ctx, const G1Affine* pts, const Fr* scalars, bool mont, size_t n, int c, G1XYZZ* d_out,
+// ---- msm_*.cu ----------------------------------------------------------------------------------
+// Fixed-base MSM over an expanded table T[j][i] = 2^(c*j) P_i (row stride `stride`, W = 254/c + 1
+// rows).  Each job: d_out[j] (XYZZ, Montgomery, device) = sum_{i < n} scalars[i] * P_i with
+// canonical scalars in device memory.  All jobs of one call share the sort / accumulate launches.
+struct MsmJob {
+  const Fr* scalars;
+  size_t n;
+};
+int msm_pick_c(size_t n_points);
+static inline int msm_windows(int c) { return 254 / c + 1; }
+int msm_g1(zkb_ctx* ctx, const G1Affine* tab, size_t stride, int c, const MsmJob* jobs, int njobs, G1XYZZ* d_out,
            int slot_base, cudaStream_t st);
-int msm_g2(zkb_ctx* ctx, const G2Affine* pts, const Fr* scalars, bool mont, size_t n, int c, G2XYZZ* d_out,
+int msm_g2(zkb_ctx* ctx, const G2Affine* tab, size_t stride, int c, const MsmJob* jobs, int njobs, G2XYZZ* d_out,
            int slot_base, cudaStream_t st);
+// fill rows 1..W-1 of the table from row 0 (columns [0, n))
+int expand_table_g1(zkb_ctx* ctx, G1Affine* tab, size_t stride, size_t n, int c, cudaStream_t st);
+int expand_table_g2(zkb_ctx* ctx, G2Affine* tab, size_t stride, size_t n, int c, cudaStream_t st);
 int fixed_base_g1(zkb_ctx* ctx, G1Affine* out, const Fr* scalars_mont, size_t n, cudaStream_t st);
 int fixed_base_g2(zkb_ctx* ctx, G2Affine* out, const Fr* scalars_mont, size_t n, cudaStream_t st);
 // canonical <-> Montgomery for arrays of Fq (point coordinates)
@@ -130,7 +145,8 @@ int sum_affine_g2(zkb_ctx* ctx, const G2Affine* pts, size_t n, G2XYZZ* d_out, cu
 struct zkb_bases {
   int group = 1;
   size_t n = 0;
-  void* d = nullptr;  // G1Affine* or G2Affine*, Montgomery form
+  int c = 0;          // window bits of the expanded table (0: not expanded yet)
+  void* d = nullptr;  // G1Affine* or G2Affine*, Montgomery form: row 0 = the points, rows 1..W-1 = 2^(c*j) multiples
 };
 
 struct zkb_qap {
@@ -159,8 +175,21 @@ struct zkb_crs {
   int rank = 0, world = 1;
   // shard ranges [lo, hi) into the logical vectors
   uint64_t xi_lo = 0, xi_hi = 0, xit_lo = 0, xit_hi = 0, sd_lo = 0, sd_hi = 0;
-  zkb::G1Affine *alpha1 = nullptr, *beta1 = nullptr, *delta1 = nullptr;  // one block of 3 points
-  zkb::G1Affine *xi1 = nullptr, *xi_t = nullptr, *sum_gamma = nullptr, *sum_delta = nullptr;
-  zkb::G2Affine *beta2 = nullptr, *gamma2 = nullptr, *delta2 = nullptr;
-  zkb::G2Affine* xi2 = nullptr;
+  // G1 table, row 0 = [xi1 shard | alpha1 beta1 delta1 | xi_t shard | sum_delta shard], rows j>0 = 2^(c1*j) multiples
+  zkb::G1Affine* g1 = nullptr;
+  uint64_t g1_cnt = 0;  // row stride
+  int c1 = 0;
+  // G2 table, row 0 = [xi2 shard | beta2 delta2]
+  zkb::G2Affine* g2 = nullptr;
+  uint64_t g2_cnt = 0;
+  int c2 = 0;
+  zkb::G1Affine* sum_gamma = nullptr;  // not on the prove path; kept for download / verify
+  zkb::G2Affine* gamma2 = nullptr;
+  uint64_t nxi() const { return xi_hi - xi_lo; }
+  uint64_t nxt() const { return xit_hi - xit_lo; }
+  uint64_t nsd() const { return sd_hi - sd_lo; }
+  // column offsets inside a table row
+  uint64_t off_fixed() const { return nxi(); }
+  uint64_t off_xit() const { return nxi() + 3; }
+  uint64_t off_sd() const { return nxi() + 3 + nxt(); }
 };

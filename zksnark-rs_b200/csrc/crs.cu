@@ -1,0 +1,224 @@
+// CRS objects of libzkb200.so: `SigmaG1<G1Local>` / `SigmaG2<G2Local>` (/root/reference/src/groth16/
+// mod.rs:105-121) resident in HBM as the window-expanded base tables the MSMs read, plus
+// groth16::setup (mod.rs:134-197) on the device for the roots-of-unity domain.
+//
+// G1 table row 0 = [xi1 shard | alpha1 beta1 delta1 | xi_t shard | sum_delta shard]; G2 table row
+// 0 = [xi2 shard | beta2 delta2]; row j = 2^(c*j) times row 0 (msm_impl.cuh).  Putting the fixed
+// points into the tables lets prove() fold alpha1 + r*delta1 etc. into the MSMs as extra terms.
+#include <string.h>
+#include "common.cuh"
+
+namespace zkb {
+
+// ------------------------------------------------------------------------------------------------
+// setup kernels (groth16/mod.rs:134-197 on the omega domain)
+// L_k(x) = (x^n - 1) w^k / (n (x - w^k))
+__global__ void k_lagrange(Fr* L, Fr x, Fr tx_over_n, Fr omega, size_t n, int* bad) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  Fr wk = pow_u64(omega, (uint64_t)k);
+  Fr den = x - wk;
+  if (den.is_zero()) { *bad = 1; L[k] = Fr::zero(); return; }
+  L[k] = tx_over_n * wk * inverse(den);
+}
+
+// one warp per wire: lin_i = (beta u_i(x) + alpha v_i(x) + w_i(x)) * (i <= n_input ? 1/gamma : 1/delta)
+__device__ __forceinline__ Fr warp_sum(Fr v) {
+  for (int off = 16; off > 0; off >>= 1) {
+    Fr o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o.v[i] = __shfl_down_sync(0xffffffffu, v.v[i], off);
+    v = v + o;
+  }
+  return v;
+}
+__device__ __forceinline__ Fr row_eval(const uint32_t* rptr, const uint32_t* gate, const Fr* coef, const Fr* L, size_t i,
+                                       int lane) {
+  Fr acc = Fr::zero();
+  for (uint32_t p = rptr[i] + lane, e = rptr[i + 1]; p < e; p += 32) acc = acc + coef[p] * L[gate[p]];
+  return warp_sum(acc);
+}
+__global__ void k_lin(const uint32_t* ru, const uint32_t* gu, const Fr* cu, const uint32_t* rv, const uint32_t* gv,
+                      const Fr* cv, const uint32_t* rw, const uint32_t* gw, const Fr* cw, const Fr* L, size_t m,
+                      size_t n_input, Fr alpha, Fr beta, Fr inv_gamma, Fr inv_delta, Fr* out) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= m) return;
+  Fr u = row_eval(ru, gu, cu, L, i, lane);
+  Fr v = row_eval(rv, gv, cv, L, i, lane);
+  Fr w = row_eval(rw, gw, cw, L, i, lane);
+  if (lane == 0) out[i] = (beta * u + alpha * v + w) * (i <= n_input ? inv_gamma : inv_delta);
+}
+
+}  // namespace zkb
+
+using namespace zkb;
+
+extern "C" {
+
+void zkb_crs_free(zkb_ctx* ctx, zkb_crs* c) {
+  if (!c) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(c->g1); cudaFree(c->g2); cudaFree(c->sum_gamma); cudaFree(c->gamma2);
+  delete c;
+}
+
+static void shard(uint64_t len, int rank, int world, uint64_t* lo, uint64_t* hi) {
+  *lo = len * (uint64_t)rank / (uint64_t)world;
+  *hi = len * (uint64_t)(rank + 1) / (uint64_t)world;
+}
+
+static int crs_new(zkb_ctx* ctx, uint64_t n, uint64_t nsg, uint64_t nsd, int rank, int world, zkb_crs** out) {
+  zkb_crs* c = new zkb_crs();
+  c->n = n; c->n_sum_gamma = nsg; c->n_sum_delta = nsd;
+  c->rank = rank; c->world = world;
+  shard(n, rank, world, &c->xi_lo, &c->xi_hi);
+  shard(n - 1, rank, world, &c->xit_lo, &c->xit_hi);
+  shard(nsd, rank, world, &c->sd_lo, &c->sd_hi);
+  c->g1_cnt = c->nxi() + 3 + c->nxt() + c->nsd();
+  c->g2_cnt = c->nxi() + 2;
+  c->c1 = msm_pick_c(c->g1_cnt);
+  c->c2 = msm_pick_c(c->g2_cnt);
+  if (cudaMalloc(&c->g1, (size_t)msm_windows(c->c1) * c->g1_cnt * sizeof(G1Affine)) ||
+      cudaMalloc(&c->g2, (size_t)msm_windows(c->c2) * c->g2_cnt * sizeof(G2Affine)) ||
+      cudaMalloc(&c->sum_gamma, (nsg + 1) * sizeof(G1Affine)) || cudaMalloc(&c->gamma2, sizeof(G2Affine))) {
+    zkb_crs_free(ctx, c);
+    return set_err(ctx, ZKB_ERR_ALLOC, "crs: cudaMalloc failed (G1 table %.1f MiB, G2 table %.1f MiB)",
+                   (double)msm_windows(c->c1) * c->g1_cnt * 64 / 1048576.0, (double)msm_windows(c->c2) * c->g2_cnt * 128 / 1048576.0);
+  }
+  *out = c;
+  return ZKB_OK;
+}
+
+static int crs_expand(zkb_ctx* ctx, zkb_crs* c, cudaStream_t st) {
+  ZKB_TRY(expand_table_g1(ctx, c->g1, c->g1_cnt, c->g1_cnt, c->c1, st));
+  ZKB_TRY(expand_table_g2(ctx, c->g2, c->g2_cnt, c->g2_cnt, c->c2, st));
+  if (cudaStreamSynchronize(st) != cudaSuccess)
+    return set_err(ctx, ZKB_ERR_CUDA, "crs: table expansion failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return ZKB_OK;
+}
+
+int zkb_crs_upload(zkb_ctx* ctx, const zkb_crs_host* h, int rank, int world, zkb_crs** out) {
+  if (!ctx || !h || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_crs_upload: NULL argument");
+  *out = nullptr;
+  if (world < 1 || rank < 0 || rank >= world) return set_err(ctx, ZKB_ERR_ARG, "bad rank/world");
+  if (h->n < 1) return set_err(ctx, ZKB_ERR_ARG, "crs.n must be >= 1");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  zkb_crs* c;
+  ZKB_TRY(crs_new(ctx, h->n, h->n_sum_gamma, h->n_sum_delta, rank, world, &c));
+  cudaStream_t st = ctx->stream;
+  const size_t nxi = c->nxi(), nxt = c->nxt(), nsd = c->nsd();
+  G1Affine* fx = c->g1 + c->off_fixed();
+  cudaMemcpyAsync(fx + 0, h->alpha1, 64, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(fx + 1, h->beta1, 64, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(fx + 2, h->delta1, 64, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(c->g2 + nxi + 0, h->beta2, 128, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(c->g2 + nxi + 1, h->delta2, 128, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(c->gamma2, h->gamma2, 128, cudaMemcpyHostToDevice, st);
+  if (nxi) cudaMemcpyAsync(c->g1, h->xi1 + c->xi_lo * 8, nxi * 64, cudaMemcpyHostToDevice, st);
+  if (nxt) cudaMemcpyAsync(c->g1 + c->off_xit(), h->xi_t + c->xit_lo * 8, nxt * 64, cudaMemcpyHostToDevice, st);
+  if (nsd) cudaMemcpyAsync(c->g1 + c->off_sd(), h->sum_delta + c->sd_lo * 8, nsd * 64, cudaMemcpyHostToDevice, st);
+  if (c->n_sum_gamma) cudaMemcpyAsync(c->sum_gamma, h->sum_gamma, c->n_sum_gamma * 64, cudaMemcpyHostToDevice, st);
+  if (nxi) cudaMemcpyAsync(c->g2, h->xi2 + c->xi_lo * 16, nxi * 128, cudaMemcpyHostToDevice, st);
+  int rc = fq_to_mont(ctx, (Fq*)c->g1, c->g1_cnt * 2, true, st);
+  if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->g2, c->g2_cnt * 4, true, st);
+  if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->gamma2, 4, true, st);
+  if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->sum_gamma, c->n_sum_gamma * 2, true, st);
+  if (rc == ZKB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = set_err(ctx, ZKB_ERR_CUDA, "crs upload failed");
+  if (rc == ZKB_OK) rc = crs_expand(ctx, c, st);
+  if (rc != ZKB_OK) { zkb_crs_free(ctx, c); return rc; }
+  *out = c;
+  return ZKB_OK;
+}
+
+int zkb_setup(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* toxic, int rank, int world, zkb_crs** out) {
+  if (!ctx || !q || !toxic || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_setup: NULL argument");
+  *out = nullptr;
+  if (world < 1 || rank < 0 || rank >= world) return set_err(ctx, ZKB_ERR_ARG, "bad rank/world");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  Fr alpha = fr_from_limbs(toxic), beta = fr_from_limbs(toxic + 4), gamma = fr_from_limbs(toxic + 8),
+     delta = fr_from_limbs(toxic + 12), x = fr_from_limbs(toxic + 16);
+  if (alpha.is_zero() || beta.is_zero() || gamma.is_zero() || delta.is_zero() || x.is_zero())
+    return set_err(ctx, ZKB_ERR_DIV_ZERO, "setup: toxic values must be non-zero (random_elem, fr.rs:90-99)");
+  const uint64_t n = q->n, m = q->m;
+  zkb_crs* c;
+  ZKB_TRY(crs_new(ctx, n, q->n_input + 1, m - q->n_input - 1, rank, world, &c));
+  int rc;
+  auto fail = [&](int code) { zkb_crs_free(ctx, c); return code; };
+  cudaStream_t st = ctx->stream;
+  const size_t nxi = c->nxi(), nxt = c->nxt(), nsd = c->nsd();
+  // scalars
+  void* p;
+  if ((rc = scratch_get(ctx, 8, (n + n + m + 8) * sizeof(Fr), &p)) != ZKB_OK) return fail(rc);
+  Fr* d_L = (Fr*)p;           // n   Lagrange basis at x; later reused for xi_t scalars
+  Fr* d_pow = d_L + n;        // n   x^i
+  Fr* d_lin = d_pow + n;      // m
+  Fr* d_six = d_lin + m;      // alpha, beta, delta | beta, delta | gamma
+  if ((rc = scratch_get(ctx, 9, sizeof(int), &p)) != ZKB_OK) return fail(rc);
+  int* d_bad = (int*)p;
+  cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+  Fr xn = pow_u64(x, n);
+  Fr tx = xn - Fr::one();  // t(x) = x^n - 1
+  Fr inv_delta = inverse(delta), inv_gamma = inverse(gamma);
+  Fr tx_over_n = tx * inverse(fr_from_u64(n));
+  Fr omega = host_omega(q->log_n, false);
+  auto launch_fail = [&](const char* what) { return fail(set_err(ctx, ZKB_ERR_CUDA, "setup: %s: %s", what, cudaGetErrorString(cudaGetLastError()))); };
+  k_lagrange<<<cdiv(n, 128), 128, 0, st>>>(d_L, x, tx_over_n, omega, n, d_bad);
+  ctx->launches++;
+  if (cudaGetLastError() != cudaSuccess) return launch_fail("k_lagrange");
+  k_lin<<<cdiv(m * 32, 256), 256, 0, st>>>(q->d_rptr[0], q->d_gate[0], q->d_rcoeff[0], q->d_rptr[1], q->d_gate[1],
+                                           q->d_rcoeff[1], q->d_rptr[2], q->d_gate[2], q->d_rcoeff[2], d_L, m,
+                                           q->n_input, alpha, beta, inv_gamma, inv_delta, d_lin);
+  ctx->launches++;
+  if (cudaGetLastError() != cudaSuccess) return launch_fail("k_lin");
+  int bad = 0;
+  cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) return launch_fail("sync");
+  if (bad) return fail(set_err(ctx, ZKB_ERR_UNSUPPORTED, "setup: x is one of the domain roots"));
+  if ((rc = fill_powers(ctx, d_pow, x, Fr::one(), n, st)) != ZKB_OK) return fail(rc);
+  if ((rc = fill_powers(ctx, d_L, x, tx * inv_delta, n, st)) != ZKB_OK) return fail(rc);  // xi_t scalars
+  Fr six[6] = {alpha, beta, delta, beta, delta, gamma};
+  cudaMemcpyAsync(d_six, six, sizeof six, cudaMemcpyHostToDevice, st);
+  if ((rc = fixed_base_g1(ctx, c->g1 + c->off_fixed(), d_six, 3, st)) != ZKB_OK) return fail(rc);
+  if ((rc = fixed_base_g2(ctx, c->g2 + nxi, d_six + 3, 2, st)) != ZKB_OK) return fail(rc);
+  if ((rc = fixed_base_g2(ctx, c->gamma2, d_six + 5, 1, st)) != ZKB_OK) return fail(rc);
+  if ((rc = fixed_base_g1(ctx, c->g1, d_pow + c->xi_lo, nxi, st)) != ZKB_OK) return fail(rc);
+  if ((rc = fixed_base_g2(ctx, c->g2, d_pow + c->xi_lo, nxi, st)) != ZKB_OK) return fail(rc);
+  if ((rc = fixed_base_g1(ctx, c->g1 + c->off_xit(), d_L + c->xit_lo, nxt, st)) != ZKB_OK) return fail(rc);
+  if ((rc = fixed_base_g1(ctx, c->sum_gamma, d_lin, c->n_sum_gamma, st)) != ZKB_OK) return fail(rc);
+  if ((rc = fixed_base_g1(ctx, c->g1 + c->off_sd(), d_lin + c->n_sum_gamma + c->sd_lo, nsd, st)) != ZKB_OK) return fail(rc);
+  if (cudaStreamSynchronize(st) != cudaSuccess) return launch_fail("fixed-base");
+  if ((rc = crs_expand(ctx, c, st)) != ZKB_OK) return fail(rc);
+  *out = c;
+  return ZKB_OK;
+}
+
+int zkb_crs_dims(const zkb_crs* c, uint64_t* n, uint64_t* nsg, uint64_t* nsd) {
+  if (!c) return ZKB_ERR_ARG;
+  if (n) *n = c->n;
+  if (nsg) *nsg = c->n_sum_gamma;
+  if (nsd) *nsd = c->n_sum_delta;
+  return ZKB_OK;
+}
+
+int zkb_crs_download(zkb_ctx* ctx, const zkb_crs* c, zkb_crs_host* d) {
+  if (!ctx || !c || !d) return set_err(ctx, ZKB_ERR_ARG, "zkb_crs_download: NULL argument");
+  if (c->world != 1) return set_err(ctx, ZKB_ERR_UNSUPPORTED, "crs download needs an unsharded CRS");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  d->n = c->n; d->n_sum_gamma = c->n_sum_gamma; d->n_sum_delta = c->n_sum_delta;
+  const G1Affine* fx = c->g1 + c->off_fixed();
+  ZKB_TRY(download_fq(ctx, (uint64_t*)d->alpha1, fx + 0, 2));
+  ZKB_TRY(download_fq(ctx, (uint64_t*)d->beta1, fx + 1, 2));
+  ZKB_TRY(download_fq(ctx, (uint64_t*)d->delta1, fx + 2, 2));
+  ZKB_TRY(download_fq(ctx, (uint64_t*)d->beta2, c->g2 + c->n + 0, 4));
+  ZKB_TRY(download_fq(ctx, (uint64_t*)d->delta2, c->g2 + c->n + 1, 4));
+  ZKB_TRY(download_fq(ctx, (uint64_t*)d->gamma2, c->gamma2, 4));
+  ZKB_TRY(download_fq(ctx, (uint64_t*)d->xi1, c->g1, c->n * 2));
+  ZKB_TRY(download_fq(ctx, (uint64_t*)d->xi_t, c->g1 + c->off_xit(), (c->n - 1) * 2));
+  ZKB_TRY(download_fq(ctx, (uint64_t*)d->sum_gamma, c->sum_gamma, c->n_sum_gamma * 2));
+  ZKB_TRY(download_fq(ctx, (uint64_t*)d->sum_delta, c->g1 + c->off_sd(), c->n_sum_delta * 2));
+  ZKB_TRY(download_fq(ctx, (uint64_t*)d->xi2, c->g2, c->n * 4));
+  return ZKB_OK;
+}
+
+}  // extern "C"

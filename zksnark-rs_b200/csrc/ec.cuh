@@ -129,6 +129,13 @@ template <class F> ZKB_HD XYZZ<F> add(const XYZZ<F>& a, const XYZZ<F>& b) {
   return r;
 }
 
+// out-of-line copies for the latency-bound reduction kernels (one body per kernel instead of one per
+// call site: an inlined Fq2 add is ~9k instructions)
+#if defined(__CUDACC__)
+template <class F> __device__ __noinline__ XYZZ<F> add_ool(const XYZZ<F>& a, const XYZZ<F>& b) { return add(a, b); }
+template <class F> __device__ __noinline__ XYZZ<F> dbl_ool(const XYZZ<F>& a) { return dbl(a); }
+#endif
+
 template <class F> ZKB_HD Affine<F> to_affine(const XYZZ<F>& p) {
   if (p.is_inf()) return Affine<F>::inf();
   // x = X/ZZ, y = Y/ZZZ; one inversion: i = 1/(ZZ*ZZZ)

@@ -1,31 +1,41 @@
-// Pippenger bucket multi-scalar multiplication over BN254 G1 / G2 for sm_100a.
+// Pippenger bucket multi-scalar multiplication over BN254 G1 / G2 for sm_100a, fixed-base form.
 //
 // Replaces the reference's MSM pattern `coeffs.zip(points).map(exp_encrypted_g*).sum()`
 // (/root/reference/src/groth16/mod.rs:255-272, 279-290), i.e. n independent MSB-first
 // double-and-add scalar multiplications (fr.rs:114-119) folded sequentially (fr.rs:191-223).
 // Group addition is exact, so any summation order gives the same affine result.
 //
-// Pipeline (all on one stream, no host round trips):
-//   1. k_digits_count   signed-digit recoding of every scalar into W windows of c bits
-//                       (digits in [-2^(c-1), 2^(c-1)]), histogram of bucket sizes
-//   2. scan             exclusive prefix sum of the W * 2^(c-1) bucket sizes
-//   3. k_digits_scatter counting-sort the (point index, sign) records by bucket
-//   4. k_accumulate_chunks  one thread per 32 sorted records: XYZZ mixed additions, flush at bucket
-//                       boundaries; k_fix_heads: per-warp fold of buckets that span chunks (shuffle tree)
-//   5. k_reduce_chunks  per window, running-sum reduction of L-bucket chunks
-//   6. k_window_finish  per window: sum_t (T_t + v0_t * S_t) with a shared-memory tree
-//   7. k_combine        Horner over the windows (c doublings per window)
+// The bases of every MSM on the prove() path are CRS vectors: fixed for the life of the CRS.  So
+// each base vector is expanded ONCE (at setup / upload) into a table
+//     T[j][i] = 2^(c*j) * P_i,   j < W = floor(254/c) + 1,   affine,
+// and a scalar k = sum_j d_j 2^(c*j) (signed digits d_j in [-2^(c-1), 2^(c-1)]) contributes the
+// W records (T[j][i], d_j).  All windows then share ONE set of 2^(c-1) buckets: there is no
+// per-window reduction and no Horner combine over windows, and c can be larger (fewer records).
+//
+// A call may carry several jobs over the same table (different scalar vectors over prefixes of
+// the table): their bucket sets are laid side by side and every stage runs once for all of them.
+//
+// Pipeline (one stream, no host round trips):
+//   1. k_digits_count    signed-digit recoding, histogram of bucket sizes           (L2 atomics)
+//   2. scan              exclusive prefix sum of the bucket sizes
+//   3. k_digits_scatter  counting sort of the (table index, sign) records by bucket (L2 atomics)
+//   4. k_accumulate_chunks  one thread per S sorted records: XYZZ mixed additions, flush at
+//                        bucket boundaries                                          (THE hot kernel)
+//   5. k_fix_heads       fold pieces of buckets that span chunks
+//   6. k_bucket_level    sum_b (b+1) B_b by a hierarchy of running sums, 16 -> 1 per level
+//
+// The kernels are templates on the coordinate field; the launches go through MsmLaunch<F> so that
+// the heavy Fq2 instantiations can live in separate translation units (parallel nvcc jobs).
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace zkb {
 
-// ------------------------------------------------------------------------------------------------
-// signed-digit recoding.  k: canonical 254-bit scalar.  Calls f(j, digit) for every window.
 struct DigitPlan {
   int c;        // window bits
   int W;        // number of windows = floor(254 / c) + 1
-  uint32_t nb;  // buckets per window = 2^(c-1); bucket value v in 1..nb
+  uint32_t nb;  // buckets = 2^(c-1); bucket b holds digit magnitude b+1
 };
 
 __host__ __device__ inline DigitPlan make_plan(int c) {
@@ -36,127 +46,106 @@ __host__ __device__ inline DigitPlan make_plan(int c) {
   return p;
 }
 
-__device__ __forceinline__ uint32_t get_bits(const uint32_t k[8], int pos, int c) {
-  // bits [pos, pos+c) of the 256-bit integer k (c <= 24)
-  int w = pos >> 5, o = pos & 31;
-  if (w >= 8) return 0;
-  uint64_t lo = k[w];
-  uint64_t hi = (w + 1 < 8) ? k[w + 1] : 0;
-  uint64_t v = (lo | (hi << 32)) >> o;
-  return (uint32_t)v & ((1u << c) - 1);
+static const int MSM_MAX_JOBS = 4;
+static const int ACC_S = 32;  // records per accumulation chunk
+static const uint32_t RED_L = 16, RED_LOG_L = 4;
+
+// window size for a table over n points (single bucket set): N*W mixed adds (10 modmul) + the
+// bucket hierarchy (2 full adds of 14 modmul per bucket, weighted x2 for its lower parallelism)
+static inline int pick_c(size_t n) {
+  if (const char* e = getenv("ZKB_MSM_C")) {
+    int c = atoi(e);
+    if (c >= 2 && c <= 23) return c;
+  }
+  int best = 2;
+  double best_cost = 1e300;
+  for (int c = 2; c <= 22; c++) {
+    double W = 254 / c + 1;
+    double cost = W * 10.0 * (double)(n ? n : 1) + 56.0 * (double)((size_t)1 << (c - 1));
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
 }
 
-__device__ __forceinline__ Fr load_scalar(const Fr* scalars, size_t i, int mont) {
-  Fr k = scalars[i];
-  if (mont) k = from_mont(k);
-  return k;
+// launch indirection (definitions: msm_g1.cu for Fq; msm_g2_*.cu for Fq2)
+template <class F>
+struct MsmLaunch {
+  static int accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
+                        size_t nacc, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind);
+  static int fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, XYZZ<F>* buckets, const XYZZ<F>* heads, cudaStream_t st);
+  // full hierarchy: buckets[njobs][nb] -> d_out[njobs]; lvlS / lvlA hold the intermediate levels
+  static int reduce(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int njobs, XYZZ<F>* lvlS, XYZZ<F>* lvlA, XYZZ<F>* d_out,
+                    cudaStream_t st);
+  static int expand_table(zkb_ctx* ctx, Affine<F>* tab, size_t stride, size_t n, int c, cudaStream_t st);
+  static int set_inf(zkb_ctx* ctx, XYZZ<F>* out, int n, cudaStream_t st);
+};
+
+// digit / scan stages (field independent; defined in msm_g1.cu)
+int msm_sort_records(zkb_ctx* ctx, const MsmJob* jobs, int njobs, size_t stride, DigitPlan pl, uint32_t* hist, uint32_t* offs,
+                     uint32_t* cursor, uint32_t* sums, uint32_t* sorted, cudaStream_t st);
+
+static inline size_t msm_level_elems(uint32_t nb, int njobs) {
+  size_t e = 0;
+  for (uint32_t m = nb; m > 1;) { m = (m + RED_L - 1) / RED_L; e += (size_t)m * njobs; }
+  return e + njobs;
 }
 
-static __global__ void k_digits_count(const Fr* __restrict__ scalars, int mont, size_t n, DigitPlan pl,
-                               uint32_t* __restrict__ hist) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fr k = load_scalar(scalars, i, mont);
-  uint32_t carry = 0;
-  for (int j = 0; j < pl.W; j++) {
-    uint32_t d = get_bits(k.v, j * pl.c, pl.c) + carry;
-    carry = d > pl.nb;
-    uint32_t mag = carry ? ((1u << pl.c) - d) : d;
-    if (mag) atomicAdd(&hist[(size_t)j * pl.nb + mag - 1], 1u);
+// results d_out[j] (device XYZZ, Montgomery) = sum_{i < jobs[j].n} jobs[j].scalars[i] * T[0][i]
+template <class F>
+static int msm_run(zkb_ctx* ctx, const Affine<F>* tab, size_t stride, int c, const MsmJob* jobs, int njobs, XYZZ<F>* d_out,
+                   int slot, cudaStream_t st, int prof_kind) {
+  if (njobs < 1 || njobs > MSM_MAX_JOBS) return set_err(ctx, ZKB_ERR_ARG, "msm: %d jobs", njobs);
+  if (c < 2 || c > 23) return set_err(ctx, ZKB_ERR_ARG, "msm: window_bits %d out of range [2,23]", c);
+  DigitPlan pl = make_plan(c);
+  size_t total_n = 0;
+  for (int j = 0; j < njobs; j++) {
+    if (jobs[j].n > stride) return set_err(ctx, ZKB_ERR_ARG, "msm: more scalars than bases");
+    total_n += jobs[j].n;
   }
+  if ((size_t)pl.W * stride >= ((size_t)1 << 31) || (size_t)pl.W * total_n >= ((size_t)1 << 32) - 64)
+    return set_err(ctx, ZKB_ERR_ARG, "msm: too many records for 32-bit indices");
+  if (total_n == 0) return MsmLaunch<F>::set_inf(ctx, d_out, njobs, st);
+  const size_t nbk = (size_t)njobs * pl.nb;
+  const size_t nscan_blocks = (nbk + 1023) / 1024;
+  const size_t max_recs = (size_t)pl.W * total_n;
+  const size_t nacc = (max_recs + ACC_S - 1) / ACC_S;
+  const size_t lvl_elems = msm_level_elems(pl.nb, njobs);
+
+  void* p;
+  // u32 scratch: hist[nbk] | offs[nbk+1] | cursor[nbk] | sums[nscan_blocks+1]
+  size_t u32_words = nbk * 3 + 1 + nscan_blocks + 8;
+  ZKB_TRY(scratch_get(ctx, slot + 0, u32_words * 4, &p));
+  uint32_t* hist = (uint32_t*)p;
+  uint32_t* offs = hist + nbk;
+  uint32_t* cursor = offs + nbk + 1;
+  uint32_t* sums = cursor + nbk;
+  ZKB_TRY(scratch_get(ctx, slot + 1, max_recs * 4, &p));
+  uint32_t* sorted = (uint32_t*)p;
+  ZKB_TRY(scratch_get(ctx, slot + 2, (nbk + nacc + 2 * lvl_elems) * sizeof(XYZZ<F>), &p));
+  XYZZ<F>* buckets = (XYZZ<F>*)p;
+  XYZZ<F>* heads = buckets + nbk;
+  XYZZ<F>* lvlS = heads + nacc;
+  XYZZ<F>* lvlA = lvlS + lvl_elems;
+
+  ZKB_TRY(msm_sort_records(ctx, jobs, njobs, stride, pl, hist, offs, cursor, sums, sorted, st));
+  ZKB_CUDA(ctx, cudaMemsetAsync(buckets, 0, nbk * sizeof(XYZZ<F>), st));  // all-zero XYZZ = identity
+  if (ctx->profile) ctx->prof_units[prof_kind] += max_recs;
+  ZKB_TRY(MsmLaunch<F>::accumulate(ctx, tab, offs, sorted, (uint32_t)nbk, nacc, buckets, heads, st, prof_kind));
+  ZKB_TRY(MsmLaunch<F>::fix_heads(ctx, offs, (uint32_t)nbk, buckets, heads, st));
+  ZKB_TRY(MsmLaunch<F>::reduce(ctx, buckets, pl.nb, njobs, lvlS, lvlA, d_out, st));
+  return ZKB_OK;
 }
 
-static __global__ void k_digits_scatter(const Fr* __restrict__ scalars, int mont, size_t n, DigitPlan pl,
-                                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fr k = load_scalar(scalars, i, mont);
-  uint32_t carry = 0;
-  for (int j = 0; j < pl.W; j++) {
-    uint32_t d = get_bits(k.v, j * pl.c, pl.c) + carry;
-    carry = d > pl.nb;
-    uint32_t mag = carry ? ((1u << pl.c) - d) : d;
-    if (mag) {
-      uint32_t pos = atomicAdd(&cursor[(size_t)j * pl.nb + mag - 1], 1u);
-      sorted[pos] = (uint32_t)i | (carry << 31);
-    }
-  }
-}
+// ================================================================================================
+// kernels
+// ================================================================================================
+#if defined(__CUDACC__)
 
-// ------------------------------------------------------------------------------------------------
-// exclusive scan of uint32 (three small kernels; total <= 2^24 entries)
-static const int SCAN_B = 1024;  // elements per block (256 threads x 4)
-
-static __global__ void k_scan_block(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ sums,
-                             size_t n) {
-  __shared__ uint32_t sh[256];
-  size_t base = (size_t)blockIdx.x * SCAN_B + threadIdx.x * 4;
-  uint32_t v[4], tot = 0;
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    v[q] = base + q < n ? in[base + q] : 0;
-    tot += v[q];
-  }
-  sh[threadIdx.x] = tot;
-  __syncthreads();
-  for (int off = 1; off < 256; off <<= 1) {
-    uint32_t x = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
-    __syncthreads();
-    sh[threadIdx.x] += x;
-    __syncthreads();
-  }
-  uint32_t excl = sh[threadIdx.x] - tot;
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    if (base + q < n) out[base + q] = excl;
-    excl += v[q];
-  }
-  if (threadIdx.x == 255) sums[blockIdx.x] = sh[255];
-}
-
-static __global__ void k_scan_sums(uint32_t* sums, size_t nblocks, uint32_t* total) {
-  // single block, sequential over chunks of 1024
-  __shared__ uint32_t sh[1024];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (size_t base = 0; base < nblocks; base += 1024) {
-    size_t i = base + threadIdx.x;
-    uint32_t v = i < nblocks ? sums[i] : 0;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      uint32_t x = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += x;
-      __syncthreads();
-    }
-    if (i < nblocks) sums[i] = carry + sh[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += sh[1023];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry;
-}
-
-static __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ out2, const uint32_t* __restrict__ sums,
-                           size_t n, const uint32_t* total) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    uint32_t v = out[i] + sums[i / SCAN_B];
-    out[i] = v;
-    out2[i] = v;
-  }
-  if (i == n) out[n] = *total;  // offsets[n] = total
-}
-
-// ------------------------------------------------------------------------------------------------
 // Bucket accumulation, load-balanced: the sorted record array is cut into chunks of S records and
 // every thread sums exactly one chunk with XYZZ mixed additions, flushing at bucket boundaries.
 // A bucket that begins inside the chunk is written to buckets[g]; the leading piece of a bucket
-// that began in an earlier chunk goes to heads[t] and is folded in by
-// k_fix_heads.  buckets[] is zero-filled (= identity) beforehand, empty buckets are never touched.
-
+// that began in an earlier chunk goes to heads[t] and is folded in by k_fix_heads.  buckets[] is
+// zero-filled (= identity) beforehand, empty buckets are never touched.
 template <class F, int S>
 __global__ void __launch_bounds__(128) k_accumulate_chunks(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
                                                            const uint32_t* __restrict__ sorted, uint32_t nbk, size_t nchunks,
@@ -214,9 +203,9 @@ __device__ __forceinline__ XYZZ<F> shfl_xyzz(const XYZZ<F>& p, int src) {
 
 // Fold the head pieces into their buckets.  One thread per bucket g: the chunks whose first record
 // lies strictly inside bucket g are t with offs[g] < t*S < offs[g+1] (computed from the offsets, so
-// no search).  Short runs (the common case: ~1 head per bucket when the mean bucket size is about
-// S) are summed by the owning thread; long runs (skewed scalars: one huge bucket) are summed by
-// the whole warp, lanes striding over the run followed by a shuffle tree.
+// no search).  Short runs (the common case) are summed by the owning thread; long runs (skewed
+// scalars: one huge bucket) are summed by the whole warp, lanes striding over the run followed by
+// a shuffle tree.
 template <class F, int S>
 __global__ void __launch_bounds__(128) k_fix_heads(const uint32_t* __restrict__ offs, uint32_t nbk,
                                                    XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ heads) {
@@ -228,164 +217,124 @@ __global__ void __launch_bounds__(128) k_fix_heads(const uint32_t* __restrict__ 
     if (hi > lo) { t0 = lo / S + 1; t1 = (hi - 1) / S; }
   }
   const uint32_t cnt = t1 >= t0 ? t1 - t0 + 1 : 0;
-  const bool big = cnt > 8;
+  const bool big = cnt > 12;
   XYZZ<F> acc = XYZZ<F>::inf();
   if (!big)
-    for (uint32_t t = t0; t <= t1; t++) acc = add(acc, heads[t]);
+    for (uint32_t t = t0; t <= t1; t++) acc = add_ool(acc, heads[t]);
   unsigned todo = __ballot_sync(0xffffffffu, big);
   while (todo) {
     const int src = __ffs(todo) - 1;
     todo &= todo - 1;
     const uint32_t b0 = __shfl_sync(0xffffffffu, t0, src), b1 = __shfl_sync(0xffffffffu, t1, src);
     XYZZ<F> part = XYZZ<F>::inf();
-    for (uint32_t t = b0 + lane; t <= b1; t += 32) part = add(part, heads[t]);
+    for (uint32_t t = b0 + lane; t <= b1; t += 32) part = add_ool(part, heads[t]);
     for (int off = 16; off > 0; off >>= 1) {
       XYZZ<F> o = shfl_down_xyzz(part, off);
-      part = add(part, o);
+      part = add_ool(part, o);
     }
     XYZZ<F> tot = shfl_xyzz(part, 0);
     if (lane == src) acc = tot;
   }
-  if (cnt) buckets[g] = add(buckets[g], acc);
+  if (cnt) buckets[g] = add_ool(buckets[g], acc);
 }
 
-// chunk t of window j covers bucket values v0+1 .. v0+L (v0 = t*L).  S = sum B_v, T = sum (v - v0) B_v.
+// Bucket reduction  R = sum_b (b+1) B_b = F(B) + G(B),  F(X) = sum_b b X_b,  G(X) = sum_b X_b.
+// Cut X into chunks of L: with S_t = sum_i X_{tL+i} and T_t = sum_i i X_{tL+i},
+//     F(X) = sum_t T_t + L * F(S),    G(X) = G(S).
+// Level k (k = 0, 1, ...) therefore maps (S^k, A^k) -> (S^{k+1}, A^{k+1}) with
+//     A^{k+1}_t = sum_i A^k_{tL+i} + L^k * T^{k+1}_t        (A^0 = 0),
+// and when one element is left R = A + S.  grid.y = job (bucket sets are contiguous, n_in each).
 template <class F>
-__global__ void __launch_bounds__(128) k_reduce_chunks(const XYZZ<F>* __restrict__ buckets, uint32_t nb, uint32_t L,
-                                                       size_t nchunks_total, XYZZ<F>* __restrict__ S,
-                                                       XYZZ<F>* __restrict__ T) {
-  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nchunks_total) return;
-  uint32_t per_win = nb / L;
-  size_t j = g / per_win;
-  uint32_t t = (uint32_t)(g % per_win);
-  const XYZZ<F>* b = buckets + j * nb + (size_t)t * L;
+__global__ void __launch_bounds__(128) k_bucket_level(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ A_in,
+                                                      uint32_t n_in, uint32_t n_out, int shift, XYZZ<F>* __restrict__ S_out,
+                                                      XYZZ<F>* __restrict__ A_out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_out) return;
+  const size_t job = blockIdx.y;
+  const XYZZ<F>* s = S_in + job * n_in + (size_t)t * RED_L;
+  const uint32_t cnt = n_in - t * RED_L < RED_L ? n_in - t * RED_L : RED_L;
   XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-  for (int v = (int)L - 1; v >= 0; v--) {
-    run = add(run, b[v]);
-    acc = add(acc, run);
+  for (int i = (int)cnt - 1; i >= 1; i--) {
+    run = add_ool(run, s[i]);
+    acc = add_ool(acc, run);
   }
-  S[g] = run;
-  T[g] = acc;
+  run = add_ool(run, s[0]);
+  for (int q = 0; q < shift; q++) acc = dbl_ool(acc);
+  if (A_in) {
+    const XYZZ<F>* a = A_in + job * n_in + (size_t)t * RED_L;
+    for (uint32_t i = 0; i < cnt; i++) acc = add_ool(acc, a[i]);
+  }
+  S_out[job * n_out + t] = run;
+  A_out[job * n_out + t] = acc;
 }
 
 template <class F>
-__device__ XYZZ<F> small_mul(const XYZZ<F>& p, uint32_t k) {
-  XYZZ<F> acc = XYZZ<F>::inf();
-  if (k == 0 || p.is_inf()) return acc;
-  int top = 31 - __clz(k);
-  for (int b = top; b >= 0; b--) {
-    acc = dbl(acc);
-    if ((k >> b) & 1u) acc = add(acc, p);
-  }
-  return acc;
-}
-
-// one block per window: X_t = T_t + (t*L) * S_t, then tree-sum over t.
-template <class F>
-__global__ void __launch_bounds__(128) k_window_finish(const XYZZ<F>* __restrict__ S, const XYZZ<F>* __restrict__ T,
-                                                       uint32_t per_win, uint32_t L, XYZZ<F>* __restrict__ wsum) {
-  extern __shared__ uint4 smem_raw[];
-  XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(smem_raw);
-  size_t j = blockIdx.x;
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t t = threadIdx.x; t < per_win; t += blockDim.x) {
-    XYZZ<F> x = add(T[j * per_win + t], small_mul(S[j * per_win + t], t * L));
-    acc = add(acc, x);
-  }
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  for (uint32_t off = blockDim.x >> 1; off > 0; off >>= 1) {
-    if (threadIdx.x < off) sh[threadIdx.x] = add(sh[threadIdx.x], sh[threadIdx.x + off]);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) wsum[j] = sh[0];
+__global__ void k_bucket_final(const XYZZ<F>* __restrict__ S, const XYZZ<F>* __restrict__ A, int njobs, XYZZ<F>* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= njobs) return;
+  out[j] = A ? add_ool(S[j], A[j]) : S[j];
 }
 
 template <class F>
-__global__ void k_combine(const XYZZ<F>* __restrict__ wsum, int W, int c, XYZZ<F>* __restrict__ out) {
-  if (threadIdx.x | blockIdx.x) return;
-  XYZZ<F> acc = wsum[W - 1];
-  for (int j = W - 2; j >= 0; j--) {
+__global__ void k_set_inf(XYZZ<F>* out, int n) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[j] = XYZZ<F>::inf();
+}
+
+// table expansion: T[j][i] = 2^(c*j) * T[0][i]
+template <class F>
+__global__ void __launch_bounds__(128) k_expand_table(Affine<F>* __restrict__ tab, size_t stride, size_t n, int c, int W) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ<F> acc = to_xyzz(tab[i]);
+  for (int j = 1; j < W; j++) {
     for (int q = 0; q < c; q++) acc = dbl(acc);
-    acc = add(acc, wsum[j]);
+    tab[(size_t)j * stride + i] = to_affine(acc);
   }
-  *out = acc;
 }
 
+// ---- launch bodies (instantiated by the .cu that owns the kernel) --------------------------------
 template <class F>
-__global__ void k_set_inf(XYZZ<F>* out) {
-  if (threadIdx.x | blockIdx.x) return;
-  *out = XYZZ<F>::inf();
+static int launch_accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
+                             size_t nacc, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind) {
+  ZKB_LAUNCH_K(ctx, prof_kind, (k_accumulate_chunks<F, ACC_S>), cdiv(nacc, 128), 128, 0, st, tab, offs, sorted, nbk, nacc, buckets,
+               heads);
+  return ZKB_OK;
 }
-
-static int pick_c(size_t n) {
-  // minimise W * (10 n + 2 * 14 * 2 * 2^(c-1)) modmuls: N*W mixed adds (10M) + bucket reduction
-  // (2 full adds of 14M per bucket, weighted x2 for its lower parallelism)
-  int best = 4;
-  double best_cost = 1e300;
-  for (int c = 4; c <= 18; c++) {
-    double W = 254 / c + 1;
-    double cost = W * (10.0 * (double)n + 56.0 * (double)((size_t)1 << (c - 1)));
-    if (cost < best_cost) { best_cost = cost; best = c; }
-  }
-  return best;
-}
-
 template <class F>
-static int msm_impl(zkb_ctx* ctx, const Affine<F>* pts, const Fr* scalars, bool mont, size_t n, int c, XYZZ<F>* d_out,
-                    int slot, cudaStream_t st) {
-  if (n == 0) {
-    ZKB_LAUNCH(ctx, k_set_inf<F>, 1, 1, 0, st, d_out);
-    return ZKB_OK;
+static int launch_fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, XYZZ<F>* buckets, const XYZZ<F>* heads,
+                            cudaStream_t st) {
+  ZKB_LAUNCH(ctx, (k_fix_heads<F, ACC_S>), cdiv(nbk, 128), 128, 0, st, offs, nbk, buckets, heads);
+  return ZKB_OK;
+}
+template <class F>
+static int launch_reduce(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int njobs, XYZZ<F>* lvlS, XYZZ<F>* lvlA, XYZZ<F>* d_out,
+                         cudaStream_t st) {
+  const XYZZ<F>*Sin = buckets, *Ain = nullptr;
+  XYZZ<F>*So = lvlS, *Ao = lvlA;
+  int shift = 0;
+  for (uint32_t m = nb; m > 1;) {
+    uint32_t mo = (m + RED_L - 1) / RED_L;
+    dim3 grid(cdiv(mo, 128), njobs);
+    ZKB_LAUNCH(ctx, k_bucket_level<F>, grid, 128, 0, st, Sin, Ain, m, mo, shift, So, Ao);
+    Sin = So; Ain = Ao;
+    So += (size_t)mo * njobs; Ao += (size_t)mo * njobs;
+    shift += RED_LOG_L;
+    m = mo;
   }
-  if (n >= ((size_t)1 << 31)) return set_err(ctx, ZKB_ERR_ARG, "msm: n too large");
-  if (c <= 0) c = pick_c(n);
-  if (c < 2 || c > 20) return set_err(ctx, ZKB_ERR_ARG, "msm: window_bits %d out of range [2,20]", c);
+  ZKB_LAUNCH(ctx, k_bucket_final<F>, 1, 32, 0, st, Sin, Ain, njobs, d_out);
+  return ZKB_OK;
+}
+template <class F>
+static int launch_expand_table(zkb_ctx* ctx, Affine<F>* tab, size_t stride, size_t n, int c, cudaStream_t st) {
+  if (!n) return ZKB_OK;
   DigitPlan pl = make_plan(c);
-  size_t nbk = (size_t)pl.W * pl.nb;
-  uint32_t L = pl.nb >= 64 ? 16 : (pl.nb >= 8 ? 4 : 1);  // chunk length for the running-sum reduction
-  uint32_t per_win = pl.nb / L;
-  size_t nchunks = (size_t)pl.W * per_win;
-  size_t nscan_blocks = (nbk + SCAN_B - 1) / SCAN_B;
-
-  uint32_t *hist, *offs, *cursor, *sums, *sorted;
-  XYZZ<F>*buckets, *S, *T, *wsum;
-  void* p;
-  // layout of the u32 scratch: hist[nbk] | offs[nbk+1] | cursor[nbk] | sums[nscan_blocks+1]
-  size_t u32_words = nbk * 3 + 1 + nscan_blocks + 8;
-  ZKB_TRY(scratch_get(ctx, slot + 0, u32_words * 4, &p));
-  hist = (uint32_t*)p;
-  offs = hist + nbk;
-  cursor = offs + nbk + 1;
-  sums = cursor + nbk;
-  ZKB_TRY(scratch_get(ctx, slot + 1, (size_t)pl.W * n * 4, &p));
-  sorted = (uint32_t*)p;
-  const int ACC_S = 32;  // records per accumulation chunk
-  size_t nacc = ((size_t)pl.W * n + ACC_S - 1) / ACC_S;
-  ZKB_TRY(scratch_get(ctx, slot + 2, (nbk + 2 * nchunks + pl.W + nacc) * sizeof(XYZZ<F>), &p));
-  buckets = (XYZZ<F>*)p;
-  S = buckets + nbk;
-  T = S + nchunks;
-  wsum = T + nchunks;
-  XYZZ<F>* heads = wsum + pl.W;
-
-  ZKB_CUDA(ctx, cudaMemsetAsync(hist, 0, nbk * 4, st));
-  ZKB_LAUNCH(ctx, k_digits_count, cdiv(n, 256), 256, 0, st, scalars, mont ? 1 : 0, n, pl, hist);
-  ZKB_LAUNCH(ctx, k_scan_block, (unsigned)nscan_blocks, 256, 0, st, hist, offs, sums, nbk);
-  ZKB_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, st, sums, nscan_blocks, sums + nscan_blocks);
-  ZKB_LAUNCH(ctx, k_scan_add, cdiv(nbk + 1, 256), 256, 0, st, offs, cursor, sums, nbk, sums + nscan_blocks);
-  ZKB_LAUNCH(ctx, k_digits_scatter, cdiv(n, 256), 256, 0, st, scalars, mont ? 1 : 0, n, pl, cursor, sorted);
-  ZKB_CUDA(ctx, cudaMemsetAsync(buckets, 0, nbk * sizeof(XYZZ<F>), st));  // all-zero XYZZ = identity
-  ZKB_LAUNCH_K(ctx, sizeof(F) == sizeof(Fq) ? PK_ACC_G1 : PK_ACC_G2, (k_accumulate_chunks<F, ACC_S>), cdiv(nacc, 128), 128, 0, st,
-               pts, offs, sorted, (uint32_t)nbk, nacc, buckets, heads);
-  if (ctx->profile) ctx->prof_units[sizeof(F) == sizeof(Fq) ? PK_ACC_G1 : PK_ACC_G2] += (uint64_t)pl.W * n;
-  ZKB_LAUNCH(ctx, (k_fix_heads<F, ACC_S>), cdiv(nbk, 128), 128, 0, st, offs, (uint32_t)nbk, buckets, heads);
-  ZKB_LAUNCH(ctx, k_reduce_chunks<F>, cdiv(nchunks, 128), 128, 0, st, buckets, pl.nb, L, nchunks, S, T);
-  unsigned fin_threads = per_win >= 128 ? 128 : (per_win >= 32 ? 32 : 1);
-  // round per_win down to a power of two thread count (per_win is a power of two)
-  ZKB_LAUNCH(ctx, k_window_finish<F>, pl.W, fin_threads, fin_threads * sizeof(XYZZ<F>), st, S, T, per_win, L, wsum);
-  ZKB_LAUNCH(ctx, k_combine<F>, 1, 32, 0, st, wsum, pl.W, pl.c, d_out);
+  if (pl.W > 1) ZKB_LAUNCH(ctx, k_expand_table<F>, cdiv(n, 128), 128, 0, st, tab, stride, n, c, pl.W);
+  return ZKB_OK;
+}
+template <class F>
+static int launch_set_inf(zkb_ctx* ctx, XYZZ<F>* out, int n, cudaStream_t st) {
+  ZKB_LAUNCH(ctx, k_set_inf<F>, 1, 32, 0, st, out, n);
   return ZKB_OK;
 }
 
@@ -458,5 +407,6 @@ static int sum_affine_impl(zkb_ctx* ctx, const Affine<F>* pts, size_t n, XYZZ<F>
   ZKB_LAUNCH(ctx, k_sum_affine<F>, 1, 64, 64 * sizeof(XYZZ<F>), st, pts, n, d_out);
   return ZKB_OK;
 }
+#endif  // __CUDACC__
 
 }  // namespace zkb

@@ -1,4 +1,4 @@
-// groth16::prove on the device + the extern "C" surface of libzkb200.so (include/zkb200.h).
+// groth16::prove on the device (include/zkb200.h: zkb_qap_*, zkb_prove*, zkb_qap_h).
 //
 // Reference path: /root/reference/src/groth16/mod.rs:213-296.  Stages here:
 //   1. witness upload, canonical -> Montgomery
@@ -10,72 +10,22 @@
 //                        t = x^n - 1, so the quotient (mod.rs:277, field/mod.rs:428-469) is
 //                        h = p_hi = (c - d g^-k) / 2.  w_sum has degree < n = deg t and cannot
 //                        influence the quotient (the remainder is discarded, coefficient_poly.rs:155).
-//   5. five MSMs (mod.rs:255-272, 279-290), the G2 one on a second stream
-//   6. k_assemble        mod.rs:274-275, 291-293
-#include <stdarg.h>
+//   5. k_msm_scalars     the MSM scalar vectors, canonical.  The reference's
+//                          A = a_g1 + alpha1 + r delta1                                  (mod.rs:274)
+//                          B = b_g2 + beta2 + s delta2                                   (mod.rs:275)
+//                          C = c_h + c_w + s A + r (beta1 + b_g1 + s delta1) - rs delta1 (mod.rs:279-293)
+//                        expand (group law, exact) to three MSMs over the CRS tables:
+//                          A = <[u_sum | 1, 0, r], [xi1 | alpha1, beta1, delta1]>
+//                          B = <[v_sum | 1, s],    [xi2 | beta2, delta2]>
+//                          C = <[s u_sum + r v_sum | s, r, rs | h | a_(l+1..)], [xi1 | alpha1, beta1, delta1 | xi_t | sum_delta]>
+//                        so no scalar multiplication of a fresh point is left.
+//   6. MSMs              A and C as two jobs of one G1 call; B (G2) on a second stream
+//   7. k_finish          three affine normalisations -> Proof{a, b, c}
 #include <string.h>
 #include <algorithm>
 #include "common.cuh"
 
 namespace zkb {
-
-thread_local std::string g_err;
-
-int set_err(zkb_ctx* ctx, int code, const char* fmt, ...) {
-  char buf[1024];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
-  g_err = buf;
-  if (ctx) ctx->err = buf;
-  return code;
-}
-
-int scratch_get(zkb_ctx* ctx, int slot, size_t bytes, void** out) {
-  DevBuf& b = ctx->scratch[slot];
-  if (b.bytes < bytes) {
-    if (b.p) {
-      ZKB_CUDA(ctx, cudaDeviceSynchronize());
-      cudaFree(b.p);
-      b.p = nullptr;
-      b.bytes = 0;
-    }
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&b.p, want);
-    if (e != cudaSuccess) {
-      b.p = nullptr;
-      return set_err(ctx, ZKB_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
-    }
-    b.bytes = want;
-  }
-  *out = b.p;
-  return ZKB_OK;
-}
-
-void prof_begin(zkb_ctx* ctx, int kind, cudaStream_t st) {
-  zkb_ctx::ProfRec r;
-  cudaEventCreate(&r.a);
-  cudaEventCreate(&r.b);
-  r.kind = kind;
-  cudaEventRecord(r.a, st);
-  ctx->prof.push_back(r);
-}
-void prof_end(zkb_ctx* ctx, cudaStream_t st) { cudaEventRecord(ctx->prof.back().b, st); }
-static void prof_clear(zkb_ctx* ctx) {
-  for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-  ctx->prof.clear();
-}
-
-static Fr fr_from_limbs(const uint64_t* l) {  // canonical limbs -> Montgomery (host)
-  Fr c;
-  memcpy(c.v, l, 32);
-  return to_mont(c);
-}
-static Fr fr_from_u64(uint64_t x) {
-  uint64_t l[4] = {x, 0, 0, 0};
-  return fr_from_limbs(l);
-}
 
 // ------------------------------------------------------------------------------------------------
 // kernels of the polynomial stage
@@ -125,239 +75,65 @@ __global__ void k_coset_tables(Fr* P, Fr* Q, Fr g, Fr ginv, Fr invn, Fr inv2n, u
   Q[i] = inv2n * pow_u64(ginv, e);
 }
 
-// ------------------------------------------------------------------------------------------------
-// final assembly, mod.rs:274-275 and 291-293.  Four worker warps (lane 0 of each).
-template <class F>
-__device__ XYZZ<F> smul_affine(const Affine<F>& p, const Fr& k_canon) {
-  return scalar_mul(p, k_canon.v);
-}
 
-struct AssembleShared {
-  G1XYZZ r_d1, s_d1, rs_d1, A, rB1;
-  G1Affine A_aff;
-  G2XYZZ s_d2;
+// MSM scalar vectors (canonical).  un, vn, hn: Montgomery, natural order; wm: witness, Montgomery.
+struct ScalarPlan {
+  uint64_t nxi, nxt, nsd, xi_lo, xit_lo, sd_lo;  // this rank's shard
+  uint64_t n_input, m;
+  int lead;                                      // rank 0 carries the fixed-point terms
 };
+__global__ void k_msm_scalars(const Fr* __restrict__ un, const Fr* __restrict__ vn, const Fr* __restrict__ hn,
+                              const Fr* __restrict__ wm, ScalarPlan pl, Fr r_m, Fr s_m, Fr* __restrict__ SA, Fr* __restrict__ SB,
+                              Fr* __restrict__ SC) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t off_xit = pl.nxi + 3, off_sd = off_xit + pl.nxt, total = off_sd + pl.nsd;
+  if (i >= total) return;
+  if (i < pl.nxi) {
+    Fr u = un[pl.xi_lo + i], v = vn[pl.xi_lo + i];
+    SA[i] = from_mont(u);
+    SB[i] = from_mont(v);
+    SC[i] = from_mont(s_m * u + r_m * v);
+  } else if (i < off_xit) {
+    const int k = (int)(i - pl.nxi);
+    Fr one = Fr::zero();
+    one.v[0] = 1;
+    Fr r = from_mont(r_m), s = from_mont(s_m), z = Fr::zero();
+    if (!pl.lead) { r = z; s = z; one = z; }
+    SA[i] = k == 0 ? one : (k == 1 ? z : r);                               // alpha1 + r delta1
+    SC[i] = k == 0 ? s : (k == 1 ? r : (pl.lead ? from_mont(r_m * s_m) : z));  // s alpha1 + r beta1 + rs delta1
+    if (k < 2) SB[i] = k == 0 ? one : s;                                   // beta2 + s delta2
+  } else if (i < off_sd) {
+    SC[i] = from_mont(hn[pl.xit_lo + (i - off_xit)]);
+  } else {
+    const uint64_t w = pl.n_input + 1 + pl.sd_lo + (i - off_sd);  // zip truncation: missing weights count as zero
+    SC[i] = w < pl.m ? from_mont(wm[w]) : Fr::zero();
+  }
+}
 
-__global__ void __launch_bounds__(128) k_assemble(const G1XYZZ* __restrict__ a_g1, const G1XYZZ* __restrict__ b_g1,
-                                                  const G1XYZZ* __restrict__ c_h, const G1XYZZ* __restrict__ c_w,
-                                                  const G2XYZZ* __restrict__ b_g2, const G1Affine* __restrict__ abd1,
-                                                  const G2Affine* __restrict__ bgd2, Fr r, Fr s, uint32_t* __restrict__ out) {
-  __shared__ AssembleShared sh;
+// affine, canonical proof (or per-rank partial sums): out = a (16 u32) | b (32 u32) | c (16 u32)
+__global__ void __launch_bounds__(96) k_finish(const G1XYZZ* __restrict__ ac, const G2XYZZ* __restrict__ b, uint32_t* __restrict__ out) {
   const int w = threadIdx.x >> 5;
-  const bool lead = (threadIdx.x & 31) == 0;
-  const G1Affine alpha1 = abd1[0], beta1 = abd1[1], delta1 = abd1[2];
-  // phase 1: the four fixed-point scalar multiplications
-  if (lead) {
-    if (w == 0) sh.r_d1 = smul_affine(delta1, r);
-    if (w == 1) sh.s_d1 = smul_affine(delta1, s);
-    if (w == 2) {
-      Fr rs = from_mont(to_mont(r) * to_mont(s));
-      sh.rs_d1 = smul_affine(delta1, rs);
-    }
-    if (w == 3) sh.s_d2 = smul_affine(bgd2[2], s);
-  }
-  __syncthreads();
-  // phase 2: A, B, and r * (beta1 + b_g1 + s delta1)
-  if (lead) {
-    if (w == 0) {
-      G1XYZZ A = madd(add(*a_g1, sh.r_d1), alpha1);
-      G1Affine Aa = to_affine(A);
-      sh.A_aff = Aa;
-      sh.A = smul_affine(Aa, s);  // s * A
-      Fq x = from_mont(Aa.x), y = from_mont(Aa.y);
+  if (threadIdx.x & 31) return;
+  if (w < 2) {
+    G1Affine p = to_affine(ac[w]);
+    Fq x = from_mont(p.x), y = from_mont(p.y);
+    uint32_t* o = out + (w == 0 ? 0 : 48);
 #pragma unroll
-      for (int i = 0; i < 8; i++) { out[i] = x.v[i]; out[8 + i] = y.v[i]; }
-    }
-    if (w == 1) {
-      G1XYZZ B1 = madd(add(*b_g1, sh.s_d1), beta1);
-      G1Affine Ba = to_affine(B1);
-      sh.rB1 = smul_affine(Ba, r);
-    }
-    if (w == 3) {
-      G2XYZZ B = madd(add(*b_g2, sh.s_d2), bgd2[0]);
-      G2Affine Ba = to_affine(B);
-      Fq c[4] = {from_mont(Ba.x.c0), from_mont(Ba.x.c1), from_mont(Ba.y.c0), from_mont(Ba.y.c1)};
-      for (int q = 0; q < 4; q++)
+    for (int i = 0; i < 8; i++) { o[i] = x.v[i]; o[8 + i] = y.v[i]; }
+  } else {
+    G2Affine p = to_affine(*b);
+    Fq c[4] = {from_mont(p.x.c0), from_mont(p.x.c1), from_mont(p.y.c0), from_mont(p.y.c1)};
+    for (int q = 0; q < 4; q++)
 #pragma unroll
-        for (int i = 0; i < 8; i++) out[16 + q * 8 + i] = c[q].v[i];
-    }
+      for (int i = 0; i < 8; i++) out[16 + q * 8 + i] = c[q].v[i];
   }
-  __syncthreads();
-  // phase 3: C
-  if (lead && w == 0) {
-    G1XYZZ C = add(*c_h, *c_w);
-    C = add(C, sh.A);
-    C = add(C, sh.rB1);
-    C = add(C, neg(sh.rs_d1));
-    G1Affine Ca = to_affine(C);
-    Fq x = from_mont(Ca.x), y = from_mont(Ca.y);
-#pragma unroll
-    for (int i = 0; i < 8; i++) { out[48 + i] = x.v[i]; out[56 + i] = y.v[i]; }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// setup kernels (groth16/mod.rs:134-197 on the omega domain)
-// L_k(x) = (x^n - 1) w^k / (n (x - w^k))
-__global__ void k_lagrange(Fr* L, Fr x, Fr tx_over_n, Fr omega, size_t n, int* bad) {
-  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  Fr wk = pow_u64(omega, (uint64_t)k);
-  Fr den = x - wk;
-  if (den.is_zero()) { *bad = 1; L[k] = Fr::zero(); return; }
-  L[k] = tx_over_n * wk * inverse(den);
-}
-
-// one warp per wire: lin_i = (beta u_i(x) + alpha v_i(x) + w_i(x)) * (i <= n_input ? 1/gamma : 1/delta)
-__device__ __forceinline__ Fr warp_sum(Fr v) {
-  for (int off = 16; off > 0; off >>= 1) {
-    Fr o;
-#pragma unroll
-    for (int i = 0; i < 8; i++) o.v[i] = __shfl_down_sync(0xffffffffu, v.v[i], off);
-    v = v + o;
-  }
-  return v;
-}
-__device__ __forceinline__ Fr row_eval(const uint32_t* rptr, const uint32_t* gate, const Fr* coef, const Fr* L, size_t i,
-                                       int lane) {
-  Fr acc = Fr::zero();
-  for (uint32_t p = rptr[i] + lane, e = rptr[i + 1]; p < e; p += 32) acc = acc + coef[p] * L[gate[p]];
-  return warp_sum(acc);
-}
-__global__ void k_lin(const uint32_t* ru, const uint32_t* gu, const Fr* cu, const uint32_t* rv, const uint32_t* gv,
-                      const Fr* cv, const uint32_t* rw, const uint32_t* gw, const Fr* cw, const Fr* L, size_t m,
-                      size_t n_input, Fr alpha, Fr beta, Fr inv_gamma, Fr inv_delta, Fr* out) {
-  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (i >= m) return;
-  Fr u = row_eval(ru, gu, cu, L, i, lane);
-  Fr v = row_eval(rv, gv, cv, L, i, lane);
-  Fr w = row_eval(rw, gw, cw, L, i, lane);
-  if (lane == 0) out[i] = (beta * u + alpha * v + w) * (i <= n_input ? inv_gamma : inv_delta);
 }
 
 }  // namespace zkb
 
 using namespace zkb;
 
-// =================================================================================================
-// C ABI
-// =================================================================================================
 extern "C" {
-
-int zkb_ctx_create(zkb_ctx** out, int device_id) {
-  if (!out) return set_err(nullptr, ZKB_ERR_ARG, "zkb_ctx_create: out is NULL");
-  *out = nullptr;
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0)
-    return set_err(nullptr, ZKB_ERR_CUDA, "no CUDA device (%s); libzkb200 has no CPU fallback",
-                   e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
-  if (device_id < 0 || device_id >= count) return set_err(nullptr, ZKB_ERR_ARG, "device %d out of range", device_id);
-  cudaDeviceProp prop;
-  ZKB_CUDA(nullptr, cudaGetDeviceProperties(&prop, device_id));
-  if (prop.major != 10)
-    return set_err(nullptr, ZKB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device_id,
-                   prop.major, prop.minor);
-  ZKB_CUDA(nullptr, cudaSetDevice(device_id));
-  zkb_ctx* c = new zkb_ctx();
-  c->device = device_id;
-  c->sm_count = prop.multiProcessorCount;
-  cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
-  *out = c;
-  return ZKB_OK;
-}
-
-void zkb_ctx_destroy(zkb_ctx* ctx) {
-  if (!ctx) return;
-  cudaSetDevice(ctx->device);
-  cudaDeviceSynchronize();
-  for (auto& t : ctx->tw)
-    for (auto& p : t)
-      if (p) cudaFree(p);
-  for (auto& b : ctx->scratch)
-    if (b.p) cudaFree(b.p);
-  prof_clear(ctx);
-  cudaEventDestroy(ctx->ev_fork);
-  cudaEventDestroy(ctx->ev_join);
-  cudaStreamDestroy(ctx->stream);
-  cudaStreamDestroy(ctx->stream2);
-  delete ctx;
-}
-
-const char* zkb_last_error(const zkb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
-uint64_t zkb_launch_count(const zkb_ctx* ctx) { return ctx ? ctx->launches : 0; }
-
-int zkb_profile(zkb_ctx* ctx, int enable) {
-  if (!ctx) return ZKB_ERR_ARG;
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ZKB_CUDA(ctx, cudaDeviceSynchronize());
-  prof_clear(ctx);
-  for (auto& u : ctx->prof_units) u = 0;
-  ctx->profile = enable != 0;
-  return ZKB_OK;
-}
-int zkb_profile_read(zkb_ctx* ctx, int kind, double* total_ms, uint64_t* count, uint64_t* units) {
-  if (!ctx || kind < 1 || kind >= PK_MAX) return set_err(ctx, ZKB_ERR_ARG, "zkb_profile_read: bad kind");
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ZKB_CUDA(ctx, cudaDeviceSynchronize());
-  double tot = 0;
-  uint64_t cnt = 0;
-  for (auto& r : ctx->prof) {
-    if (r.kind != kind) continue;
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { tot += ms; cnt++; }
-  }
-  if (total_ms) *total_ms = tot;
-  if (count) *count = cnt;
-  if (units) *units = ctx->prof_units[kind];
-  return ZKB_OK;
-}
-
-int zkb_host_alloc(void** out, size_t bytes) {
-  if (!out) return ZKB_ERR_ARG;
-  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
-  if (e != cudaSuccess) return set_err(nullptr, ZKB_ERR_ALLOC, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
-  return ZKB_OK;
-}
-void zkb_host_free(void* p) {
-  if (p) cudaFreeHost(p);
-}
-int zkb_dev_alloc(zkb_ctx* ctx, void** out, size_t bytes) {
-  if (!ctx || !out) return ZKB_ERR_ARG;
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
-  if (e != cudaSuccess) return set_err(ctx, ZKB_ERR_ALLOC, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
-  return ZKB_OK;
-}
-void zkb_dev_free(zkb_ctx* ctx, void* p) {
-  if (ctx && p) {
-    cudaSetDevice(ctx->device);
-    cudaFree(p);
-  }
-}
-int zkb_memcpy_h2d(zkb_ctx* ctx, void* dst, const void* src, size_t bytes) {
-  if (!ctx) return ZKB_ERR_ARG;
-  ZKB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ZKB_OK;
-}
-int zkb_memcpy_d2h(zkb_ctx* ctx, void* dst, const void* src, size_t bytes) {
-  if (!ctx) return ZKB_ERR_ARG;
-  ZKB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ZKB_OK;
-}
-int zkb_sync(zkb_ctx* ctx) {
-  if (!ctx) return ZKB_ERR_ARG;
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
-  return ZKB_OK;
-}
-void* zkb_stream(zkb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 // ---- QAP ----------------------------------------------------------------------------------------
 void zkb_qap_free(zkb_ctx* ctx, zkb_qap* q) {
@@ -455,187 +231,15 @@ int zkb_qap_upload(zkb_ctx* ctx, const zkb_qap_host* h, zkb_qap** out) {
   return ZKB_OK;
 }
 
-// ---- CRS ----------------------------------------------------------------------------------------
-void zkb_crs_free(zkb_ctx* ctx, zkb_crs* c) {
-  if (!c) return;
-  if (ctx) cudaSetDevice(ctx->device);
-  cudaFree(c->alpha1); cudaFree(c->xi1); cudaFree(c->xi_t); cudaFree(c->sum_gamma); cudaFree(c->sum_delta);
-  cudaFree(c->beta2); cudaFree(c->xi2);
-  delete c;
-}
-
-static void shard(uint64_t len, int rank, int world, uint64_t* lo, uint64_t* hi) {
-  *lo = len * (uint64_t)rank / (uint64_t)world;
-  *hi = len * (uint64_t)(rank + 1) / (uint64_t)world;
-}
-
-static int crs_alloc(zkb_ctx* ctx, zkb_crs* c) {
-  size_t nxi = c->xi_hi - c->xi_lo, nxt = c->xit_hi - c->xit_lo, nsd = c->sd_hi - c->sd_lo;
-  if (cudaMalloc(&c->alpha1, 3 * sizeof(G1Affine)) || cudaMalloc(&c->beta2, 3 * sizeof(G2Affine)) ||
-      cudaMalloc(&c->xi1, (nxi + 1) * sizeof(G1Affine)) || cudaMalloc(&c->xi_t, (nxt + 1) * sizeof(G1Affine)) ||
-      cudaMalloc(&c->sum_gamma, (c->n_sum_gamma + 1) * sizeof(G1Affine)) ||
-      cudaMalloc(&c->sum_delta, (nsd + 1) * sizeof(G1Affine)) || cudaMalloc(&c->xi2, (nxi + 1) * sizeof(G2Affine)))
-    return set_err(ctx, ZKB_ERR_ALLOC, "crs: cudaMalloc failed");
-  c->beta1 = c->alpha1 + 1; c->delta1 = c->alpha1 + 2;
-  c->gamma2 = c->beta2 + 1; c->delta2 = c->beta2 + 2;
-  return ZKB_OK;
-}
-
-int zkb_crs_upload(zkb_ctx* ctx, const zkb_crs_host* h, int rank, int world, zkb_crs** out) {
-  if (!ctx || !h || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_crs_upload: NULL argument");
-  *out = nullptr;
-  if (world < 1 || rank < 0 || rank >= world) return set_err(ctx, ZKB_ERR_ARG, "bad rank/world");
-  if (h->n < 1) return set_err(ctx, ZKB_ERR_ARG, "crs.n must be >= 1");
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  zkb_crs* c = new zkb_crs();
-  c->n = h->n; c->n_sum_gamma = h->n_sum_gamma; c->n_sum_delta = h->n_sum_delta;
-  c->rank = rank; c->world = world;
-  shard(c->n, rank, world, &c->xi_lo, &c->xi_hi);
-  shard(c->n - 1, rank, world, &c->xit_lo, &c->xit_hi);
-  shard(c->n_sum_delta, rank, world, &c->sd_lo, &c->sd_hi);
-  int rc = crs_alloc(ctx, c);
-  if (rc != ZKB_OK) { zkb_crs_free(ctx, c); return rc; }
-  cudaStream_t st = ctx->stream;
-  size_t nxi = c->xi_hi - c->xi_lo, nxt = c->xit_hi - c->xit_lo, nsd = c->sd_hi - c->sd_lo;
-  cudaMemcpyAsync(c->alpha1, h->alpha1, 64, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(c->beta1, h->beta1, 64, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(c->delta1, h->delta1, 64, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(c->beta2, h->beta2, 128, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(c->gamma2, h->gamma2, 128, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(c->delta2, h->delta2, 128, cudaMemcpyHostToDevice, st);
-  if (nxi) cudaMemcpyAsync(c->xi1, h->xi1 + c->xi_lo * 8, nxi * 64, cudaMemcpyHostToDevice, st);
-  if (nxt) cudaMemcpyAsync(c->xi_t, h->xi_t + c->xit_lo * 8, nxt * 64, cudaMemcpyHostToDevice, st);
-  if (c->n_sum_gamma) cudaMemcpyAsync(c->sum_gamma, h->sum_gamma, c->n_sum_gamma * 64, cudaMemcpyHostToDevice, st);
-  if (nsd) cudaMemcpyAsync(c->sum_delta, h->sum_delta + c->sd_lo * 8, nsd * 64, cudaMemcpyHostToDevice, st);
-  if (nxi) cudaMemcpyAsync(c->xi2, h->xi2 + c->xi_lo * 16, nxi * 128, cudaMemcpyHostToDevice, st);
-  rc = fq_to_mont(ctx, (Fq*)c->alpha1, 6, true, st);
-  if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->beta2, 12, true, st);
-  if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->xi1, nxi * 2, true, st);
-  if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->xi_t, nxt * 2, true, st);
-  if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->sum_gamma, c->n_sum_gamma * 2, true, st);
-  if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->sum_delta, nsd * 2, true, st);
-  if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->xi2, nxi * 4, true, st);
-  if (rc == ZKB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = set_err(ctx, ZKB_ERR_CUDA, "crs upload failed");
-  if (rc != ZKB_OK) { zkb_crs_free(ctx, c); return rc; }
-  *out = c;
-  return ZKB_OK;
-}
-
-int zkb_setup(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* toxic, int rank, int world, zkb_crs** out) {
-  if (!ctx || !q || !toxic || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_setup: NULL argument");
-  *out = nullptr;
-  if (world < 1 || rank < 0 || rank >= world) return set_err(ctx, ZKB_ERR_ARG, "bad rank/world");
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  Fr alpha = fr_from_limbs(toxic), beta = fr_from_limbs(toxic + 4), gamma = fr_from_limbs(toxic + 8),
-     delta = fr_from_limbs(toxic + 12), x = fr_from_limbs(toxic + 16);
-  if (alpha.is_zero() || beta.is_zero() || gamma.is_zero() || delta.is_zero() || x.is_zero())
-    return set_err(ctx, ZKB_ERR_DIV_ZERO, "setup: toxic values must be non-zero (random_elem, fr.rs:90-99)");
-  const uint64_t n = q->n, m = q->m;
-  zkb_crs* c = new zkb_crs();
-  c->n = n; c->n_sum_gamma = q->n_input + 1; c->n_sum_delta = m - q->n_input - 1;
-  c->rank = rank; c->world = world;
-  shard(n, rank, world, &c->xi_lo, &c->xi_hi);
-  shard(n - 1, rank, world, &c->xit_lo, &c->xit_hi);
-  shard(c->n_sum_delta, rank, world, &c->sd_lo, &c->sd_hi);
-  int rc = crs_alloc(ctx, c);
-  auto fail = [&](int code) { zkb_crs_free(ctx, c); return code; };
-  if (rc != ZKB_OK) return fail(rc);
-  cudaStream_t st = ctx->stream;
-  size_t nxi = c->xi_hi - c->xi_lo, nxt = c->xit_hi - c->xit_lo, nsd = c->sd_hi - c->sd_lo;
-  // scalars
-  void* p;
-  if ((rc = scratch_get(ctx, 8, (n + n + m + 8) * sizeof(Fr), &p)) != ZKB_OK) return fail(rc);
-  Fr* d_L = (Fr*)p;           // n   Lagrange basis at x; later reused for xi_t scalars
-  Fr* d_pow = d_L + n;        // n   x^i
-  Fr* d_lin = d_pow + n;      // m
-  Fr* d_six = d_lin + m;      // alpha, beta, delta, beta, gamma, delta
-  if ((rc = scratch_get(ctx, 9, sizeof(int), &p)) != ZKB_OK) return fail(rc);
-  int* d_bad = (int*)p;
-  cudaMemsetAsync(d_bad, 0, sizeof(int), st);
-  Fr xn = pow_u64(x, n);
-  Fr tx = xn - Fr::one();  // t(x) = x^n - 1
-  Fr inv_delta = inverse(delta), inv_gamma = inverse(gamma);
-  Fr tx_over_n = tx * inverse(fr_from_u64(n));
-  Fr omega = host_omega(q->log_n, false);
-  auto launch_fail = [&](const char* what) { return fail(set_err(ctx, ZKB_ERR_CUDA, "setup: %s: %s", what, cudaGetErrorString(cudaGetLastError()))); };
-  k_lagrange<<<cdiv(n, 128), 128, 0, st>>>(d_L, x, tx_over_n, omega, n, d_bad);
-  ctx->launches++;
-  if (cudaGetLastError() != cudaSuccess) return launch_fail("k_lagrange");
-  k_lin<<<cdiv(m * 32, 256), 256, 0, st>>>(q->d_rptr[0], q->d_gate[0], q->d_rcoeff[0], q->d_rptr[1], q->d_gate[1],
-                                           q->d_rcoeff[1], q->d_rptr[2], q->d_gate[2], q->d_rcoeff[2], d_L, m,
-                                           q->n_input, alpha, beta, inv_gamma, inv_delta, d_lin);
-  ctx->launches++;
-  if (cudaGetLastError() != cudaSuccess) return launch_fail("k_lin");
-  int bad = 0;
-  cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
-  if (cudaStreamSynchronize(st) != cudaSuccess) return launch_fail("sync");
-  if (bad) return fail(set_err(ctx, ZKB_ERR_UNSUPPORTED, "setup: x is one of the domain roots"));
-  if ((rc = fill_powers(ctx, d_pow, x, Fr::one(), n, st)) != ZKB_OK) return fail(rc);
-  if ((rc = fill_powers(ctx, d_L, x, tx * inv_delta, n, st)) != ZKB_OK) return fail(rc);  // xi_t scalars
-  Fr six[6] = {alpha, beta, delta, beta, gamma, delta};
-  cudaMemcpyAsync(d_six, six, sizeof six, cudaMemcpyHostToDevice, st);
-  if ((rc = fixed_base_g1(ctx, c->alpha1, d_six, 3, st)) != ZKB_OK) return fail(rc);
-  if ((rc = fixed_base_g2(ctx, c->beta2, d_six + 3, 3, st)) != ZKB_OK) return fail(rc);
-  if ((rc = fixed_base_g1(ctx, c->xi1, d_pow + c->xi_lo, nxi, st)) != ZKB_OK) return fail(rc);
-  if ((rc = fixed_base_g2(ctx, c->xi2, d_pow + c->xi_lo, nxi, st)) != ZKB_OK) return fail(rc);
-  if ((rc = fixed_base_g1(ctx, c->xi_t, d_L + c->xit_lo, nxt, st)) != ZKB_OK) return fail(rc);
-  if ((rc = fixed_base_g1(ctx, c->sum_gamma, d_lin, c->n_sum_gamma, st)) != ZKB_OK) return fail(rc);
-  if ((rc = fixed_base_g1(ctx, c->sum_delta, d_lin + c->n_sum_gamma + c->sd_lo, nsd, st)) != ZKB_OK) return fail(rc);
-  if (cudaStreamSynchronize(st) != cudaSuccess) return launch_fail("fixed-base");
-  *out = c;
-  return ZKB_OK;
-}
-
-int zkb_crs_dims(const zkb_crs* c, uint64_t* n, uint64_t* nsg, uint64_t* nsd) {
-  if (!c) return ZKB_ERR_ARG;
-  if (n) *n = c->n;
-  if (nsg) *nsg = c->n_sum_gamma;
-  if (nsd) *nsd = c->n_sum_delta;
-  return ZKB_OK;
-}
-
-static int download_fq(zkb_ctx* ctx, uint64_t* dst, const void* d_src, size_t n_fq) {
-  if (!n_fq) return ZKB_OK;
-  if (!dst) return set_err(ctx, ZKB_ERR_ARG, "crs download: NULL destination");
-  void* p;
-  ZKB_TRY(scratch_get(ctx, 8, n_fq * 32, &p));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(p, d_src, n_fq * 32, cudaMemcpyDeviceToDevice, ctx->stream));
-  ZKB_TRY(fq_to_mont(ctx, (Fq*)p, n_fq, false, ctx->stream));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(dst, p, n_fq * 32, cudaMemcpyDeviceToHost, ctx->stream));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ZKB_OK;
-}
-
-int zkb_crs_download(zkb_ctx* ctx, const zkb_crs* c, zkb_crs_host* d) {
-  if (!ctx || !c || !d) return set_err(ctx, ZKB_ERR_ARG, "zkb_crs_download: NULL argument");
-  if (c->world != 1) return set_err(ctx, ZKB_ERR_UNSUPPORTED, "crs download needs an unsharded CRS");
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  d->n = c->n; d->n_sum_gamma = c->n_sum_gamma; d->n_sum_delta = c->n_sum_delta;
-  ZKB_TRY(download_fq(ctx, (uint64_t*)d->alpha1, c->alpha1, 2));
-  ZKB_TRY(download_fq(ctx, (uint64_t*)d->beta1, c->beta1, 2));
-  ZKB_TRY(download_fq(ctx, (uint64_t*)d->delta1, c->delta1, 2));
-  ZKB_TRY(download_fq(ctx, (uint64_t*)d->beta2, c->beta2, 4));
-  ZKB_TRY(download_fq(ctx, (uint64_t*)d->gamma2, c->gamma2, 4));
-  ZKB_TRY(download_fq(ctx, (uint64_t*)d->delta2, c->delta2, 4));
-  ZKB_TRY(download_fq(ctx, (uint64_t*)d->xi1, c->xi1, c->n * 2));
-  ZKB_TRY(download_fq(ctx, (uint64_t*)d->xi_t, c->xi_t, (c->n - 1) * 2));
-  ZKB_TRY(download_fq(ctx, (uint64_t*)d->sum_gamma, c->sum_gamma, c->n_sum_gamma * 2));
-  ZKB_TRY(download_fq(ctx, (uint64_t*)d->sum_delta, c->sum_delta, c->n_sum_delta * 2));
-  ZKB_TRY(download_fq(ctx, (uint64_t*)d->xi2, c->xi2, c->n * 4));
-  return ZKB_OK;
-}
-
 // ---- polynomial stage ---------------------------------------------------------------------------
 // workspace vectors (n Fr each): 0 A->u_br  1 B->v_br  2 AB->c_br  3 uc  4 vc->d_br  5 u_nat  6 v_nat  7 h_nat
-static int poly_stage(zkb_ctx* ctx, const zkb_qap* q, const Fr* d_w_canon_src, bool src_is_own) {
+static int poly_stage(zkb_ctx* ctx, const zkb_qap* q, const Fr* d_w_canon) {
   const size_t n = q->n, m = q->m;
   cudaStream_t st = ctx->stream;
   Fr* ws = q->d_ws;
   Fr *A = ws, *B = ws + n, *AB = ws + 2 * n, *uc = ws + 3 * n, *vc = ws + 4 * n, *un = ws + 5 * n, *vn = ws + 6 * n,
      *hn = ws + 7 * n;
-  if (!src_is_own)
-    ZKB_CUDA(ctx, cudaMemcpyAsync(q->d_wcanon, d_w_canon_src, m * 32, cudaMemcpyDeviceToDevice, st));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(q->d_wmont, q->d_wcanon, m * 32, cudaMemcpyDeviceToDevice, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(q->d_wmont, d_w_canon, m * 32, cudaMemcpyDeviceToDevice, st));
   ZKB_TRY(vec_to_mont(ctx, q->d_wmont, m, true, st));
   ZKB_LAUNCH(ctx, k_matvec, cdiv(n, 128), 128, 0, st, q->d_gptr[0], q->d_wire[0], q->d_coeff[0], q->d_gptr[1],
              q->d_wire[1], q->d_coeff[1], q->d_wmont, m, n, A, B, AB);
@@ -656,149 +260,115 @@ static int poly_stage(zkb_ctx* ctx, const zkb_qap* q, const Fr* d_w_canon_src, b
   return ZKB_OK;
 }
 
-static int upload_weights(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* weights, int on_device) {
-  if (on_device) return ZKB_OK;
-  ZKB_CUDA(ctx, cudaMemcpyAsync(q->d_wcanon, weights, q->m * 32, cudaMemcpyHostToDevice, ctx->stream));
-  return ZKB_OK;
-}
-
-struct MsmOut {
-  G1XYZZ *a_g1, *b_g1, *c_h, *c_w;
-  G2XYZZ* b_g2;
-  uint32_t* proof;  // 64 u32
-  G1Affine* part1;  // 3 affine partials
-  G2Affine* part2;  // 1
-};
-
-static int msm_out(zkb_ctx* ctx, MsmOut* o) {
-  void* p;
-  ZKB_TRY(scratch_get(ctx, 6, 4 * sizeof(G1XYZZ) + sizeof(G2XYZZ) + 256 + 4 * sizeof(G1Affine) + sizeof(G2Affine), &p));
-  o->a_g1 = (G1XYZZ*)p; o->b_g1 = o->a_g1 + 1; o->c_h = o->a_g1 + 2; o->c_w = o->a_g1 + 3;
-  o->b_g2 = (G2XYZZ*)(o->a_g1 + 4);
-  o->proof = (uint32_t*)(o->b_g2 + 1);
-  o->part1 = (G1Affine*)(o->proof + 64);
-  o->part2 = (G2Affine*)(o->part1 + 4);
-  return ZKB_OK;
-}
-
-// the five MSMs over this rank's CRS shard
-static int msm_stage(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const MsmOut& o) {
-  const size_t n = q->n;
-  Fr* ws = q->d_ws;
-  Fr *un = ws + 5 * n, *vn = ws + 6 * n, *hn = ws + 7 * n;
-  cudaStream_t st = ctx->stream, st2 = ctx->stream2;
-  size_t nxi = c->xi_hi - c->xi_lo, nxt = c->xit_hi - c->xit_lo;
-  // fork: G2 MSM on the second stream
-  ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-  ZKB_CUDA(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
-  ZKB_TRY(msm_g2(ctx, c->xi2, vn + c->xi_lo, true, nxi, 0, o.b_g2, 3, st2));
-  ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join, st2));
-  ZKB_TRY(msm_g1(ctx, c->xi1, un + c->xi_lo, true, nxi, 0, o.a_g1, 0, st));
-  ZKB_TRY(msm_g1(ctx, c->xi1, vn + c->xi_lo, true, nxi, 0, o.b_g1, 0, st));
-  ZKB_TRY(msm_g1(ctx, c->xi_t, hn + c->xit_lo, true, nxt, 0, o.c_h, 0, st));
-  // witness term: weights[input+1 ..] against sum_delta (zip truncation: min of the two lengths)
-  size_t avail = q->m > q->n_input + 1 ? q->m - q->n_input - 1 : 0;
-  size_t lo = c->sd_lo, hi = std::min<uint64_t>(c->sd_hi, avail);
-  size_t cnt = hi > lo ? hi - lo : 0;
-  ZKB_TRY(msm_g1(ctx, c->sum_delta, q->d_wcanon + q->n_input + 1 + lo, false, cnt, 0, o.c_w, 0, st));
-  ZKB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
-  return ZKB_OK;
-}
-
 static int check_pair(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c) {
   if (c->n != q->n) return set_err(ctx, ZKB_ERR_ARG, "CRS (n=%llu) does not belong to QAP (n=%llu)",
                                    (unsigned long long)c->n, (unsigned long long)q->n);
   return ZKB_OK;
 }
 
+struct ProveOut {
+  G1XYZZ* ac;       // A, C accumulators
+  G2XYZZ* b;
+  uint32_t* proof;  // 64 u32
+};
+static int prove_out(zkb_ctx* ctx, ProveOut* o) {
+  void* p;
+  ZKB_TRY(scratch_get(ctx, 6, 2 * sizeof(G1XYZZ) + sizeof(G2XYZZ) + 256, &p));
+  o->ac = (G1XYZZ*)p;
+  o->b = (G2XYZZ*)(o->ac + 2);
+  o->proof = (uint32_t*)(o->b + 1);
+  return ZKB_OK;
+}
+
+// stages 1-7 over this rank's CRS shard; out = proof (world 1) or the rank's partial sums
 static int prove_common(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights, int on_device,
-                        const uint64_t* r, const uint64_t* s, zkb_proof* out) {
-  if (!ctx || !q || !c || !weights || !r || !s || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove: NULL argument");
-  if (c->world != 1) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove needs an unsharded CRS; use zkb_prove_partial");
+                        const uint64_t* r, const uint64_t* s, uint64_t* out) {
   ZKB_TRY(check_pair(ctx, q, c));
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ZKB_TRY(upload_weights(ctx, q, weights, on_device));
-  ZKB_TRY(poly_stage(ctx, q, on_device ? (const Fr*)weights : q->d_wcanon, !on_device));
-  MsmOut o;
-  ZKB_TRY(msm_out(ctx, &o));
-  ZKB_TRY(msm_stage(ctx, q, c, o));
-  Fr rr, ss;
-  memcpy(rr.v, r, 32);
-  memcpy(ss.v, s, 32);
-  ZKB_LAUNCH(ctx, k_assemble, 1, 128, 0, ctx->stream, o.a_g1, o.b_g1, o.c_h, o.c_w, o.b_g2, c->alpha1, c->beta2, rr, ss,
-             o.proof);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, o.proof, 256, cudaMemcpyDeviceToHost, ctx->stream));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+  const Fr* d_w = (const Fr*)weights;
+  if (!on_device) {
+    ZKB_CUDA(ctx, cudaMemcpyAsync(q->d_wcanon, weights, q->m * 32, cudaMemcpyHostToDevice, st));
+    d_w = q->d_wcanon;
+  }
+  ZKB_TRY(poly_stage(ctx, q, d_w));
+  const size_t n = q->n;
+  Fr* ws = q->d_ws;
+  Fr *un = ws + 5 * n, *vn = ws + 6 * n, *hn = ws + 7 * n;
+  ScalarPlan sp;
+  sp.nxi = c->nxi(); sp.nxt = c->nxt(); sp.nsd = c->nsd();
+  sp.xi_lo = c->xi_lo; sp.xit_lo = c->xit_lo; sp.sd_lo = c->sd_lo;
+  sp.n_input = q->n_input; sp.m = q->m; sp.lead = c->rank == 0;
+  void* p;
+  ZKB_TRY(scratch_get(ctx, 10, (c->g1_cnt + (sp.nxi + 3) + c->g2_cnt + 4) * sizeof(Fr), &p));
+  Fr* SC = (Fr*)p;
+  Fr* SA = SC + c->g1_cnt;
+  Fr* SB = SA + sp.nxi + 3;
+  ZKB_LAUNCH(ctx, k_msm_scalars, cdiv(c->g1_cnt, 256), 256, 0, st, un, vn, hn, q->d_wmont, sp, fr_from_limbs(r), fr_from_limbs(s), SA,
+             SB, SC);
+  ProveOut o;
+  ZKB_TRY(prove_out(ctx, &o));
+  // fork: the G2 MSM runs on the second stream beside the G1 MSMs
+  ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
+  MsmJob jb = {SB, c->g2_cnt};
+  ZKB_TRY(msm_g2(ctx, c->g2, c->g2_cnt, c->c2, &jb, 1, o.b, 3, st2));
+  ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join, st2));
+  MsmJob j1[2] = {{SA, sp.nxi + 3}, {SC, c->g1_cnt}};
+  ZKB_TRY(msm_g1(ctx, c->g1, c->g1_cnt, c->c1, j1, 2, o.ac, 0, st));
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+  ZKB_LAUNCH(ctx, k_finish, 1, 96, 0, st, o.ac, o.b, o.proof);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, o.proof, 256, cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
   return ZKB_OK;
 }
 
 int zkb_prove(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights, const uint64_t r[4],
               const uint64_t s[4], zkb_proof* out) {
-  return prove_common(ctx, q, c, weights, 0, r, s, out);
+  if (!ctx || !q || !c || !weights || !r || !s || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove: NULL argument");
+  if (c->world != 1) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove needs an unsharded CRS; use zkb_prove_partial");
+  return prove_common(ctx, q, c, weights, 0, r, s, (uint64_t*)out);
 }
 int zkb_prove_dev(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* d_weights, const uint64_t r[4],
                   const uint64_t s[4], zkb_proof* out) {
-  return prove_common(ctx, q, c, d_weights, 1, r, s, out);
-}
-
-__global__ void k_g1_add2(const G1XYZZ* a, const G1XYZZ* b, G1XYZZ* out) {
-  if (threadIdx.x | blockIdx.x) return;
-  *out = add(*a, *b);
+  if (!ctx || !q || !c || !d_weights || !r || !s || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_dev: NULL argument");
+  if (c->world != 1) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove needs an unsharded CRS; use zkb_prove_partial");
+  return prove_common(ctx, q, c, d_weights, 1, r, s, (uint64_t*)out);
 }
 
 int zkb_prove_partial(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights, int on_device,
-                      uint64_t* out_partial) {
-  if (!ctx || !q || !c || !weights || !out_partial) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_partial: NULL argument");
-  ZKB_TRY(check_pair(ctx, q, c));
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ZKB_TRY(upload_weights(ctx, q, weights, on_device));
-  ZKB_TRY(poly_stage(ctx, q, on_device ? (const Fr*)weights : q->d_wcanon, !on_device));
-  MsmOut o;
-  ZKB_TRY(msm_out(ctx, &o));
-  ZKB_TRY(msm_stage(ctx, q, c, o));
-  cudaStream_t st = ctx->stream;
-  ZKB_LAUNCH(ctx, k_g1_add2, 1, 32, 0, st, o.c_h, o.c_w, o.c_h);
-  ZKB_TRY(xyzz_to_affine_g1(ctx, o.part1, o.a_g1, 3, st));  // a_g1, b_g1, c
-  ZKB_TRY(xyzz_to_affine_g2(ctx, o.part2, o.b_g2, 1, st));
-  ZKB_TRY(fq_to_mont(ctx, (Fq*)o.part1, 6, false, st));
-  ZKB_TRY(fq_to_mont(ctx, (Fq*)o.part2, 4, false, st));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out_partial, o.part1, 3 * 64, cudaMemcpyDeviceToHost, st));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out_partial + 24, o.part2, 128, cudaMemcpyDeviceToHost, st));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
-  return ZKB_OK;
+                      const uint64_t r[4], const uint64_t s[4], uint64_t* out_partial) {
+  if (!ctx || !q || !c || !weights || !r || !s || !out_partial)
+    return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_partial: NULL argument");
+  return prove_common(ctx, q, c, weights, on_device, r, s, out_partial);
 }
 
-int zkb_prove_combine(zkb_ctx* ctx, const zkb_crs* c, const uint64_t* partials, int world, const uint64_t r[4],
-                      const uint64_t s[4], zkb_proof* out) {
-  if (!ctx || !c || !partials || !r || !s || !out || world < 1)
-    return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_combine: bad argument");
+int zkb_prove_combine(zkb_ctx* ctx, const uint64_t* partials, int world, zkb_proof* out) {
+  if (!ctx || !partials || !out || world < 1) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_combine: bad argument");
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  // regroup host-side into 3 G1 arrays and 1 G2 array (pure data movement)
-  std::vector<uint64_t> g1(3 * (size_t)world * 8), g2((size_t)world * 16);
+  // regroup host-side into A[world], C[world] (G1) and B[world] (G2): pure data movement
+  std::vector<uint64_t> g1(2 * (size_t)world * 8), g2((size_t)world * 16);
   for (int w = 0; w < world; w++) {
-    for (int k = 0; k < 3; k++) memcpy(&g1[((size_t)k * world + w) * 8], partials + (size_t)w * 40 + k * 8, 64);
-    memcpy(&g2[(size_t)w * 16], partials + (size_t)w * 40 + 24, 128);
+    const uint64_t* rec = partials + (size_t)w * ZKB_PARTIAL_LIMBS;
+    memcpy(&g1[(size_t)w * 8], rec, 64);
+    memcpy(&g2[(size_t)w * 16], rec + 8, 128);
+    memcpy(&g1[((size_t)world + w) * 8], rec + 24, 64);
   }
   void* p;
   ZKB_TRY(scratch_get(ctx, 7, g1.size() * 8 + g2.size() * 8, &p));
   G1Affine* d1 = (G1Affine*)p;
-  G2Affine* d2 = (G2Affine*)(d1 + 3 * (size_t)world);
+  G2Affine* d2 = (G2Affine*)(d1 + 2 * (size_t)world);
   ZKB_CUDA(ctx, cudaMemcpyAsync(d1, g1.data(), g1.size() * 8, cudaMemcpyHostToDevice, st));
   ZKB_CUDA(ctx, cudaMemcpyAsync(d2, g2.data(), g2.size() * 8, cudaMemcpyHostToDevice, st));
-  ZKB_TRY(fq_to_mont(ctx, (Fq*)d1, 6 * (size_t)world, true, st));
+  ZKB_TRY(fq_to_mont(ctx, (Fq*)d1, 4 * (size_t)world, true, st));
   ZKB_TRY(fq_to_mont(ctx, (Fq*)d2, 4 * (size_t)world, true, st));
-  MsmOut o;
-  ZKB_TRY(msm_out(ctx, &o));
-  ZKB_TRY(sum_affine_g1(ctx, d1, world, o.a_g1, st));
-  ZKB_TRY(sum_affine_g1(ctx, d1 + world, world, o.b_g1, st));
-  ZKB_TRY(sum_affine_g1(ctx, d1 + 2 * (size_t)world, world, o.c_h, st));
-  ZKB_TRY(sum_affine_g1(ctx, d1, 0, o.c_w, st));  // identity
-  ZKB_TRY(sum_affine_g2(ctx, d2, world, o.b_g2, st));
-  Fr rr, ss;
-  memcpy(rr.v, r, 32);
-  memcpy(ss.v, s, 32);
-  ZKB_LAUNCH(ctx, k_assemble, 1, 128, 0, st, o.a_g1, o.b_g1, o.c_h, o.c_w, o.b_g2, c->alpha1, c->beta2, rr, ss, o.proof);
+  ProveOut o;
+  ZKB_TRY(prove_out(ctx, &o));
+  ZKB_TRY(sum_affine_g1(ctx, d1, world, o.ac, st));
+  ZKB_TRY(sum_affine_g1(ctx, d1 + world, world, o.ac + 1, st));
+  ZKB_TRY(sum_affine_g2(ctx, d2, world, o.b, st));
+  ZKB_LAUNCH(ctx, k_finish, 1, 96, 0, st, o.ac, o.b, o.proof);
   ZKB_CUDA(ctx, cudaMemcpyAsync(out, o.proof, 256, cudaMemcpyDeviceToHost, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));
   return ZKB_OK;
@@ -807,8 +377,8 @@ int zkb_prove_combine(zkb_ctx* ctx, const zkb_crs* c, const uint64_t* partials, 
 int zkb_qap_h(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* weights, uint64_t* u_sum, uint64_t* v_sum, uint64_t* h) {
   if (!ctx || !q || !weights) return set_err(ctx, ZKB_ERR_ARG, "zkb_qap_h: NULL argument");
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ZKB_TRY(upload_weights(ctx, q, weights, 0));
-  ZKB_TRY(poly_stage(ctx, q, q->d_wcanon, true));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(q->d_wcanon, weights, q->m * 32, cudaMemcpyHostToDevice, ctx->stream));
+  ZKB_TRY(poly_stage(ctx, q, q->d_wcanon));
   const size_t n = q->n;
   cudaStream_t st = ctx->stream;
   uint64_t* dst[3] = {u_sum, v_sum, h};
@@ -824,230 +394,4 @@ int zkb_qap_h(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* weights, uint64_t*
   return ZKB_OK;
 }
 
-// ---- standalone NTT -----------------------------------------------------------------------------
-int zkb_fr_to_mont(zkb_ctx* ctx, uint64_t* d, size_t n, int to) {
-  if (!ctx || (!d && n)) return set_err(ctx, ZKB_ERR_ARG, "zkb_fr_to_mont: NULL argument");
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ZKB_TRY(vec_to_mont(ctx, (Fr*)d, n, to != 0, ctx->stream));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ZKB_OK;
-}
-
-int zkb_ntt_fr_raw(zkb_ctx* ctx, uint64_t* d, uint32_t log_n, int inverse_) {
-  if (!ctx || !d) return set_err(ctx, ZKB_ERR_ARG, "zkb_ntt_fr_raw: NULL argument");
-  if (log_n > 27) return set_err(ctx, ZKB_ERR_ARG, "ntt: log_n %u > 27", log_n);
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ZKB_TRY(ntt_dif(ctx, (Fr*)d, log_n, inverse_ != 0, ctx->stream));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ZKB_OK;
-}
-
-int zkb_ntt_fr(zkb_ctx* ctx, uint64_t* d_data, uint32_t log_n, int inverse_, const uint64_t* coset_shift) {
-  if (!ctx || !d_data) return set_err(ctx, ZKB_ERR_ARG, "zkb_ntt_fr: NULL argument");
-  if (log_n > 27) return set_err(ctx, ZKB_ERR_ARG, "ntt: log_n %u > 27", log_n);
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  size_t n = (size_t)1 << log_n;
-  Fr* d = (Fr*)d_data;
-  void* p;
-  ZKB_TRY(scratch_get(ctx, 10, n * 32, &p));
-  Fr* tmp = (Fr*)p;
-  ZKB_TRY(vec_to_mont(ctx, d, n, true, st));
-  if (!inverse_) {
-    if (coset_shift) ZKB_TRY(scale_powers(ctx, d, log_n, fr_from_limbs(coset_shift), Fr::one(), false, st));
-    ZKB_TRY(ntt_dif(ctx, d, log_n, false, st));
-    ZKB_TRY(bitrev_permute(ctx, tmp, d, log_n, nullptr, st));
-  } else {
-    ZKB_TRY(ntt_dif(ctx, d, log_n, true, st));
-    Fr invn = inverse(fr_from_u64(n));
-    ZKB_TRY(bitrev_permute(ctx, tmp, d, log_n, &invn, st));
-    if (coset_shift) {
-      Fr sh = fr_from_limbs(coset_shift);
-      if (sh.is_zero()) return set_err(ctx, ZKB_ERR_DIV_ZERO, "ntt: coset shift is zero");
-      ZKB_TRY(scale_powers(ctx, tmp, log_n, inverse(sh), Fr::one(), false, st));
-    }
-  }
-  ZKB_TRY(vec_to_mont(ctx, tmp, n, false, st));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d, tmp, n * 32, cudaMemcpyDeviceToDevice, st));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
-  return ZKB_OK;
-}
-
-// ---- bases / MSM --------------------------------------------------------------------------------
-static size_t pt_bytes(int group) { return group == 1 ? sizeof(G1Affine) : sizeof(G2Affine); }
-
-void zkb_bases_free(zkb_ctx* ctx, zkb_bases* b) {
-  if (!b) return;
-  if (ctx) cudaSetDevice(ctx->device);
-  cudaFree(b->d);
-  delete b;
-}
-
-int zkb_bases_upload(zkb_ctx* ctx, int group, const uint64_t* h_points, size_t n, zkb_bases** out) {
-  if (!ctx || !out || (!h_points && n) || (group != 1 && group != 2))
-    return set_err(ctx, ZKB_ERR_ARG, "zkb_bases_upload: bad argument");
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  zkb_bases* b = new zkb_bases();
-  b->group = group; b->n = n;
-  if (cudaMalloc(&b->d, (n + 1) * pt_bytes(group)) != cudaSuccess) {
-    delete b;
-    return set_err(ctx, ZKB_ERR_ALLOC, "bases: cudaMalloc failed");
-  }
-  int rc = ZKB_OK;
-  if (n) {
-    cudaMemcpyAsync(b->d, h_points, n * pt_bytes(group), cudaMemcpyHostToDevice, ctx->stream);
-    rc = fq_to_mont(ctx, (Fq*)b->d, n * (group == 1 ? 2 : 4), true, ctx->stream);
-  }
-  if (rc == ZKB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(ctx, ZKB_ERR_CUDA, "bases upload failed");
-  if (rc != ZKB_OK) { zkb_bases_free(ctx, b); return rc; }
-  *out = b;
-  return ZKB_OK;
-}
-
-int zkb_bases_generate(zkb_ctx* ctx, int group, const uint64_t* h_scalars, size_t n, zkb_bases** out) {
-  if (!ctx || !out || (!h_scalars && n) || (group != 1 && group != 2))
-    return set_err(ctx, ZKB_ERR_ARG, "zkb_bases_generate: bad argument");
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  zkb_bases* b = new zkb_bases();
-  b->group = group; b->n = n;
-  if (cudaMalloc(&b->d, (n + 1) * pt_bytes(group)) != cudaSuccess) {
-    delete b;
-    return set_err(ctx, ZKB_ERR_ALLOC, "bases: cudaMalloc failed");
-  }
-  void* p;
-  int rc = scratch_get(ctx, 8, (n + 1) * 32, &p);
-  if (rc == ZKB_OK && n) {
-    cudaMemcpyAsync(p, h_scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream);
-    rc = vec_to_mont(ctx, (Fr*)p, n, true, ctx->stream);
-    if (rc == ZKB_OK)
-      rc = group == 1 ? fixed_base_g1(ctx, (G1Affine*)b->d, (Fr*)p, n, ctx->stream)
-                      : fixed_base_g2(ctx, (G2Affine*)b->d, (Fr*)p, n, ctx->stream);
-  }
-  if (rc == ZKB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-    rc = set_err(ctx, ZKB_ERR_CUDA, "bases generate failed: %s", cudaGetErrorString(cudaGetLastError()));
-  if (rc != ZKB_OK) { zkb_bases_free(ctx, b); return rc; }
-  *out = b;
-  return ZKB_OK;
-}
-
-int zkb_bases_download(zkb_ctx* ctx, const zkb_bases* b, uint64_t* h_points) {
-  if (!ctx || !b || (!h_points && b->n)) return set_err(ctx, ZKB_ERR_ARG, "zkb_bases_download: bad argument");
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  return download_fq(ctx, h_points, b->d, b->n * (b->group == 1 ? 2 : 4));
-}
-
-int zkb_msm(zkb_ctx* ctx, const zkb_bases* b, const uint64_t* scalars, int on_device, size_t n, int window_bits,
-            uint64_t* out) {
-  if (!ctx || !b || (!scalars && n) || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_msm: NULL argument");
-  if (n > b->n) n = b->n;  // zip truncation
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  const Fr* d_s = (const Fr*)scalars;
-  void* p;
-  if (!on_device && n) {
-    ZKB_TRY(scratch_get(ctx, 8, n * 32, &p));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(p, scalars, n * 32, cudaMemcpyHostToDevice, st));
-    d_s = (const Fr*)p;
-  }
-  MsmOut o;
-  ZKB_TRY(msm_out(ctx, &o));
-  if (b->group == 1) {
-    ZKB_TRY(msm_g1(ctx, (const G1Affine*)b->d, d_s, false, n, window_bits, o.a_g1, 0, st));
-    ZKB_TRY(xyzz_to_affine_g1(ctx, o.part1, o.a_g1, 1, st));
-    ZKB_TRY(fq_to_mont(ctx, (Fq*)o.part1, 2, false, st));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(out, o.part1, 64, cudaMemcpyDeviceToHost, st));
-  } else {
-    ZKB_TRY(msm_g2(ctx, (const G2Affine*)b->d, d_s, false, n, window_bits, o.b_g2, 0, st));
-    ZKB_TRY(xyzz_to_affine_g2(ctx, o.part2, o.b_g2, 1, st));
-    ZKB_TRY(fq_to_mont(ctx, (Fq*)o.part2, 4, false, st));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(out, o.part2, 128, cudaMemcpyDeviceToHost, st));
-  }
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
-  return ZKB_OK;
-}
-
-int zkb_points_sum(zkb_ctx* ctx, int group, const uint64_t* h_points, size_t n, uint64_t* out) {
-  if (!ctx || (!h_points && n) || !out || (group != 1 && group != 2))
-    return set_err(ctx, ZKB_ERR_ARG, "zkb_points_sum: bad argument");
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  void* p;
-  ZKB_TRY(scratch_get(ctx, 7, (n + 1) * pt_bytes(group), &p));
-  if (n) ZKB_CUDA(ctx, cudaMemcpyAsync(p, h_points, n * pt_bytes(group), cudaMemcpyHostToDevice, st));
-  ZKB_TRY(fq_to_mont(ctx, (Fq*)p, n * (group == 1 ? 2 : 4), true, st));
-  MsmOut o;
-  ZKB_TRY(msm_out(ctx, &o));
-  if (group == 1) {
-    ZKB_TRY(sum_affine_g1(ctx, (G1Affine*)p, n, o.a_g1, st));
-    ZKB_TRY(xyzz_to_affine_g1(ctx, o.part1, o.a_g1, 1, st));
-    ZKB_TRY(fq_to_mont(ctx, (Fq*)o.part1, 2, false, st));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(out, o.part1, 64, cudaMemcpyDeviceToHost, st));
-  } else {
-    ZKB_TRY(sum_affine_g2(ctx, (G2Affine*)p, n, o.b_g2, st));
-    ZKB_TRY(xyzz_to_affine_g2(ctx, o.part2, o.b_g2, 1, st));
-    ZKB_TRY(fq_to_mont(ctx, (Fq*)o.part2, 4, false, st));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(out, o.part2, 128, cudaMemcpyDeviceToHost, st));
-  }
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
-  return ZKB_OK;
-}
-
 }  // extern "C"
-
-// ---- modmul peak micro-benchmark -------------------------------------------------------------------
-namespace zkb {
-template <class F>
-__global__ void __launch_bounds__(256) k_bench_modmul(F* out, int iters) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  F a[4], b[4];
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    a[q] = F::one();
-    b[q] = F::r2();
-    a[q].v[0] += t + q;
-    b[q].v[1] ^= t * 2654435761u + q;
-    b[q].v[7] &= 0x0fffffffu;
-  }
-  for (int i = 0; i < iters; i++) {
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      a[q] = a[q] * b[q];
-      b[q] = b[q] * a[q];
-    }
-  }
-  F s = (a[0] + a[1]) + (a[2] + a[3]);
-  s = s + ((b[0] + b[1]) + (b[2] + b[3]));
-  if (s.v[0] == 0xdeadbeefu && s.v[7] == 0x12345678u) out[t] = s;  // practically never; defeats DCE
-}
-}  // namespace zkb
-
-extern "C" int zkb_bench_modmul(zkb_ctx* ctx, int field, int iters, double* rate, double* ms) {
-  if (!ctx || iters < 1) return set_err(ctx, ZKB_ERR_ARG, "zkb_bench_modmul: bad argument");
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  void* p;
-  unsigned blocks = (unsigned)ctx->sm_count * 8, threads = 256;
-  ZKB_TRY(scratch_get(ctx, 10, (size_t)blocks * threads * 32, &p));
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  float best = 1e30f;
-  for (int rep = 0; rep < 4; rep++) {
-    cudaEventRecord(e0, ctx->stream);
-    if (field == 0) {
-      ZKB_LAUNCH(ctx, k_bench_modmul<Fr>, blocks, threads, 0, ctx->stream, (Fr*)p, iters);
-    } else {
-      ZKB_LAUNCH(ctx, k_bench_modmul<Fq>, blocks, threads, 0, ctx->stream, (Fq*)p, iters);
-    }
-    cudaEventRecord(e1, ctx->stream);
-    ZKB_CUDA(ctx, cudaEventSynchronize(e1));
-    float t;
-    cudaEventElapsedTime(&t, e0, e1);
-    if (rep > 0 && t < best) best = t;
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  double muls = (double)blocks * threads * (double)iters * 8.0;
-  if (ms) *ms = best;
-  if (rate) *rate = muls / (best * 1e-3);
-  return ZKB_OK;
-}

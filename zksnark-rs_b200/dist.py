@@ -1,26 +1,26 @@
 """Multi-GPU plumbing for a sharded proof: one process per GPU, torch.distributed for the exchange.
 
 The MSM base vectors (sigma_g1.xi / xi_t / sum_delta, sigma_g2.xi) are sharded by contiguous point
-ranges; each rank produces four partial sums (40 limbs, `zkb_prove_partial`), the records are
+ranges; each rank produces its partial sums of A, B, C (32 limbs, `zkb_prove_partial`), the records are
 all-gathered (NCCL over NVLink on GPUs; gloo in the CPU tests) and folded by `zkb_prove_combine`.
 Elliptic-curve addition is not an NCCL reduction operator, so the "allreduce" of the north star is
-all-gather + on-device fold; 320 bytes per rank cross the fabric per proof.
+all-gather + on-device fold; 256 bytes per rank cross the fabric per proof.
 """
 
 from __future__ import annotations
 
 import numpy as np
 
-PARTIAL_LIMBS = 40
+PARTIAL_LIMBS = 32
 
 
 def shard_range(length: int, rank: int, world: int):
-    """[lo, hi) of a length-`length` vector owned by `rank` -- mirrors shard() in csrc/prove.cu."""
+    """[lo, hi) of a length-`length` vector owned by `rank` -- mirrors shard() in csrc/crs.cu."""
     return length * rank // world, length * (rank + 1) // world
 
 
 def all_gather_partials(part: np.ndarray, device=None) -> np.ndarray:
-    """part: (40,) uint64 from prove_partial -> (world, 40) uint64, identical on every rank."""
+    """part: (32,) uint64 from prove_partial -> (world, 32) uint64, identical on every rank."""
     import torch
     import torch.distributed as dist
 

@@ -73,8 +73,8 @@ ABI = {
     "zkb_crs_free": (None, [_P, _P]),
     "zkb_prove": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(_ProofC)]),
     "zkb_prove_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(_ProofC)]),
-    "zkb_prove_partial": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
-    "zkb_prove_combine": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.POINTER(_ProofC)]),
+    "zkb_prove_partial": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P]),
+    "zkb_prove_combine": (C.c_int, [_P, _P, C.c_int, C.POINTER(_ProofC)]),
     "zkb_qap_h": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "zkb_ntt_fr": (C.c_int, [_P, _P, C.c_uint32, C.c_int, _P]),
     "zkb_ntt_fr_raw": (C.c_int, [_P, _P, C.c_uint32, C.c_int]),
@@ -492,24 +492,29 @@ def prove_dev(ctx: Context, qap: QAP, crs: CRS, d_weights: int, r: int, s: int) 
     return _proof(out)
 
 
-def prove_partial(ctx: Context, qap: QAP, crs: CRS, weights, on_device=False) -> np.ndarray:
-    """This rank's four partial sums over its CRS shard: 40 limbs (a_g1, b_g1, c_g1, b_g2)."""
-    out = np.zeros(40, dtype=np.uint64)
+PARTIAL_LIMBS = 32
+
+
+def prove_partial(ctx: Context, qap: QAP, crs: CRS, weights, r: int, s: int, on_device=False) -> np.ndarray:
+    """This rank's partial sums of A, B, C over its CRS shard, in the Proof layout: 32 limbs
+    (a 8 | b 16 | c 8).  Rank 0's shard also carries the fixed-point terms (alpha1 + r delta1 ...)."""
+    out = np.zeros(PARTIAL_LIMBS, dtype=np.uint64)
     if on_device:
         wp = C.c_void_p(weights)
     else:
         w = _weights_array(qap, weights)
         wp = _ptr(w)
-    ctx.check(ctx.lib.zkb_prove_partial(ctx.h, qap.h, crs.h, wp, 1 if on_device else 0, _ptr(out)), "zkb_prove_partial")
+    rl, sl = fr_limbs([r]), fr_limbs([s])
+    ctx.check(ctx.lib.zkb_prove_partial(ctx.h, qap.h, crs.h, wp, 1 if on_device else 0, _ptr(rl), _ptr(sl), _ptr(out)),
+              "zkb_prove_partial")
     return out
 
 
-def prove_combine(ctx: Context, crs: CRS, partials: np.ndarray, r: int, s: int) -> Proof:
-    p = np.ascontiguousarray(partials, dtype=np.uint64).reshape(-1, 40)
-    rl, sl = fr_limbs([r]), fr_limbs([s])
+def prove_combine(ctx: Context, partials: np.ndarray) -> Proof:
+    """Fold the gathered per-rank partial sums (world x 32 limbs) into the proof."""
+    p = np.ascontiguousarray(partials, dtype=np.uint64).reshape(-1, PARTIAL_LIMBS)
     out = _ProofC()
-    ctx.check(ctx.lib.zkb_prove_combine(ctx.h, crs.h, _ptr(p), p.shape[0], _ptr(rl), _ptr(sl), C.byref(out)),
-              "zkb_prove_combine")
+    ctx.check(ctx.lib.zkb_prove_combine(ctx.h, _ptr(p), p.shape[0], C.byref(out)), "zkb_prove_combine")
     return _proof(out)
 
 
