@@ -54,6 +54,11 @@ uint64_t zkb_launch_count(const zkb_ctx* ctx);
  * the work those launches covered (NTT: elements x passes; accumulation: point records = points x
  * windows, an upper bound that counts the ~2^-c fraction of zero digits). */
 int zkb_profile(zkb_ctx* ctx, int enable);
+/* zkb_profile(ctx, 2) additionally brackets EVERY kernel launch with events (tracing; adds a few
+ * microseconds per launch); zkb_trace_dump writes "stream,kernel,start_ms,end_ms,dur_ms" rows
+ * (times relative to the zkb_profile call) -- the per-stage timeline the reference only prints as
+ * averages (fr.rs:339-358). */
+int zkb_trace_dump(zkb_ctx* ctx, const char* path);
 int zkb_profile_read(zkb_ctx* ctx, int kind, double* total_ms, uint64_t* count, uint64_t* units);
 /* Pinned host memory for buffers that are copied every proof (weights).  Optional. */
 int zkb_host_alloc(void** out, size_t bytes);
@@ -126,6 +131,14 @@ int zkb_prove(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const uint64
 /* Same with the weights already resident in device memory (m x 4 limbs, canonical). */
 int zkb_prove_dev(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const uint64_t* d_weights,
                   const uint64_t r[4], const uint64_t s[4], zkb_proof* out);
+/* Throughput mode: `count` independent proofs over the same QAP and CRS (weights[i]: m x 4 limbs each,
+ * all host or all device pointers; r, s: count x 4 limbs).  Two proofs are kept in flight on two
+ * internal stream pairs so that the short / low-occupancy stages of one proof (polynomial stage,
+ * record sort, bucket reduction) overlap the SM-filling bucket accumulation of the other.  Results
+ * are identical to `count` calls of zkb_prove.  Host weights should be pinned (zkb_host_alloc) for the
+ * copies to overlap. */
+int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const uint64_t* const* weights,
+                    int weights_on_device, const uint64_t* r, const uint64_t* s, size_t count, zkb_proof* out);
 /* Multi-GPU: each rank runs the polynomial stage and the MSMs over ITS shard of the CRS (rank 0 also
  * carries the fixed-point terms alpha1 + r delta1 etc.) and returns its partial sums of A, B, C in the
  * zkb_proof layout (affine, canonical: a 8 | b 16 | c 8 = 32 limbs).  The caller all-gathers the

@@ -334,6 +334,35 @@ def test_prove_sharded_equals_single(ctx):
         assert (got.a, got.b, got.c) == (full.a, full.b, full.c)
 
 
+def test_prove_batch_equals_single(ctx):
+    """zkb_prove_batch (two proofs in flight on two stream pairs) == independent zkb_prove calls,
+    for 1..5 proofs with different witnesses and (r, s); host and device-resident weights."""
+    n = 256
+    rng = random.Random(91)
+    m, n_input, rows = zg.horner_qap_rows(n)
+    q = zk.QAP(ctx, n, m, n_input, rows)
+    crs = zk.setup(ctx, q, tuple(rand_fr(rng, True) for _ in range(5)))
+    wits = [zg.horner_witness(n, rand_fr(rng, True), [rand_fr(rng) for _ in range(n)]) for _ in range(5)]
+    wits[3][5] = (wits[3][5] + 1) % P  # one invalid witness in the middle
+    rs = [rand_fr(rng, True) for _ in range(5)]
+    ss = [rand_fr(rng, True) for _ in range(5)]
+    single = [zk.prove(ctx, q, crs, w, r, s) for w, r, s in zip(wits, rs, ss)]
+    for k in (1, 2, 3, 5):
+        got = zk.prove_batch(ctx, q, crs, wits[:k], rs[:k], ss[:k])
+        assert [(p.a, p.b, p.c) for p in got] == [(p.a, p.b, p.c) for p in single[:k]]
+    dptrs = []
+    for w in wits:
+        a = zg.fr_limbs(w)
+        d = ctx.dev_alloc(a.nbytes)
+        ctx.h2d(d, a)
+        dptrs.append(d)
+    got = zk.prove_batch(ctx, q, crs, dptrs, rs, ss, on_device=True)
+    assert [(p.a, p.b, p.c) for p in got] == [(p.a, p.b, p.c) for p in single]
+    for d in dptrs:
+        ctx.dev_free(d)
+    assert zk.prove_batch(ctx, q, crs, [], [], []) == []
+
+
 def test_error_paths(ctx):
     with pytest.raises(zk.ZkbError):
         zk.QAP(ctx, 6, 4, 1, [(np.zeros(5, dtype=np.uint64), np.zeros(0, dtype=np.uint32), np.zeros((0, 4), dtype=np.uint64))] * 3)

@@ -1,6 +1,7 @@
 // Context, memory, profiling hooks, standalone NTT / MSM entry points and the modmul peak probe of
 // libzkb200.so (include/zkb200.h).  The prove() pipeline lives in prove.cu, the CRS in crs.cu.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "common.cuh"
@@ -20,8 +21,8 @@ int set_err(zkb_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
-int scratch_get(zkb_ctx* ctx, int slot, size_t bytes, void** out) {
-  DevBuf& b = ctx->scratch[slot];
+int scratch_get_in(zkb_ctx* ctx, DevBuf* slots, int slot, size_t bytes, void** out) {
+  DevBuf& b = slots[slot];
   if (b.bytes < bytes) {
     if (b.p) {
       ZKB_CUDA(ctx, cudaDeviceSynchronize());
@@ -40,12 +41,15 @@ int scratch_get(zkb_ctx* ctx, int slot, size_t bytes, void** out) {
   *out = b.p;
   return ZKB_OK;
 }
+int scratch_get(zkb_ctx* ctx, int slot, size_t bytes, void** out) { return scratch_get_in(ctx, ctx->scratch, slot, bytes, out); }
 
-void prof_begin(zkb_ctx* ctx, int kind, cudaStream_t st) {
+void prof_begin(zkb_ctx* ctx, int kind, cudaStream_t st, const char* name) {
   zkb_ctx::ProfRec r;
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   r.kind = kind;
+  r.name = name;
+  r.stream_id = st == ctx->lanes[0].hi ? 1 : (st == ctx->lanes[0].lo ? 2 : (st == ctx->lanes[1].hi ? 3 : 4));
   cudaEventRecord(r.a, st);
   ctx->prof.push_back(r);
 }
@@ -101,10 +105,24 @@ int zkb_ctx_create(zkb_ctx** out, int device_id) {
   zkb_ctx* c = new zkb_ctx();
   c->device = device_id;
   c->sm_count = prop.multiProcessorCount;
-  cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  // per lane: latency-class stream at high priority, throughput-class (bucket accumulation) at low
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (const char* e = getenv("ZKB_PRIO")) {  // developer switch: 0 = no priorities, -1 = reversed
+    if (atoi(e) == 0) prio_hi = prio_lo;
+    if (atoi(e) < 0) std::swap(prio_lo, prio_hi);
+  }
+  for (auto& l : c->lanes) {
+    cudaStreamCreateWithPriority(&l.hi, cudaStreamNonBlocking, prio_hi);
+    cudaStreamCreateWithPriority(&l.lo, cudaStreamNonBlocking, prio_lo);
+    for (auto& e : l.ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (cudaHostAlloc(&l.h_proof, 256, cudaHostAllocDefault) != cudaSuccess) {
+      zkb_ctx_destroy(c);
+      return set_err(nullptr, ZKB_ERR_ALLOC, "cudaHostAlloc failed");
+    }
+  }
+  c->stream = c->lanes[0].hi;
+  c->stream2 = c->lanes[0].lo;
   *out = c;
   return ZKB_OK;
 }
@@ -119,10 +137,16 @@ void zkb_ctx_destroy(zkb_ctx* ctx) {
   for (auto& b : ctx->scratch)
     if (b.p) cudaFree(b.p);
   prof_clear(ctx);
-  cudaEventDestroy(ctx->ev_fork);
-  cudaEventDestroy(ctx->ev_join);
-  cudaStreamDestroy(ctx->stream);
-  cudaStreamDestroy(ctx->stream2);
+  if (ctx->trace_base) cudaEventDestroy(ctx->trace_base);
+  for (auto& l : ctx->lanes) {
+    for (auto& b : l.scratch)
+      if (b.p) cudaFree(b.p);
+    for (auto& e : l.ev)
+      if (e) cudaEventDestroy(e);
+    if (l.hi) cudaStreamDestroy(l.hi);
+    if (l.lo) cudaStreamDestroy(l.lo);
+    if (l.h_proof) cudaFreeHost(l.h_proof);
+  }
   delete ctx;
 }
 
@@ -136,6 +160,28 @@ int zkb_profile(zkb_ctx* ctx, int enable) {
   prof_clear(ctx);
   for (auto& u : ctx->prof_units) u = 0;
   ctx->profile = enable != 0;
+  ctx->trace = enable == 2;
+  if (ctx->trace) {
+    if (!ctx->trace_base) cudaEventCreate(&ctx->trace_base);
+    cudaEventRecord(ctx->trace_base, ctx->stream);
+  }
+  return ZKB_OK;
+}
+int zkb_trace_dump(zkb_ctx* ctx, const char* path) {
+  if (!ctx || !path) return set_err(ctx, ZKB_ERR_ARG, "zkb_trace_dump: NULL argument");
+  if (!ctx->trace_base) return set_err(ctx, ZKB_ERR_ARG, "zkb_trace_dump: tracing was never enabled (zkb_profile(ctx, 2))");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZKB_CUDA(ctx, cudaDeviceSynchronize());
+  FILE* f = fopen(path, "w");
+  if (!f) return set_err(ctx, ZKB_ERR_ARG, "zkb_trace_dump: cannot open %s", path);
+  fprintf(f, "stream,kernel,start_ms,end_ms,dur_ms\n");
+  for (auto& r : ctx->prof) {
+    float t0 = 0, t1 = 0;
+    if (cudaEventElapsedTime(&t0, ctx->trace_base, r.a) != cudaSuccess) continue;
+    if (cudaEventElapsedTime(&t1, ctx->trace_base, r.b) != cudaSuccess) continue;
+    fprintf(f, "%d,\"%s\",%.4f,%.4f,%.4f\n", r.stream_id, r.name ? r.name : "", t0, t1, t1 - t0);
+  }
+  fclose(f);
   return ZKB_OK;
 }
 int zkb_profile_read(zkb_ctx* ctx, int kind, double* total_ms, uint64_t* count, uint64_t* units) {
@@ -191,8 +237,10 @@ int zkb_memcpy_d2h(zkb_ctx* ctx, void* dst, const void* src, size_t bytes) {
 }
 int zkb_sync(zkb_ctx* ctx) {
   if (!ctx) return ZKB_ERR_ARG;
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
+  for (auto& l : ctx->lanes) {
+    ZKB_CUDA(ctx, cudaStreamSynchronize(l.hi));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(l.lo));
+  }
   return ZKB_OK;
 }
 void* zkb_stream(zkb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

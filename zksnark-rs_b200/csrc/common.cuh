@@ -20,21 +20,35 @@ struct DevBuf {
 
 }  // namespace zkb
 
+// One proof in flight uses one lane: a latency-class stream (high priority: polynomial stage, record
+// sort, head folding, bucket hierarchy, finish -- short or low-occupancy kernels) and a
+// throughput-class stream (low priority: the bucket accumulations that fill every SM), tied together
+// by events.  With two lanes, the latency-class work of proof i+1 and the tails of proof i run in
+// the gaps of the accumulations instead of serially (zkb_prove_batch).
+struct zkb_lane {
+  cudaStream_t hi = nullptr, lo = nullptr;
+  cudaEvent_t ev[4] = {};        // 0/1: G1 records sorted / accumulated; 2/3: same for G2
+  zkb::DevBuf scratch[16];       // per-lane scratch (MSM buffers, polynomial workspace, outputs)
+  void* h_proof = nullptr;       // pinned staging for the 256-byte result
+};
+
 struct zkb_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // second queue: the G2 MSM runs beside the G1 MSMs
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  zkb_lane lanes[2];
+  cudaStream_t stream = nullptr;   // = lanes[0].hi: everything outside the prove pipeline runs here
+  cudaStream_t stream2 = nullptr;  // = lanes[0].lo
   int sm_count = 148;
   uint64_t launches = 0;
   std::string err;
   // twiddle tables tw[log_n][inverse]: omega^k (k < n/2) in Montgomery form, built lazily
   zkb::Fr* tw[28][2] = {};
-  // reusable scratch (grown on demand, never shrunk)
+  // reusable scratch (grown on demand, never shrunk) for the non-pipelined entry points
   zkb::DevBuf scratch[16];
   // optional per-kernel-class CUDA-event timing (zkb_profile): pairs recorded around tracked launches
   bool profile = false;
-  struct ProfRec { cudaEvent_t a, b; int kind; };
+  bool trace = false;  // zkb_profile(ctx, 2): events around EVERY launch, dumped by zkb_trace_dump
+  struct ProfRec { cudaEvent_t a, b; int kind; const char* name; int stream_id; };
+  cudaEvent_t trace_base = nullptr;
   uint64_t prof_units[16] = {};  // work units per tracked class (NTT: elements x passes; ACC: records)
   std::vector<ProfRec> prof;
 };
@@ -62,7 +76,9 @@ int set_err(zkb_ctx* ctx, int code, const char* fmt, ...);
 // kernel launch bookkeeping: count + check
 #define ZKB_LAUNCH(ctx, kernel, grid, block, smem, strm, ...)                                   \
   do {                                                                                          \
+    if ((ctx)->trace) ::zkb::prof_begin(ctx, 0, strm, #kernel);                                 \
     kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                                   \
+    if ((ctx)->trace) ::zkb::prof_end(ctx, strm);                                               \
     (ctx)->launches++;                                                                          \
     cudaError_t e__ = cudaGetLastError();                                                       \
     if (e__ != cudaSuccess)                                                                     \
@@ -72,13 +88,13 @@ int set_err(zkb_ctx* ctx, int code, const char* fmt, ...);
 
 // tracked kernel classes for zkb_profile
 enum ProfKind { PK_NTT = 1, PK_ACC_G1 = 2, PK_ACC_G2 = 3, PK_SORT = 4, PK_REDUCE = 5, PK_POINTWISE = 6, PK_ASSEMBLE = 7, PK_MAX = 8 };
-void prof_begin(zkb_ctx* ctx, int kind, cudaStream_t st);
+void prof_begin(zkb_ctx* ctx, int kind, cudaStream_t st, const char* name = "");
 void prof_end(zkb_ctx* ctx, cudaStream_t st);
 
 // tracked launch: CUDA events on the launching stream around the kernel when profiling is on
 #define ZKB_LAUNCH_K(ctx, kind, kernel, grid, block, smem, strm, ...)                           \
   do {                                                                                          \
-    if ((ctx)->profile) ::zkb::prof_begin(ctx, kind, strm);                                     \
+    if ((ctx)->profile) ::zkb::prof_begin(ctx, kind, strm, #kernel);                            \
     kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                                   \
     if ((ctx)->profile) ::zkb::prof_end(ctx, strm);                                             \
     (ctx)->launches++;                                                                          \
@@ -88,8 +104,9 @@ void prof_end(zkb_ctx* ctx, cudaStream_t st);
                             #kernel, cudaGetErrorString(e__));                                  \
   } while (0)
 
-// grow-only scratch slot
+// grow-only scratch slot (ctx->scratch, or an explicit slot array such as a lane's)
 int scratch_get(zkb_ctx* ctx, int slot, size_t bytes, void** out);
+int scratch_get_in(zkb_ctx* ctx, DevBuf* slots, int slot, size_t bytes, void** out);
 void prof_clear(zkb_ctx* ctx);
 // host helpers (api.cu): canonical limbs / small integers -> Montgomery Fr; device Fq array -> canonical host limbs
 Fr fr_from_limbs(const uint64_t* l);
@@ -124,6 +141,27 @@ struct MsmJob {
 };
 int msm_pick_c(size_t n_points);
 static inline int msm_windows(int c) { return 254 / c + 1; }
+// An MSM call in three phases so that a pipeline can put them on different streams:
+//   msm_sort (digits, scan, scatter) -> msm_accumulate (zero buckets + THE hot kernel) -> msm_tail
+//   (head folding + bucket hierarchy -> d_out).  msm_prepare validates and carves the scratch
+//   (3 consecutive slots of `slots`, starting at slot_base).
+struct MsmPlan {
+  int group = 1;  // 1: G1 (Fq), 2: G2 (Fq2)
+  const void* tab = nullptr;
+  size_t stride = 0;
+  int c = 0, njobs = 0, S = 32;
+  MsmJob jobs[4];
+  bool empty = true;
+  size_t nbk = 0, max_recs = 0, nacc = 0, lvl_elems = 0;
+  uint32_t *hist = nullptr, *offs = nullptr, *cursor = nullptr, *sums = nullptr, *sorted = nullptr;
+  void *buckets = nullptr, *heads = nullptr, *lvlS = nullptr, *lvlA = nullptr, *d_out = nullptr;
+};
+int msm_prepare(zkb_ctx* ctx, DevBuf* slots, int slot_base, int group, const void* tab, size_t stride, int c, const MsmJob* jobs,
+                int njobs, void* d_out, MsmPlan* plan);
+int msm_sort(zkb_ctx* ctx, const MsmPlan& p, cudaStream_t st);
+int msm_accumulate(zkb_ctx* ctx, const MsmPlan& p, cudaStream_t st);
+int msm_tail(zkb_ctx* ctx, const MsmPlan& p, cudaStream_t st);
+// all phases on one stream with ctx->scratch (standalone zkb_msm)
 int msm_g1(zkb_ctx* ctx, const G1Affine* tab, size_t stride, int c, const MsmJob* jobs, int njobs, G1XYZZ* d_out,
            int slot_base, cudaStream_t st);
 int msm_g2(zkb_ctx* ctx, const G2Affine* tab, size_t stride, int c, const MsmJob* jobs, int njobs, G2XYZZ* d_out,
@@ -164,10 +202,8 @@ struct zkb_qap {
   // coset tables in bit-reversed position order: P[i] = g^br(i) / n, Q[i] = g^-br(i) / (2n), g = omega_2n
   zkb::Fr* d_cosP = nullptr;
   zkb::Fr* d_cosQ = nullptr;
-  // per-QAP workspace: 8 vectors of n Fr, and the witness in canonical + Montgomery form (m Fr each)
-  zkb::Fr* d_ws = nullptr;
-  zkb::Fr* d_wcanon = nullptr;
-  zkb::Fr* d_wmont = nullptr;
+  // (the polynomial workspace -- 8 vectors of n Fr and the witness, canonical + Montgomery -- lives in
+  // the lane scratch, so proofs in flight on different lanes can share one QAP)
 };
 
 struct zkb_crs {

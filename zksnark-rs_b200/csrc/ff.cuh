@@ -175,7 +175,9 @@ namespace dev_impl {
         "+r"(acc[6]), "+r"(acc[7]), "+r"(top)                                                      \
       : "r"(s0), "r"(s2), "r"(s4), "r"(s6), "r"(m))
 
-// same without a carry-out (the caller guarantees none: top limb has >= 2 spare bits)
+// same without a carry-out (the caller guarantees none: top limb has >= 2 spare bits).  The last
+// instruction still says .cc so that ptxas pairs it with its madc.lo into one IMAD.WIDE.U32.X
+// (a lone madc.hi is issued as a separate IMAD.HI).
 #define ZKB_CMAD(acc, s0, s2, s4, s6, m)                                                           \
   asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"                                                         \
       "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"                                                        \
@@ -184,12 +186,12 @@ namespace dev_impl {
       "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"                                                       \
       "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"                                                       \
       "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"                                                       \
-      "madc.hi.u32 %7, %11, %12, %7;"                                                              \
+      "madc.hi.cc.u32 %7, %11, %12, %7;"                                                           \
       : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),        \
         "+r"(acc[6]), "+r"(acc[7])                                                                 \
       : "r"(s0), "r"(s2), "r"(s4), "r"(s6), "r"(m))
 
-// X[0] += Y[1] (carry c); Y = (Y >> 64) + {s1,s3,s5,s7} * m + c
+// X[0] += Y[1] (carry c); Y = (Y >> 64) + {s1,s3,s5,s7} * m + c   (tlo, thi = s7 * m, in scope at the call site)
 #define ZKB_SHIFT_MAD(X0, Y, s1, s3, s5, s7, m)                                                    \
   asm("add.cc.u32 %0, %0, %2;\n\t"                                                                 \
       "madc.lo.cc.u32 %1, %9, %13, %3;\n\t"                                                        \
@@ -198,11 +200,11 @@ namespace dev_impl {
       "madc.hi.cc.u32 %4, %10, %13, %6;\n\t"                                                       \
       "madc.lo.cc.u32 %5, %11, %13, %7;\n\t"                                                       \
       "madc.hi.cc.u32 %6, %11, %13, %8;\n\t"                                                       \
-      "madc.lo.cc.u32 %7, %12, %13, 0;\n\t"                                                        \
-      "madc.hi.u32 %8, %12, %13, 0;"                                                               \
+      "addc.cc.u32 %7, %14, 0;\n\t"                                                                \
+      "addc.u32 %8, %15, 0;"                                                                       \
       : "+r"(X0), "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]),          \
         "+r"(Y[6]), "+r"(Y[7])                                                                     \
-      : "r"(s1), "r"(s3), "r"(s5), "r"(s7), "r"(m))
+      : "r"(s1), "r"(s3), "r"(s5), "r"(s7), "r"(m), "r"(tlo), "r"(thi))
 
 template <class P>
 __device__ __forceinline__ void mont_round(uint32_t (&X)[8], uint32_t (&Y)[8], const uint32_t* a,
@@ -210,10 +212,15 @@ __device__ __forceinline__ void mont_round(uint32_t (&X)[8], uint32_t (&Y)[8], c
   if (first) {
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-      asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=&r"(X[j]), "=&r"(X[j + 1]) : "r"(a[j]), "r"(bi));
-      asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=&r"(Y[j]), "=&r"(Y[j + 1]) : "r"(a[j + 1]), "r"(bi));
+      // mul.wide + unpack: one IMAD.WIDE.U32 (a mul.lo / mul.hi pair is an IMAD plus an IMAD.HI, 1.5x the pipe time)
+      asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(X[j]), "=r"(X[j + 1]) : "r"(a[j]), "r"(bi));
+      asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(Y[j]), "=r"(Y[j + 1]) : "r"(a[j + 1]), "r"(bi));
     }
   } else {
+    // top product a[7] * bi has no addend: one IMAD.WIDE, its halves join the carry chain as plain adds
+    // (madc.lo / madc.hi with a zero addend would be issued as IMAD + IMAD.HI, 1.5x the pipe time)
+    uint32_t tlo, thi;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(tlo), "=r"(thi) : "r"(a[7]), "r"(bi));
     ZKB_SHIFT_MAD(X[0], Y, a[1], a[3], a[5], a[7], bi);
     ZKB_CMAD_TOP(X, Y[7], a[0], a[2], a[4], a[6], bi);
   }
@@ -403,19 +410,28 @@ struct alignas(16) Fq2 {
 };
 ZKB_HD Fq2 operator+(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
 ZKB_HD Fq2 operator-(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
+// Base-field product used inside Fq2: inline by default; a translation unit may define
+// ZKB_FQ2_OOL before including this header to call one shared out-of-line copy instead (an inlined
+// G2 mixed addition is ~90 KB of code and thrashes the instruction cache).
+#if defined(__CUDA_ARCH__) && defined(ZKB_FQ2_OOL)
+__device__ __noinline__ Fq fq_mul_ool(const Fq& a, const Fq& b) { return dev_impl::mul(a, b); }
+#define ZKB_FQ2_BASEMUL(a, b) fq_mul_ool((a), (b))
+#else
+#define ZKB_FQ2_BASEMUL(a, b) ((a) * (b))
+#endif
 ZKB_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
   // Karatsuba: 3 base multiplications
-  Fq v0 = a.c0 * b.c0, v1 = a.c1 * b.c1;
-  Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
+  Fq v0 = ZKB_FQ2_BASEMUL(a.c0, b.c0), v1 = ZKB_FQ2_BASEMUL(a.c1, b.c1);
+  Fq s = ZKB_FQ2_BASEMUL(a.c0 + a.c1, b.c0 + b.c1);
   Fq2 r;
   r.c0 = v0 - v1;
   r.c1 = s - v0 - v1;
   return r;
 }
 ZKB_HD Fq2 sqr(const Fq2& a) {
-  Fq t = a.c0 * a.c1;
+  Fq t = ZKB_FQ2_BASEMUL(a.c0, a.c1);
   Fq2 r;
-  r.c0 = (a.c0 + a.c1) * (a.c0 - a.c1);
+  r.c0 = ZKB_FQ2_BASEMUL(a.c0 + a.c1, a.c0 - a.c1);
   r.c1 = t + t;
   return r;
 }

@@ -130,12 +130,16 @@ int msm_sort_records(zkb_ctx* ctx, const MsmJob* jobs, int njobs, size_t stride,
 int msm_pick_c(size_t n) { return pick_c(n); }
 
 template <> int MsmLaunch<Fq>::accumulate(zkb_ctx* ctx, const G1Affine* tab, const uint32_t* offs, const uint32_t* sorted,
-                                          uint32_t nbk, size_t nacc, G1XYZZ* buckets, G1XYZZ* heads, cudaStream_t st, int pk) {
-  return launch_accumulate<Fq>(ctx, tab, offs, sorted, nbk, nacc, buckets, heads, st, pk);
+                                          uint32_t nbk, size_t nacc, int S, G1XYZZ* buckets, G1XYZZ* heads, cudaStream_t st, int pk) {
+  if (S == 128) return launch_accumulate_s<Fq, 128>(ctx, tab, offs, sorted, nbk, nacc, buckets, heads, st, pk);
+  if (S == 64) return launch_accumulate_s<Fq, 64>(ctx, tab, offs, sorted, nbk, nacc, buckets, heads, st, pk);
+  return launch_accumulate_s<Fq, 32>(ctx, tab, offs, sorted, nbk, nacc, buckets, heads, st, pk);
 }
-template <> int MsmLaunch<Fq>::fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, G1XYZZ* buckets, const G1XYZZ* heads,
-                                         cudaStream_t st) {
-  return launch_fix_heads<Fq>(ctx, offs, nbk, buckets, heads, st);
+template <> int MsmLaunch<Fq>::fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, int S, G1XYZZ* buckets,
+                                         const G1XYZZ* heads, cudaStream_t st) {
+  if (S == 128) return launch_fix_heads_s<Fq, 128>(ctx, offs, nbk, buckets, heads, st);
+  if (S == 64) return launch_fix_heads_s<Fq, 64>(ctx, offs, nbk, buckets, heads, st);
+  return launch_fix_heads_s<Fq, 32>(ctx, offs, nbk, buckets, heads, st);
 }
 template <> int MsmLaunch<Fq>::reduce(zkb_ctx* ctx, const G1XYZZ* buckets, uint32_t nb, int njobs, G1XYZZ* lvlS, G1XYZZ* lvlA,
                                       G1XYZZ* d_out, cudaStream_t st) {
@@ -146,9 +150,17 @@ template <> int MsmLaunch<Fq>::expand_table(zkb_ctx* ctx, G1Affine* tab, size_t 
 }
 template <> int MsmLaunch<Fq>::set_inf(zkb_ctx* ctx, G1XYZZ* out, int n, cudaStream_t st) { return launch_set_inf<Fq>(ctx, out, n, st); }
 
+int msm_sort(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
+  if (P.empty) return ZKB_OK;
+  return msm_sort_records(ctx, P.jobs, P.njobs, P.stride, make_plan(P.c), P.hist, P.offs, P.cursor, P.sums, P.sorted, st);
+}
 int msm_g1(zkb_ctx* ctx, const G1Affine* tab, size_t stride, int c, const MsmJob* jobs, int njobs, G1XYZZ* d_out, int slot,
            cudaStream_t st) {
-  return msm_run<Fq>(ctx, tab, stride, c, jobs, njobs, d_out, slot, st, PK_ACC_G1);
+  MsmPlan P;
+  ZKB_TRY(msm_prepare(ctx, ctx->scratch, slot, 1, tab, stride, c, jobs, njobs, d_out, &P));
+  ZKB_TRY(msm_sort(ctx, P, st));
+  ZKB_TRY(msm_accumulate(ctx, P, st));
+  return msm_tail(ctx, P, st);
 }
 int expand_table_g1(zkb_ctx* ctx, G1Affine* tab, size_t stride, size_t n, int c, cudaStream_t st) {
   return MsmLaunch<Fq>::expand_table(ctx, tab, stride, n, c, st);

@@ -47,8 +47,22 @@ __host__ __device__ inline DigitPlan make_plan(int c) {
 }
 
 static const int MSM_MAX_JOBS = 4;
-static const int ACC_S = 32;  // records per accumulation chunk
-static const uint32_t RED_L = 16, RED_LOG_L = 4;
+// records per accumulation chunk (one thread each).  Larger chunks mean fewer head pieces for
+// k_fix_heads but fewer threads; G1 has ~4x the records of G2 on the prove path.
+template <class F> struct AccChunk;
+template <> struct AccChunk<Fq> { static int get(size_t max_recs); };
+template <> struct AccChunk<Fq2> { static int get(size_t max_recs); };
+static inline int acc_chunk_env(int dflt) {
+  if (const char* e = getenv("ZKB_ACC_S")) {
+    int v = atoi(e);
+    if (v == 32 || v == 64 || v == 128) return v;
+  }
+  return dflt;
+}
+inline int AccChunk<Fq>::get(size_t max_recs) {
+  return acc_chunk_env(max_recs >= ((size_t)1 << 25) ? 128 : (max_recs >= ((size_t)1 << 23) ? 64 : 32));
+}
+inline int AccChunk<Fq2>::get(size_t max_recs) { int v = acc_chunk_env(32); return v > 64 ? 64 : v; }
 
 // window size for a table over n points (single bucket set): N*W mixed adds (10 modmul) + the
 // bucket hierarchy (2 full adds of 14 modmul per bucket, weighted x2 for its lower parallelism)
@@ -71,8 +85,9 @@ static inline int pick_c(size_t n) {
 template <class F>
 struct MsmLaunch {
   static int accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
-                        size_t nacc, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind);
-  static int fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, XYZZ<F>* buckets, const XYZZ<F>* heads, cudaStream_t st);
+                        size_t nacc, int S, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind);
+  static int fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, int S, XYZZ<F>* buckets, const XYZZ<F>* heads,
+                       cudaStream_t st);
   // full hierarchy: buckets[njobs][nb] -> d_out[njobs]; lvlS / lvlA hold the intermediate levels
   static int reduce(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int njobs, XYZZ<F>* lvlS, XYZZ<F>* lvlA, XYZZ<F>* d_out,
                     cudaStream_t st);
@@ -85,15 +100,14 @@ int msm_sort_records(zkb_ctx* ctx, const MsmJob* jobs, int njobs, size_t stride,
                      uint32_t* cursor, uint32_t* sums, uint32_t* sorted, cudaStream_t st);
 
 static inline size_t msm_level_elems(uint32_t nb, int njobs) {
-  size_t e = 0;
-  for (uint32_t m = nb; m > 1;) { m = (m + RED_L - 1) / RED_L; e += (size_t)m * njobs; }
-  return e + njobs;
+  // upper bound for any level plan with fan-in >= 4: nb/4 + nb/16 + ... < nb/3 (+ one per level)
+  return ((size_t)nb / 3 + 40) * njobs;
 }
 
-// results d_out[j] (device XYZZ, Montgomery) = sum_{i < jobs[j].n} jobs[j].scalars[i] * T[0][i]
+// phases of one MSM call (see MsmPlan in common.cuh); F-typed views of the plan's buffers
 template <class F>
-static int msm_run(zkb_ctx* ctx, const Affine<F>* tab, size_t stride, int c, const MsmJob* jobs, int njobs, XYZZ<F>* d_out,
-                   int slot, cudaStream_t st, int prof_kind) {
+static int msm_prepare_t(zkb_ctx* ctx, DevBuf* slots, int slot, const Affine<F>* tab, size_t stride, int c, const MsmJob* jobs,
+                         int njobs, XYZZ<F>* d_out, MsmPlan* P) {
   if (njobs < 1 || njobs > MSM_MAX_JOBS) return set_err(ctx, ZKB_ERR_ARG, "msm: %d jobs", njobs);
   if (c < 2 || c > 23) return set_err(ctx, ZKB_ERR_ARG, "msm: window_bits %d out of range [2,23]", c);
   DigitPlan pl = make_plan(c);
@@ -101,39 +115,55 @@ static int msm_run(zkb_ctx* ctx, const Affine<F>* tab, size_t stride, int c, con
   for (int j = 0; j < njobs; j++) {
     if (jobs[j].n > stride) return set_err(ctx, ZKB_ERR_ARG, "msm: more scalars than bases");
     total_n += jobs[j].n;
+    P->jobs[j] = jobs[j];
   }
   if ((size_t)pl.W * stride >= ((size_t)1 << 31) || (size_t)pl.W * total_n >= ((size_t)1 << 32) - 64)
     return set_err(ctx, ZKB_ERR_ARG, "msm: too many records for 32-bit indices");
-  if (total_n == 0) return MsmLaunch<F>::set_inf(ctx, d_out, njobs, st);
-  const size_t nbk = (size_t)njobs * pl.nb;
-  const size_t nscan_blocks = (nbk + 1023) / 1024;
-  const size_t max_recs = (size_t)pl.W * total_n;
-  const size_t nacc = (max_recs + ACC_S - 1) / ACC_S;
-  const size_t lvl_elems = msm_level_elems(pl.nb, njobs);
-
+  P->group = sizeof(F) == sizeof(Fq) ? 1 : 2;
+  P->tab = tab; P->stride = stride; P->c = c; P->njobs = njobs; P->d_out = d_out;
+  P->empty = total_n == 0;
+  if (P->empty) return ZKB_OK;
+  P->nbk = (size_t)njobs * pl.nb;
+  const size_t nscan_blocks = (P->nbk + 1023) / 1024;
+  P->max_recs = (size_t)pl.W * total_n;
+  P->S = AccChunk<F>::get(P->max_recs);
+  P->nacc = (P->max_recs + P->S - 1) / P->S;
+  P->lvl_elems = msm_level_elems(pl.nb, njobs);
   void* p;
   // u32 scratch: hist[nbk] | offs[nbk+1] | cursor[nbk] | sums[nscan_blocks+1]
-  size_t u32_words = nbk * 3 + 1 + nscan_blocks + 8;
-  ZKB_TRY(scratch_get(ctx, slot + 0, u32_words * 4, &p));
-  uint32_t* hist = (uint32_t*)p;
-  uint32_t* offs = hist + nbk;
-  uint32_t* cursor = offs + nbk + 1;
-  uint32_t* sums = cursor + nbk;
-  ZKB_TRY(scratch_get(ctx, slot + 1, max_recs * 4, &p));
-  uint32_t* sorted = (uint32_t*)p;
-  ZKB_TRY(scratch_get(ctx, slot + 2, (nbk + nacc + 2 * lvl_elems) * sizeof(XYZZ<F>), &p));
+  size_t u32_words = P->nbk * 3 + 1 + nscan_blocks + 8;
+  ZKB_TRY(scratch_get_in(ctx, slots, slot + 0, u32_words * 4, &p));
+  P->hist = (uint32_t*)p;
+  P->offs = P->hist + P->nbk;
+  P->cursor = P->offs + P->nbk + 1;
+  P->sums = P->cursor + P->nbk;
+  ZKB_TRY(scratch_get_in(ctx, slots, slot + 1, P->max_recs * 4, &p));
+  P->sorted = (uint32_t*)p;
+  ZKB_TRY(scratch_get_in(ctx, slots, slot + 2, (P->nbk + P->nacc + 2 * P->lvl_elems) * sizeof(XYZZ<F>), &p));
   XYZZ<F>* buckets = (XYZZ<F>*)p;
-  XYZZ<F>* heads = buckets + nbk;
-  XYZZ<F>* lvlS = heads + nacc;
-  XYZZ<F>* lvlA = lvlS + lvl_elems;
-
-  ZKB_TRY(msm_sort_records(ctx, jobs, njobs, stride, pl, hist, offs, cursor, sums, sorted, st));
-  ZKB_CUDA(ctx, cudaMemsetAsync(buckets, 0, nbk * sizeof(XYZZ<F>), st));  // all-zero XYZZ = identity
-  if (ctx->profile) ctx->prof_units[prof_kind] += max_recs;
-  ZKB_TRY(MsmLaunch<F>::accumulate(ctx, tab, offs, sorted, (uint32_t)nbk, nacc, buckets, heads, st, prof_kind));
-  ZKB_TRY(MsmLaunch<F>::fix_heads(ctx, offs, (uint32_t)nbk, buckets, heads, st));
-  ZKB_TRY(MsmLaunch<F>::reduce(ctx, buckets, pl.nb, njobs, lvlS, lvlA, d_out, st));
+  P->buckets = buckets;
+  P->heads = buckets + P->nbk;
+  P->lvlS = buckets + P->nbk + P->nacc;
+  P->lvlA = buckets + P->nbk + P->nacc + P->lvl_elems;
   return ZKB_OK;
+}
+
+template <class F>
+static int msm_accumulate_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
+  if (P.empty) return ZKB_OK;
+  const int prof_kind = P.group == 1 ? PK_ACC_G1 : PK_ACC_G2;
+  ZKB_CUDA(ctx, cudaMemsetAsync(P.buckets, 0, P.nbk * sizeof(XYZZ<F>), st));  // all-zero XYZZ = identity
+  if (ctx->profile) ctx->prof_units[prof_kind] += P.max_recs;
+  return MsmLaunch<F>::accumulate(ctx, (const Affine<F>*)P.tab, P.offs, P.sorted, (uint32_t)P.nbk, P.nacc, P.S, (XYZZ<F>*)P.buckets,
+                                  (XYZZ<F>*)P.heads, st, prof_kind);
+}
+
+template <class F>
+static int msm_tail_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
+  if (P.empty) return MsmLaunch<F>::set_inf(ctx, (XYZZ<F>*)P.d_out, P.njobs, st);
+  ZKB_TRY(MsmLaunch<F>::fix_heads(ctx, P.offs, (uint32_t)P.nbk, P.S, (XYZZ<F>*)P.buckets, (const XYZZ<F>*)P.heads, st));
+  return MsmLaunch<F>::reduce(ctx, (const XYZZ<F>*)P.buckets, make_plan(P.c).nb, P.njobs, (XYZZ<F>*)P.lvlS, (XYZZ<F>*)P.lvlA,
+                              (XYZZ<F>*)P.d_out, st);
 }
 
 // ================================================================================================
@@ -146,8 +176,11 @@ static int msm_run(zkb_ctx* ctx, const Affine<F>* tab, size_t stride, int c, con
 // A bucket that begins inside the chunk is written to buckets[g]; the leading piece of a bucket
 // that began in an earlier chunk goes to heads[t] and is folded in by k_fix_heads.  buckets[] is
 // zero-filled (= identity) beforehand, empty buckets are never touched.
+#ifndef ZKB_ACC_MIN_BLOCKS
+#define ZKB_ACC_MIN_BLOCKS 1
+#endif
 template <class F, int S>
-__global__ void __launch_bounds__(128) k_accumulate_chunks(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
+__global__ void __launch_bounds__(128, ZKB_ACC_MIN_BLOCKS) k_accumulate_chunks(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
                                                            const uint32_t* __restrict__ sorted, uint32_t nbk, size_t nchunks,
                                                            XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -246,13 +279,13 @@ __global__ void __launch_bounds__(128) k_fix_heads(const uint32_t* __restrict__ 
 // and when one element is left R = A + S.  grid.y = job (bucket sets are contiguous, n_in each).
 template <class F>
 __global__ void __launch_bounds__(128) k_bucket_level(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ A_in,
-                                                      uint32_t n_in, uint32_t n_out, int shift, XYZZ<F>* __restrict__ S_out,
-                                                      XYZZ<F>* __restrict__ A_out) {
+                                                      uint32_t n_in, uint32_t n_out, uint32_t L, int shift,
+                                                      XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ A_out) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_out) return;
   const size_t job = blockIdx.y;
-  const XYZZ<F>* s = S_in + job * n_in + (size_t)t * RED_L;
-  const uint32_t cnt = n_in - t * RED_L < RED_L ? n_in - t * RED_L : RED_L;
+  const XYZZ<F>* s = S_in + job * n_in + (size_t)t * L;
+  const uint32_t cnt = n_in - t * L < L ? n_in - t * L : L;
   XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
   for (int i = (int)cnt - 1; i >= 1; i--) {
     run = add_ool(run, s[i]);
@@ -261,11 +294,42 @@ __global__ void __launch_bounds__(128) k_bucket_level(const XYZZ<F>* __restrict_
   run = add_ool(run, s[0]);
   for (int q = 0; q < shift; q++) acc = dbl_ool(acc);
   if (A_in) {
-    const XYZZ<F>* a = A_in + job * n_in + (size_t)t * RED_L;
+    const XYZZ<F>* a = A_in + job * n_in + (size_t)t * L;
     for (uint32_t i = 0; i < cnt; i++) acc = add_ool(acc, a[i]);
   }
   S_out[job * n_out + t] = run;
   A_out[job * n_out + t] = acc;
+}
+
+// The same level map with L = 32 and one WARP per chunk (lane i holds X_{32t+i}): a shuffle suffix
+// scan gives Suf_i = sum_{k>=i} X_k (so S_t = Suf_0 and T_t = sum_{i>=1} Suf_i), then one shuffle
+// tree sums 2^shift Suf_i + A_i over the lanes.  11 + shift dependent additions per level instead of
+// ~3L: used once the level is too small to fill the SMs with one thread per chunk.
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_level_warp(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ A_in,
+                                                           uint32_t n_in, uint32_t n_out, int shift, XYZZ<F>* __restrict__ S_out,
+                                                           XYZZ<F>* __restrict__ A_out) {
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= n_out) return;
+  const size_t job = blockIdx.y;
+  const uint32_t e = t * 32 + lane;
+  XYZZ<F> x = e < n_in ? S_in[job * n_in + e] : XYZZ<F>::inf();
+  for (int off = 1; off < 32; off <<= 1) {
+    XYZZ<F> y = shfl_down_xyzz(x, off);
+    if (lane + off < 32) x = add_ool(x, y);
+  }
+  XYZZ<F> v = lane ? x : XYZZ<F>::inf();
+  for (int q = 0; q < shift; q++) v = dbl_ool(v);
+  if (A_in && e < n_in) v = add_ool(v, A_in[job * n_in + e]);
+  for (int off = 16; off > 0; off >>= 1) {
+    XYZZ<F> y = shfl_down_xyzz(v, off);
+    v = add_ool(v, y);
+  }
+  if (lane == 0) {
+    S_out[job * n_out + t] = x;
+    A_out[job * n_out + t] = v;
+  }
 }
 
 template <class F>
@@ -294,32 +358,47 @@ __global__ void __launch_bounds__(128) k_expand_table(Affine<F>* __restrict__ ta
 }
 
 // ---- launch bodies (instantiated by the .cu that owns the kernel) --------------------------------
-template <class F>
-static int launch_accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
-                             size_t nacc, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind) {
-  ZKB_LAUNCH_K(ctx, prof_kind, (k_accumulate_chunks<F, ACC_S>), cdiv(nacc, 128), 128, 0, st, tab, offs, sorted, nbk, nacc, buckets,
+template <class F, int S>
+static int launch_accumulate_s(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
+                               size_t nacc, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind) {
+  ZKB_LAUNCH_K(ctx, prof_kind, (k_accumulate_chunks<F, S>), cdiv(nacc, 128), 128, 0, st, tab, offs, sorted, nbk, nacc, buckets,
                heads);
   return ZKB_OK;
 }
-template <class F>
-static int launch_fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, XYZZ<F>* buckets, const XYZZ<F>* heads,
-                            cudaStream_t st) {
-  ZKB_LAUNCH(ctx, (k_fix_heads<F, ACC_S>), cdiv(nbk, 128), 128, 0, st, offs, nbk, buckets, heads);
+template <class F, int S>
+static int launch_fix_heads_s(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, XYZZ<F>* buckets, const XYZZ<F>* heads,
+                              cudaStream_t st) {
+  ZKB_LAUNCH(ctx, (k_fix_heads<F, S>), cdiv(nbk, 128), 128, 0, st, offs, nbk, buckets, heads);
   return ZKB_OK;
 }
+// level plan shared by the scratch sizing and the launches: first level one thread per chunk of L
+// (16 when that still gives >= 32K threads, else 4), then warp levels (32 per warp)
+static inline uint32_t msm_first_L(uint32_t nb, int njobs) { return (size_t)nb * njobs / 16 >= 32768 ? 16 : 4; }
+
 template <class F>
 static int launch_reduce(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int njobs, XYZZ<F>* lvlS, XYZZ<F>* lvlA, XYZZ<F>* d_out,
                          cudaStream_t st) {
   const XYZZ<F>*Sin = buckets, *Ain = nullptr;
   XYZZ<F>*So = lvlS, *Ao = lvlA;
   int shift = 0;
-  for (uint32_t m = nb; m > 1;) {
-    uint32_t mo = (m + RED_L - 1) / RED_L;
+  uint32_t m = nb;
+  if (m > 1) {
+    const uint32_t L = msm_first_L(nb, njobs);
+    uint32_t mo = (m + L - 1) / L;
     dim3 grid(cdiv(mo, 128), njobs);
-    ZKB_LAUNCH(ctx, k_bucket_level<F>, grid, 128, 0, st, Sin, Ain, m, mo, shift, So, Ao);
+    ZKB_LAUNCH(ctx, k_bucket_level<F>, grid, 128, 0, st, Sin, Ain, m, mo, L, shift, So, Ao);
     Sin = So; Ain = Ao;
     So += (size_t)mo * njobs; Ao += (size_t)mo * njobs;
-    shift += RED_LOG_L;
+    shift += L == 16 ? 4 : 2;
+    m = mo;
+  }
+  while (m > 1) {
+    uint32_t mo = (m + 31) / 32;
+    dim3 grid(cdiv((size_t)mo * 32, 128), njobs);
+    ZKB_LAUNCH(ctx, k_bucket_level_warp<F>, grid, 128, 0, st, Sin, Ain, m, mo, shift, So, Ao);
+    Sin = So; Ain = Ao;
+    So += (size_t)mo * njobs; Ao += (size_t)mo * njobs;
+    shift += 5;
     m = mo;
   }
   ZKB_LAUNCH(ctx, k_bucket_final<F>, 1, 32, 0, st, Sin, Ain, njobs, d_out);

@@ -143,7 +143,7 @@ void zkb_qap_free(zkb_ctx* ctx, zkb_qap* q) {
     cudaFree(q->d_gptr[t]); cudaFree(q->d_wire[t]); cudaFree(q->d_coeff[t]);
     cudaFree(q->d_rptr[t]); cudaFree(q->d_gate[t]); cudaFree(q->d_rcoeff[t]);
   }
-  cudaFree(q->d_cosP); cudaFree(q->d_cosQ); cudaFree(q->d_ws); cudaFree(q->d_wcanon); cudaFree(q->d_wmont);
+  cudaFree(q->d_cosP); cudaFree(q->d_cosQ);
   delete q;
 }
 
@@ -211,8 +211,7 @@ int zkb_qap_upload(zkb_ctx* ctx, const zkb_qap_host* h, zkb_qap** out) {
     if (rc == ZKB_OK) rc = vec_to_mont(ctx, q->d_rcoeff[t], nnz, true, st);
   }
   if (rc != ZKB_OK) return fail(rc);
-  if (cudaMalloc(&q->d_cosP, n * 32) || cudaMalloc(&q->d_cosQ, n * 32) || cudaMalloc(&q->d_ws, 8 * n * 32) ||
-      cudaMalloc(&q->d_wcanon, m * 32) || cudaMalloc(&q->d_wmont, m * 32))
+  if (cudaMalloc(&q->d_cosP, n * 32) || cudaMalloc(&q->d_cosQ, n * 32))
     return fail(set_err(ctx, ZKB_ERR_ALLOC, "qap upload: workspace cudaMalloc failed"));
   Fr g = host_omega(q->log_n + 1, false), ginv = host_omega(q->log_n + 1, true);
   Fr invn = inverse(fr_from_u64(n)), inv2n = inverse(fr_from_u64(2 * n));
@@ -232,17 +231,31 @@ int zkb_qap_upload(zkb_ctx* ctx, const zkb_qap_host* h, zkb_qap** out) {
 }
 
 // ---- polynomial stage ---------------------------------------------------------------------------
-// workspace vectors (n Fr each): 0 A->u_br  1 B->v_br  2 AB->c_br  3 uc  4 vc->d_br  5 u_nat  6 v_nat  7 h_nat
-static int poly_stage(zkb_ctx* ctx, const zkb_qap* q, const Fr* d_w_canon) {
+// lane workspace: 8 vectors of n Fr (0 A->u_br  1 B->v_br  2 AB->c_br  3 uc  4 vc->d_br  5 u_nat  6 v_nat
+// 7 h_nat), the witness as uploaded (canonical) and in Montgomery form
+struct Work {
+  Fr *ws, *wcanon, *wmont;
+};
+static int work_get(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, Work* w) {
+  void* p;
+  ZKB_TRY(scratch_get_in(ctx, L->scratch, 11, 8 * q->n * sizeof(Fr), &p));
+  w->ws = (Fr*)p;
+  ZKB_TRY(scratch_get_in(ctx, L->scratch, 12, q->m * sizeof(Fr), &p));
+  w->wcanon = (Fr*)p;
+  ZKB_TRY(scratch_get_in(ctx, L->scratch, 13, q->m * sizeof(Fr), &p));
+  w->wmont = (Fr*)p;
+  return ZKB_OK;
+}
+
+static int poly_stage(zkb_ctx* ctx, const zkb_qap* q, const Work& w, const Fr* d_w_canon, cudaStream_t st) {
   const size_t n = q->n, m = q->m;
-  cudaStream_t st = ctx->stream;
-  Fr* ws = q->d_ws;
+  Fr* ws = w.ws;
   Fr *A = ws, *B = ws + n, *AB = ws + 2 * n, *uc = ws + 3 * n, *vc = ws + 4 * n, *un = ws + 5 * n, *vn = ws + 6 * n,
      *hn = ws + 7 * n;
-  ZKB_CUDA(ctx, cudaMemcpyAsync(q->d_wmont, d_w_canon, m * 32, cudaMemcpyDeviceToDevice, st));
-  ZKB_TRY(vec_to_mont(ctx, q->d_wmont, m, true, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(w.wmont, d_w_canon, m * 32, cudaMemcpyDeviceToDevice, st));
+  ZKB_TRY(vec_to_mont(ctx, w.wmont, m, true, st));
   ZKB_LAUNCH(ctx, k_matvec, cdiv(n, 128), 128, 0, st, q->d_gptr[0], q->d_wire[0], q->d_coeff[0], q->d_gptr[1],
-             q->d_wire[1], q->d_coeff[1], q->d_wmont, m, n, A, B, AB);
+             q->d_wire[1], q->d_coeff[1], w.wmont, m, n, A, B, AB);
   ZKB_TRY(ntt_dif(ctx, A, q->log_n, true, st));   // n * u_sum, bit-reversed
   ZKB_TRY(ntt_dif(ctx, B, q->log_n, true, st));
   ZKB_TRY(ntt_dif(ctx, AB, q->log_n, true, st));  // n * (p_lo + p_hi), bit-reversed
@@ -271,56 +284,81 @@ struct ProveOut {
   G2XYZZ* b;
   uint32_t* proof;  // 64 u32
 };
-static int prove_out(zkb_ctx* ctx, ProveOut* o) {
+static int prove_out(zkb_ctx* ctx, DevBuf* slots, ProveOut* o) {
   void* p;
-  ZKB_TRY(scratch_get(ctx, 6, 2 * sizeof(G1XYZZ) + sizeof(G2XYZZ) + 256, &p));
+  ZKB_TRY(scratch_get_in(ctx, slots, 6, 2 * sizeof(G1XYZZ) + sizeof(G2XYZZ) + 256, &p));
   o->ac = (G1XYZZ*)p;
   o->b = (G2XYZZ*)(o->ac + 2);
   o->proof = (uint32_t*)(o->b + 1);
   return ZKB_OK;
 }
 
-// stages 1-7 over this rank's CRS shard; out = proof (world 1) or the rank's partial sums
-static int prove_common(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights, int on_device,
-                        const uint64_t* r, const uint64_t* s, uint64_t* out) {
-  ZKB_TRY(check_pair(ctx, q, c));
-  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+// Enqueue stages 1-7 over this rank's CRS shard on lane L; nothing waits on the host.  The 256-byte
+// result (proof for world 1, else the rank's partial sums) lands in L->h_proof when L->hi drains.
+//   L->hi: [H2D] polynomial stage, scalars, sort G2, sort G1 ... tail G2, tail G1, finish, D2H
+//   L->lo:                                   accumulate G2, accumulate G1
+static int prove_enqueue(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights,
+                         int on_device, const uint64_t* r, const uint64_t* s) {
+  cudaStream_t hi = L->hi, lo = L->lo;
+  Work w;
+  ZKB_TRY(work_get(ctx, L, q, &w));
   const Fr* d_w = (const Fr*)weights;
   if (!on_device) {
-    ZKB_CUDA(ctx, cudaMemcpyAsync(q->d_wcanon, weights, q->m * 32, cudaMemcpyHostToDevice, st));
-    d_w = q->d_wcanon;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(w.wcanon, weights, q->m * 32, cudaMemcpyHostToDevice, hi));
+    d_w = w.wcanon;
   }
-  ZKB_TRY(poly_stage(ctx, q, d_w));
+  ZKB_TRY(poly_stage(ctx, q, w, d_w, hi));
   const size_t n = q->n;
-  Fr* ws = q->d_ws;
-  Fr *un = ws + 5 * n, *vn = ws + 6 * n, *hn = ws + 7 * n;
+  Fr *un = w.ws + 5 * n, *vn = w.ws + 6 * n, *hn = w.ws + 7 * n;
   ScalarPlan sp;
   sp.nxi = c->nxi(); sp.nxt = c->nxt(); sp.nsd = c->nsd();
   sp.xi_lo = c->xi_lo; sp.xit_lo = c->xit_lo; sp.sd_lo = c->sd_lo;
   sp.n_input = q->n_input; sp.m = q->m; sp.lead = c->rank == 0;
   void* p;
-  ZKB_TRY(scratch_get(ctx, 10, (c->g1_cnt + (sp.nxi + 3) + c->g2_cnt + 4) * sizeof(Fr), &p));
+  ZKB_TRY(scratch_get_in(ctx, L->scratch, 10, (c->g1_cnt + (sp.nxi + 3) + c->g2_cnt + 4) * sizeof(Fr), &p));
   Fr* SC = (Fr*)p;
   Fr* SA = SC + c->g1_cnt;
   Fr* SB = SA + sp.nxi + 3;
-  ZKB_LAUNCH(ctx, k_msm_scalars, cdiv(c->g1_cnt, 256), 256, 0, st, un, vn, hn, q->d_wmont, sp, fr_from_limbs(r), fr_from_limbs(s), SA,
+  ZKB_LAUNCH(ctx, k_msm_scalars, cdiv(c->g1_cnt, 256), 256, 0, hi, un, vn, hn, w.wmont, sp, fr_from_limbs(r), fr_from_limbs(s), SA,
              SB, SC);
   ProveOut o;
-  ZKB_TRY(prove_out(ctx, &o));
-  // fork: the G2 MSM runs on the second stream beside the G1 MSMs
-  ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-  ZKB_CUDA(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
+  ZKB_TRY(prove_out(ctx, L->scratch, &o));
   MsmJob jb = {SB, c->g2_cnt};
-  ZKB_TRY(msm_g2(ctx, c->g2, c->g2_cnt, c->c2, &jb, 1, o.b, 3, st2));
-  ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join, st2));
   MsmJob j1[2] = {{SA, sp.nxi + 3}, {SC, c->g1_cnt}};
-  ZKB_TRY(msm_g1(ctx, c->g1, c->g1_cnt, c->c1, j1, 2, o.ac, 0, st));
-  ZKB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
-  ZKB_LAUNCH(ctx, k_finish, 1, 96, 0, st, o.ac, o.b, o.proof);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, o.proof, 256, cudaMemcpyDeviceToHost, st));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  MsmPlan P2, P1;
+  ZKB_TRY(msm_prepare(ctx, L->scratch, 3, 2, c->g2, c->g2_cnt, c->c2, &jb, 1, o.b, &P2));
+  ZKB_TRY(msm_prepare(ctx, L->scratch, 0, 1, c->g1, c->g1_cnt, c->c1, j1, 2, o.ac, &P1));
+  ZKB_TRY(msm_sort(ctx, P2, hi));
+  ZKB_CUDA(ctx, cudaEventRecord(L->ev[2], hi));
+  ZKB_TRY(msm_sort(ctx, P1, hi));
+  ZKB_CUDA(ctx, cudaEventRecord(L->ev[0], hi));
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(lo, L->ev[2], 0));
+  ZKB_TRY(msm_accumulate(ctx, P2, lo));
+  ZKB_CUDA(ctx, cudaEventRecord(L->ev[3], lo));
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(lo, L->ev[0], 0));
+  ZKB_TRY(msm_accumulate(ctx, P1, lo));
+  ZKB_CUDA(ctx, cudaEventRecord(L->ev[1], lo));
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(hi, L->ev[3], 0));
+  ZKB_TRY(msm_tail(ctx, P2, hi));
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(hi, L->ev[1], 0));
+  ZKB_TRY(msm_tail(ctx, P1, hi));
+  ZKB_LAUNCH(ctx, k_finish, 1, 96, 0, hi, o.ac, o.b, o.proof);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(L->h_proof, o.proof, 256, cudaMemcpyDeviceToHost, hi));
   return ZKB_OK;
+}
+
+static int prove_collect(zkb_ctx* ctx, zkb_lane* L, void* out) {
+  ZKB_CUDA(ctx, cudaStreamSynchronize(L->hi));
+  memcpy(out, L->h_proof, 256);
+  return ZKB_OK;
+}
+
+static int prove_common(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights, int on_device,
+                        const uint64_t* r, const uint64_t* s, uint64_t* out) {
+  ZKB_TRY(check_pair(ctx, q, c));
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZKB_TRY(prove_enqueue(ctx, &ctx->lanes[0], q, c, weights, on_device, r, s));
+  return prove_collect(ctx, &ctx->lanes[0], out);
 }
 
 int zkb_prove(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights, const uint64_t r[4],
@@ -334,6 +372,33 @@ int zkb_prove_dev(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64
   if (!ctx || !q || !c || !d_weights || !r || !s || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_dev: NULL argument");
   if (c->world != 1) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove needs an unsharded CRS; use zkb_prove_partial");
   return prove_common(ctx, q, c, d_weights, 1, r, s, (uint64_t*)out);
+}
+
+// Throughput mode: `count` independent proofs over the same QAP / CRS, two in flight (one per lane),
+// so the latency-class stages of proof i+1 and the tails of proof i fill the gaps of the bucket
+// accumulations.  Same results as `count` zkb_prove calls.
+int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* const* weights, int on_device,
+                    const uint64_t* r, const uint64_t* s, size_t count, zkb_proof* out) {
+  if (!ctx || !q || !c || (count && (!weights || !r || !s || !out))) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_batch: NULL argument");
+  if (c->world != 1) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_batch needs an unsharded CRS");
+  ZKB_TRY(check_pair(ctx, q, c));
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (size_t i = 0; i < count; i++)
+    if (!weights[i]) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_batch: weights[%zu] is NULL", i);
+  int rc = ZKB_OK;
+  size_t done = 0;
+  for (size_t i = 0; i < count && rc == ZKB_OK; i++) {
+    zkb_lane* L = &ctx->lanes[i & 1];
+    if (i >= 2) {
+      rc = prove_collect(ctx, L, &out[i - 2]);
+      done = i - 1;
+      if (rc != ZKB_OK) break;
+    }
+    rc = prove_enqueue(ctx, L, q, c, weights[i], on_device, r + 4 * i, s + 4 * i);
+  }
+  for (size_t i = done; i < count && rc == ZKB_OK; i++) rc = prove_collect(ctx, &ctx->lanes[i & 1], &out[i]);
+  if (rc != ZKB_OK) cudaDeviceSynchronize();  // leave no work in flight behind an error
+  return rc;
 }
 
 int zkb_prove_partial(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights, int on_device,
@@ -364,7 +429,7 @@ int zkb_prove_combine(zkb_ctx* ctx, const uint64_t* partials, int world, zkb_pro
   ZKB_TRY(fq_to_mont(ctx, (Fq*)d1, 4 * (size_t)world, true, st));
   ZKB_TRY(fq_to_mont(ctx, (Fq*)d2, 4 * (size_t)world, true, st));
   ProveOut o;
-  ZKB_TRY(prove_out(ctx, &o));
+  ZKB_TRY(prove_out(ctx, ctx->scratch, &o));
   ZKB_TRY(sum_affine_g1(ctx, d1, world, o.ac, st));
   ZKB_TRY(sum_affine_g1(ctx, d1 + world, world, o.ac + 1, st));
   ZKB_TRY(sum_affine_g2(ctx, d2, world, o.b, st));
@@ -377,15 +442,17 @@ int zkb_prove_combine(zkb_ctx* ctx, const uint64_t* partials, int world, zkb_pro
 int zkb_qap_h(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* weights, uint64_t* u_sum, uint64_t* v_sum, uint64_t* h) {
   if (!ctx || !q || !weights) return set_err(ctx, ZKB_ERR_ARG, "zkb_qap_h: NULL argument");
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(q->d_wcanon, weights, q->m * 32, cudaMemcpyHostToDevice, ctx->stream));
-  ZKB_TRY(poly_stage(ctx, q, q->d_wcanon));
-  const size_t n = q->n;
   cudaStream_t st = ctx->stream;
+  Work w;
+  ZKB_TRY(work_get(ctx, &ctx->lanes[0], q, &w));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(w.wcanon, weights, q->m * 32, cudaMemcpyHostToDevice, st));
+  ZKB_TRY(poly_stage(ctx, q, w, w.wcanon, st));
+  const size_t n = q->n;
   uint64_t* dst[3] = {u_sum, v_sum, h};
   for (int k = 0; k < 3; k++) {
     if (!dst[k]) continue;
-    Fr* v = q->d_ws + (5 + k) * n;
-    Fr* tmp = q->d_ws + 3 * n;
+    Fr* v = w.ws + (5 + k) * n;
+    Fr* tmp = w.ws + 3 * n;
     ZKB_CUDA(ctx, cudaMemcpyAsync(tmp, v, n * 32, cudaMemcpyDeviceToDevice, st));
     ZKB_TRY(vec_to_mont(ctx, tmp, n, false, st));
     ZKB_CUDA(ctx, cudaMemcpyAsync(dst[k], tmp, n * 32, cudaMemcpyDeviceToHost, st));

@@ -28,7 +28,8 @@ class ZkbError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libzkb200.so")
+    """The in-tree library; ZKB200_LIB overrides it (developer A/B builds of one kernel)."""
+    return os.environ.get("ZKB200_LIB") or os.path.join(_HERE, "libzkb200.so")
 
 
 class _QapHost(C.Structure):
@@ -73,6 +74,8 @@ ABI = {
     "zkb_crs_free": (None, [_P, _P]),
     "zkb_prove": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(_ProofC)]),
     "zkb_prove_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(_ProofC)]),
+    "zkb_trace_dump": (C.c_int, [_P, C.c_char_p]),
+    "zkb_prove_batch": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "zkb_prove_partial": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P]),
     "zkb_prove_combine": (C.c_int, [_P, _P, C.c_int, C.POINTER(_ProofC)]),
     "zkb_qap_h": (C.c_int, [_P, _P, _P, _P, _P, _P]),
@@ -222,8 +225,12 @@ class Context:
         self._pinned = getattr(self, "_pinned", []) + [p]
         return arr
 
-    def profile(self, enable: bool):
-        self.check(self.lib.zkb_profile(self.h, 1 if enable else 0), "zkb_profile")
+    def profile(self, enable):
+        """False/0 off, True/1 tracked kernel classes, 2 = trace every launch (see trace_dump)."""
+        self.check(self.lib.zkb_profile(self.h, int(enable)), "zkb_profile")
+
+    def trace_dump(self, path: str):
+        self.check(self.lib.zkb_trace_dump(self.h, path.encode()), "zkb_trace_dump")
 
     def profile_read(self, kind: int):
         """(total ms, launches, work units) of one tracked kernel class: 1 NTT passes, 2 G1 / 3 G2 bucket accumulation."""
@@ -490,6 +497,24 @@ def prove_dev(ctx: Context, qap: QAP, crs: CRS, d_weights: int, r: int, s: int) 
     ctx.check(ctx.lib.zkb_prove_dev(ctx.h, qap.h, crs.h, C.c_void_p(d_weights), _ptr(rl), _ptr(sl), C.byref(out)),
               "zkb_prove_dev")
     return _proof(out)
+
+
+def prove_batch(ctx: Context, qap: QAP, crs: CRS, weights, rs, ss, on_device=False) -> list:
+    """`len(weights)` proofs with two in flight (zkb_prove_batch).  weights: list of witness vectors
+    (host: anything _weights_array accepts, ideally pinned (m, 4) uint64 arrays; device: pointers)."""
+    k = len(weights)
+    if on_device:
+        keep = None
+        ptrs = (C.c_void_p * k)(*[C.c_void_p(w) for w in weights])
+    else:
+        keep = [_weights_array(qap, w) for w in weights]
+        ptrs = (C.c_void_p * k)(*[a.ctypes.data for a in keep])
+    rl, sl = fr_limbs(list(rs)), fr_limbs(list(ss))
+    out = (_ProofC * k)()
+    ctx.check(ctx.lib.zkb_prove_batch(ctx.h, qap.h, crs.h, ptrs, 1 if on_device else 0, _ptr(rl), _ptr(sl), k, out),
+              "zkb_prove_batch")
+    del keep
+    return [_proof(out[i]) for i in range(k)]
 
 
 PARTIAL_LIMBS = 32
