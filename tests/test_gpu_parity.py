@@ -110,6 +110,41 @@ def test_ntt_roundtrip_and_linearity_full_size(ctx, log_n):
 
 
 # ------------------------------------------------------------------------------------------------
+# device field arithmetic (crate bn's Fr / Fq / Fq2 as reached through fr.rs:18-56)
+@pytest.mark.parametrize("field", [0, 1])
+def test_field_ops_match_bigint(ctx, field):
+    """mul (CIOS), sqr (36-product wide square + REDC), a*b - c*d (two wide products, one REDC), add,
+    sub, inverse on edge values and 4096 random elements, against Python integers."""
+    p = FR.p if field == 0 else bn.Q
+    rng = random.Random(300 + field)
+    edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, (1 << 253), (1 << 224) - 1, (1 << 32) - 1, 1 << 32]
+    a = edge * len(edge) + [rng.randrange(p) for _ in range(4096)]
+    b = [y for y in edge for _ in edge] + [rng.randrange(p) for _ in range(4096)]
+    c = list(reversed(a))
+    d = list(reversed(b))
+    assert zg.field_op(ctx, field, 0, a, b) == [x * y % p for x, y in zip(a, b)]
+    assert zg.field_op(ctx, field, 1, a) == [x * x % p for x in a]
+    assert zg.field_op(ctx, field, 2, a, b, c, d) == [(x * y - z * w) % p for x, y, z, w in zip(a, b, c, d)]
+    assert zg.field_op(ctx, field, 3, a, b) == [(x + y) % p for x, y in zip(a, b)]
+    assert zg.field_op(ctx, field, 4, a, b) == [(x - y) % p for x, y in zip(a, b)]
+    assert zg.field_op(ctx, field, 5, a[:200]) == [pow(x, p - 2, p) for x in a[:200]]
+
+
+def test_fq2_ops_match_bigint(ctx):
+    """Fq2 = Fq[u]/(u^2+1): Karatsuba on unreduced 512-bit products (3 products, 2 reductions)."""
+    p = bn.Q
+    rng = random.Random(310)
+    edge = [0, 1, p - 1, (p - 1) // 2, 1 << 253]
+    a = [(x, y) for x in edge for y in edge] + [(rng.randrange(p), rng.randrange(p)) for _ in range(2048)]
+    b = list(reversed(a[:25])) + [(rng.randrange(p), rng.randrange(p)) for _ in range(2048)]
+    mul = lambda x, y: ((x[0] * y[0] - x[1] * y[1]) % p, (x[0] * y[1] + x[1] * y[0]) % p)
+    assert zg.field_op(ctx, 2, 0, a, b) == [mul(x, y) for x, y in zip(a, b)]
+    assert zg.field_op(ctx, 2, 1, a) == [mul(x, x) for x in a]
+    inv = zg.field_op(ctx, 2, 2, a[25:125])
+    assert [mul(x, y) for x, y in zip(a[25:125], inv)] == [(1, 0)] * 100
+
+
+# ------------------------------------------------------------------------------------------------
 # fixed-base generation + MSM
 def test_bases_generate_matches_oracle(ctx):
     rng = random.Random(5)

@@ -450,6 +450,66 @@ int zkb_points_sum(zkb_ctx* ctx, int group, const uint64_t* h_points, size_t n, 
 
 }  // extern "C"
 
+// ---- element-wise field operations (validation hook for the device arithmetic) -------------------
+namespace zkb {
+template <class F>
+__global__ void k_field_op(int op, const F* a, const F* b, const F* c, const F* d, F* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  F x = to_mont(a[i]), y = to_mont(b[i]), z = to_mont(c[i]), w = to_mont(d[i]), r;
+  switch (op) {
+    case 0: r = x * y; break;
+    case 1: r = sqr(x); break;
+    case 2: r = mul_sub_mul(x, y, z, w); break;
+    case 3: r = x + y; break;
+    case 4: r = x - y; break;
+    default: r = inverse(x); break;
+  }
+  out[i] = from_mont(r);
+}
+__global__ void k_fq2_op(int op, const Fq2* a, const Fq2* b, Fq2* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fq2 x, y, r;
+  x.c0 = to_mont(a[i].c0); x.c1 = to_mont(a[i].c1);
+  y.c0 = to_mont(b[i].c0); y.c1 = to_mont(b[i].c1);
+  switch (op) {
+    case 0: r = x * y; break;
+    case 1: r = sqr(x); break;
+    default: r = inverse(x); break;
+  }
+  out[i].c0 = from_mont(r.c0);
+  out[i].c1 = from_mont(r.c1);
+}
+}  // namespace zkb
+
+extern "C" int zkb_field_op(zkb_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+                            const uint64_t* d, uint64_t* out, size_t n) {
+  if (!ctx || !a || !b || !c || !d || !out || field < 0 || field > 2) return set_err(ctx, ZKB_ERR_ARG, "zkb_field_op: bad argument");
+  if (!n) return ZKB_OK;
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t esz = field == 2 ? 64 : 32;
+  void* p;
+  ZKB_TRY(scratch_get(ctx, 8, 5 * n * esz, &p));
+  char* base = (char*)p;
+  const uint64_t* src[4] = {a, b, c, d};
+  for (int k = 0; k < 4; k++) ZKB_CUDA(ctx, cudaMemcpyAsync(base + k * n * esz, src[k], n * esz, cudaMemcpyHostToDevice, st));
+  char* o = base + 4 * n * esz;
+  if (field == 0) {
+    ZKB_LAUNCH(ctx, k_field_op<Fr>, cdiv(n, 128), 128, 0, st, op, (Fr*)base, (Fr*)(base + n * esz), (Fr*)(base + 2 * n * esz),
+               (Fr*)(base + 3 * n * esz), (Fr*)o, n);
+  } else if (field == 1) {
+    ZKB_LAUNCH(ctx, k_field_op<Fq>, cdiv(n, 128), 128, 0, st, op, (Fq*)base, (Fq*)(base + n * esz), (Fq*)(base + 2 * n * esz),
+               (Fq*)(base + 3 * n * esz), (Fq*)o, n);
+  } else {
+    ZKB_LAUNCH(ctx, k_fq2_op, cdiv(n, 128), 128, 0, st, op, (Fq2*)base, (Fq2*)(base + n * esz), (Fq2*)o, n);
+  }
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, o, n * esz, cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
 // ---- modmul peak micro-benchmark -------------------------------------------------------------------
 namespace zkb {
 template <class F>

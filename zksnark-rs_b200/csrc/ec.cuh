@@ -98,7 +98,7 @@ template <class F> ZKB_HD XYZZ<F> madd(const XYZZ<F>& a, const Affine<F>& p) {
   F ppp = pp_ * pp;
   F q = a.x * pp;
   r.x = sqr(rr) - ppp - dbl(q);
-  r.y = rr * (q - r.x) - a.y * ppp;
+  r.y = mul_sub_mul(rr, q - r.x, a.y, ppp);  // rr (q - x3) - y1 ppp with one reduction
   r.zz = a.zz * pp;
   r.zzz = a.zzz * ppp;
   return r;

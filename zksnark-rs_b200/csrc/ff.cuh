@@ -175,9 +175,7 @@ namespace dev_impl {
         "+r"(acc[6]), "+r"(acc[7]), "+r"(top)                                                      \
       : "r"(s0), "r"(s2), "r"(s4), "r"(s6), "r"(m))
 
-// same without a carry-out (the caller guarantees none: top limb has >= 2 spare bits).  The last
-// instruction still says .cc so that ptxas pairs it with its madc.lo into one IMAD.WIDE.U32.X
-// (a lone madc.hi is issued as a separate IMAD.HI).
+// same without a carry-out (the caller guarantees none: top limb has >= 2 spare bits)
 #define ZKB_CMAD(acc, s0, s2, s4, s6, m)                                                           \
   asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"                                                         \
       "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"                                                        \
@@ -186,12 +184,12 @@ namespace dev_impl {
       "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"                                                       \
       "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"                                                       \
       "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"                                                       \
-      "madc.hi.cc.u32 %7, %11, %12, %7;"                                                           \
+      "madc.hi.u32 %7, %11, %12, %7;"                                                              \
       : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),        \
         "+r"(acc[6]), "+r"(acc[7])                                                                 \
       : "r"(s0), "r"(s2), "r"(s4), "r"(s6), "r"(m))
 
-// X[0] += Y[1] (carry c); Y = (Y >> 64) + {s1,s3,s5,s7} * m + c   (tlo, thi = s7 * m, in scope at the call site)
+// X[0] += Y[1] (carry c); Y = (Y >> 64) + {s1,s3,s5,s7} * m + c
 #define ZKB_SHIFT_MAD(X0, Y, s1, s3, s5, s7, m)                                                    \
   asm("add.cc.u32 %0, %0, %2;\n\t"                                                                 \
       "madc.lo.cc.u32 %1, %9, %13, %3;\n\t"                                                        \
@@ -200,11 +198,11 @@ namespace dev_impl {
       "madc.hi.cc.u32 %4, %10, %13, %6;\n\t"                                                       \
       "madc.lo.cc.u32 %5, %11, %13, %7;\n\t"                                                       \
       "madc.hi.cc.u32 %6, %11, %13, %8;\n\t"                                                       \
-      "addc.cc.u32 %7, %14, 0;\n\t"                                                                \
-      "addc.u32 %8, %15, 0;"                                                                       \
+      "madc.lo.cc.u32 %7, %12, %13, 0;\n\t"                                                        \
+      "madc.hi.u32 %8, %12, %13, 0;"                                                               \
       : "+r"(X0), "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]),          \
         "+r"(Y[6]), "+r"(Y[7])                                                                     \
-      : "r"(s1), "r"(s3), "r"(s5), "r"(s7), "r"(m), "r"(tlo), "r"(thi))
+      : "r"(s1), "r"(s3), "r"(s5), "r"(s7), "r"(m))
 
 template <class P>
 __device__ __forceinline__ void mont_round(uint32_t (&X)[8], uint32_t (&Y)[8], const uint32_t* a,
@@ -212,15 +210,10 @@ __device__ __forceinline__ void mont_round(uint32_t (&X)[8], uint32_t (&Y)[8], c
   if (first) {
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-      // mul.wide + unpack: one IMAD.WIDE.U32 (a mul.lo / mul.hi pair is an IMAD plus an IMAD.HI, 1.5x the pipe time)
-      asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(X[j]), "=r"(X[j + 1]) : "r"(a[j]), "r"(bi));
-      asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(Y[j]), "=r"(Y[j + 1]) : "r"(a[j + 1]), "r"(bi));
+      asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=&r"(X[j]), "=&r"(X[j + 1]) : "r"(a[j]), "r"(bi));
+      asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=&r"(Y[j]), "=&r"(Y[j + 1]) : "r"(a[j + 1]), "r"(bi));
     }
   } else {
-    // top product a[7] * bi has no addend: one IMAD.WIDE, its halves join the carry chain as plain adds
-    // (madc.lo / madc.hi with a zero addend would be issued as IMAD + IMAD.HI, 1.5x the pipe time)
-    uint32_t tlo, thi;
-    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(tlo), "=r"(thi) : "r"(a[7]), "r"(bi));
     ZKB_SHIFT_MAD(X[0], Y, a[1], a[3], a[5], a[7], bi);
     ZKB_CMAD_TOP(X, Y[7], a[0], a[2], a[4], a[6], bi);
   }
@@ -277,6 +270,249 @@ __device__ __forceinline__ Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
   Fp<P> r;
 #pragma unroll
   for (int i = 0; i < 8; i++) r.v[i] = X[i];
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wide (512-bit) products and a stand-alone Montgomery reduction, for LAZY reduction: several
+// products are summed as 16-limb integers and reduced once (Fq2 Karatsuba: 3 products + 2
+// reductions instead of 3 + 3; a*b - c*d: 2 + 1 instead of 2 + 2), and squarings use the 36
+// distinct limb products instead of 64.  Same even/odd accumulator idea as mul(): E collects the
+// limb products a_i b_j with i+j even, O (worth 2^32 more) those with i+j odd, so every product is
+// one IMAD.WIDE.U32.X in a carry chain; each chain's carry out is absorbed by the next limb up.
+// Bookkeeping validated instruction by instruction in tools/emul_wide.py.
+
+// acc[0..2n-1] += {s...} * m (n = 1..3 pairs), carry out added to `top`
+#define ZKB_WCHAIN1(acc, top, s0, m)                                                               \
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"                                                         \
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"                                                        \
+      "addc.u32 %2, %2, 0;"                                                                        \
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(top)                                                      \
+      : "r"(s0), "r"(m))
+#define ZKB_WCHAIN2(acc, top, s0, s1, m)                                                           \
+  asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"                                                         \
+      "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"                                                        \
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"                                                        \
+      "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"                                                        \
+      "addc.u32 %4, %4, 0;"                                                                        \
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(top)                          \
+      : "r"(s0), "r"(s1), "r"(m))
+#define ZKB_WCHAIN3(acc, top, s0, s1, s2, m)                                                       \
+  asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"                                                        \
+      "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"                                                       \
+      "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"                                                       \
+      "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"                                                       \
+      "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"                                                       \
+      "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"                                                       \
+      "addc.u32 %6, %6, 0;"                                                                        \
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(top) \
+      : "r"(s0), "r"(s1), "r"(s2), "r"(m))
+
+// r[0..7] = x[0..7] + y[0..7] + cin, cout = carry out   (cin, cout are 0 / 1 registers)
+#define ZKB_ADD8(r, x, y, cin, cout)                                                               \
+  asm("{\n\t.reg .u32 t;\n\t"                                                                    \
+      "add.cc.u32 t, %25, 0xffffffff;\n\t"                                                        \
+      "addc.cc.u32 %0, %9, %17;\n\t"                                                              \
+      "addc.cc.u32 %1, %10, %18;\n\t"                                                             \
+      "addc.cc.u32 %2, %11, %19;\n\t"                                                             \
+      "addc.cc.u32 %3, %12, %20;\n\t"                                                             \
+      "addc.cc.u32 %4, %13, %21;\n\t"                                                             \
+      "addc.cc.u32 %5, %14, %22;\n\t"                                                             \
+      "addc.cc.u32 %6, %15, %23;\n\t"                                                             \
+      "addc.cc.u32 %7, %16, %24;\n\t"                                                             \
+      "addc.u32 %8, 0, 0;\n\t}"                                                                   \
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(cout) \
+      : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]),    \
+        "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]), "r"(cin))
+// r = x - y - bin, bout = borrow out
+#define ZKB_SUB8(r, x, y, bin, bout)                                                               \
+  asm("{\n\t.reg .u32 t;\n\t"                                                                    \
+      "sub.cc.u32 t, 0, %25;\n\t"                                                                 \
+      "subc.cc.u32 %0, %9, %17;\n\t"                                                              \
+      "subc.cc.u32 %1, %10, %18;\n\t"                                                             \
+      "subc.cc.u32 %2, %11, %19;\n\t"                                                             \
+      "subc.cc.u32 %3, %12, %20;\n\t"                                                             \
+      "subc.cc.u32 %4, %13, %21;\n\t"                                                             \
+      "subc.cc.u32 %5, %14, %22;\n\t"                                                             \
+      "subc.cc.u32 %6, %15, %23;\n\t"                                                             \
+      "subc.cc.u32 %7, %16, %24;\n\t"                                                             \
+      "subc.u32 %8, 0, 0;\n\t"                                                                    \
+      "and.b32 %8, %8, 1;\n\t}"                                                                   \
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(bout) \
+      : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]),    \
+        "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]), "r"(bin))
+
+// 16-limb add / subtract (callers guarantee no carry / borrow out of the top)
+__device__ __forceinline__ void wide_add(uint32_t (&r)[16], const uint32_t (&x)[16], const uint32_t (&y)[16]) {
+  uint32_t c, c2;
+  const uint32_t zero = 0;
+  ZKB_ADD8(r, x, y, zero, c);
+  ZKB_ADD8((r + 8), (x + 8), (y + 8), c, c2);
+}
+__device__ __forceinline__ void wide_sub(uint32_t (&r)[16], const uint32_t (&x)[16], const uint32_t (&y)[16]) {
+  uint32_t b, b2;
+  const uint32_t zero = 0;
+  ZKB_SUB8(r, x, y, zero, b);
+  ZKB_SUB8((r + 8), (x + 8), (y + 8), b, b2);
+}
+// 8-limb add without reduction (a + b < 2^256 guaranteed by the caller: both < p < 2^254)
+__device__ __forceinline__ void add_nored(uint32_t (&r)[8], const uint32_t (&x)[8], const uint32_t (&y)[8]) {
+  uint32_t c;
+  const uint32_t zero = 0;
+  ZKB_ADD8(r, x, y, zero, c);
+}
+
+// r = E + (O << 32)
+__device__ __forceinline__ void wide_merge(uint32_t (&r)[16], const uint32_t* E, const uint32_t* O) {
+  uint32_t c, c2;
+  const uint32_t zero = 0;
+  uint32_t lo[8] = {0, O[0], O[1], O[2], O[3], O[4], O[5], O[6]};
+  uint32_t hi[8] = {O[7], O[8], O[9], O[10], O[11], O[12], O[13], O[14]};
+  ZKB_ADD8(r, E, lo, zero, c);
+  ZKB_ADD8((r + 8), (E + 8), hi, c, c2);
+}
+
+// r = a * b (both < 2^256)
+__device__ __forceinline__ void mul_wide(uint32_t (&r)[16], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+  uint32_t E[17], O[16];
+#pragma unroll
+  for (int i = 0; i < 17; i++) E[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) O[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    ZKB_CMAD_TOP((E + i), E[i + 8], a[0], a[2], a[4], a[6], b[i]);
+    ZKB_CMAD_TOP((O + i), O[i + 8], a[1], a[3], a[5], a[7], b[i]);
+    ZKB_CMAD_TOP((O + i), O[i + 8], a[0], a[2], a[4], a[6], b[i + 1]);
+    ZKB_CMAD_TOP((E + i + 2), E[i + 10], a[1], a[3], a[5], a[7], b[i + 1]);  // E[16] stays 0 (product < 2^512)
+  }
+  wide_merge(r, E, O);
+}
+
+// r = a * a: 28 off-diagonal products, doubled, plus the 8 diagonal squares
+__device__ __forceinline__ void sqr_wide(uint32_t (&r)[16], const uint32_t (&a)[8]) {
+  uint32_t E[17], O[16];
+#pragma unroll
+  for (int i = 0; i < 17; i++) E[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) O[i] = 0;
+  // row i: a_i * a_j, j > i;  i + j odd -> O at 2i, 2i+2, ...;  i + j even -> E at 2i+2, 2i+4, ...
+  ZKB_CMAD_TOP((O + 0), O[8], a[1], a[3], a[5], a[7], a[0]);
+  ZKB_WCHAIN3((E + 2), E[8], a[2], a[4], a[6], a[0]);
+  ZKB_WCHAIN3((O + 2), O[8], a[2], a[4], a[6], a[1]);
+  ZKB_WCHAIN3((E + 4), E[10], a[3], a[5], a[7], a[1]);
+  ZKB_WCHAIN3((O + 4), O[10], a[3], a[5], a[7], a[2]);
+  ZKB_WCHAIN2((E + 6), E[10], a[4], a[6], a[2]);
+  ZKB_WCHAIN2((O + 6), O[10], a[4], a[6], a[3]);
+  ZKB_WCHAIN2((E + 8), E[12], a[5], a[7], a[3]);
+  ZKB_WCHAIN2((O + 8), O[12], a[5], a[7], a[4]);
+  ZKB_WCHAIN1((E + 10), E[12], a[6], a[4]);
+  ZKB_WCHAIN1((O + 10), O[12], a[6], a[5]);
+  ZKB_WCHAIN1((E + 12), E[14], a[7], a[5]);
+  ZKB_WCHAIN1((O + 12), O[14], a[7], a[6]);
+  uint32_t S[16];
+  wide_merge(S, E, O);
+  uint32_t D[16];
+  D[0] = S[0] << 1;
+#pragma unroll
+  for (int i = 1; i < 16; i++) D[i] = __funnelshift_l(S[i - 1], S[i], 1);
+  // r = D + sum_i a_i^2 2^(64 i): the diagonal products ride the carry chain as multiply-adds
+  asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+      "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+      "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+      "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+      "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+      "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+      "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+      "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+      "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+      "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+      "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+      "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+      "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+      "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+      "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+      "madc.hi.cc.u32 %15, %23, %23, %15;"
+      : "+r"(D[0]), "+r"(D[1]), "+r"(D[2]), "+r"(D[3]), "+r"(D[4]), "+r"(D[5]), "+r"(D[6]), "+r"(D[7]), "+r"(D[8]),
+        "+r"(D[9]), "+r"(D[10]), "+r"(D[11]), "+r"(D[12]), "+r"(D[13]), "+r"(D[14]), "+r"(D[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#pragma unroll
+  for (int i = 0; i < 16; i++) r[i] = D[i];
+}
+
+// r = T / 2^256 mod p for T < p * 2^256 (fully reduced result).  State t = E + (O << 32); a round
+// clears the low limb (m = E[0] * inv; O += m * p_odd; E += m * p_even), the shift renames O to E
+// and (E >> 64) to O, adds the stray limb E[1] at limb 0 and brings T[8 + i] in at limb 7.
+template <class P>
+__device__ __forceinline__ void redc(uint32_t (&r)[8], const uint32_t (&T)[16]) {
+  const uint32_t p0 = P::P0, p1 = P::P1, p2 = P::P2, p3 = P::P3, p4 = P::P4, p5 = P::P5, p6 = P::P6, p7 = P::P7;
+  uint32_t E[8], O[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { E[k] = T[k]; O[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t mi = E[0] * P::INV;
+    ZKB_CMAD(O, p1, p3, p5, p7, mi);
+    ZKB_CMAD_TOP(E, O[7], p0, p2, p4, p6, mi);
+    if (i == 7) break;
+    uint32_t nO[8];
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %10, 0;\n\t"
+        "addc.cc.u32 %2, %11, 0;\n\t"
+        "addc.cc.u32 %3, %12, 0;\n\t"
+        "addc.cc.u32 %4, %13, 0;\n\t"
+        "addc.cc.u32 %5, %14, 0;\n\t"
+        "addc.cc.u32 %6, %15, 0;\n\t"
+        "addc.cc.u32 %7, %16, 0;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(O[0]), "=&r"(nO[0]), "=&r"(nO[1]), "=&r"(nO[2]), "=&r"(nO[3]), "=&r"(nO[4]), "=&r"(nO[5]), "=&r"(nO[6]), "=&r"(nO[7])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(T[8 + i]));
+#pragma unroll
+    for (int k = 0; k < 8; k++) { E[k] = O[k]; O[k] = nO[k]; }
+  }
+  // (E >> 32) + O + (T[15] << 224)
+  asm("add.cc.u32 %0, %8, %15;\n\t"
+      "addc.cc.u32 %1, %9, %16;\n\t"
+      "addc.cc.u32 %2, %10, %17;\n\t"
+      "addc.cc.u32 %3, %11, %18;\n\t"
+      "addc.cc.u32 %4, %12, %19;\n\t"
+      "addc.cc.u32 %5, %13, %20;\n\t"
+      "addc.cc.u32 %6, %14, %21;\n\t"
+      "addc.u32 %7, %22, %23;"
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
+      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+        "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(T[15]));
+  final_sub<P>(r);
+}
+
+template <class P>
+__device__ __forceinline__ void psq(uint32_t (&q2)[16]) {
+  q2[0] = P::PSQ0; q2[1] = P::PSQ1; q2[2] = P::PSQ2; q2[3] = P::PSQ3; q2[4] = P::PSQ4; q2[5] = P::PSQ5;
+  q2[6] = P::PSQ6; q2[7] = P::PSQ7; q2[8] = P::PSQ8; q2[9] = P::PSQ9; q2[10] = P::PSQ10; q2[11] = P::PSQ11;
+  q2[12] = P::PSQ12; q2[13] = P::PSQ13; q2[14] = P::PSQ14; q2[15] = P::PSQ15;
+}
+
+// a^2 (Montgomery)
+template <class P>
+__device__ __forceinline__ Fp<P> sqr(const Fp<P>& a) {
+  uint32_t T[16];
+  sqr_wide(T, a.v);
+  Fp<P> r;
+  redc<P>(r.v, T);
+  return r;
+}
+
+// a * b - c * d (Montgomery), one reduction
+template <class P>
+__device__ __forceinline__ Fp<P> mul_sub_mul(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+  uint32_t T[16], U[16], Q2[16];
+  mul_wide(T, a.v, b.v);
+  mul_wide(U, c.v, d.v);
+  psq<P>(Q2);
+  wide_add(T, T, Q2);  // < 2 p^2 < p * 2^256
+  wide_sub(T, T, U);
+  Fp<P> r;
+  redc<P>(r.v, T);
   return r;
 }
 
@@ -339,8 +575,22 @@ __device__ __forceinline__ Fp<P> sub(const Fp<P>& a, const Fp<P>& b) {
 // ------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------
-template <class P> ZKB_HD Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) {
+// A translation unit may define ZKB_FP_OOL (ZKB_FQ2_OOL for the Fq2 layer) before including this
+// header: products are then calls to one shared out-of-line copy per operation (operands by value,
+// i.e. in registers) instead of being inlined at every use.  A fully inlined mixed addition is
+// 35 KB (G1) / 100 KB (G2) of code; whether the instruction cache or the call overhead costs more is
+// measured per kernel (profiles/).  ZKB_NO_LAZY selects the plain CIOS product everywhere.
 #if defined(__CUDA_ARCH__)
+template <class P> static __device__ __noinline__ Fp<P> fp_mul_ool(Fp<P> a, Fp<P> b) { return dev_impl::mul(a, b); }
+template <class P> static __device__ __noinline__ Fp<P> fp_sqr_ool(Fp<P> a) { return dev_impl::sqr(a); }
+template <class P> static __device__ __noinline__ Fp<P> fp_msm_ool(Fp<P> a, Fp<P> b, Fp<P> c, Fp<P> d) {
+  return dev_impl::mul_sub_mul(a, b, c, d);
+}
+#endif
+template <class P> ZKB_HD Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__) && defined(ZKB_FP_OOL)
+  return fp_mul_ool<P>(a, b);
+#elif defined(__CUDA_ARCH__)
   return dev_impl::mul(a, b);
 #else
   return host_impl::mul(a, b);
@@ -361,7 +611,25 @@ template <class P> ZKB_HD Fp<P> operator-(const Fp<P>& a, const Fp<P>& b) {
 #endif
 }
 template <class P> ZKB_HD Fp<P> neg(const Fp<P>& a) { return Fp<P>::zero() - a; }
-template <class P> ZKB_HD Fp<P> sqr(const Fp<P>& a) { return a * a; }
+template <class P> ZKB_HD Fp<P> sqr(const Fp<P>& a) {
+#if defined(__CUDA_ARCH__) && !defined(ZKB_NO_LAZY) && defined(ZKB_FP_OOL)
+  return fp_sqr_ool<P>(a);
+#elif defined(__CUDA_ARCH__) && !defined(ZKB_NO_LAZY)
+  return dev_impl::sqr(a);
+#else
+  return a * a;
+#endif
+}
+// a * b - c * d
+template <class P> ZKB_HD Fp<P> mul_sub_mul(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+#if defined(__CUDA_ARCH__) && !defined(ZKB_NO_LAZY) && defined(ZKB_FP_OOL)
+  return fp_msm_ool<P>(a, b, c, d);
+#elif defined(__CUDA_ARCH__) && !defined(ZKB_NO_LAZY)
+  return dev_impl::mul_sub_mul(a, b, c, d);
+#else
+  return a * b - c * d;
+#endif
+}
 template <class P> ZKB_HD Fp<P> dbl(const Fp<P>& a) { return a + a; }
 
 // canonical residue (4x u64 LE at the C ABI == 8x u32 LE) <-> Montgomery form
@@ -410,30 +678,79 @@ struct alignas(16) Fq2 {
 };
 ZKB_HD Fq2 operator+(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
 ZKB_HD Fq2 operator-(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
-// Base-field product used inside Fq2: inline by default; a translation unit may define
-// ZKB_FQ2_OOL before including this header to call one shared out-of-line copy instead (an inlined
-// G2 mixed addition is ~90 KB of code and thrashes the instruction cache).
-#if defined(__CUDA_ARCH__) && defined(ZKB_FQ2_OOL)
-__device__ __noinline__ Fq fq_mul_ool(const Fq& a, const Fq& b) { return dev_impl::mul(a, b); }
-#define ZKB_FQ2_BASEMUL(a, b) fq_mul_ool((a), (b))
+#if defined(__CUDA_ARCH__)
+namespace dev_impl {
+// Karatsuba on unreduced 512-bit products: 3 wide products, 2 Montgomery reductions
+__device__ __forceinline__ Fq2 fq2_mul_lazy(const Fq2& a, const Fq2& b) {
+  uint32_t v0[16], v1[16], v2[16], sa[8], sb[8], q2[16];
+  mul_wide(v0, a.c0.v, b.c0.v);
+  mul_wide(v1, a.c1.v, b.c1.v);
+  add_nored(sa, a.c0.v, a.c1.v);
+  add_nored(sb, b.c0.v, b.c1.v);
+  mul_wide(v2, sa, sb);
+  wide_sub(v2, v2, v0);
+  wide_sub(v2, v2, v1);  // a0 b1 + a1 b0 < 2 q^2
+  psq<FqParams>(q2);
+  wide_add(v0, v0, q2);
+  wide_sub(v0, v0, v1);  // a0 b0 - a1 b1 + q^2 in (0, 2 q^2)
+  Fq2 r;
+  redc<FqParams>(r.c0.v, v0);
+  redc<FqParams>(r.c1.v, v2);
+  return r;
+}
+__device__ __forceinline__ Fq2 fq2_mul_plain(const Fq2& a, const Fq2& b) {
+  Fq v0 = mul(a.c0, b.c0), v1 = mul(a.c1, b.c1);
+  Fq s = mul(add(a.c0, a.c1), add(b.c0, b.c1));
+  Fq2 r;
+  r.c0 = sub(v0, v1);
+  r.c1 = sub(sub(s, v0), v1);
+  return r;
+}
+__device__ __forceinline__ Fq2 fq2_sqr(const Fq2& a) {
+  Fq t = mul(a.c0, a.c1);
+  Fq2 r;
+  r.c0 = mul(add(a.c0, a.c1), sub(a.c0, a.c1));
+  r.c1 = add(t, t);
+  return r;
+}
+}  // namespace dev_impl
+#if defined(ZKB_NO_LAZY)
+#define ZKB_FQ2_MUL_IMPL dev_impl::fq2_mul_plain
 #else
-#define ZKB_FQ2_BASEMUL(a, b) ((a) * (b))
+#define ZKB_FQ2_MUL_IMPL dev_impl::fq2_mul_lazy
+#endif
+static __device__ __noinline__ Fq2 fq2_mul_ool(Fq2 a, Fq2 b) { return ZKB_FQ2_MUL_IMPL(a, b); }
+static __device__ __noinline__ Fq2 fq2_sqr_ool(Fq2 a) { return dev_impl::fq2_sqr(a); }
 #endif
 ZKB_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
+#if defined(__CUDA_ARCH__) && defined(ZKB_FQ2_OOL)
+  return fq2_mul_ool(a, b);
+#elif defined(__CUDA_ARCH__)
+  return ZKB_FQ2_MUL_IMPL(a, b);
+#else
   // Karatsuba: 3 base multiplications
-  Fq v0 = ZKB_FQ2_BASEMUL(a.c0, b.c0), v1 = ZKB_FQ2_BASEMUL(a.c1, b.c1);
-  Fq s = ZKB_FQ2_BASEMUL(a.c0 + a.c1, b.c0 + b.c1);
+  Fq v0 = a.c0 * b.c0, v1 = a.c1 * b.c1;
+  Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
   Fq2 r;
   r.c0 = v0 - v1;
   r.c1 = s - v0 - v1;
   return r;
+#endif
 }
+// a * b - c * d over Fq2
+ZKB_HD Fq2 mul_sub_mul(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) { return a * b - c * d; }
 ZKB_HD Fq2 sqr(const Fq2& a) {
-  Fq t = ZKB_FQ2_BASEMUL(a.c0, a.c1);
+#if defined(__CUDA_ARCH__) && defined(ZKB_FQ2_OOL)
+  return fq2_sqr_ool(a);
+#elif defined(__CUDA_ARCH__)
+  return dev_impl::fq2_sqr(a);
+#else
+  Fq t = a.c0 * a.c1;
   Fq2 r;
-  r.c0 = ZKB_FQ2_BASEMUL(a.c0 + a.c1, a.c0 - a.c1);
+  r.c0 = (a.c0 + a.c1) * (a.c0 - a.c1);
   r.c1 = t + t;
   return r;
+#endif
 }
 ZKB_HD Fq2 neg(const Fq2& a) { Fq2 r; r.c0 = neg(a.c0); r.c1 = neg(a.c1); return r; }
 ZKB_HD Fq2 dbl(const Fq2& a) { return a + a; }

@@ -1,4 +1,8 @@
 // G2 bucket accumulation kernel (k_accumulate_chunks<Fq2>), see msm_impl.cuh.
+// Fq2 products as calls to one shared out-of-line copy (operands in registers): the fully inlined G2
+// mixed addition is ~100 KB of code and ran instruction-fetch bound (ncu: no_instruction 1.2 per issue,
+// fmaheavy pipe 64 %); out of line it reaches 0.89 of the modmul peak (profiles/r01_*).
+#define ZKB_FQ2_OOL 1
 #include "msm_impl.cuh"
 namespace zkb {
 template <> int MsmLaunch<Fq2>::accumulate(zkb_ctx* ctx, const G2Affine* tab, const uint32_t* offs, const uint32_t* sorted,

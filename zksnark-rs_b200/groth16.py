@@ -74,6 +74,7 @@ ABI = {
     "zkb_crs_free": (None, [_P, _P]),
     "zkb_prove": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(_ProofC)]),
     "zkb_prove_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(_ProofC)]),
+    "zkb_field_op": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t]),
     "zkb_trace_dump": (C.c_int, [_P, C.c_char_p]),
     "zkb_prove_batch": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "zkb_prove_partial": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P]),
@@ -541,6 +542,23 @@ def prove_combine(ctx: Context, partials: np.ndarray) -> Proof:
     out = _ProofC()
     ctx.check(ctx.lib.zkb_prove_combine(ctx.h, _ptr(p), p.shape[0], C.byref(out)), "zkb_prove_combine")
     return _proof(out)
+
+
+def field_op(ctx: Context, field: int, op: int, a, b=None, c=None, d=None) -> list:
+    """Element-wise device field arithmetic (zkb_field_op).  Fr/Fq: lists of ints; Fq2: lists of (c0, c1)."""
+    n = len(a)
+    b = a if b is None else b
+    c = a if c is None else c
+    d = a if d is None else d
+    if field == 2:
+        arrs = [fr_limbs([x for pair in v for x in pair]) for v in (a, b, c, d)]
+    else:
+        arrs = [fr_limbs(v) for v in (a, b, c, d)]
+    out = np.zeros_like(arrs[0])
+    ctx.check(ctx.lib.zkb_field_op(ctx.h, field, op, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), _ptr(arrs[3]), _ptr(out), n),
+              "zkb_field_op")
+    vals = limbs_to_ints(out)
+    return [(vals[2 * i], vals[2 * i + 1]) for i in range(n)] if field == 2 else vals
 
 
 def qap_h(ctx: Context, qap: QAP, weights):
