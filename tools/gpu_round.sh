@@ -1,13 +1,19 @@
 #!/bin/bash
-# One GPU visit: parity tests, the contract bench, an ncu launch list of one bench run.
+# One full GPU visit: parity tests, the contract bench (both arms), an ncu launch list of one bench
+# run and `ncu --set full` captures of the three kernels the roofline talks about.
 # Usage (under gpurun): bash tools/gpu_round.sh [tag]
-tag=${1:-r1}
+tag=${1:-r01}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/${tag}_gpu.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log
-tail -5 gpurun_out/${tag}_pytest.log
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench exit $?"
-cat gpurun_out/${tag}_bench.json
-timeout 300 python tools/quick_bench.py 16 20 > gpurun_out/${tag}_quick.log 2>&1
-cat gpurun_out/${tag}_quick.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu exit $?"
+tail -3 gpurun_out/${tag}_pytest.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench exit $?"
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2>> gpurun_out/${tag}_bench.err
+timeout 600 python tools/quick_bench.py 16 20 > gpurun_out/${tag}_quick.log 2>&1
+timeout 600 python tools/msm_bench.py --g1 18 20 22 24 > gpurun_out/${tag}_msm_sweep.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu list exit $?"
+for k in "acc_g1:k_accumulate_chunks.*FqParams" "acc_g2:k_accumulate_chunks.*Fq2" "ntt:k_ntt_pass"; do
+  name=${k%%:*}; rx=${k#*:}
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s 8 -c 1 -f -o gpurun_out/${tag}_${name} python bench.py --steps 2 --warmup 1 > gpurun_out/${tag}_full_${name}.log 2>&1; echo "ncu full $name exit $?"
+done
+ls -la gpurun_out/ | tail -20

@@ -145,11 +145,31 @@ static inline int msm_windows(int c) { return 254 / c + 1; }
 //   msm_sort (digits, scan, scatter) -> msm_accumulate (zero buckets + THE hot kernel) -> msm_tail
 //   (head folding + bucket hierarchy -> d_out).  msm_prepare validates and carves the scratch
 //   (3 consecutive slots of `slots`, starting at slot_base).
+// Chunk t of the sorted record array starts at start(t): the first T1 chunks have S1 records, the
+// rest S2 < S1.  Blocks are dispatched in index order, so the short chunks run last and the grid
+// drains in a fraction of a long chunk's duration (with one chunk size the last wave idles about
+// half a chunk time: ~9 % of the kernel at 5-6 waves), while most records still sit in long chunks,
+// which keeps the number of head pieces (one per chunk boundary inside a bucket) small.
+struct ChunkPlan {
+  uint32_t S1 = 32, S2 = 32, T1 = 0;
+  __host__ __device__ uint32_t R1() const { return T1 * S1; }
+  __host__ __device__ uint32_t start(uint32_t t) const { return t < T1 ? t * S1 : R1() + (t - T1) * S2; }
+  __host__ __device__ uint32_t len(uint32_t t) const { return t < T1 ? S1 : S2; }
+  // smallest t with start(t) >= x
+  __host__ __device__ uint32_t first_at_or_after(uint32_t x) const {
+    return x <= R1() ? (x + S1 - 1) / S1 : T1 + (x - R1() + S2 - 1) / S2;
+  }
+  size_t count(size_t max_recs) const {
+    size_t r1 = (size_t)T1 * S1;
+    return max_recs <= r1 ? (max_recs + S1 - 1) / S1 : T1 + (max_recs - r1 + S2 - 1) / S2;
+  }
+};
 struct MsmPlan {
   int group = 1;  // 1: G1 (Fq), 2: G2 (Fq2)
   const void* tab = nullptr;
   size_t stride = 0;
-  int c = 0, njobs = 0, S = 32;
+  int c = 0, njobs = 0;
+  ChunkPlan ch;  // how the sorted records are cut into per-thread chunks
   MsmJob jobs[4];
   bool empty = true;
   size_t nbk = 0, max_recs = 0, nacc = 0, lvl_elems = 0;

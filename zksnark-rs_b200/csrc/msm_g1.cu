@@ -130,16 +130,13 @@ int msm_sort_records(zkb_ctx* ctx, const MsmJob* jobs, int njobs, size_t stride,
 int msm_pick_c(size_t n) { return pick_c(n); }
 
 template <> int MsmLaunch<Fq>::accumulate(zkb_ctx* ctx, const G1Affine* tab, const uint32_t* offs, const uint32_t* sorted,
-                                          uint32_t nbk, size_t nacc, int S, G1XYZZ* buckets, G1XYZZ* heads, cudaStream_t st, int pk) {
-  if (S == 128) return launch_accumulate_s<Fq, 128>(ctx, tab, offs, sorted, nbk, nacc, buckets, heads, st, pk);
-  if (S == 64) return launch_accumulate_s<Fq, 64>(ctx, tab, offs, sorted, nbk, nacc, buckets, heads, st, pk);
-  return launch_accumulate_s<Fq, 32>(ctx, tab, offs, sorted, nbk, nacc, buckets, heads, st, pk);
+                                          uint32_t nbk, size_t nacc, ChunkPlan ch, G1XYZZ* buckets, G1XYZZ* heads, cudaStream_t st,
+                                          int pk) {
+  return launch_accumulate<Fq>(ctx, tab, offs, sorted, nbk, nacc, ch, buckets, heads, st, pk);
 }
-template <> int MsmLaunch<Fq>::fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, int S, G1XYZZ* buckets,
+template <> int MsmLaunch<Fq>::fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, ChunkPlan ch, G1XYZZ* buckets,
                                          const G1XYZZ* heads, cudaStream_t st) {
-  if (S == 128) return launch_fix_heads_s<Fq, 128>(ctx, offs, nbk, buckets, heads, st);
-  if (S == 64) return launch_fix_heads_s<Fq, 64>(ctx, offs, nbk, buckets, heads, st);
-  return launch_fix_heads_s<Fq, 32>(ctx, offs, nbk, buckets, heads, st);
+  return launch_fix_heads<Fq>(ctx, offs, nbk, ch, buckets, heads, st);
 }
 template <> int MsmLaunch<Fq>::reduce(zkb_ctx* ctx, const G1XYZZ* buckets, uint32_t nb, int njobs, G1XYZZ* lvlS, G1XYZZ* lvlA,
                                       G1XYZZ* d_out, cudaStream_t st) {

@@ -6,8 +6,8 @@
 #include "msm_impl.cuh"
 namespace zkb {
 template <> int MsmLaunch<Fq2>::accumulate(zkb_ctx* ctx, const G2Affine* tab, const uint32_t* offs, const uint32_t* sorted,
-                                           uint32_t nbk, size_t nacc, int S, G2XYZZ* buckets, G2XYZZ* heads, cudaStream_t st, int pk) {
-  if (S == 64) return launch_accumulate_s<Fq2, 64>(ctx, tab, offs, sorted, nbk, nacc, buckets, heads, st, pk);
-  return launch_accumulate_s<Fq2, 32>(ctx, tab, offs, sorted, nbk, nacc, buckets, heads, st, pk);
+                                           uint32_t nbk, size_t nacc, ChunkPlan ch, G2XYZZ* buckets, G2XYZZ* heads, cudaStream_t st,
+                                           int pk) {
+  return launch_accumulate<Fq2>(ctx, tab, offs, sorted, nbk, nacc, ch, buckets, heads, st, pk);
 }
 }  // namespace zkb

@@ -1,10 +1,9 @@
 // G2 head folding and bucket hierarchy kernels (k_fix_heads<Fq2>, k_bucket_level<Fq2>), see msm_impl.cuh.
 #include "msm_impl.cuh"
 namespace zkb {
-template <> int MsmLaunch<Fq2>::fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, int S, G2XYZZ* buckets,
+template <> int MsmLaunch<Fq2>::fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, ChunkPlan ch, G2XYZZ* buckets,
                                           const G2XYZZ* heads, cudaStream_t st) {
-  if (S == 64) return launch_fix_heads_s<Fq2, 64>(ctx, offs, nbk, buckets, heads, st);
-  return launch_fix_heads_s<Fq2, 32>(ctx, offs, nbk, buckets, heads, st);
+  return launch_fix_heads<Fq2>(ctx, offs, nbk, ch, buckets, heads, st);
 }
 template <> int MsmLaunch<Fq2>::reduce(zkb_ctx* ctx, const G2XYZZ* buckets, uint32_t nb, int njobs, G2XYZZ* lvlS, G2XYZZ* lvlA,
                                        G2XYZZ* d_out, cudaStream_t st) {

@@ -47,22 +47,24 @@ __host__ __device__ inline DigitPlan make_plan(int c) {
 }
 
 static const int MSM_MAX_JOBS = 4;
-// records per accumulation chunk (one thread each).  Larger chunks mean fewer head pieces for
-// k_fix_heads but fewer threads; G1 has ~4x the records of G2 on the prove path.
-template <class F> struct AccChunk;
-template <> struct AccChunk<Fq> { static int get(size_t max_recs); };
-template <> struct AccChunk<Fq2> { static int get(size_t max_recs); };
-static inline int acc_chunk_env(int dflt) {
+// chunk plan for max_recs records: long chunks for the first ~7/8, short ones for the rest
+template <class F>
+static inline ChunkPlan chunk_plan(size_t max_recs) {
+  const bool g1 = sizeof(F) == sizeof(Fq);
+  uint32_t S1 = g1 ? (max_recs >= ((size_t)1 << 25) ? 128 : (max_recs >= ((size_t)1 << 23) ? 64 : 32)) : (max_recs >= ((size_t)1 << 23) ? 128 : 32);
   if (const char* e = getenv("ZKB_ACC_S")) {
     int v = atoi(e);
-    if (v == 32 || v == 64 || v == 128) return v;
+    if (v == 16 || v == 32 || v == 64 || v == 128 || v == 256) S1 = v;
   }
-  return dflt;
+  ChunkPlan ch;
+  ch.S1 = S1;
+  ch.S2 = S1 >= 32 ? S1 / 4 : S1;
+  double frac = 0.875;
+  if (const char* e = getenv("ZKB_ACC_FRAC")) frac = atof(e);
+  ch.T1 = (uint32_t)((double)max_recs * frac / S1);
+  if (max_recs < ((size_t)1 << 20) || ch.S2 == ch.S1) ch.T1 = (uint32_t)((max_recs + S1 - 1) / S1);  // one chunk size
+  return ch;
 }
-inline int AccChunk<Fq>::get(size_t max_recs) {
-  return acc_chunk_env(max_recs >= ((size_t)1 << 25) ? 128 : (max_recs >= ((size_t)1 << 23) ? 64 : 32));
-}
-inline int AccChunk<Fq2>::get(size_t max_recs) { int v = acc_chunk_env(32); return v > 64 ? 64 : v; }
 
 // window size for a table over n points (single bucket set): N*W mixed adds (10 modmul) + the
 // bucket hierarchy (2 full adds of 14 modmul per bucket, weighted x2 for its lower parallelism)
@@ -85,8 +87,8 @@ static inline int pick_c(size_t n) {
 template <class F>
 struct MsmLaunch {
   static int accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
-                        size_t nacc, int S, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind);
-  static int fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, int S, XYZZ<F>* buckets, const XYZZ<F>* heads,
+                        size_t nacc, ChunkPlan ch, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind);
+  static int fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, ChunkPlan ch, XYZZ<F>* buckets, const XYZZ<F>* heads,
                        cudaStream_t st);
   // full hierarchy: buckets[njobs][nb] -> d_out[njobs]; lvlS / lvlA hold the intermediate levels
   static int reduce(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int njobs, XYZZ<F>* lvlS, XYZZ<F>* lvlA, XYZZ<F>* d_out,
@@ -126,8 +128,8 @@ static int msm_prepare_t(zkb_ctx* ctx, DevBuf* slots, int slot, const Affine<F>*
   P->nbk = (size_t)njobs * pl.nb;
   const size_t nscan_blocks = (P->nbk + 1023) / 1024;
   P->max_recs = (size_t)pl.W * total_n;
-  P->S = AccChunk<F>::get(P->max_recs);
-  P->nacc = (P->max_recs + P->S - 1) / P->S;
+  P->ch = chunk_plan<F>(P->max_recs);
+  P->nacc = P->ch.count(P->max_recs);
   P->lvl_elems = msm_level_elems(pl.nb, njobs);
   void* p;
   // u32 scratch: hist[nbk] | offs[nbk+1] | cursor[nbk] | sums[nscan_blocks+1]
@@ -154,14 +156,14 @@ static int msm_accumulate_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
   const int prof_kind = P.group == 1 ? PK_ACC_G1 : PK_ACC_G2;
   ZKB_CUDA(ctx, cudaMemsetAsync(P.buckets, 0, P.nbk * sizeof(XYZZ<F>), st));  // all-zero XYZZ = identity
   if (ctx->profile) ctx->prof_units[prof_kind] += P.max_recs;
-  return MsmLaunch<F>::accumulate(ctx, (const Affine<F>*)P.tab, P.offs, P.sorted, (uint32_t)P.nbk, P.nacc, P.S, (XYZZ<F>*)P.buckets,
+  return MsmLaunch<F>::accumulate(ctx, (const Affine<F>*)P.tab, P.offs, P.sorted, (uint32_t)P.nbk, P.nacc, P.ch, (XYZZ<F>*)P.buckets,
                                   (XYZZ<F>*)P.heads, st, prof_kind);
 }
 
 template <class F>
 static int msm_tail_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
   if (P.empty) return MsmLaunch<F>::set_inf(ctx, (XYZZ<F>*)P.d_out, P.njobs, st);
-  ZKB_TRY(MsmLaunch<F>::fix_heads(ctx, P.offs, (uint32_t)P.nbk, P.S, (XYZZ<F>*)P.buckets, (const XYZZ<F>*)P.heads, st));
+  ZKB_TRY(MsmLaunch<F>::fix_heads(ctx, P.offs, (uint32_t)P.nbk, P.ch, (XYZZ<F>*)P.buckets, (const XYZZ<F>*)P.heads, st));
   return MsmLaunch<F>::reduce(ctx, (const XYZZ<F>*)P.buckets, make_plan(P.c).nb, P.njobs, (XYZZ<F>*)P.lvlS, (XYZZ<F>*)P.lvlA,
                               (XYZZ<F>*)P.d_out, st);
 }
@@ -179,17 +181,17 @@ static int msm_tail_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
 #ifndef ZKB_ACC_MIN_BLOCKS
 #define ZKB_ACC_MIN_BLOCKS 1
 #endif
-template <class F, int S>
+template <class F>
 __global__ void __launch_bounds__(128, ZKB_ACC_MIN_BLOCKS) k_accumulate_chunks(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
                                                            const uint32_t* __restrict__ sorted, uint32_t nbk, size_t nchunks,
-                                                           XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads) {
+                                                           ChunkPlan ch, XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nchunks) return;
   const uint32_t total = offs[nbk];
-  const size_t start64 = t * (size_t)S;
-  if (start64 >= total) return;
-  const uint32_t start = (uint32_t)start64;
-  const uint32_t end = (total - start > (uint32_t)S) ? start + S : total;
+  const uint32_t start = ch.start((uint32_t)t);
+  if (start >= total) return;
+  const uint32_t S = ch.len((uint32_t)t);
+  const uint32_t end = (total - start > S) ? start + S : total;
   // g: offs[g] <= start < offs[g+1]
   uint32_t lo = 0, hi = nbk;
   while (lo < hi) {
@@ -235,22 +237,22 @@ __device__ __forceinline__ XYZZ<F> shfl_xyzz(const XYZZ<F>& p, int src) {
 }
 
 // Fold the head pieces into their buckets.  One thread per bucket g: the chunks whose first record
-// lies strictly inside bucket g are t with offs[g] < t*S < offs[g+1] (computed from the offsets, so
-// no search).  Short runs (the common case) are summed by the owning thread; long runs (skewed
+// lies strictly inside bucket g are t with offs[g] < start(t) < offs[g+1] (computed from the offsets
+// and the chunk plan, so no search).  Short runs (the common case) are summed by the owning thread; long runs (skewed
 // scalars: one huge bucket) are summed by the whole warp, lanes striding over the run followed by
 // a shuffle tree.
-template <class F, int S>
-__global__ void __launch_bounds__(128) k_fix_heads(const uint32_t* __restrict__ offs, uint32_t nbk,
+template <class F>
+__global__ void __launch_bounds__(128) k_fix_heads(const uint32_t* __restrict__ offs, uint32_t nbk, ChunkPlan ch,
                                                    XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ heads) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   uint32_t t0 = 1, t1 = 0;
   if (g < nbk) {
     const uint32_t lo = offs[g], hi = offs[g + 1];
-    if (hi > lo) { t0 = lo / S + 1; t1 = (hi - 1) / S; }
+    if (hi > lo) { t0 = ch.first_at_or_after(lo + 1); t1 = ch.first_at_or_after(hi) - 1; }
   }
   const uint32_t cnt = t1 >= t0 ? t1 - t0 + 1 : 0;
-  const bool big = cnt > 12;
+  const bool big = cnt > 64;
   XYZZ<F> acc = XYZZ<F>::inf();
   if (!big)
     for (uint32_t t = t0; t <= t1; t++) acc = add_ool(acc, heads[t]);
@@ -358,17 +360,16 @@ __global__ void __launch_bounds__(128) k_expand_table(Affine<F>* __restrict__ ta
 }
 
 // ---- launch bodies (instantiated by the .cu that owns the kernel) --------------------------------
-template <class F, int S>
-static int launch_accumulate_s(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
-                               size_t nacc, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind) {
-  ZKB_LAUNCH_K(ctx, prof_kind, (k_accumulate_chunks<F, S>), cdiv(nacc, 128), 128, 0, st, tab, offs, sorted, nbk, nacc, buckets,
-               heads);
+template <class F>
+static int launch_accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
+                             size_t nacc, ChunkPlan ch, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind) {
+  ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks<F>, cdiv(nacc, 128), 128, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
   return ZKB_OK;
 }
-template <class F, int S>
-static int launch_fix_heads_s(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, XYZZ<F>* buckets, const XYZZ<F>* heads,
-                              cudaStream_t st) {
-  ZKB_LAUNCH(ctx, (k_fix_heads<F, S>), cdiv(nbk, 128), 128, 0, st, offs, nbk, buckets, heads);
+template <class F>
+static int launch_fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, ChunkPlan ch, XYZZ<F>* buckets, const XYZZ<F>* heads,
+                            cudaStream_t st) {
+  ZKB_LAUNCH(ctx, k_fix_heads<F>, cdiv(nbk, 128), 128, 0, st, offs, nbk, ch, buckets, heads);
   return ZKB_OK;
 }
 // level plan shared by the scratch sizing and the launches: first level one thread per chunk of L
