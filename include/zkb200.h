@@ -135,7 +135,8 @@ int zkb_prove_dev(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const ui
  * all host or all device pointers; r, s: count x 4 limbs).  Two proofs are kept in flight on two
  * internal stream pairs so that the short / low-occupancy stages of one proof (polynomial stage,
  * record sort, bucket reduction) overlap the SM-filling bucket accumulation of the other.  Results
- * are identical to `count` calls of zkb_prove.  Host weights should be pinned (zkb_host_alloc) for the
+ * are identical to `count` calls of zkb_prove (over a sharded CRS: of zkb_prove_partial, `out` then holds
+ * this rank's partial records).  Host weights should be pinned (zkb_host_alloc) for the
  * copies to overlap. */
 int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const uint64_t* const* weights,
                     int weights_on_device, const uint64_t* r, const uint64_t* s, size_t count, zkb_proof* out);
@@ -149,6 +150,11 @@ int zkb_prove_partial(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, cons
                       int weights_on_device, const uint64_t r[4], const uint64_t s[4],
                       uint64_t* out_partial /* 32 limbs, host */);
 int zkb_prove_combine(zkb_ctx* ctx, const uint64_t* partials /* world x 32, host */, int world, zkb_proof* out);
+/* The same for `count` proofs at once.  zkb_prove_batch over a SHARDED CRS returns this rank's `count`
+ * partial records (count x 32 limbs); all-gathering them gives partials[world][count][32], which one
+ * kernel launch folds into `count` proofs. */
+int zkb_prove_combine_batch(zkb_ctx* ctx, const uint64_t* partials /* world x count x 32, host */, int world,
+                            size_t count, zkb_proof* out);
 /* h(x) alone: h = (u_sum * v_sum - w_sum) / t  (mod.rs:277; coefficient_poly.rs:93-157;
  * field/mod.rs:428-469).  Outputs (host, canonical, n x 4 limbs each; any may be NULL):
  * u_sum, v_sum coefficient vectors and h (n-1 meaningful coefficients, h[n-1] = 0). */

@@ -369,6 +369,30 @@ def test_prove_sharded_equals_single(ctx):
         assert (got.a, got.b, got.c) == (full.a, full.b, full.c)
 
 
+def test_prove_batch_sharded_equals_single(ctx):
+    """The N>1 bench path on one device: zkb_prove_batch over each rank's CRS shard (partial records),
+    gathered to (world, count, 32) and folded by one zkb_prove_combine_batch launch."""
+    n = 128
+    rng = random.Random(78)
+    m, n_input, rows = zg.horner_qap_rows(n)
+    q = zk.QAP(ctx, n, m, n_input, rows)
+    toxic = tuple(rand_fr(rng, True) for _ in range(5))
+    wits = [zg.horner_witness(n, rand_fr(rng, True), [rand_fr(rng) for _ in range(n)]) for _ in range(3)]
+    rs = [rand_fr(rng, True) for _ in range(3)]
+    ss = [rand_fr(rng, True) for _ in range(3)]
+    full_crs = zk.setup(ctx, q, toxic)
+    want = [zk.prove(ctx, q, full_crs, w, r, s) for w, r, s in zip(wits, rs, ss)]
+    for world in (2, 4):
+        parts = []
+        for k in range(world):
+            shard = zk.setup(ctx, q, toxic, rank=k, world=world)
+            rec = zk.prove_batch(ctx, q, shard, wits, rs, ss)
+            assert rec.shape == (3, 32)
+            parts.append(rec)
+        got = zk.prove_combine_batch(ctx, np.stack(parts))
+        assert [(p.a, p.b, p.c) for p in got] == [(p.a, p.b, p.c) for p in want]
+
+
 def test_prove_batch_equals_single(ctx):
     """zkb_prove_batch (two proofs in flight on two stream pairs) == independent zkb_prove calls,
     for 1..5 proofs with different witnesses and (r, s); host and device-resident weights."""

@@ -8,7 +8,7 @@ computes raises ``ZkbError`` unless the CUDA library is built and a B200 is pres
 """
 
 from .groth16 import (CRS, QAP, Bases, Context, Proof, ZkbError, fr_limbs, horner_qap_rows, lib_path,
-                      load_library, msm, ntt, prove, prove_batch, prove_partial, prove_combine, qap_h, setup)
+                      load_library, msm, ntt, prove, prove_batch, prove_partial, prove_combine, prove_combine_batch, qap_h, setup)
 
 __all__ = ["CRS", "QAP", "Bases", "Context", "Proof", "ZkbError", "fr_limbs", "horner_qap_rows", "lib_path",
-           "load_library", "msm", "ntt", "prove", "prove_batch", "prove_partial", "prove_combine", "qap_h", "setup"]
+           "load_library", "msm", "ntt", "prove", "prove_batch", "prove_partial", "prove_combine", "prove_combine_batch", "qap_h", "setup"]

@@ -129,6 +129,51 @@ __global__ void __launch_bounds__(96) k_finish(const G1XYZZ* __restrict__ ac, co
   }
 }
 
+// Fold per-rank partial sums (canonical affine, proof layout, partials[w][count][64 u32]) into proofs:
+// one block per proof, warp 0 -> A, warp 1 -> C, warp 2 -> B (sequential mixed additions over the ranks).
+__device__ __forceinline__ Fq ld_fq_canon(const uint32_t* p) {
+  Fq c;
+#pragma unroll
+  for (int i = 0; i < 8; i++) c.v[i] = p[i];
+  return to_mont(c);
+}
+__global__ void __launch_bounds__(96) k_combine_partials(const uint32_t* __restrict__ partials, int world, size_t count,
+                                                         uint32_t* __restrict__ out) {
+  const size_t k = blockIdx.x;
+  const int w = threadIdx.x >> 5;
+  if (k >= count || (threadIdx.x & 31)) return;
+  uint32_t* o = out + k * 64;
+  if (w < 2) {
+    const int off = w == 0 ? 0 : 48;
+    G1XYZZ acc = G1XYZZ::inf();
+    for (int r = 0; r < world; r++) {
+      const uint32_t* rec = partials + ((size_t)r * count + k) * 64 + off;
+      G1Affine p;
+      p.x = ld_fq_canon(rec);
+      p.y = ld_fq_canon(rec + 8);
+      acc = madd(acc, p);
+    }
+    G1Affine a = to_affine(acc);
+    Fq x = from_mont(a.x), y = from_mont(a.y);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { o[off + i] = x.v[i]; o[off + 8 + i] = y.v[i]; }
+  } else {
+    G2XYZZ acc = G2XYZZ::inf();
+    for (int r = 0; r < world; r++) {
+      const uint32_t* rec = partials + ((size_t)r * count + k) * 64 + 16;
+      G2Affine p;
+      p.x.c0 = ld_fq_canon(rec); p.x.c1 = ld_fq_canon(rec + 8);
+      p.y.c0 = ld_fq_canon(rec + 16); p.y.c1 = ld_fq_canon(rec + 24);
+      acc = madd(acc, p);
+    }
+    G2Affine a = to_affine(acc);
+    Fq c[4] = {from_mont(a.x.c0), from_mont(a.x.c1), from_mont(a.y.c0), from_mont(a.y.c1)};
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) o[16 + q * 8 + i] = c[q].v[i];
+  }
+}
+
 }  // namespace zkb
 
 using namespace zkb;
@@ -380,7 +425,6 @@ int zkb_prove_dev(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64
 int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* const* weights, int on_device,
                     const uint64_t* r, const uint64_t* s, size_t count, zkb_proof* out) {
   if (!ctx || !q || !c || (count && (!weights || !r || !s || !out))) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_batch: NULL argument");
-  if (c->world != 1) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_batch needs an unsharded CRS");
   ZKB_TRY(check_pair(ctx, q, c));
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   for (size_t i = 0; i < count; i++)
@@ -408,35 +452,25 @@ int zkb_prove_partial(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const ui
   return prove_common(ctx, q, c, weights, on_device, r, s, out_partial);
 }
 
-int zkb_prove_combine(zkb_ctx* ctx, const uint64_t* partials, int world, zkb_proof* out) {
-  if (!ctx || !partials || !out || world < 1) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_combine: bad argument");
+int zkb_prove_combine_batch(zkb_ctx* ctx, const uint64_t* partials, int world, size_t count, zkb_proof* out) {
+  if (!ctx || (count && (!partials || !out)) || world < 1) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_combine: bad argument");
+  if (!count) return ZKB_OK;
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  // regroup host-side into A[world], C[world] (G1) and B[world] (G2): pure data movement
-  std::vector<uint64_t> g1(2 * (size_t)world * 8), g2((size_t)world * 16);
-  for (int w = 0; w < world; w++) {
-    const uint64_t* rec = partials + (size_t)w * ZKB_PARTIAL_LIMBS;
-    memcpy(&g1[(size_t)w * 8], rec, 64);
-    memcpy(&g2[(size_t)w * 16], rec + 8, 128);
-    memcpy(&g1[((size_t)world + w) * 8], rec + 24, 64);
-  }
+  const size_t in_bytes = (size_t)world * count * 256, out_bytes = count * 256;
   void* p;
-  ZKB_TRY(scratch_get(ctx, 7, g1.size() * 8 + g2.size() * 8, &p));
-  G1Affine* d1 = (G1Affine*)p;
-  G2Affine* d2 = (G2Affine*)(d1 + 2 * (size_t)world);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d1, g1.data(), g1.size() * 8, cudaMemcpyHostToDevice, st));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d2, g2.data(), g2.size() * 8, cudaMemcpyHostToDevice, st));
-  ZKB_TRY(fq_to_mont(ctx, (Fq*)d1, 4 * (size_t)world, true, st));
-  ZKB_TRY(fq_to_mont(ctx, (Fq*)d2, 4 * (size_t)world, true, st));
-  ProveOut o;
-  ZKB_TRY(prove_out(ctx, ctx->scratch, &o));
-  ZKB_TRY(sum_affine_g1(ctx, d1, world, o.ac, st));
-  ZKB_TRY(sum_affine_g1(ctx, d1 + world, world, o.ac + 1, st));
-  ZKB_TRY(sum_affine_g2(ctx, d2, world, o.b, st));
-  ZKB_LAUNCH(ctx, k_finish, 1, 96, 0, st, o.ac, o.b, o.proof);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, o.proof, 256, cudaMemcpyDeviceToHost, st));
+  ZKB_TRY(scratch_get(ctx, 7, in_bytes + out_bytes, &p));
+  uint32_t* d_in = (uint32_t*)p;
+  uint32_t* d_out = d_in + in_bytes / 4;
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_in, partials, in_bytes, cudaMemcpyHostToDevice, st));
+  ZKB_LAUNCH(ctx, k_combine_partials, (unsigned)count, 96, 0, st, d_in, world, count, d_out);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));
   return ZKB_OK;
+}
+
+int zkb_prove_combine(zkb_ctx* ctx, const uint64_t* partials, int world, zkb_proof* out) {
+  return zkb_prove_combine_batch(ctx, partials, world, 1, out);
 }
 
 int zkb_qap_h(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* weights, uint64_t* u_sum, uint64_t* v_sum, uint64_t* h) {

@@ -79,6 +79,7 @@ ABI = {
     "zkb_prove_batch": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "zkb_prove_partial": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P]),
     "zkb_prove_combine": (C.c_int, [_P, _P, C.c_int, C.POINTER(_ProofC)]),
+    "zkb_prove_combine_batch": (C.c_int, [_P, _P, C.c_int, C.c_size_t, _P]),
     "zkb_qap_h": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "zkb_ntt_fr": (C.c_int, [_P, _P, C.c_uint32, C.c_int, _P]),
     "zkb_ntt_fr_raw": (C.c_int, [_P, _P, C.c_uint32, C.c_int]),
@@ -515,6 +516,8 @@ def prove_batch(ctx: Context, qap: QAP, crs: CRS, weights, rs, ss, on_device=Fal
     ctx.check(ctx.lib.zkb_prove_batch(ctx.h, qap.h, crs.h, ptrs, 1 if on_device else 0, _ptr(rl), _ptr(sl), k, out),
               "zkb_prove_batch")
     del keep
+    if crs.world != 1:  # sharded CRS: the records are this rank's partial sums, (k, 32) limbs
+        return np.frombuffer(bytes(out), dtype=np.uint64).reshape(k, PARTIAL_LIMBS).copy()
     return [_proof(out[i]) for i in range(k)]
 
 
@@ -559,6 +562,15 @@ def field_op(ctx: Context, field: int, op: int, a, b=None, c=None, d=None) -> li
               "zkb_field_op")
     vals = limbs_to_ints(out)
     return [(vals[2 * i], vals[2 * i + 1]) for i in range(n)] if field == 2 else vals
+
+
+def prove_combine_batch(ctx: Context, partials: np.ndarray) -> list:
+    """partials: (world, count, 32) limbs (all-gathered prove_batch records of a sharded CRS) -> count proofs."""
+    p = np.ascontiguousarray(partials, dtype=np.uint64)
+    world, count = p.shape[0], p.shape[1]
+    out = (_ProofC * count)()
+    ctx.check(ctx.lib.zkb_prove_combine_batch(ctx.h, _ptr(p), world, count, out), "zkb_prove_combine_batch")
+    return [_proof(out[i]) for i in range(count)]
 
 
 def qap_h(ctx: Context, qap: QAP, weights):
