@@ -588,7 +588,7 @@ template <class P> static __device__ __noinline__ Fp<P> fp_msm_ool(Fp<P> a, Fp<P
 }
 #endif
 template <class P> ZKB_HD Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) {
-#if defined(__CUDA_ARCH__) && defined(ZKB_FP_OOL)
+#if defined(__CUDA_ARCH__) && (defined(ZKB_FP_OOL) || defined(ZKB_FP_MUL_OOL))
   return fp_mul_ool<P>(a, b);
 #elif defined(__CUDA_ARCH__)
   return dev_impl::mul(a, b);
