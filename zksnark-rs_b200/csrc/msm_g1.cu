@@ -1,5 +1,10 @@
 // G1 (Fq) instantiation of the MSM / point kernels (see msm_impl.cuh) and the field-independent
 // record sort (signed-digit recoding + counting sort by bucket).
+// Measured on B200 (profiles/r01_notes.md): for the G1 mixed addition the plain CIOS product with five
+// 128-thread blocks per SM (96 registers) beats the wide-product / lazy-reduction code (fewer multiplies
+// but a longer dependency chain): 0.968 vs 0.957 of the modmul peak.
+#define ZKB_NO_LAZY 1
+#define ZKB_ACC_MIN_BLOCKS 5
 #include "msm_impl.cuh"
 namespace zkb {
 

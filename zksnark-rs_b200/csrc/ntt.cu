@@ -11,6 +11,7 @@
 // of the vector per pass (2-3 passes for 2^20..2^26).  Tiles of the strided passes are
 // (2^B rows) x (C = 2^(10-B) adjacent columns) so that every global access is a >=128-byte run.
 // Twiddles omega^k (k < n/2) live in a per-size table (L2-resident: 16 MB at 2^20).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace zkb {
@@ -79,10 +80,28 @@ int get_twiddles(zkb_ctx* ctx, uint32_t log_n, bool inverse, Fr** out) {
 // ------------------------------------------------------------------------------------------------
 // one pass = stages [lo, hi) of the size-2^log_n transform on 2^(hi-lo+logC)-element tiles.
 // DIF (Gentleman-Sande) runs the stages downwards, DIT (Cooley-Tukey) upwards.
-struct alignas(16) Half { uint32_t v[4]; };
+//
+// Radix-4 rounds in registers: a thread owns the four tile elements e0 + {0, h, 2h, 3h} of two
+// consecutive stages (half distances h and 2h), so a round trip through shared memory and a barrier
+// buy TWO stages, and the two butterflies of a stage are independent multiplies in one thread.  The
+// multiplication count is that of radix 2 (the "multiply by i" of a radix-4 butterfly is a generic
+// Fr product): 4 per round.  Twiddles of a round: w_a for both butterflies of the lower stage s;
+// w_b and w_c = w_b * omega^(n/4) (read from the same table) for the upper stage.  An odd last
+// stage is a plain radix-2 step, two butterflies per thread.  Stage 0 (all twiddles 1) skips its
+// products.
+__device__ __forceinline__ Fr lds_fr(const uint4* p0, const uint4* p1, uint32_t e) {
+  Fr a;
+  *reinterpret_cast<uint4*>(&a.v[0]) = p0[e];
+  *reinterpret_cast<uint4*>(&a.v[4]) = p1[e];
+  return a;
+}
+__device__ __forceinline__ void sts_fr(uint4* p0, uint4* p1, uint32_t e, const Fr& x) {
+  p0[e] = *reinterpret_cast<const uint4*>(&x.v[0]);
+  p1[e] = *reinterpret_cast<const uint4*>(&x.v[4]);
+}
 
 template <bool DIT>
-__global__ void __launch_bounds__(512) k_ntt_pass(Fr* __restrict__ d, const Fr* __restrict__ tw, uint32_t log_n,
+__global__ void __launch_bounds__(128) k_ntt_pass(Fr* __restrict__ d, const Fr* __restrict__ tw, uint32_t log_n,
                                                   uint32_t hi, uint32_t lo, uint32_t logC) {
   extern __shared__ uint4 smem[];
   const uint32_t B = hi - lo;
@@ -91,6 +110,7 @@ __global__ void __launch_bounds__(512) k_ntt_pass(Fr* __restrict__ d, const Fr* 
   uint4* p0 = smem;       // limbs 0..3 of tile element e
   uint4* p1 = smem + T;   // limbs 4..7
   const uint32_t t = threadIdx.x;
+  const uint32_t nthr = blockDim.x;  // T / 4 (T / 2 for tiles of two elements)
   const uint32_t C = 1u << logC;
   const uint64_t groups_per_H = ((uint64_t)1 << lo) >> logC;
   const uint64_t H = blockIdx.x / groups_per_H;
@@ -99,52 +119,86 @@ __global__ void __launch_bounds__(512) k_ntt_pass(Fr* __restrict__ d, const Fr* 
   const uint4* g4 = reinterpret_cast<const uint4*>(d);
   uint4* gw4 = reinterpret_cast<uint4*>(d);
 
-  // load: thread handles tile elements t and t + T/2
-#pragma unroll
-  for (int r = 0; r < 2; r++) {
-    uint32_t e = t + r * (T >> 1);
+  for (uint32_t e = t; e < T; e += nthr) {
     uint64_t gi = base + ((uint64_t)(e >> logC) << lo) + (e & (C - 1));
     p0[e] = g4[gi * 2];
     p1[e] = g4[gi * 2 + 1];
   }
   __syncthreads();
 
-  for (uint32_t k = 0; k < B; k++) {
-    const uint32_t ls = DIT ? k : (B - 1 - k);  // local stage
+  // twiddle of the butterfly whose lower element is tile element e, in stage s = lo + ls
+  auto twiddle = [&](uint32_t e, uint32_t ls) -> Fr {
     const uint32_t s = lo + ls;
-    const uint32_t sh = ls + logC;              // log2 of the half distance in tile units
-    const uint32_t half = 1u << sh;
-    const uint32_t e0 = ((t >> sh) << (sh + 1)) | (t & (half - 1));
-    const uint32_t e1 = e0 + half;
-    // twiddle exponent: (global index of e0 mod 2^s) << (log_n - 1 - s)
-    const uint64_t m0 = (e0 >> logC) & ((1u << ls) - 1);
-    const uint64_t j = (m0 << lo) + Lbase + (e0 & (C - 1));
+    const uint64_t m0 = (e >> logC) & ((1u << ls) - 1);
+    const uint64_t j = (m0 << lo) + Lbase + (e & (C - 1));
     const uint64_t jj = (s == 0) ? 0 : (j & (((uint64_t)1 << s) - 1));
-    const Fr w = tw[jj << (log_n - 1 - s)];
-    Fr a, b;
-    *reinterpret_cast<uint4*>(&a.v[0]) = p0[e0];
-    *reinterpret_cast<uint4*>(&a.v[4]) = p1[e0];
-    *reinterpret_cast<uint4*>(&b.v[0]) = p0[e1];
-    *reinterpret_cast<uint4*>(&b.v[4]) = p1[e1];
-    Fr x, y;
-    if (DIT) {
-      Fr wb = w * b;
-      x = a + wb;
-      y = a - wb;
+    return tw[jj << (log_n - 1 - s)];
+  };
+
+  const uint32_t pairs = B >> 1;
+  const bool odd = B & 1;
+  // DIT: rounds (0,1), (2,3), ..., then the odd top stage.  DIF: the odd top stage first, then rounds downwards.
+  for (uint32_t step = 0; step < pairs + (odd ? 1 : 0); step++) {
+    const bool single = odd && (DIT ? step == pairs : step == 0);
+    if (single) {
+      const uint32_t ls = B - 1;
+      const uint32_t sh = ls + logC;
+      const uint32_t half = 1u << sh;
+      for (uint32_t q = t; q < (T >> 1); q += nthr) {
+        const uint32_t e0 = ((q >> sh) << (sh + 1)) | (q & (half - 1));
+        const uint32_t e1 = e0 + half;
+        const Fr w = twiddle(e0, ls);
+        Fr a = lds_fr(p0, p1, e0), b = lds_fr(p0, p1, e1), x, y;
+        if (DIT) {
+          Fr wb = (lo + ls == 0) ? b : w * b;
+          x = a + wb;
+          y = a - wb;
+        } else {
+          x = a + b;
+          y = (lo + ls == 0) ? a - b : (a - b) * w;
+        }
+        sts_fr(p0, p1, e0, x);
+        sts_fr(p0, p1, e1, y);
+      }
     } else {
-      x = a + b;
-      y = (a - b) * w;
+      const uint32_t r = DIT ? step : (pairs - 1 - (odd ? step - 1 : step));
+      const uint32_t ls = 2 * r;  // lower stage of the round
+      const uint32_t sh = ls + logC;
+      const uint32_t h = 1u << sh;
+      for (uint32_t q = t; q < (T >> 2); q += nthr) {
+        const uint32_t e0 = ((q >> sh) << (sh + 2)) | (q & (h - 1));
+        const uint32_t e1 = e0 + h, e2 = e0 + 2 * h, e3 = e0 + 3 * h;
+        const bool unit = (lo + ls == 0);  // stage 0: every twiddle is 1
+        const Fr wa = twiddle(e0, ls);
+        const Fr wb = twiddle(e0, ls + 1);
+        const Fr wc = twiddle(e1, ls + 1);
+        Fr x0 = lds_fr(p0, p1, e0), x1 = lds_fr(p0, p1, e1), x2 = lds_fr(p0, p1, e2), x3 = lds_fr(p0, p1, e3);
+        Fr y0, y1, y2, y3;
+        if (DIT) {
+          Fr t1 = unit ? x1 : wa * x1;
+          Fr t3 = unit ? x3 : wa * x3;
+          Fr a0 = x0 + t1, a1 = x0 - t1, a2 = x2 + t3, a3 = x2 - t3;
+          Fr u2 = wb * a2, u3 = wc * a3;
+          y0 = a0 + u2; y2 = a0 - u2;
+          y1 = a1 + u3; y3 = a1 - u3;
+        } else {
+          Fr a0 = x0 + x2, a2 = (x0 - x2) * wb;
+          Fr a1 = x1 + x3, a3 = (x1 - x3) * wc;
+          y0 = a0 + a1;
+          y1 = unit ? a0 - a1 : (a0 - a1) * wa;
+          y2 = a2 + a3;
+          y3 = unit ? a2 - a3 : (a2 - a3) * wa;
+        }
+        sts_fr(p0, p1, e0, y0);
+        sts_fr(p0, p1, e1, y1);
+        sts_fr(p0, p1, e2, y2);
+        sts_fr(p0, p1, e3, y3);
+      }
     }
-    p0[e0] = *reinterpret_cast<uint4*>(&x.v[0]);
-    p1[e0] = *reinterpret_cast<uint4*>(&x.v[4]);
-    p0[e1] = *reinterpret_cast<uint4*>(&y.v[0]);
-    p1[e1] = *reinterpret_cast<uint4*>(&y.v[4]);
     __syncthreads();
   }
 
-#pragma unroll
-  for (int r = 0; r < 2; r++) {
-    uint32_t e = t + r * (T >> 1);
+  for (uint32_t e = t; e < T; e += nthr) {
     uint64_t gi = base + ((uint64_t)(e >> logC) << lo) + (e & (C - 1));
     gw4[gi * 2] = p0[e];
     gw4[gi * 2 + 1] = p1[e];
@@ -182,7 +236,10 @@ static int run_ntt(zkb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, cudaStream
     uint32_t logT = p.hi - p.lo + p.logC;
     uint32_t T = 1u << logT;
     unsigned grid = (unsigned)(((size_t)1 << log_n) >> logT);
-    unsigned block = T / 2;
+    unsigned block = T >= 4 ? T / 4 : 1;
+    if (block > 128) block = 128;  // two radix-4 groups per thread per round: four 128-thread blocks per SM beat two of 256
+    static const int env_threads = getenv("ZKB_NTT_THREADS") ? atoi(getenv("ZKB_NTT_THREADS")) : 0;  // developer switch
+    if (env_threads >= 32 && (unsigned)env_threads < block) block = (unsigned)env_threads;
     size_t smem = (size_t)T * 32;
     if (ctx->profile) ctx->prof_units[PK_NTT] += (uint64_t)1 << log_n;
     ZKB_LAUNCH_K(ctx, PK_NTT, k_ntt_pass<DIT>, grid, block, smem, st, d, tw, log_n, p.hi, p.lo, p.logC);
