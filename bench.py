@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- Groth16 proofs/sec on the synthetic 2^20-constraint Horner QAP (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n 20] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n 20] [--impl ours|reference] [--mode shard|replicas]
 
 A step is ONE groth16::prove() (src/groth16/mod.rs:213-296): witness -> u_sum, v_sum, h (6 NTTs) ->
 three fixed-base MSMs over the window-expanded CRS tables (A and C over G1 as two jobs of one call,
 B over G2) -> Proof{a,b,c}.  N = 1: the K steps go through zkb_prove_batch, which keeps two proofs in
 flight (identical results to K zkb_prove calls; single-proof latency is reported in config).  N > 1
 (torchrun, one rank per GPU): the MSM base vectors are sharded by points, every rank proves over its
-shard, the 32-limb partial sums are all-gathered over NCCL and folded -- one proof, strong scaling.
+shard, the 32-limb partial sums are all-gathered over NCCL and folded -- one proof, strong scaling
+(`--mode shard`, the default: the north-star configuration).  `--mode replicas` runs one proof stream
+per rank with a full CRS each (no data-path collective, weak scaling): the throughput-optimal layout.
 
 `value`  : proofs/s with the witness already resident in HBM (CUDA events on the library's stream).
 `e2e`    : proofs/s through the same C ABI call with the witnesses in pinned HOST memory: the H2D copy
@@ -167,8 +169,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL prints its version banner on stdout at communicator creation: send fd 1 to stderr until the
+        # JSON line, so that rank 0's stdout carries exactly one line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = 1 << args.log_n
     ctx = zk.Context(local)
@@ -177,7 +182,10 @@ def run_ours(args):
     m = qap.m
     rng = random.Random(3)
     toxic = tuple(rng.randrange(1, FR) for _ in range(5))
-    crs = zk.setup(ctx, qap, toxic, rank=rank, world=world)
+    # shard: ONE proof per step over all ranks (MSM bases sharded by points, NCCL all-gather of the partial
+    # sums).  replicas: every rank proves its own stream with a full CRS (no data-path collective).
+    sw = world if args.mode == "shard" else 1
+    crs = zk.setup(ctx, qap, toxic, rank=rank if sw > 1 else 0, world=sw)
     r, s = rng.randrange(1, FR), rng.randrange(1, FR)
     w_np = make_witness(zg, n, 2)
     w_pin = ctx.pinned((m, 4))
@@ -193,7 +201,7 @@ def run_ours(args):
     pins = [w_pin, w_pin2]
 
     def run_steps(on_device, steps):
-        if world == 1:
+        if sw == 1:
             ws = [d_w] * steps if on_device else [pins[i & 1] for i in range(steps)]
             return zk.prove_batch(ctx, qap, crs, ws, [r] * steps, [s] * steps, on_device=on_device)[-1]
         # sharded: K partial records per rank (two proofs in flight), ONE all-gather, one fold kernel
@@ -232,8 +240,8 @@ def run_ours(args):
     # single-proof latency (zkb_prove_dev, one proof in flight), for context
     lat0 = time.perf_counter()
     for _ in range(3):
-        single = zg.prove_dev(ctx, qap, crs, d_w, r, s) if world == 1 else None
-    latency_ms = (time.perf_counter() - lat0) / 3 * 1e3 if world == 1 else None
+        single = zg.prove_dev(ctx, qap, crs, d_w, r, s) if sw == 1 else None
+    latency_ms = (time.perf_counter() - lat0) / 3 * 1e3 if sw == 1 else None
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -245,7 +253,7 @@ def run_ours(args):
     ctx.profile(True)
     t_prof0 = time.perf_counter()
     for _ in range(args.steps):
-        if world == 1:
+        if sw == 1:
             zg.prove_dev(ctx, qap, crs, d_w, r, s)
         else:
             zk.prove_partial(ctx, qap, crs, d_w, r, s, on_device=True)
@@ -262,6 +270,7 @@ def run_ours(args):
         sec, desc = reference_sample(args.log_n, 1.0)
         cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
 
+    jobs = 1 if sw > 1 else world  # proofs completed per step by the whole job
     if rank == 0:
         peaks = {}
         try:
@@ -302,16 +311,19 @@ def run_ours(args):
         }
         g2_ms, g2_cnt, g2_recs = prof[3]
         line = {
-            "metric": METRIC, "value": args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": jobs * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (256-bit modular integers)", "data": "synthetic",
+            "scaling": "strong" if sw > 1 else "weak", "vs_baseline": None, "dtype": "u32x8 (256-bit modular integers)",
+            "data": "synthetic",
             "config": {"workload": workload_name(args.log_n),
-                       "parallelism": "1 GPU, zkb_prove_batch (two proofs in flight)" if world == 1 else f"msm-point-shard x{world}",
+                       "parallelism": ("1 GPU, zkb_prove_batch (two proofs in flight)" if world == 1 else
+                                       (f"msm-point-shard x{world}: one proof per step over all ranks" if sw > 1 else
+                                        f"replicas x{world}: one proof per step on EVERY rank")),
                        "single_proof_latency_ms": latency_ms,
                        "l2_policy": "inputs larger than L2 (CRS window tables ~5 GiB gathered at random + 64 MiB witness per proof; L2 is 126 MB)",
                        "timing": "CUDA events on the library stream, max over ranks"},
-            "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(w_np.nbytes),
-                    "d2h_bytes_per_step": 256 if world == 1 else 256 + 256 * world, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": jobs * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(w_np.nbytes) * world,
+                    "d2h_bytes_per_step": 256 * world if sw == 1 else 256 * world + 256 * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_ntt": roofline_ntt,
             "msm_g2": {"kernel": "k_accumulate_chunks<Fq2>", "total_ms": g2_ms, "launches": g2_cnt, "records": g2_recs,
@@ -321,6 +333,9 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if world > 1:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -370,6 +385,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
+                    help="N > 1: shard one proof over the ranks (default, the north-star configuration) or run one proof stream per rank")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
