@@ -321,9 +321,9 @@ def _rows_from_csr(rows):
     return out
 
 
-@pytest.mark.parametrize("log_n", [6, 10, 12, 16])
+@pytest.mark.parametrize("log_n", [6, 10, 12, 16, 20])
 def test_prove_closed_form_and_pairing(ctx, log_n):
-    """Device setup + prove on the synthetic Horner QAP (BASELINE config 2 at 2^16) against the
+    """Device setup + prove on the synthetic Horner QAP (BASELINE config 2 at 2^16, config 3 at 2^20) against the
     closed-form proof from the toxic waste (bit-exact) and, for 2^6, the reference's own
     acceptance criterion verify(...) == true (lib.rs:156-190) through the oracle pairing."""
     n = 1 << log_n
