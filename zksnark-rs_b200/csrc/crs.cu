@@ -5,6 +5,7 @@
 // G1 table row 0 = [xi1 shard | alpha1 beta1 delta1 | xi_t shard | sum_delta shard]; G2 table row
 // 0 = [xi2 shard | beta2 delta2]; row j = 2^(c*j) times row 0 (msm_impl.cuh).  Putting the fixed
 // points into the tables lets prove() fold alpha1 + r*delta1 etc. into the MSMs as extra terms.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -79,6 +80,10 @@ static int crs_new(zkb_ctx* ctx, uint64_t n, uint64_t nsg, uint64_t nsd, int ran
   c->g2_cnt = c->nxi() + 2;
   c->c1 = msm_pick_c(c->g1_cnt);
   c->c2 = msm_pick_c(c->g2_cnt);
+  if (const char* e = getenv("ZKB_MSM_C2")) {  // developer switch: window size of the G2 table only
+    int v = atoi(e);
+    if (v >= 2 && v <= 23) c->c2 = v;
+  }
   if (cudaMalloc(&c->g1, (size_t)msm_windows(c->c1) * c->g1_cnt * sizeof(G1Affine)) ||
       cudaMalloc(&c->g2, (size_t)msm_windows(c->c2) * c->g2_cnt * sizeof(G2Affine)) ||
       cudaMalloc(&c->sum_gamma, (nsg + 1) * sizeof(G1Affine)) || cudaMalloc(&c->gamma2, sizeof(G2Affine))) {

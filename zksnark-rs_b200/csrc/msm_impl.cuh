@@ -51,7 +51,7 @@ static const int MSM_MAX_JOBS = 4;
 template <class F>
 static inline ChunkPlan chunk_plan(size_t max_recs) {
   const bool g1 = sizeof(F) == sizeof(Fq);
-  uint32_t S1 = g1 ? (max_recs >= ((size_t)1 << 25) ? 128 : (max_recs >= ((size_t)1 << 23) ? 64 : 32)) : (max_recs >= ((size_t)1 << 23) ? 64 : 32);
+  uint32_t S1 = g1 ? (max_recs >= ((size_t)1 << 25) ? 128 : (max_recs >= ((size_t)1 << 23) ? 64 : 32)) : (max_recs >= ((size_t)1 << 23) ? 128 : 32);
   if (const char* e = getenv("ZKB_ACC_S")) {
     int v = atoi(e);
     if (v == 16 || v == 32 || v == 64 || v == 128 || v == 256) S1 = v;
