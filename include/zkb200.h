@@ -77,8 +77,12 @@ void* zkb_stream(zkb_ctx* ctx);
  * a dense coefficient vector (3*M*n field elements); this type stores the same polynomials by
  * their non-zero evaluations on the root domain -- exactly the `DummyRep` data model
  * (circuit/dummy_rep.rs:7-13).  Rows are CSR by wire: row i of u holds (gate index k, value) for
- * every root_k where u_i(root_k) != 0.  Domain: the n-th roots of unity, gate k <-> omega^k
- * (omega = 5^((r-1)/n)); n must be a power of two, 2 <= n <= 2^27. */
+ * every root_k where u_i(root_k) != 0.  Fast domain (roots == NULL): the n-th roots of unity, gate
+ * k <-> omega^k (omega = 5^((r-1)/n)); n must be a power of two, 2 <= n <= 2^27: O(n log n) NTTs.
+ * Generic domain (roots != NULL): what `QAP::from(DummyRep)` accepts for parser-produced circuits
+ * (fr.rs:140-173): same results as the reference's Lagrange interpolation (coefficient_poly.rs:159-190),
+ * schoolbook product (:93-130) and long division (field/mod.rs:428-469), computed with dense O(n^2)
+ * device kernels, n <= 4096. */
 typedef struct {
   uint64_t n;         /* number of gates = qap.degree                                   */
   uint64_t m;         /* number of rows (wires incl. the unity wire) = qap.u.len()      */
@@ -86,6 +90,10 @@ typedef struct {
   const uint64_t* row_ptr[3];  /* u, v, w: m+1 offsets into gate/coeff                  */
   const uint32_t* gate[3];     /* nnz gate indices (0-based)                            */
   const uint64_t* coeff[3];    /* nnz x 4 limbs, canonical                              */
+  const uint64_t* roots;       /* NULL: the n-th roots of unity (n a power of two).  Else n x 4 limbs:
+                                  explicit pairwise-distinct roots, gate k <-> roots[k] (the reference's
+                                  ASTParser uses 1..=n, circuit/mod.rs:517); any n in [1, 4096]; dense
+                                  O(n^2) interpolation / product / division on the device            */
 } zkb_qap_host;
 int zkb_qap_upload(zkb_ctx* ctx, const zkb_qap_host* qap, zkb_qap** out);
 void zkb_qap_free(zkb_ctx* ctx, zkb_qap* qap);

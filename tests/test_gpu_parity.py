@@ -15,7 +15,7 @@ import pytest
 from oracle import bn254 as bn
 from oracle import closed_form as cf
 from oracle import groth16 as og
-from oracle import poly, synthetic
+from oracle import circuit, poly, synthetic
 from oracle.fields import FR
 
 pytestmark = pytest.mark.gpu
@@ -367,6 +367,93 @@ def test_prove_sharded_equals_single(ctx):
             parts.append(zk.prove_partial(ctx, q, shards[k], wit, r, s))
         got = zk.prove_combine(ctx, np.stack(parts))
         assert (got.a, got.b, got.c) == (full.a, full.b, full.c)
+
+
+# ------------------------------------------------------------------------------------------------
+# generic root domain: the reference's own circuits (ASTParser numbers the gates 1..=n, circuit/mod.rs:517)
+from test_oracle_kats import QUAD, SIMPLE  # noqa: E402
+
+MIXED = """(in x a b)
+(out y z)
+(verify x y z)
+
+(program
+    (= t1 (* x x))
+    (= t2 (* (+ t1 a) (+ x b 7)))
+    (= y (* 1 (+ t2 t1 3)))
+    (= z (* t2 (+ y x))))"""
+
+
+def _parser_case(text, n_inputs, seed):
+    rng = random.Random(seed)
+    rep = circuit.try_parse(FR, text)
+    wit = circuit.weights(FR, text, [rand_fr(rng, True) for _ in range(n_inputs)])
+    toxic = tuple(rand_fr(rng, True) for _ in range(5))
+    return rep, wit, toxic, rand_fr(rng, True), rand_fr(rng, True)
+
+
+@pytest.mark.parametrize("name,text,n_inputs", [("simple", SIMPLE, 3), ("quad", QUAD, 4), ("mixed", MIXED, 3),
+                                                ("deg_15", synthetic.horner_program_text(16), 17)])
+@pytest.mark.parametrize("valid", [True, False])
+def test_parser_circuits_generic_domain(ctx, name, text, n_inputs, valid):
+    """Circuits as the reference's parser emits them (roots 1..=n: simple.zk of lib.rs:156-190, the quad
+    share of fr.rs:273-302, deg_15 of fr.rs:361-416, a mixed one) through the device path: h, the
+    device CRS and the proof are bit-exact vs the literal restatement, and the proof verifies."""
+    rep, wit, toxic, r, s = _parser_case(text, n_inputs, sum(map(ord, name)))
+    if not valid:
+        wit = list(wit)
+        wit[-1] = (wit[-1] + 1) % P
+    assert rep.roots == list(range(1, len(rep.roots) + 1))
+    dense = og.qap_from_root_rep(FR, rep)
+    B = og.BN254Backend()
+    sig = og.setup(B, dense, toxic)
+    want = og.prove(B, dense, sig, wit, r, s)
+    q = zk.QAP.from_root_representation(ctx, rep)
+    # h(x) and the weighted sums against the reference's Mul / Div on coefficient vectors
+    u_sum, v_sum, w_sum = og.weighted_sums(FR, dense, wit)
+    h = og.quotient_h(FR, dense, u_sum, v_sum, w_sum)
+    gu, gv, gh = zg.qap_h(ctx, q, wit)
+    n = len(rep.roots)
+    pad = lambda v: (list(v) + [0] * n)[:n]
+    assert gu == pad(u_sum) and gv == pad(v_sum) and gh == pad(h)[: n - 1]
+    # device setup == reference setup (same toxic waste), then prove over both CRS routes
+    crs = zk.setup(ctx, q, toxic)
+    d = crs.download()
+    assert (d["alpha1"], d["beta1"], d["delta1"]) == (sig[0].alpha, sig[0].beta, sig[0].delta)
+    assert d["xi1"] == sig[0].xi and d["xi_t"] == sig[0].xi_t
+    assert d["sum_gamma"] == sig[0].sum_gamma and d["sum_delta"] == sig[0].sum_delta
+    assert (d["beta2"], d["gamma2"], d["delta2"], d["xi2"]) == (sig[1].beta, sig[1].gamma, sig[1].delta, sig[1].xi)
+    got = zk.prove(ctx, q, crs, wit, r, s)
+    assert (got.a, got.b, got.c) == (want.a, want.b, want.c)
+    got2 = zk.prove(ctx, q, zk.CRS.upload(ctx, sig[0], sig[1]), wit, r, s)
+    assert (got2.a, got2.b, got2.c) == (want.a, want.b, want.c)
+    n_pub = rep.input
+    assert og.verify(B, sig, wit[1:1 + n_pub], og.Proof(got.a, got.b, got.c)) == valid
+
+
+def test_generic_domain_random_roots_and_limits(ctx):
+    """Arbitrary pairwise-distinct roots (not 1..n, n not a power of two); repeated roots are refused
+    (the reference's lagrange_basis would divide by zero); n > 4096 on an explicit domain is refused."""
+    rng = random.Random(33)
+    n = 11
+    roots = rng.sample(range(2, 10 ** 6), n)
+    rep = synthetic.horner_rep(FR, n, roots)
+    wit = synthetic.horner_witness(FR, n, rand_fr(rng, True), [rand_fr(rng) for _ in range(n)])
+    toxic = tuple(rand_fr(rng, True) for _ in range(5))
+    r, s = rand_fr(rng, True), rand_fr(rng, True)
+    dense = og.qap_from_root_rep(FR, rep)
+    B = og.BN254Backend()
+    sig = og.setup(B, dense, toxic)
+    want = og.prove(B, dense, sig, wit, r, s)
+    q = zk.QAP.from_root_representation(ctx, rep)
+    got = zk.prove(ctx, q, zk.setup(ctx, q, toxic), wit, r, s)
+    assert (got.a, got.b, got.c) == (want.a, want.b, want.c)
+    bad = synthetic.horner_rep(FR, 4, [5, 6, 5, 7])
+    with pytest.raises(zk.ZkbError):
+        zk.QAP.from_root_representation(ctx, bad)
+    m, n_input, rows = zg.horner_qap_rows(8192)
+    with pytest.raises(zk.ZkbError):
+        zk.QAP(ctx, 8192, m, n_input, rows, roots=list(range(1, 8193)))
 
 
 def test_prove_batch_sharded_equals_single(ctx):

@@ -207,6 +207,7 @@ struct zkb_bases {
   void* d = nullptr;  // G1Affine* or G2Affine*, Montgomery form: row 0 = the points, rows 1..W-1 = 2^(c*j) multiples
 };
 
+static const uint64_t ZKB_GENERIC_MAX_N = 4096;
 struct zkb_qap {
   uint64_t n = 0, m = 0, n_input = 0;
   uint32_t log_n = 0;
@@ -222,6 +223,15 @@ struct zkb_qap {
   // coset tables in bit-reversed position order: P[i] = g^br(i) / n, Q[i] = g^-br(i) / (2n), g = omega_2n
   zkb::Fr* d_cosP = nullptr;
   zkb::Fr* d_cosQ = nullptr;
+  // generic root domain (explicit pairwise-distinct roots, n <= ZKB_GENERIC_MAX_N; the reference's
+  // ASTParser numbers its gates 1..=n, circuit/mod.rs:517): dense O(n^2) tables built at upload
+  bool generic = false;
+  std::vector<zkb::Fr> h_roots;  // host copy (Montgomery) for t(x) in setup
+  zkb::Fr* d_roots = nullptr;   // n
+  zkb::Fr* d_Lc = nullptr;      // n x n: Lc[k*n + i] = coefficient i of the Lagrange basis polynomial L_k
+  zkb::Fr* d_dinv = nullptr;    // n: 1 / t'(r_k)
+  zkb::Fr* d_tc = nullptr;      // n + 1 coefficients of t(x) = prod (x - r_k)
+  zkb::Fr* d_ginv = nullptr;    // n - 1 coefficients of 1 / rev(t) mod x^(n-1)
   // (the polynomial workspace -- 8 vectors of n Fr and the witness, canonical + Montgomery -- lives in
   // the lane scratch, so proofs in flight on different lanes can share one QAP)
 };

@@ -23,6 +23,15 @@ __global__ void k_lagrange(Fr* L, Fr x, Fr tx_over_n, Fr omega, size_t n, int* b
   L[k] = tx_over_n * wk * inverse(den);
 }
 
+// generic root domain: L_k(x) = t(x) / ((x - r_k) t'(r_k))
+__global__ void k_lagrange_generic(Fr* L, Fr x, Fr tx, const Fr* __restrict__ roots, const Fr* __restrict__ dinv, size_t n, int* bad) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  Fr den = x - roots[k];
+  if (den.is_zero()) { *bad = 1; L[k] = Fr::zero(); return; }
+  L[k] = tx * dinv[k] * inverse(den);
+}
+
 // one warp per wire: lin_i = (beta u_i(x) + alpha v_i(x) + w_i(x)) * (i <= n_input ? 1/gamma : 1/delta)
 __device__ __forceinline__ Fr warp_sum(Fr v) {
   for (int off = 16; off > 0; off >>= 1) {
@@ -162,13 +171,19 @@ int zkb_setup(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* toxic, int rank, i
   if ((rc = scratch_get(ctx, 9, sizeof(int), &p)) != ZKB_OK) return fail(rc);
   int* d_bad = (int*)p;
   cudaMemsetAsync(d_bad, 0, sizeof(int), st);
-  Fr xn = pow_u64(x, n);
-  Fr tx = xn - Fr::one();  // t(x) = x^n - 1
+  Fr tx;
+  if (q->generic) {  // t(x) = prod (x - r_k)
+    tx = Fr::one();
+    for (const Fr& rk : q->h_roots) tx = tx * (x - rk);
+  } else {
+    tx = pow_u64(x, n) - Fr::one();  // t(x) = x^n - 1
+  }
   Fr inv_delta = inverse(delta), inv_gamma = inverse(gamma);
   Fr tx_over_n = tx * inverse(fr_from_u64(n));
-  Fr omega = host_omega(q->log_n, false);
+  Fr omega = q->generic ? Fr::one() : host_omega(q->log_n, false);
   auto launch_fail = [&](const char* what) { return fail(set_err(ctx, ZKB_ERR_CUDA, "setup: %s: %s", what, cudaGetErrorString(cudaGetLastError()))); };
-  k_lagrange<<<cdiv(n, 128), 128, 0, st>>>(d_L, x, tx_over_n, omega, n, d_bad);
+  if (q->generic) k_lagrange_generic<<<cdiv(n, 128), 128, 0, st>>>(d_L, x, tx, q->d_roots, q->d_dinv, n, d_bad);
+  else k_lagrange<<<cdiv(n, 128), 128, 0, st>>>(d_L, x, tx_over_n, omega, n, d_bad);
   ctx->launches++;
   if (cudaGetLastError() != cudaSuccess) return launch_fail("k_lagrange");
   k_lin<<<cdiv(m * 32, 256), 256, 0, st>>>(q->d_rptr[0], q->d_gate[0], q->d_rcoeff[0], q->d_rptr[1], q->d_gate[1],

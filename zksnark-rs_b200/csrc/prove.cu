@@ -76,6 +76,102 @@ __global__ void k_coset_tables(Fr* P, Fr* Q, Fr g, Fr ginv, Fr invn, Fr inv2n, u
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Generic root domain (explicit roots, n <= 4096): the reference's own algorithms restated as dense
+// O(n^2) kernels.  Upload builds t(x) = prod (x - r_k) (root_poly, coefficient_poly.rs:192-200), the
+// coefficient rows of the Lagrange basis L_k = t / ((x - r_k) t'(r_k)) (lagrange_basis, :173-190)
+// and g = 1 / rev(t) mod x^(n-1); a proof then needs u = sum_k A_k L_k, v likewise (the unique
+// interpolants: same coefficient vectors as mod.rs:233-246), the high half of the schoolbook product
+// (coefficient_poly.rs:93-130) and the quotient by the monic t (field/mod.rs:428-469) as
+// rev(h) = rev(p_hi) * g mod x^(n-1).  As on the fast domain, w_sum (degree < n) cannot reach the quotient.
+__global__ void __launch_bounds__(1024) k_gen_tcoef(const Fr* __restrict__ roots, size_t n, Fr* buf0, Fr* buf1, Fr* __restrict__ out) {
+  for (size_t i = threadIdx.x; i <= n; i += blockDim.x) buf0[i] = i == 0 ? Fr::one() : Fr::zero();
+  __syncthreads();
+  Fr *cur = buf0, *nxt = buf1;
+  for (size_t k = 0; k < n; k++) {
+    const Fr r = roots[k];
+    for (size_t i = threadIdx.x; i <= k + 1; i += blockDim.x) {
+      Fr lo = i > 0 ? cur[i - 1] : Fr::zero();
+      Fr hi = i <= k ? cur[i] : Fr::zero();
+      nxt[i] = lo - r * hi;
+    }
+    __syncthreads();
+    Fr* t = cur; cur = nxt; nxt = t;
+  }
+  for (size_t i = threadIdx.x; i <= n; i += blockDim.x) out[i] = cur[i];
+}
+
+__global__ void k_gen_lagrange_coef(const Fr* __restrict__ roots, const Fr* __restrict__ tc, size_t n, Fr* __restrict__ Lc,
+                                    Fr* __restrict__ dinv, int* bad) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const Fr r = roots[k];
+  Fr* row = Lc + k * n;
+  Fr b = tc[n], d = b;  // synthetic division of t by (x - r); d = quotient evaluated at r = t'(r)
+  row[n - 1] = b;
+  for (size_t i = n - 1; i >= 1; i--) {
+    b = tc[i] + r * b;
+    row[i - 1] = b;
+    d = d * r + b;
+  }
+  if (d.is_zero()) { *bad = 1; dinv[k] = Fr::zero(); return; }  // repeated root
+  const Fr inv = inverse(d);
+  dinv[k] = inv;
+  for (size_t i = 0; i < n; i++) row[i] = row[i] * inv;
+}
+
+__global__ void __launch_bounds__(512) k_gen_ginv(const Fr* __restrict__ tc, size_t n, Fr* g) {
+  __shared__ Fr sh[512];
+  if (n < 2) return;
+  if (threadIdx.x == 0) g[0] = Fr::one();  // t is monic
+  __syncthreads();
+  for (size_t j = 1; j + 1 < n; j++) {
+    Fr acc = Fr::zero();
+    for (size_t i = 1 + threadIdx.x; i <= j; i += blockDim.x) acc = acc + tc[n - i] * g[j - i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t off = blockDim.x >> 1; off > 0; off >>= 1) {
+      if (threadIdx.x < off) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + off];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) g[j] = neg(sh[0]);
+    __syncthreads();
+  }
+}
+
+__global__ void k_gen_interp(const Fr* __restrict__ A, const Fr* __restrict__ B, const Fr* __restrict__ Lc, size_t n,
+                             Fr* __restrict__ u, Fr* __restrict__ v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr su = Fr::zero(), sv = Fr::zero();
+  for (size_t k = 0; k < n; k++) {
+    const Fr l = Lc[k * n + i];
+    su = su + A[k] * l;
+    sv = sv + B[k] * l;
+  }
+  u[i] = su;
+  v[i] = sv;
+}
+
+// rp[n-2-k] = (u * v)[n + k] = sum_{i=k+1}^{n-1} u[i] v[n+k-i],  k = 0 .. n-2
+__global__ void k_gen_prod_high(const Fr* __restrict__ u, const Fr* __restrict__ v, size_t n, Fr* __restrict__ rp) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k + 1 >= n) return;
+  Fr acc = Fr::zero();
+  for (size_t i = k + 1; i < n; i++) acc = acc + u[i] * v[n + k - i];
+  rp[n - 2 - k] = acc;
+}
+
+// h[n-2-j] = sum_{i=0}^{j} rp[i] g[j-i],  j = 0 .. n-2;  h[n-1] = 0
+__global__ void k_gen_quotient(const Fr* __restrict__ rp, const Fr* __restrict__ g, size_t n, Fr* __restrict__ h) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  if (j == n - 1) { h[n - 1] = Fr::zero(); return; }
+  Fr acc = Fr::zero();
+  for (size_t i = 0; i <= j; i++) acc = acc + rp[i] * g[j - i];
+  h[n - 2 - j] = acc;
+}
+
 // MSM scalar vectors (canonical).  un, vn, hn: Montgomery, natural order; wm: witness, Montgomery.
 struct ScalarPlan {
   uint64_t nxi, nxt, nsd, xi_lo, xit_lo, sd_lo;  // this rank's shard
@@ -189,6 +285,7 @@ void zkb_qap_free(zkb_ctx* ctx, zkb_qap* q) {
     cudaFree(q->d_rptr[t]); cudaFree(q->d_gate[t]); cudaFree(q->d_rcoeff[t]);
   }
   cudaFree(q->d_cosP); cudaFree(q->d_cosQ);
+  cudaFree(q->d_roots); cudaFree(q->d_Lc); cudaFree(q->d_dinv); cudaFree(q->d_tc); cudaFree(q->d_ginv);
   delete q;
 }
 
@@ -196,8 +293,13 @@ int zkb_qap_upload(zkb_ctx* ctx, const zkb_qap_host* h, zkb_qap** out) {
   if (!ctx || !h || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_qap_upload: NULL argument");
   *out = nullptr;
   uint64_t n = h->n, m = h->m;
-  if (n < 2 || (n & (n - 1)) || n > ((uint64_t)1 << 27))
-    return set_err(ctx, ZKB_ERR_ARG, "qap.n = %llu must be a power of two in [2, 2^27]", (unsigned long long)n);
+  const bool generic = h->roots != nullptr;
+  if (!generic && (n < 2 || (n & (n - 1)) || n > ((uint64_t)1 << 27)))
+    return set_err(ctx, ZKB_ERR_ARG, "qap.n = %llu must be a power of two in [2, 2^27] on the roots-of-unity domain",
+                   (unsigned long long)n);
+  if (generic && (n < 1 || n > ZKB_GENERIC_MAX_N))
+    return set_err(ctx, ZKB_ERR_UNSUPPORTED, "qap.n = %llu: explicit root domains are limited to n <= %llu (dense O(n^2) path)",
+                   (unsigned long long)n, (unsigned long long)ZKB_GENERIC_MAX_N);
   if (m == 0 || m >= ((uint64_t)1 << 31) || h->n_input + 1 > m)
     return set_err(ctx, ZKB_ERR_ARG, "qap.m = %llu / n_input = %llu invalid", (unsigned long long)m,
                    (unsigned long long)h->n_input);
@@ -256,19 +358,46 @@ int zkb_qap_upload(zkb_ctx* ctx, const zkb_qap_host* h, zkb_qap** out) {
     if (rc == ZKB_OK) rc = vec_to_mont(ctx, q->d_rcoeff[t], nnz, true, st);
   }
   if (rc != ZKB_OK) return fail(rc);
-  if (cudaMalloc(&q->d_cosP, n * 32) || cudaMalloc(&q->d_cosQ, n * 32))
-    return fail(set_err(ctx, ZKB_ERR_ALLOC, "qap upload: workspace cudaMalloc failed"));
-  Fr g = host_omega(q->log_n + 1, false), ginv = host_omega(q->log_n + 1, true);
-  Fr invn = inverse(fr_from_u64(n)), inv2n = inverse(fr_from_u64(2 * n));
-  {
-    zkb_ctx* c = ctx;
-    k_coset_tables<<<cdiv(n, 256), 256, 0, st>>>(q->d_cosP, q->d_cosQ, g, ginv, invn, inv2n, q->log_n);
-    c->launches++;
+  q->generic = generic;
+  if (!generic) {
+    if (cudaMalloc(&q->d_cosP, n * 32) || cudaMalloc(&q->d_cosQ, n * 32))
+      return fail(set_err(ctx, ZKB_ERR_ALLOC, "qap upload: workspace cudaMalloc failed"));
+    Fr g = host_omega(q->log_n + 1, false), ginv = host_omega(q->log_n + 1, true);
+    Fr invn = inverse(fr_from_u64(n)), inv2n = inverse(fr_from_u64(2 * n));
+    {
+      zkb_ctx* c = ctx;
+      k_coset_tables<<<cdiv(n, 256), 256, 0, st>>>(q->d_cosP, q->d_cosQ, g, ginv, invn, inv2n, q->log_n);
+      c->launches++;
+    }
+    Fr* tw;
+    rc = get_twiddles(ctx, q->log_n, false, &tw);
+    if (rc == ZKB_OK) rc = get_twiddles(ctx, q->log_n, true, &tw);
+    if (rc != ZKB_OK) return fail(rc);
+  } else {
+    q->h_roots.resize(n);
+    for (uint64_t k = 0; k < n; k++) q->h_roots[k] = fr_from_limbs(h->roots + 4 * k);
+    void* p;
+    if ((rc = scratch_get(ctx, 8, 2 * (n + 1) * sizeof(Fr), &p)) != ZKB_OK) return fail(rc);
+    Fr* buf = (Fr*)p;
+    if ((rc = scratch_get(ctx, 9, sizeof(int), &p)) != ZKB_OK) return fail(rc);
+    int* d_bad = (int*)p;
+    if (cudaMalloc(&q->d_roots, n * 32) || cudaMalloc(&q->d_Lc, n * n * 32) || cudaMalloc(&q->d_dinv, n * 32) ||
+        cudaMalloc(&q->d_tc, (n + 1) * 32) || cudaMalloc(&q->d_ginv, n * 32))
+      return fail(set_err(ctx, ZKB_ERR_ALLOC, "qap upload: generic-domain tables (%.1f MiB) cudaMalloc failed",
+                          (double)n * n * 32 / 1048576.0));
+    cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+    cudaMemcpyAsync(q->d_roots, q->h_roots.data(), n * 32, cudaMemcpyHostToDevice, st);
+    k_gen_tcoef<<<1, 1024, 0, st>>>(q->d_roots, n, buf, buf + n + 1, q->d_tc);
+    k_gen_lagrange_coef<<<cdiv(n, 64), 64, 0, st>>>(q->d_roots, q->d_tc, n, q->d_Lc, q->d_dinv, d_bad);
+    k_gen_ginv<<<1, 512, 0, st>>>(q->d_tc, n, q->d_ginv);
+    ctx->launches += 3;
+    int bad = 0;
+    cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (e2 != cudaSuccess) return fail(set_err(ctx, ZKB_ERR_CUDA, "qap upload (generic domain): %s", cudaGetErrorString(e2)));
+    if (bad) return fail(set_err(ctx, ZKB_ERR_DIV_ZERO, "qap roots are not pairwise distinct (the reference's lagrange_basis "
+                                                        "would divide by zero, coefficient_poly.rs:183)"));
   }
-  Fr* tw;
-  rc = get_twiddles(ctx, q->log_n, false, &tw);
-  if (rc == ZKB_OK) rc = get_twiddles(ctx, q->log_n, true, &tw);
-  if (rc != ZKB_OK) return fail(rc);
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return fail(set_err(ctx, ZKB_ERR_CUDA, "qap upload: %s", cudaGetErrorString(e)));
   *out = q;
@@ -301,6 +430,12 @@ static int poly_stage(zkb_ctx* ctx, const zkb_qap* q, const Work& w, const Fr* d
   ZKB_TRY(vec_to_mont(ctx, w.wmont, m, true, st));
   ZKB_LAUNCH(ctx, k_matvec, cdiv(n, 128), 128, 0, st, q->d_gptr[0], q->d_wire[0], q->d_coeff[0], q->d_gptr[1],
              q->d_wire[1], q->d_coeff[1], w.wmont, m, n, A, B, AB);
+  if (q->generic) {  // dense path: interpolate, high half of the product, quotient by t
+    ZKB_LAUNCH(ctx, k_gen_interp, cdiv(n, 64), 64, 0, st, A, B, q->d_Lc, n, un, vn);
+    if (n > 1) ZKB_LAUNCH(ctx, k_gen_prod_high, cdiv(n, 64), 64, 0, st, un, vn, n, AB);
+    ZKB_LAUNCH(ctx, k_gen_quotient, cdiv(n, 64), 64, 0, st, AB, q->d_ginv, n, hn);
+    return ZKB_OK;
+  }
   ZKB_TRY(ntt_dif(ctx, A, q->log_n, true, st));   // n * u_sum, bit-reversed
   ZKB_TRY(ntt_dif(ctx, B, q->log_n, true, st));
   ZKB_TRY(ntt_dif(ctx, AB, q->log_n, true, st));  // n * (p_lo + p_hi), bit-reversed

@@ -34,7 +34,7 @@ def lib_path() -> str:
 
 class _QapHost(C.Structure):
     _fields_ = [("n", C.c_uint64), ("m", C.c_uint64), ("n_input", C.c_uint64),
-                ("row_ptr", C.c_void_p * 3), ("gate", C.c_void_p * 3), ("coeff", C.c_void_p * 3)]
+                ("row_ptr", C.c_void_p * 3), ("gate", C.c_void_p * 3), ("coeff", C.c_void_p * 3), ("roots", C.c_void_p)]
 
 
 class _CrsHost(C.Structure):
@@ -327,12 +327,21 @@ class QAP:
     """Device-resident `QAP<CoefficientPoly<FrLocal>>` (groth16/mod.rs:60-67), stored as sparse
     evaluation rows on the roots-of-unity domain instead of 3*m dense coefficient vectors."""
 
-    def __init__(self, ctx: Context, n: int, m: int, n_input: int, rows):
+    def __init__(self, ctx: Context, n: int, m: int, n_input: int, rows, roots=None):
+        """rows: (row_ptr, gate, coeff) CSR triples for u, v, w.  roots: None = the n-th roots of unity
+        (fast NTT path); else the n explicit roots (ints), e.g. ASTParser's 1..=n (dense O(n^2) path)."""
         self.ctx, self.n, self.m, self.input = ctx, n, m, n_input
         self.degree = n
         host = _QapHost()
         host.n, host.m, host.n_input = n, m, n_input
         keep = []
+        if roots is not None:
+            ra = fr_limbs([r % FR_MODULUS for r in roots])
+            assert ra.shape == (n, 4)
+            keep.append(ra)
+            host.roots = ra.ctypes.data
+        else:
+            host.roots = None
         for t, (ptr, gate, coeff) in enumerate(rows):
             ptr = np.ascontiguousarray(ptr, dtype=np.uint64)
             gate = np.ascontiguousarray(gate, dtype=np.uint32)
@@ -347,25 +356,30 @@ class QAP:
     @classmethod
     def from_root_representation(cls, ctx: Context, rep) -> "QAP":
         """`From<RootRepresentation> for QAP` (fr.rs:140-173).  ``rep`` has u, v, w (per wire: list of
-        (root, value)), roots, input -- the DummyRep data model (circuit/dummy_rep.rs:7-13).  The roots
-        must be the powers of omega_n in order (the only domain this build accelerates)."""
+        (root, value)), roots, input -- the DummyRep data model (circuit/dummy_rep.rs:7-13).  Roots that
+        are omega_n^0 .. omega_n^(n-1) in order take the NTT path; any other pairwise-distinct roots (the
+        parser's 1..=n, circuit/mod.rs:517) take the dense O(n^2) device path (n <= 4096)."""
         n = len(rep.roots)
-        if n < 2 or n & (n - 1):
-            raise ZkbError("QAP: the number of roots must be a power of two >= 2")
-        w = omega(n.bit_length() - 1)
-        index, acc = {}, 1
-        for k in range(n):
-            index[acc] = k
-            acc = acc * w % FR_MODULUS
-        if [index.get(r % FR_MODULUS) for r in rep.roots] != list(range(n)):
-            raise ZkbError("QAP: roots must be omega^0 .. omega^(n-1) (roots-of-unity domain)")
         if not (len(rep.u) == len(rep.v) == len(rep.w)):
             raise ZkbError("QAP: u, v, w must have the same number of rows")  # assert at fr.rs:157-158
         m = len(rep.u)
+        roots = [r % FR_MODULUS for r in rep.roots]
+        index = {r: k for k, r in enumerate(roots)}
+        fast = n >= 2 and n & (n - 1) == 0
+        if fast:  # omega^0 .. omega^(n-1) in order -> NTT path
+            w, acc = omega(n.bit_length() - 1), 1
+            for k in range(n):
+                if roots[k] != acc:
+                    fast = False
+                    break
+                acc = acc * w % FR_MODULUS
         rows = []
         for mat in (rep.u, rep.v, rep.w):
-            rows.append(_csr([[(index[r % FR_MODULUS], c % FR_MODULUS) for r, c in row] for row in mat], m))
-        return cls(ctx, n, m, rep.input, rows)
+            try:
+                rows.append(_csr([[(index[r % FR_MODULUS], c % FR_MODULUS) for r, c in row] for row in mat], m))
+            except KeyError as e:  # the reference's Lagrange interpolation would silently ignore nothing: a point off the domain is a bug
+                raise ZkbError(f"QAP: row entry at {e} is not one of the roots") from None
+        return cls(ctx, n, m, rep.input, rows, roots=None if fast else roots)
 
     @classmethod
     def horner(cls, ctx: Context, n: int) -> "QAP":
