@@ -169,6 +169,24 @@ int zkb_prove_combine_batch(zkb_ctx* ctx, const uint64_t* partials /* world x co
 int zkb_qap_h(zkb_ctx* ctx, const zkb_qap* qap, const uint64_t* weights, uint64_t* u_sum,
               uint64_t* v_sum, uint64_t* h);
 
+/* ---- groth16::verify (groth16/mod.rs:299-320) ----------------------------------------------- */
+/* *ok = 1 iff  e(alpha1, beta2) * e(sum_term, gamma2) * e(proof.c, delta2) == e(proof.a, proof.b)
+ * with sum_term = sum over zip(sigma_g1.sum_gamma, [1] ++ inputs) of a * point (mod.rs:312-316: the
+ * shorter side ends the sum).  inputs: n_inputs x 4 limbs (host, canonical).  The CRS is borrowed, not
+ * consumed (the reference takes it by value, mod.rs:300); a sharded CRS works on every rank (each
+ * rank keeps the fixed points and sum_gamma).  Proof points that are not on their curve (impossible
+ * to construct through the reference's types) give *ok = 0.  The pairing is the optimal-ate pairing
+ * on BN254 (crate `bn`'s `pairing`, fr.rs:120-122); GT "+" is the Fq12 product (fr.rs:225-231). */
+int zkb_verify(zkb_ctx* ctx, const zkb_crs* crs, const uint64_t* inputs, size_t n_inputs, const zkb_proof* proof, int* ok);
+/* `count` proofs against the same CRS, one verdict each (inputs: count x n_inputs x 4 limbs): the
+ * independent Miller loops and final exponentiations run side by side on the device. */
+int zkb_verify_batch(zkb_ctx* ctx, const zkb_crs* crs, const uint64_t* inputs, size_t n_inputs,
+                     const zkb_proof* proofs, size_t count, int* ok);
+/* prod_i e(g1s[i], g2s[i]) as a GT element (fr.rs:120-122, 225-231): 12 Fq residues = the Fq2
+ * coefficients (c0, c1) of w^0 .. w^5 in Fq12 = Fq2[w]/(w^6 - (9 + u)); 48 limbs, host.  g1s: n x 8,
+ * g2s: n x 16 limbs (host); the identity in either slot contributes 1; n = 0 gives 1. */
+int zkb_pairing(zkb_ctx* ctx, const uint64_t* g1s, const uint64_t* g2s, size_t n, uint64_t* gt);
+
 /* ---- the two kernels standalone ------------------------------------------------------------- */
 /* In-place size-2^log_n transform of a DEVICE vector of canonical Fr residues with the reference's
  * convention (field/mod.rs:508-537): out[i] = sum_j in[j] * root^(i*j), natural order in and out,

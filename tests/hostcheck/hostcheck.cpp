@@ -2,7 +2,7 @@
 // (zksnark-rs_b200/csrc/ff.cuh, ec.cuh) with g++ so their algebra can be checked against Oracle A
 // on a machine without a GPU.  Never linked into libzkb200.so and never used by the product path.
 #include <cstring>
-#include "ec.cuh"
+#include "pairing.cuh"
 using namespace zkb;
 
 template <class F> static F ld(const uint64_t* p) { F r; memcpy(r.v, p, 32); return to_mont(r); }
@@ -55,5 +55,20 @@ void hc_g2_add(const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t* ou
 void hc_g2_mul(const uint64_t* a, const uint64_t* k, uint64_t* out) {
   uint32_t kk[8]; memcpy(kk, k, 32);
   stg2(out, to_affine(scalar_mul(ldg2(a), kk)));
+}
+// GT element as 12 Fq residues: the Fq2 coefficient (c0, c1) of w^i, i = 0..5.  stage 0: Miller loop only,
+// 1: reduced pairing, 2: final exponentiation of the product of n Miller loops (g1s: n x 8, g2s: n x 16)
+static void st12(uint64_t* out, const Fq12& f) { for (int i = 0; i < 6; i++) st2(out + 8 * i, f.w(i)); }
+void hc_pairing(int stage, int n, const uint64_t* g1s, const uint64_t* g2s, uint64_t* out) {
+  Fq12 f = Fq12::one();
+  for (int i = 0; i < n; i++) f = f * miller_loop(ldg1(g1s + 8 * i), ldg2(g2s + 16 * i));
+  if (stage) f = final_exponentiation(f);
+  st12(out, f);
+}
+// Fq12 arithmetic on its own: op 0 a*b, 1 a^2, 2 1/a, 3 a^(q^2), 4 a^(q^6)
+void hc_fq12(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+  Fq12 x, y;
+  for (int i = 0; i < 6; i++) { x.w(i) = ld2(a + 8 * i); y.w(i) = ld2(b + 8 * i); }
+  st12(out, op == 0 ? x * y : op == 1 ? sqr(x) : op == 2 ? inverse(x) : op == 3 ? frobenius2(x) : conj(x));
 }
 }

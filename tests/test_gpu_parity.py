@@ -290,6 +290,7 @@ def test_prove_matches_reference(ctx, n, valid):
     assert (got.a, got.b, got.c) == (want.a, want.b, want.c)
     if valid:
         assert og.verify(B, sig, wit[1:rep.input + 1], og.Proof(got.a, got.b, got.c))
+    assert zk.verify(ctx, crs, wit[1:rep.input + 1], got) == valid  # groth16::verify on the device (mod.rs:299-320)
     # zip truncation of the weights (mod.rs:237..288): a short witness == zero-padded witness
     short = wit[: len(wit) - 2]
     want2 = og.prove(B, dense, sig, short, r, s)
@@ -339,6 +340,10 @@ def test_prove_closed_form_and_pairing(ctx, log_n):
     ru, rv, rw = _rows_from_csr(rows)
     want = cf.expected_proof(n, synthetic.omega(log_n), ru, rv, rw, n_input, wit, toxic, r, s)
     assert (got.a, got.b, got.c) == want
+    # groth16::verify on the device at every size (the CRS stays resident; O(1) pairings)
+    wrong = [wit[1], (wit[2] + 1) % P]  # wrong public output -> reject (lib.rs:182-189)
+    assert zk.verify(ctx, crs, wit[1:3], got)
+    assert not zk.verify(ctx, crs, wrong, got)
     if log_n == 6:
         d = crs.download()
         s1 = og.SigmaG1(d["alpha1"], d["beta1"], d["delta1"], d["xi1"], d["sum_gamma"], d["sum_delta"], d["xi_t"])
@@ -429,6 +434,7 @@ def test_parser_circuits_generic_domain(ctx, name, text, n_inputs, valid):
     assert (got2.a, got2.b, got2.c) == (want.a, want.b, want.c)
     n_pub = rep.input
     assert og.verify(B, sig, wit[1:1 + n_pub], og.Proof(got.a, got.b, got.c)) == valid
+    assert zk.verify(ctx, crs, wit[1:1 + n_pub], got) == valid
 
 
 def test_generic_domain_random_roots_and_limits(ctx):
@@ -521,3 +527,65 @@ def test_error_paths(ctx):
     crs4 = zk.setup(ctx, q, (1, 2, 3, 4, 5))
     with pytest.raises(zk.ZkbError):
         zk.prove(ctx, q8, crs4, [1] * 18, 1, 1)  # CRS of another QAP
+
+
+# ------------------------------------------------------------------------------------------------
+# pairing / verify  (fr.rs:120-122, 225-231; groth16/mod.rs:299-320)
+def _gt_to_flat(c):
+    """Device GT layout ((c0, c1) of the w^i coefficient, i = 0..5; u = w^6 - 9) -> the oracle's dense w-polynomial."""
+    f = [0] * 12
+    for i in range(6):
+        f[i] = (f[i] + c[2 * i] - 9 * c[2 * i + 1]) % bn.Q
+        f[i + 6] = (f[i + 6] + c[2 * i + 1]) % bn.Q
+    return bn.Fq12(f)
+
+
+def test_pairing_matches_oracle(ctx):
+    rng = random.Random(77)
+    a, b, c = (rand_fr(rng, True) for _ in range(3))
+    Pa, Qb = bn.g1_mul(bn.BASE_G1, a), bn.g2_mul(bn.BASE_G2, b)
+    assert _gt_to_flat(zk.pairing(ctx, [(Pa, Qb)])) == bn.pairing(Pa, Qb)
+    # GT "+" (fr.rs:225-231) is the Fq12 product: e(aG, bH) e(cG, H) == e((ab + c)G, H)
+    lhs = _gt_to_flat(zk.pairing(ctx, [(Pa, Qb), (bn.g1_mul(bn.BASE_G1, c), bn.BASE_G2)]))
+    rhs = _gt_to_flat(zk.pairing(ctx, [(bn.g1_mul(bn.BASE_G1, (a * b + c) % P), bn.BASE_G2)]))
+    assert lhs == rhs and lhs != bn.Fq12.one()
+    # identity in either slot, the empty product, P with -P
+    one = bn.Fq12.one()
+    assert _gt_to_flat(zk.pairing(ctx, [(None, Qb)])) == one
+    assert _gt_to_flat(zk.pairing(ctx, [(Pa, None)])) == one
+    assert _gt_to_flat(zk.pairing(ctx, [])) == one
+    assert _gt_to_flat(zk.pairing(ctx, [(Pa, Qb), (bn.g1_neg(Pa), Qb)])) == one
+    # a point off the curve is an argument error, not a silent value
+    with pytest.raises(zk.ZkbError):
+        zk.pairing(ctx, [((Pa[0], (Pa[1] + 1) % bn.Q), Qb)])
+
+
+def test_verify_batch_and_edge_cases(ctx):
+    """verify over a batch: valid proofs, a wrong public input, a tampered proof, an off-curve point, identity points;
+    zip truncation of the inputs (mod.rs:312-316) -- every verdict equals the oracle's verify()."""
+    n = 8
+    rep, wit, toxic, r, s = _horner_case(n, 404)
+    B = og.BN254Backend()
+    dense = og.qap_from_root_rep(FR, rep)
+    sig = og.setup(B, dense, toxic)
+    q = zk.QAP.from_root_representation(ctx, rep)
+    crs = zk.CRS.upload(ctx, sig[0], sig[1])
+    good = zk.prove(ctx, q, crs, wit, r, s)
+    good2 = zk.prove(ctx, q, crs, wit, r + 1, s + 5)
+    pub = wit[1:rep.input + 1]
+    tampered = zg.Proof(good.a, good.b, bn.g1_add(good.c, bn.BASE_G1))
+    offcurve = zg.Proof((good.a[0], (good.a[1] + 1) % bn.Q), good.b, good.c)
+    ident = zg.Proof(None, good.b, good.c)
+    proofs = [good, good2, good, tampered, offcurve, ident]
+    inputs = [pub, pub, [pub[0], (pub[1] + 1) % P], pub, pub, pub]
+    got = zg.verify_batch(ctx, crs, inputs, proofs)
+    want = [og.verify(B, sig, i, og.Proof(p.a, p.b, p.c)) if p is not offcurve else False for i, p in zip(inputs, proofs)]
+    assert want == [True, True, False, False, False, False]
+    assert got == want
+    # zip truncation: extra inputs are ignored, missing ones end the sum early (and change the verdict)
+    assert zk.verify(ctx, crs, pub + [5, 6], good) == og.verify(B, sig, pub + [5, 6], og.Proof(good.a, good.b, good.c)) is True
+    assert zk.verify(ctx, crs, pub[:1], good) == og.verify(B, sig, pub[:1], og.Proof(good.a, good.b, good.c))
+    assert zk.verify(ctx, crs, [], good) == og.verify(B, sig, [], og.Proof(good.a, good.b, good.c))
+    # a sharded CRS verifies on every rank (fixed points and sum_gamma are replicated)
+    crs1 = zk.CRS.upload(ctx, sig[0], sig[1], rank=1, world=2)
+    assert zk.verify(ctx, crs1, pub, good) and not zk.verify(ctx, crs1, pub, tampered)

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(HERE)
 def hc():
     src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
     so = os.path.join(HERE, "hostcheck", "_hostcheck.so")
-    deps = [src] + [os.path.join(ROOT, "zksnark-rs_b200", "csrc", f) for f in ("ff.cuh", "ec.cuh", "constants.h")]
+    deps = [src] + [os.path.join(ROOT, "zksnark-rs_b200", "csrc", f) for f in ("ff.cuh", "ec.cuh", "pairing.cuh", "constants.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
                                "-I", os.path.join(ROOT, "zksnark-rs_b200", "csrc"), "-o", so, src])

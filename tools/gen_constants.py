@@ -83,6 +83,27 @@ def main(out):
     B1 = smul(g1_add, G1, 69)   # reference base point, src/groth16/fr.rs:106-109
     B2 = smul(g2_add, G2, 96)   # src/groth16/fr.rs:110-113
     b2 = f2mul((3, 0), f2inv((9, 1)))
+    # pairing constants: Frobenius twists xi^((q-1)/3), xi^((q-1)/2), xi^((q^2-1)/3) (xi = 9 + u), the final
+    # exponent (q^12 - 1)/r and the optimal-ate loop count 6u + 2 (u = 4965661367192848881)
+    def f2pow(a, e):
+        r = (1, 0)
+        while e:
+            if e & 1: r = f2mul(r, a)
+            a = f2mul(a, a); e >>= 1
+        return r
+    fg2, fg3 = f2pow((9, 1), (Q_MOD - 1) // 3), f2pow((9, 1), (Q_MOD - 1) // 2)
+    fg2s = f2pow((9, 1), (Q_MOD * Q_MOD - 1) // 3)
+    assert fg2s[1] == 0 and f2pow((9, 1), (Q_MOD * Q_MOD - 1) // 2) == (Q_MOD - 1, 0)
+    # final exponentiation = easy part (q^6 - 1)(q^2 + 1) by conjugation / inversion / Frobenius^2, then the hard
+    # part (q^4 - q^2 + 1)/r as a plain exponent; Frobenius^2 on Fq12 = Fq2[w]/(w^6 - xi) multiplies the w^i
+    # coefficient by xi^(i (q^2-1)/6), which lies in Fq
+    fexp = (Q_MOD ** 4 - Q_MOD ** 2 + 1) // R_MOD
+    assert (Q_MOD ** 4 - Q_MOD ** 2 + 1) % R_MOD == 0
+    assert (Q_MOD ** 12 - 1) // R_MOD == (Q_MOD ** 6 - 1) * (Q_MOD ** 2 + 1) * fexp
+    fr2 = [f2pow((9, 1), i * (Q_MOD * Q_MOD - 1) // 6) for i in range(6)]
+    assert all(c[1] == 0 for c in fr2) and fr2[2] == fg2s
+    fwords = [(fexp >> (32 * i)) & 0xffffffff for i in range((fexp.bit_length() + 31) // 32)]
+    ate = 6 * 4965661367192848881 + 2
     txt = ["// GENERATED by tools/gen_constants.py -- do not edit.",
            "// BN254 (alt_bn128) constants; Montgomery form with R = 2^256, 8 x 32-bit little-endian limbs.",
            "#pragma once", "#include <stdint.h>", "namespace zkb {",
@@ -104,6 +125,18 @@ def main(out):
            f"#define ZKB_G1_B {arr(mont(3, Q_MOD))}",
            f"#define ZKB_G2_B0 {arr(mont(b2[0], Q_MOD))}",
            f"#define ZKB_G2_B1 {arr(mont(b2[1], Q_MOD))}",
+           f"// pairing: Frobenius constants (Montgomery form), hard part of the final exponent (q^4-q^2+1)/r ({fexp.bit_length()} bits), ate loop 6u+2 ({ate.bit_length()} bits)",
+           f"#define ZKB_FROB_G2_C0 {arr(mont(fg2[0], Q_MOD))}",
+           f"#define ZKB_FROB_G2_C1 {arr(mont(fg2[1], Q_MOD))}",
+           f"#define ZKB_FROB_G3_C0 {arr(mont(fg3[0], Q_MOD))}",
+           f"#define ZKB_FROB_G3_C1 {arr(mont(fg3[1], Q_MOD))}",
+           f"#define ZKB_FROB_G2SQ {arr(mont(fg2s[0], Q_MOD))}",
+           "#define ZKB_FROB2_W {" + ", ".join(arr(mont(c[0], Q_MOD)) for c in fr2) + "}",
+           f"#define ZKB_FINAL_EXP_BITS {fexp.bit_length()}",
+           f"#define ZKB_FINAL_EXP_WORDS {len(fwords)}",
+           "#define ZKB_FINAL_EXP {" + ", ".join("0x%08xu" % w for w in fwords) + "}",
+           f"#define ZKB_ATE_LOOP_BITS {ate.bit_length()}",
+           "#define ZKB_ATE_LOOP {" + ", ".join("0x%08xu" % ((ate >> (32 * i)) & 0xffffffff) for i in range(3)) + "}",
            "}  // namespace zkb", ""]
     with open(out, "w") as f:
         f.write("\n".join(txt))

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libzkb200.so")
-SOURCES = ["msm_g2_acc.cu", "msm_g2_red.cu", "msm_g2_tab.cu", "msm_g1.cu", "msm_g2.cu", "crs.cu", "prove.cu", "api.cu", "ntt.cu"]
+SOURCES = ["msm_g2_acc.cu", "msm_g2_red.cu", "msm_g2_tab.cu", "msm_g1.cu", "msm_g2.cu", "crs.cu", "prove.cu", "api.cu", "ntt.cu", "pairing.cu"]
 HEADERS = ["ff.cuh", "ec.cuh", "constants.h", "common.cuh", "msm_impl.cuh", os.path.join("..", "..", "include", "zkb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -46,9 +46,12 @@ def _stamp(target: str, digest: str) -> None:
         f.write(digest)
 
 
+EXTRA_HEADERS = {"pairing.cu": ["pairing.cuh"]}  # headers only one translation unit includes
+
+
 def _compile(src: str) -> str:
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-    deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS]
+    deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS + EXTRA_HEADERS.get(src, [])]
     digest = _digest(deps, " ".join(NVCC_FLAGS))
     if not _fresh(obj, digest):
         cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]

@@ -90,6 +90,9 @@ ABI = {
     "zkb_bases_free": (None, [_P, _P]),
     "zkb_msm": (C.c_int, [_P, _P, _P, C.c_int, C.c_size_t, C.c_int, _P]),
     "zkb_points_sum": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P]),
+    "zkb_verify": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(_ProofC), C.POINTER(C.c_int)]),
+    "zkb_verify_batch": (C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    "zkb_pairing": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "zkb_bench_modmul": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
@@ -559,6 +562,49 @@ def prove_combine(ctx: Context, partials: np.ndarray) -> Proof:
     out = _ProofC()
     ctx.check(ctx.lib.zkb_prove_combine(ctx.h, _ptr(p), p.shape[0], C.byref(out)), "zkb_prove_combine")
     return _proof(out)
+
+
+def _proof_c(proof: Proof) -> _ProofC:
+    pc = _ProofC()
+    pc.a[:] = [int(v) for v in g1_pack([proof.a]).reshape(-1)]
+    pc.b[:] = [int(v) for v in g2_pack([proof.b]).reshape(-1)]
+    pc.c[:] = [int(v) for v in g1_pack([proof.c]).reshape(-1)]
+    return pc
+
+
+def verify(ctx: Context, crs: CRS, inputs, proof: Proof) -> bool:
+    """groth16::verify (mod.rs:299-320): e(alpha1, beta2) e(sum_term, gamma2) e(C, delta2) == e(A, B), with
+    sum_term over zip(sum_gamma, [1] ++ inputs).  The CRS is borrowed (the reference consumes it)."""
+    inp = fr_limbs(list(inputs))
+    pc = _proof_c(proof)
+    ok = C.c_int(-1)
+    ctx.check(ctx.lib.zkb_verify(ctx.h, crs.h, _ptr(inp) if len(inp) else None, len(inp), C.byref(pc), C.byref(ok)), "zkb_verify")
+    return bool(ok.value)
+
+
+def verify_batch(ctx: Context, crs: CRS, inputs, proofs) -> list:
+    """One verdict per (inputs[i], proofs[i]) against the same CRS (zkb_verify_batch); every inputs[i] has the
+    same length."""
+    k = len(proofs)
+    n_in = len(inputs[0]) if k else 0
+    assert all(len(x) == n_in for x in inputs)
+    inp = fr_limbs([v for row in inputs for v in row])
+    arr = (_ProofC * k)(*[_proof_c(p) for p in proofs])
+    ok = np.full(k, -1, dtype=np.int32)
+    ctx.check(ctx.lib.zkb_verify_batch(ctx.h, crs.h, _ptr(inp) if inp.size else None, n_in, arr, k, _ptr(ok)), "zkb_verify_batch")
+    return [bool(v) for v in ok]
+
+
+def pairing(ctx: Context, pairs) -> list:
+    """prod_i e(P_i, Q_i) for pairs (G1 point, G2 point) -- `EllipticEncryptable::pairing` (fr.rs:120-122) and the GT
+    product (fr.rs:225-231).  Returns the 12 Fq residues of the GT element: (c0, c1) of the w^i coefficient, i = 0..5,
+    in Fq12 = Fq2[w]/(w^6 - (9 + u))."""
+    g1 = g1_pack([P for P, _ in pairs])
+    g2 = g2_pack([Q for _, Q in pairs])
+    out = np.zeros((12, 4), dtype=np.uint64)
+    ctx.check(ctx.lib.zkb_pairing(ctx.h, _ptr(g1) if len(pairs) else None, _ptr(g2) if len(pairs) else None, len(pairs), _ptr(out)),
+              "zkb_pairing")
+    return limbs_to_ints(out)
 
 
 def field_op(ctx: Context, field: int, op: int, a, b=None, c=None, d=None) -> list:
