@@ -215,6 +215,13 @@ void zkb_bases_free(zkb_ctx* ctx, zkb_bases* b);
  * window size first (slow; meant for tests and tuning). */
 int zkb_msm(zkb_ctx* ctx, zkb_bases* bases, const uint64_t* scalars, int scalars_on_device,
             size_t n, int window_bits, uint64_t* out);
+/* Window sharding (BASELINE.json config 4): the partial sum over the table rows
+ * (windows) j = win_rank (mod win_world) of the same MSM.  Every rank holds the full base vector and
+ * all scalars, sorts and accumulates only its windows' records (1/win_world of the point additions),
+ * and the win_world partial points -- all-gathered over NCCL -- sum to the zkb_msm result
+ * (zkb_points_sum; compared in affine form, so bit-exact against one GPU). */
+int zkb_msm_windows(zkb_ctx* ctx, zkb_bases* bases, const uint64_t* scalars, int scalars_on_device,
+                    size_t n, int win_rank, int win_world, uint64_t* out);
 /* Sum of n affine points (fold of per-GPU partial results; `Sum for G1Local`, fr.rs:191-198). */
 int zkb_points_sum(zkb_ctx* ctx, int group, const uint64_t* h_points, size_t n, uint64_t* out);
 

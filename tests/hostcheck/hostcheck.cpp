@@ -56,19 +56,21 @@ void hc_g2_mul(const uint64_t* a, const uint64_t* k, uint64_t* out) {
   uint32_t kk[8]; memcpy(kk, k, 32);
   stg2(out, to_affine(scalar_mul(ldg2(a), kk)));
 }
-// GT element as 12 Fq residues: the Fq2 coefficient (c0, c1) of w^i, i = 0..5.  stage 0: Miller loop only,
-// 1: reduced pairing, 2: final exponentiation of the product of n Miller loops (g1s: n x 8, g2s: n x 16)
+// GT element as 12 Fq residues: the Fq2 coefficient (c0, c1) of w^i, i = 0..5.  stage 0: product of the n Miller
+// loops only, 1: its final exponentiation; +2: the plain versions (affine steps, 761-bit exponent)
 static void st12(uint64_t* out, const Fq12& f) { for (int i = 0; i < 6; i++) st2(out + 8 * i, f.w(i)); }
 void hc_pairing(int stage, int n, const uint64_t* g1s, const uint64_t* g2s, uint64_t* out) {
   Fq12 f = Fq12::one();
-  for (int i = 0; i < n; i++) f = f * miller_loop(ldg1(g1s + 8 * i), ldg2(g2s + 16 * i));
-  if (stage) f = final_exponentiation(f);
+  for (int i = 0; i < n; i++)
+    f = f * ((stage & 2) ? miller_loop_affine(ldg1(g1s + 8 * i), ldg2(g2s + 16 * i)) : miller_loop(ldg1(g1s + 8 * i), ldg2(g2s + 16 * i)));
+  if (stage & 1) f = (stage & 2) ? final_exponentiation_plain(f) : final_exponentiation(f);
   st12(out, f);
 }
-// Fq12 arithmetic on its own: op 0 a*b, 1 a^2, 2 1/a, 3 a^(q^2), 4 a^(q^6)
+// Fq12 arithmetic on its own: op 0 a*b, 1 a^2, 2 1/a, 3 a^(q^2), 4 a^(q^6), 5 a^q, 6 a^u, 7 a * sparse line (b_0, b_1, b_3)
 void hc_fq12(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
   Fq12 x, y;
   for (int i = 0; i < 6; i++) { x.w(i) = ld2(a + 8 * i); y.w(i) = ld2(b + 8 * i); }
-  st12(out, op == 0 ? x * y : op == 1 ? sqr(x) : op == 2 ? inverse(x) : op == 3 ? frobenius2(x) : conj(x));
+  if (op == 7) { mul_by_line(x, y.w(0), y.w(1), y.w(3)); st12(out, x); return; }
+  st12(out, op == 0 ? x * y : op == 1 ? sqr(x) : op == 2 ? inverse(x) : op == 3 ? frobenius2(x) : op == 4 ? conj(x) : op == 5 ? frobenius(x) : pow_u(x));
 }
 }

@@ -210,6 +210,27 @@ def test_msm_2pow20_collapse(ctx):
     assert zk.msm(ctx, b, s) == bn.g1_mul(bn.BASE_G1, e)
 
 
+@pytest.mark.parametrize("group,log_n,world", [(1, 10, 2), (1, 12, 4), (2, 9, 3), (1, 6, 8)])
+def test_msm_window_sharded_equals_single(ctx, group, log_n, world):
+    """Window sharding (BASELINE config 4): rank g takes the table rows j = g (mod world); the `world` partial
+    points fold (zkb_points_sum, what the ranks do after the NCCL all-gather) to the single-GPU result, including
+    for more ranks than some scalars have non-zero windows."""
+    n = 1 << log_n
+    rng = random.Random(700 + log_n + group)
+    ks = [rand_fr(rng) for _ in range(n)]
+    ss = [rand_fr(rng) for _ in range(n)]
+    for i in range(0, n, 7):
+        ss[i] = i % 3  # witness-like small scalars: only window 0 is non-zero
+    b = zk.Bases.generate(ctx, group, ks)
+    full = zk.msm(ctx, b, ss)
+    parts = [zk.msm(ctx, b, ss, windows=(g, world)) for g in range(world)]
+    assert zg.points_sum(ctx, group, parts) == full
+    e = sum(s * k for s, k in zip(ss, ks)) % P
+    assert full == (bn.g1_mul(bn.BASE_G1, e) if group == 1 else bn.g2_mul(bn.BASE_G2, e))
+    with pytest.raises(zk.ZkbError):
+        zk.msm(ctx, b, ss, windows=(world, world))
+
+
 def test_points_sum(ctx):
     pts = [bn.g1_mul(bn.BASE_G1, k) for k in (3, 5, 7)] + [None]
     assert zg.points_sum(ctx, 1, pts) == bn.g1_mul(bn.BASE_G1, 15)

@@ -100,6 +100,8 @@ def main(out):
     fexp = (Q_MOD ** 4 - Q_MOD ** 2 + 1) // R_MOD
     assert (Q_MOD ** 4 - Q_MOD ** 2 + 1) % R_MOD == 0
     assert (Q_MOD ** 12 - 1) // R_MOD == (Q_MOD ** 6 - 1) * (Q_MOD ** 2 + 1) * fexp
+    fr1 = [f2pow((9, 1), i * (Q_MOD - 1) // 6) for i in range(6)]  # Frobenius on Fq12: conj(a_i) * fr1[i]
+    assert fr1[2] == fg2 and fr1[3] == fg3
     fr2 = [f2pow((9, 1), i * (Q_MOD * Q_MOD - 1) // 6) for i in range(6)]
     assert all(c[1] == 0 for c in fr2) and fr2[2] == fg2s
     fwords = [(fexp >> (32 * i)) & 0xffffffff for i in range((fexp.bit_length() + 31) // 32)]
@@ -126,11 +128,9 @@ def main(out):
            f"#define ZKB_G2_B0 {arr(mont(b2[0], Q_MOD))}",
            f"#define ZKB_G2_B1 {arr(mont(b2[1], Q_MOD))}",
            f"// pairing: Frobenius constants (Montgomery form), hard part of the final exponent (q^4-q^2+1)/r ({fexp.bit_length()} bits), ate loop 6u+2 ({ate.bit_length()} bits)",
-           f"#define ZKB_FROB_G2_C0 {arr(mont(fg2[0], Q_MOD))}",
-           f"#define ZKB_FROB_G2_C1 {arr(mont(fg2[1], Q_MOD))}",
-           f"#define ZKB_FROB_G3_C0 {arr(mont(fg3[0], Q_MOD))}",
-           f"#define ZKB_FROB_G3_C1 {arr(mont(fg3[1], Q_MOD))}",
-           f"#define ZKB_FROB_G2SQ {arr(mont(fg2s[0], Q_MOD))}",
+           "#define ZKB_FROB1_W {" + ", ".join(arr(mont(c[k], Q_MOD)) for c in fr1 for k in (0, 1)) + "}",
+           f"#define ZKB_FQ_INV2 {arr(mont(pow(2, -1, Q_MOD), Q_MOD))}",
+           f"#define ZKB_BN_U 4965661367192848881ull",
            "#define ZKB_FROB2_W {" + ", ".join(arr(mont(c[0], Q_MOD)) for c in fr2) + "}",
            f"#define ZKB_FINAL_EXP_BITS {fexp.bit_length()}",
            f"#define ZKB_FINAL_EXP_WORDS {len(fwords)}",

@@ -408,8 +408,10 @@ static int result_to_host(zkb_ctx* ctx, int group, G2XYZZ* acc, G2Affine* aff, u
   return ZKB_OK;
 }
 
-int zkb_msm(zkb_ctx* ctx, zkb_bases* b, const uint64_t* scalars, int on_device, size_t n, int window_bits, uint64_t* out) {
+static int msm_entry(zkb_ctx* ctx, zkb_bases* b, const uint64_t* scalars, int on_device, size_t n, int window_bits, int win_rank,
+                     int win_world, uint64_t* out) {
   if (!ctx || !b || (!scalars && n) || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_msm: NULL argument");
+  if (win_world < 1 || win_rank < 0 || win_rank >= win_world) return set_err(ctx, ZKB_ERR_ARG, "zkb_msm: bad window rank/world");
   if (n > b->n) n = b->n;  // zip truncation
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   if (window_bits) ZKB_TRY(bases_expand(ctx, b, window_bits));
@@ -426,9 +428,18 @@ int zkb_msm(zkb_ctx* ctx, zkb_bases* b, const uint64_t* scalars, int on_device, 
   ZKB_TRY(result_slot(ctx, &acc, &aff));
   MsmJob job = {d_s, n};
   const size_t stride = b->n ? b->n : 1;
-  if (b->group == 1) ZKB_TRY(msm_g1(ctx, (const G1Affine*)b->d, stride, b->c, &job, 1, (G1XYZZ*)acc, 0, st));
-  else ZKB_TRY(msm_g2(ctx, (const G2Affine*)b->d, stride, b->c, &job, 1, acc, 3, st));
+  if (b->group == 1) ZKB_TRY(msm_g1(ctx, (const G1Affine*)b->d, stride, b->c, &job, 1, (G1XYZZ*)acc, 0, st, win_rank, win_world));
+  else ZKB_TRY(msm_g2(ctx, (const G2Affine*)b->d, stride, b->c, &job, 1, acc, 3, st, win_rank, win_world));
   return result_to_host(ctx, b->group, acc, aff, out, st);
+}
+
+int zkb_msm(zkb_ctx* ctx, zkb_bases* b, const uint64_t* scalars, int on_device, size_t n, int window_bits, uint64_t* out) {
+  return msm_entry(ctx, b, scalars, on_device, n, window_bits, 0, 1, out);
+}
+
+int zkb_msm_windows(zkb_ctx* ctx, zkb_bases* b, const uint64_t* scalars, int on_device, size_t n, int win_rank, int win_world,
+                    uint64_t* out) {
+  return msm_entry(ctx, b, scalars, on_device, n, 0, win_rank, win_world, out);
 }
 
 int zkb_points_sum(zkb_ctx* ctx, int group, const uint64_t* h_points, size_t n, uint64_t* out) {

@@ -170,6 +170,7 @@ struct MsmPlan {
   size_t stride = 0;
   int c = 0, njobs = 0;
   ChunkPlan ch;  // how the sorted records are cut into per-thread chunks
+  int win_rank = 0, win_world = 1;  // window sharding: only table rows j = win_rank (mod win_world) emit records
   MsmJob jobs[4];
   bool empty = true;
   size_t nbk = 0, max_recs = 0, nacc = 0, lvl_elems = 0;
@@ -182,10 +183,11 @@ int msm_sort(zkb_ctx* ctx, const MsmPlan& p, cudaStream_t st);
 int msm_accumulate(zkb_ctx* ctx, const MsmPlan& p, cudaStream_t st);
 int msm_tail(zkb_ctx* ctx, const MsmPlan& p, cudaStream_t st);
 // all phases on one stream with ctx->scratch (standalone zkb_msm)
+// win_rank / win_world: the partial sum over the table rows (windows) j = win_rank (mod win_world) only
 int msm_g1(zkb_ctx* ctx, const G1Affine* tab, size_t stride, int c, const MsmJob* jobs, int njobs, G1XYZZ* d_out,
-           int slot_base, cudaStream_t st);
+           int slot_base, cudaStream_t st, int win_rank = 0, int win_world = 1);
 int msm_g2(zkb_ctx* ctx, const G2Affine* tab, size_t stride, int c, const MsmJob* jobs, int njobs, G2XYZZ* d_out,
-           int slot_base, cudaStream_t st);
+           int slot_base, cudaStream_t st, int win_rank = 0, int win_world = 1);
 // fill rows 1..W-1 of the table from row 0 (columns [0, n))
 int expand_table_g1(zkb_ctx* ctx, G1Affine* tab, size_t stride, size_t n, int c, cudaStream_t st);
 int expand_table_g2(zkb_ctx* ctx, G2Affine* tab, size_t stride, size_t n, int c, cudaStream_t st);

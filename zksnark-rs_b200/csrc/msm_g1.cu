@@ -28,7 +28,7 @@ __global__ void k_digits_count(const Fr* __restrict__ scalars, size_t n, DigitPl
     uint32_t d = get_bits(k.v, j * pl.c, pl.c) + carry;
     carry = d > pl.nb;
     uint32_t mag = carry ? ((1u << pl.c) - d) : d;
-    if (mag) atomicAdd(&hist[mag - 1], 1u);
+    if (mag && (pl.ww == 1 || j % pl.ww == pl.wr)) atomicAdd(&hist[mag - 1], 1u);
   }
 }
 
@@ -42,7 +42,7 @@ __global__ void k_digits_scatter(const Fr* __restrict__ scalars, size_t n, size_
     uint32_t d = get_bits(k.v, j * pl.c, pl.c) + carry;
     carry = d > pl.nb;
     uint32_t mag = carry ? ((1u << pl.c) - d) : d;
-    if (mag) {
+    if (mag && (pl.ww == 1 || j % pl.ww == pl.wr)) {
       uint32_t pos = atomicAdd(&cursor[mag - 1], 1u);
       sorted[pos] = (uint32_t)((size_t)j * stride + i) | (carry << 31);
     }
@@ -154,12 +154,16 @@ template <> int MsmLaunch<Fq>::set_inf(zkb_ctx* ctx, G1XYZZ* out, int n, cudaStr
 
 int msm_sort(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
   if (P.empty) return ZKB_OK;
-  return msm_sort_records(ctx, P.jobs, P.njobs, P.stride, make_plan(P.c), P.hist, P.offs, P.cursor, P.sums, P.sorted, st);
+  DigitPlan pl = make_plan(P.c);
+  pl.wr = P.win_rank;
+  pl.ww = P.win_world;
+  return msm_sort_records(ctx, P.jobs, P.njobs, P.stride, pl, P.hist, P.offs, P.cursor, P.sums, P.sorted, st);
 }
 int msm_g1(zkb_ctx* ctx, const G1Affine* tab, size_t stride, int c, const MsmJob* jobs, int njobs, G1XYZZ* d_out, int slot,
-           cudaStream_t st) {
+           cudaStream_t st, int win_rank, int win_world) {
   MsmPlan P;
   ZKB_TRY(msm_prepare(ctx, ctx->scratch, slot, 1, tab, stride, c, jobs, njobs, d_out, &P));
+  P.win_rank = win_rank; P.win_world = win_world;
   ZKB_TRY(msm_sort(ctx, P, st));
   ZKB_TRY(msm_accumulate(ctx, P, st));
   return msm_tail(ctx, P, st);

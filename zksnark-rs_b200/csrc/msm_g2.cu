@@ -16,9 +16,10 @@ int msm_tail(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
   return P.group == 1 ? msm_tail_t<Fq>(ctx, P, st) : msm_tail_t<Fq2>(ctx, P, st);
 }
 int msm_g2(zkb_ctx* ctx, const G2Affine* tab, size_t stride, int c, const MsmJob* jobs, int njobs, G2XYZZ* d_out, int slot,
-           cudaStream_t st) {
+           cudaStream_t st, int win_rank, int win_world) {
   MsmPlan P;
   ZKB_TRY(msm_prepare(ctx, ctx->scratch, slot, 2, tab, stride, c, jobs, njobs, d_out, &P));
+  P.win_rank = win_rank; P.win_world = win_world;
   ZKB_TRY(msm_sort(ctx, P, st));
   ZKB_TRY(msm_accumulate(ctx, P, st));
   return msm_tail(ctx, P, st);

@@ -36,6 +36,7 @@ struct DigitPlan {
   int c;        // window bits
   int W;        // number of windows = floor(254 / c) + 1
   uint32_t nb;  // buckets = 2^(c-1); bucket b holds digit magnitude b+1
+  int wr, ww;   // window sharding: digit j emits a record only if j % ww == wr (ww = 1: all)
 };
 
 __host__ __device__ inline DigitPlan make_plan(int c) {
@@ -43,6 +44,8 @@ __host__ __device__ inline DigitPlan make_plan(int c) {
   p.c = c;
   p.W = 254 / c + 1;
   p.nb = 1u << (c - 1);
+  p.wr = 0;
+  p.ww = 1;
   return p;
 }
 

@@ -122,9 +122,135 @@ ZKB_HD Fq2 fq2_const(const uint32_t a[8], const uint32_t b[8]) {
   return r;
 }
 
-// One step R <- R + S on the twist (S == R: tangent), multiplying the line through them, evaluated at
-// P, into f.  R and S are finite and R != -S on every step of the loop for points of order r.
-ZKB_OOL void miller_step(Fq12& f, Affine<Fq2>& R, const Affine<Fq2>& S, bool tangent, const Fq& xP, const Fq& yP) {
+// a^q: conjugate every Fq2 coefficient, w^i picks up xi^(i (q - 1)/6) in Fq2
+ZKB_OOL Fq12 frobenius(const Fq12& a) {
+  const uint32_t g[12][8] = ZKB_FROB1_W;
+  Fq12 r;
+  r.w(0) = conj(a.w(0));
+  for (int i = 1; i < 6; i++) r.w(i) = conj(a.w(i)) * fq2_const(g[2 * i], g[2 * i + 1]);
+  return r;
+}
+
+// f * (l0 + l1 w + l3 w^3): the sparse product with a line (13 Fq2 products instead of 18).
+// With f = A + B w (A, B in Fq6) and the line = a + b w, a = (l0, 0, 0), b = (l1, l3, 0):
+//   f * line = (A a + v B b) + ((A + B)(a + b) - A a - B b) w
+ZKB_HD Fq6 mul_by_01(const Fq6& x, const Fq2& b0, const Fq2& b1) {  // x * (b0 + b1 v)
+  Fq2 v0 = x.c[0] * b0, v1 = x.c[1] * b1;
+  Fq6 r;
+  r.c[0] = v0 + mul_xi((x.c[1] + x.c[2]) * b1 - v1);
+  r.c[1] = (x.c[0] + x.c[1]) * (b0 + b1) - v0 - v1;
+  r.c[2] = (x.c[0] + x.c[2]) * b0 - v0 + v1;
+  return r;
+}
+ZKB_OOL void mul_by_line(Fq12& f, const Fq2& l0, const Fq2& l1, const Fq2& l3) {
+  Fq6 aa; aa.c[0] = f.c[0].c[0] * l0; aa.c[1] = f.c[0].c[1] * l0; aa.c[2] = f.c[0].c[2] * l0;
+  Fq6 bb = mul_by_01(f.c[1], l1, l3);
+  Fq6 e = mul_by_01(f.c[0] + f.c[1], l0 + l1, l3);
+  f.c[1] = e - aa - bb;
+  f.c[0] = aa + mul_v(bb);
+}
+
+// Homogeneous projective point on the twist and the two Miller steps (Costello-Lange-Naehrig
+// formulas for a = 0, D-type twist).  Each returns the line through the points evaluated at P up to
+// a factor in Fq2 (killed by the final exponentiation): l0 = c0 yP, l1 = c1 xP, l3 = c2.
+struct G2Proj { Fq2 x, y, z; };
+ZKB_OOL void miller_double(Fq12& f, G2Proj& r, const Fq& xP, const Fq& yP) {
+  const uint32_t h2[8] = ZKB_FQ_INV2, tb0[8] = ZKB_G2_B0, tb1[8] = ZKB_G2_B1;
+  Fq half; for (int j = 0; j < 8; j++) half.v[j] = h2[j];
+  Fq2 a = mul_fq(r.x * r.y, half);
+  Fq2 b = sqr(r.y), c = sqr(r.z);
+  Fq2 e = fq2_const(tb0, tb1) * (dbl(c) + c);
+  Fq2 f3 = dbl(e) + e;
+  Fq2 g = mul_fq(b + f3, half);
+  Fq2 h = sqr(r.y + r.z) - (b + c);
+  Fq2 i = e - b;
+  Fq2 j = sqr(r.x);
+  Fq2 ee = sqr(e);
+  r.x = a * (b - f3);
+  r.y = sqr(g) - (dbl(ee) + ee);
+  r.z = b * h;
+  mul_by_line(f, mul_fq(neg(h), yP), mul_fq(dbl(j) + j, xP), i);
+}
+ZKB_OOL void miller_add(Fq12& f, G2Proj& r, const Affine<Fq2>& q, const Fq& xP, const Fq& yP) {
+  Fq2 theta = r.y - q.y * r.z;
+  Fq2 lambda = r.x - q.x * r.z;
+  Fq2 c = sqr(theta), d = sqr(lambda);
+  Fq2 e = lambda * d;
+  Fq2 ff = r.z * c;
+  Fq2 g = r.x * d;
+  Fq2 h = e + ff - dbl(g);
+  r.x = lambda * h;
+  r.y = theta * (g - h) - e * r.y;
+  r.z = r.z * e;
+  Fq2 j = theta * q.x - lambda * q.y;
+  mul_by_line(f, mul_fq(lambda, yP), mul_fq(neg(theta), xP), j);
+}
+
+// Miller loop of the optimal-ate pairing; identity in either slot gives 1 (as `bn` does)
+ZKB_HD Fq12 miller_loop(const Affine<Fq>& P, const Affine<Fq2>& Q) {
+  Fq12 f = Fq12::one();
+  if (P.is_inf() || Q.is_inf()) return f;
+  const uint32_t loop[3] = ZKB_ATE_LOOP;
+  G2Proj R; R.x = Q.x; R.y = Q.y; R.z = Fq2::one();
+  for (int i = ZKB_ATE_LOOP_BITS - 2; i >= 0; i--) {
+    f = sqr(f);
+    miller_double(f, R, P.x, P.y);
+    if ((loop[i >> 5] >> (i & 31)) & 1u) miller_add(f, R, Q, P.x, P.y);
+  }
+  // Q1 = pi(Q), nQ2 = -pi^2(Q) in twist coordinates
+  const uint32_t g1[12][8] = ZKB_FROB1_W;
+  const uint32_t g2[6][8] = ZKB_FROB2_W;
+  Affine<Fq2> Q1, nQ2;
+  Q1.x = conj(Q.x) * fq2_const(g1[4], g1[5]);   // xi^((q-1)/3)
+  Q1.y = conj(Q.y) * fq2_const(g1[6], g1[7]);   // xi^((q-1)/2)
+  Fq k; for (int j = 0; j < 8; j++) k.v[j] = g2[2][j];  // xi^((q^2-1)/3)
+  nQ2.x = mul_fq(Q.x, k);
+  nQ2.y = Q.y;
+  miller_add(f, R, Q1, P.x, P.y);
+  miller_add(f, R, nQ2, P.x, P.y);
+  return f;
+}
+
+ZKB_OOL Fq12 pow_u(const Fq12& a) {  // a^u, u = 4965661367192848881 (63 bits)
+  const uint64_t u = ZKB_BN_U;
+  Fq12 acc = a;
+  for (int i = 61; i >= 0; i--) {
+    acc = sqr(acc);
+    if ((u >> i) & 1ull) acc = acc * a;
+  }
+  return acc;
+}
+
+// f^((q^12 - 1)/r) = ((f^(q^6 - 1))^(q^2 + 1))^((q^4 - q^2 + 1)/r); the hard part by the
+// lambda_0 + lambda_1 q + lambda_2 q^2 + lambda_3 q^3 decomposition with three powers of u
+// (Scott et al.; exact, not a multiple: checked against the plain exponent in tests/test_host_pairing.py)
+ZKB_HD Fq12 final_exponentiation(const Fq12& f) {
+  Fq12 t = conj(f) * inverse(f);
+  t = frobenius2(t) * t;
+  Fq12 fp = frobenius(t), fp2 = frobenius2(t);
+  Fq12 fp3 = frobenius(fp2);
+  Fq12 fu = pow_u(t);
+  Fq12 fu2 = pow_u(fu);
+  Fq12 fu3 = pow_u(fu2);
+  Fq12 y0 = fp * fp2 * fp3;
+  Fq12 y1 = conj(t);
+  Fq12 y2 = frobenius2(fu2);
+  Fq12 y3 = conj(frobenius(fu));
+  Fq12 y4 = conj(fu * frobenius(fu2));
+  Fq12 y5 = conj(fu2);
+  Fq12 y6 = conj(fu3 * frobenius(fu3));
+  Fq12 t0 = sqr(y6) * y4 * y5;
+  Fq12 t1 = y3 * y5 * t0;
+  t0 = t0 * y2;
+  t1 = sqr(sqr(t1) * t0);
+  t0 = t1 * y1;
+  t1 = t1 * y0;
+  return sqr(t0) * t1;
+}
+
+// ---- plain versions (affine Miller steps with one inversion each; the hard part as a 761-bit
+// exponent): the definition the fast versions above are checked against
+ZKB_OOL void miller_step_affine(Fq12& f, Affine<Fq2>& R, const Affine<Fq2>& S, bool tangent, const Fq& xP, const Fq& yP) {
   Fq2 lambda;
   if (tangent) { Fq2 xx = sqr(R.x); lambda = (dbl(xx) + xx) * inverse(dbl(R.y)); }
   else lambda = (S.y - R.y) * inverse(S.x - R.x);
@@ -133,36 +259,29 @@ ZKB_OOL void miller_step(Fq12& f, Affine<Fq2>& R, const Affine<Fq2>& S, bool tan
   R.y = lambda * (R.x - x3) - R.y;
   R.x = x3;
 }
-
-// Miller loop of the optimal-ate pairing; identity in either slot gives 1 (as `bn` does)
-ZKB_HD Fq12 miller_loop(const Affine<Fq>& P, const Affine<Fq2>& Q) {
+ZKB_HD Fq12 miller_loop_affine(const Affine<Fq>& P, const Affine<Fq2>& Q) {
   Fq12 f = Fq12::one();
   if (P.is_inf() || Q.is_inf()) return f;
   const uint32_t loop[3] = ZKB_ATE_LOOP;
   Affine<Fq2> R = Q;
   for (int i = ZKB_ATE_LOOP_BITS - 2; i >= 0; i--) {
     f = sqr(f);
-    miller_step(f, R, R, true, P.x, P.y);
-    if ((loop[i >> 5] >> (i & 31)) & 1u) miller_step(f, R, Q, false, P.x, P.y);
+    miller_step_affine(f, R, R, true, P.x, P.y);
+    if ((loop[i >> 5] >> (i & 31)) & 1u) miller_step_affine(f, R, Q, false, P.x, P.y);
   }
-  // Q1 = pi(Q), nQ2 = -pi^2(Q) in twist coordinates
-  const uint32_t g2a[8] = ZKB_FROB_G2_C0, g2b[8] = ZKB_FROB_G2_C1, g3a[8] = ZKB_FROB_G3_C0, g3b[8] = ZKB_FROB_G3_C1;
-  const uint32_t g2s[8] = ZKB_FROB_G2SQ;
+  const uint32_t g1[12][8] = ZKB_FROB1_W;
+  const uint32_t g2[6][8] = ZKB_FROB2_W;
   Affine<Fq2> Q1, nQ2;
-  Q1.x = conj(Q.x) * fq2_const(g2a, g2b);
-  Q1.y = conj(Q.y) * fq2_const(g3a, g3b);
-  Fq k; for (int j = 0; j < 8; j++) k.v[j] = g2s[j];
+  Q1.x = conj(Q.x) * fq2_const(g1[4], g1[5]);
+  Q1.y = conj(Q.y) * fq2_const(g1[6], g1[7]);
+  Fq k; for (int j = 0; j < 8; j++) k.v[j] = g2[2][j];
   nQ2.x = mul_fq(Q.x, k);
   nQ2.y = Q.y;
-  miller_step(f, R, Q1, false, P.x, P.y);
-  // the last line only contributes its value (the point sum is not needed)
+  miller_step_affine(f, R, Q1, false, P.x, P.y);
   Fq2 lambda = (nQ2.y - R.y) * inverse(nQ2.x - R.x);
-  f = f * line_value(lambda, R.x, R.y, P.x, P.y);
-  return f;
+  return f * line_value(lambda, R.x, R.y, P.x, P.y);
 }
-
-// f^((q^12 - 1)/r) = ((f^(q^6 - 1))^(q^2 + 1))^((q^4 - q^2 + 1)/r)
-ZKB_HD Fq12 final_exponentiation(const Fq12& f) {
+ZKB_HD Fq12 final_exponentiation_plain(const Fq12& f) {
   Fq12 t = conj(f) * inverse(f);
   t = frobenius2(t) * t;
   const uint32_t e[ZKB_FINAL_EXP_WORDS] = ZKB_FINAL_EXP;

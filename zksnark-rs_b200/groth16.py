@@ -89,6 +89,7 @@ ABI = {
     "zkb_bases_download": (C.c_int, [_P, _P, _P]),
     "zkb_bases_free": (None, [_P, _P]),
     "zkb_msm": (C.c_int, [_P, _P, _P, C.c_int, C.c_size_t, C.c_int, _P]),
+    "zkb_msm_windows": (C.c_int, [_P, _P, _P, C.c_int, C.c_size_t, C.c_int, C.c_int, _P]),
     "zkb_points_sum": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P]),
     "zkb_verify": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(_ProofC), C.POINTER(C.c_int)]),
     "zkb_verify_batch": (C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
@@ -700,8 +701,10 @@ class Bases:
             pass
 
 
-def msm(ctx: Context, bases: Bases, scalars, window_bits: int = 0, on_device=False, n=None):
-    """sum_i scalars[i] * bases[i] -- the `.zip().map(exp_encrypted_g*).sum()` pattern (mod.rs:255-272)."""
+def msm(ctx: Context, bases: Bases, scalars, window_bits: int = 0, on_device=False, n=None, windows=None):
+    """sum_i scalars[i] * bases[i] -- the `.zip().map(exp_encrypted_g*).sum()` pattern (mod.rs:255-272).
+    windows=(rank, world): only the table rows (windows) j = rank (mod world) -- the per-GPU partial sum of a
+    window-sharded MSM (zkb_msm_windows); the `world` partial points sum to the full result."""
     out = np.zeros(8 if bases.group == 1 else 16, dtype=np.uint64)
     if on_device:
         sp, cnt = C.c_void_p(scalars), n
@@ -709,7 +712,11 @@ def msm(ctx: Context, bases: Bases, scalars, window_bits: int = 0, on_device=Fal
         arr = scalars if isinstance(scalars, np.ndarray) else fr_limbs(scalars)
         arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
         sp, cnt = (_ptr(arr) if arr.size else None), arr.shape[0]
-    ctx.check(ctx.lib.zkb_msm(ctx.h, bases.h, sp, 1 if on_device else 0, cnt, window_bits, _ptr(out)), "zkb_msm")
+    if windows is not None:
+        ctx.check(ctx.lib.zkb_msm_windows(ctx.h, bases.h, sp, 1 if on_device else 0, cnt, windows[0], windows[1], _ptr(out)),
+                  "zkb_msm_windows")
+    else:
+        ctx.check(ctx.lib.zkb_msm(ctx.h, bases.h, sp, 1 if on_device else 0, cnt, window_bits, _ptr(out)), "zkb_msm")
     return (g1_unpack(out) if bases.group == 1 else g2_unpack(out))[0]
 
 
