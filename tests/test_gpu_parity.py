@@ -319,6 +319,31 @@ def test_prove_matches_reference(ctx, n, valid):
     assert (got2.a, got2.b, got2.c) == (want2.a, want2.b, want2.c)
 
 
+def test_single_gate_qap(ctx):
+    """n = 1: xi_t is empty (mod.rs:168, asserted :412) and h = [0].  One gate y = x * c1 on the root {1} (the 1st
+    root of unity and ASTParser's 1..=n coincide; served by the explicit-roots path)."""
+    rng = random.Random(31)
+    one = FR.from_usize(1)
+    rep = circuit.DummyRep(u=[[], [(1, one)], [], []], v=[[], [], [], [(1, one)]], w=[[], [], [(1, one)], []], roots=[1], input=2)
+    x, c1 = rand_fr(rng, True), rand_fr(rng, True)
+    wit = [1, x, x * c1 % P, c1]
+    toxic = tuple(rand_fr(rng, True) for _ in range(5))
+    r, s = rand_fr(rng, True), rand_fr(rng, True)
+    B = og.BN254Backend()
+    dense = og.qap_from_root_rep(FR, rep)
+    sig = og.setup(B, dense, toxic)
+    assert sig[0].xi_t == []
+    want = og.prove(B, dense, sig, wit, r, s)
+    q = zk.QAP.from_root_representation(ctx, rep)
+    crs = zk.setup(ctx, q, toxic)
+    d = crs.download()
+    assert d["xi_t"] == [] and d["xi1"] == sig[0].xi and d["sum_delta"] == sig[0].sum_delta and d["sum_gamma"] == sig[0].sum_gamma
+    got = zk.prove(ctx, q, crs, wit, r, s)
+    assert (got.a, got.b, got.c) == (want.a, want.b, want.c)
+    assert zk.verify(ctx, crs, wit[1:3], got)
+    assert not zk.verify(ctx, crs, [wit[1], (wit[2] + 1) % P], got)
+
+
 def test_prove_with_identity_in_crs(ctx):
     """encrypt_g1(0) entries (identity points) are legal CRS members (mod.rs:407)."""
     n = 4

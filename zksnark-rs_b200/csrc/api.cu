@@ -123,6 +123,10 @@ int zkb_ctx_create(zkb_ctx** out, int device_id) {
   }
   c->stream = c->lanes[0].hi;
   c->stream2 = c->lanes[0].lo;
+  if (const char* e = getenv("ZKB_LANES")) {
+    int v = atoi(e);
+    if (v >= 1 && v <= 4) c->batch_lanes = v;
+  }
   *out = c;
   return ZKB_OK;
 }

@@ -34,7 +34,8 @@ struct zkb_lane {
 
 struct zkb_ctx {
   int device = 0;
-  zkb_lane lanes[2];
+  zkb_lane lanes[4];               // all created; zkb_prove_batch keeps `batch_lanes` proofs in flight
+  int batch_lanes = 2;             // ZKB_LANES=1..4 overrides (developer switch; 2 measured best, profiles/)
   cudaStream_t stream = nullptr;   // = lanes[0].hi: everything outside the prove pipeline runs here
   cudaStream_t stream2 = nullptr;  // = lanes[0].lo
   int sm_count = 148;

@@ -566,16 +566,17 @@ int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint
     if (!weights[i]) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_batch: weights[%zu] is NULL", i);
   int rc = ZKB_OK;
   size_t done = 0;
+  const size_t nl = (size_t)ctx->batch_lanes;
   for (size_t i = 0; i < count && rc == ZKB_OK; i++) {
-    zkb_lane* L = &ctx->lanes[i & 1];
-    if (i >= 2) {
-      rc = prove_collect(ctx, L, &out[i - 2]);
-      done = i - 1;
+    zkb_lane* L = &ctx->lanes[i % nl];
+    if (i >= nl) {
+      rc = prove_collect(ctx, L, &out[i - nl]);
+      done = i - nl + 1;
       if (rc != ZKB_OK) break;
     }
     rc = prove_enqueue(ctx, L, q, c, weights[i], on_device, r + 4 * i, s + 4 * i);
   }
-  for (size_t i = done; i < count && rc == ZKB_OK; i++) rc = prove_collect(ctx, &ctx->lanes[i & 1], &out[i]);
+  for (size_t i = done; i < count && rc == ZKB_OK; i++) rc = prove_collect(ctx, &ctx->lanes[i % nl], &out[i]);
   if (rc != ZKB_OK) cudaDeviceSynchronize();  // leave no work in flight behind an error
   return rc;
 }
