@@ -66,11 +66,14 @@ void hc_pairing(int stage, int n, const uint64_t* g1s, const uint64_t* g2s, uint
   if (stage & 1) f = (stage & 2) ? final_exponentiation_plain(f) : final_exponentiation(f);
   st12(out, f);
 }
-// Fq12 arithmetic on its own: op 0 a*b, 1 a^2, 2 1/a, 3 a^(q^2), 4 a^(q^6), 5 a^q, 6 a^u, 7 a * sparse line (b_0, b_1, b_3)
+// Fq12 arithmetic on its own: op 0 a*b, 1 a^2, 2 1/a, 3 a^(q^2), 4 a^(q^6), 5 a^q, 6 a^u (a in the
+// cyclotomic subgroup), 7 a * sparse line (b_0, b_1, b_3), 8 cyclotomic square, 9 the easy part a^((q^6-1)(q^2+1))
 void hc_fq12(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
   Fq12 x, y;
   for (int i = 0; i < 6; i++) { x.w(i) = ld2(a + 8 * i); y.w(i) = ld2(b + 8 * i); }
   if (op == 7) { mul_by_line(x, y.w(0), y.w(1), y.w(3)); st12(out, x); return; }
+  if (op == 8) { st12(out, cyclotomic_sqr(x)); return; }
+  if (op == 9) { Fq12 t = conj(x) * inverse(x); st12(out, frobenius2(t) * t); return; }
   st12(out, op == 0 ? x * y : op == 1 ? sqr(x) : op == 2 ? inverse(x) : op == 3 ? frobenius2(x) : op == 4 ? conj(x) : op == 5 ? frobenius(x) : pow_u(x));
 }
 }

@@ -51,6 +51,12 @@ def main():
     parts = [zk.prove_batch(ctx, q, zk.setup(ctx, q, toxic, rank=k, world=2), wits, rs, ss) for k in range(2)]
     got = zk.prove_combine_batch(ctx, np.stack(parts))
     assert [(p.a, p.b, p.c) for p in got] == [(p.a, p.b, p.c) for p in single]
+    # verify (Miller loops + final exponentiation, 13 KB of per-thread stack), batch with a rejected proof; window-sharded MSM
+    pubs = [w[1:3] for w in wits]
+    assert zg.verify_batch(ctx, crs, pubs + [[pubs[0][0], (pubs[0][1] + 1) % P]], single + [single[0]]) == [True, True, True, False]
+    b = zk.Bases.generate(ctx, 1, ks[:256])
+    sc = [rng.randrange(P) for _ in range(256)]
+    assert zg.points_sum(ctx, 1, [zk.msm(ctx, b, sc, windows=(g, 3)) for g in range(3)]) == zk.msm(ctx, b, sc)
     print(f"sanitize case ok: {ctx.launches} kernel launches")
     ctx.close()
 

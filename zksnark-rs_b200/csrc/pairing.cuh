@@ -211,11 +211,35 @@ ZKB_HD Fq12 miller_loop(const Affine<Fq>& P, const Affine<Fq2>& Q) {
   return f;
 }
 
-ZKB_OOL Fq12 pow_u(const Fq12& a) {  // a^u, u = 4965661367192848881 (63 bits)
+// a^2 for a in the cyclotomic subgroup (a^(q^6+1) = 1, true after the easy part of the final exponentiation):
+// Granger-Scott squaring, three Fq4 squarings = 6 Fq2 products instead of 12
+ZKB_HD void fq4_sqr(const Fq2& a, const Fq2& b, Fq2& t0, Fq2& t1) {  // (a + b y)^2, y^2 = xi
+  Fq2 tmp = a * b;
+  t0 = (a + b) * (mul_xi(b) + a) - tmp - mul_xi(tmp);
+  t1 = dbl(tmp);
+}
+ZKB_OOL Fq12 cyclotomic_sqr(const Fq12& a) {
+  const Fq2 &z0 = a.c[0].c[0], &z4 = a.c[0].c[1], &z3 = a.c[0].c[2], &z2 = a.c[1].c[0], &z1 = a.c[1].c[1], &z5 = a.c[1].c[2];
+  Fq2 t0, t1, t2, t3, t4, t5;
+  fq4_sqr(z0, z1, t0, t1);
+  fq4_sqr(z2, z3, t2, t3);
+  fq4_sqr(z4, z5, t4, t5);
+  Fq2 t5x = mul_xi(t5);
+  Fq12 r;
+  r.c[0].c[0] = dbl(t0 - z0) + t0;   // 3 t0 - 2 z0
+  r.c[1].c[1] = dbl(t1 + z1) + t1;   // 3 t1 + 2 z1
+  r.c[1].c[0] = dbl(t5x + z2) + t5x; // 3 xi t5 + 2 z2
+  r.c[0].c[2] = dbl(t4 - z3) + t4;   // 3 t4 - 2 z3
+  r.c[0].c[1] = dbl(t2 - z4) + t2;   // 3 t2 - 2 z4
+  r.c[1].c[2] = dbl(t3 + z5) + t3;   // 3 t3 + 2 z5
+  return r;
+}
+
+ZKB_OOL Fq12 pow_u(const Fq12& a) {  // a^u, u = 4965661367192848881 (63 bits), a in the cyclotomic subgroup
   const uint64_t u = ZKB_BN_U;
   Fq12 acc = a;
   for (int i = 61; i >= 0; i--) {
-    acc = sqr(acc);
+    acc = cyclotomic_sqr(acc);
     if ((u >> i) & 1ull) acc = acc * a;
   }
   return acc;
