@@ -100,8 +100,17 @@ __device__ __forceinline__ void sts_fr(uint4* p0, uint4* p1, uint32_t e, const F
   p1[e] = *reinterpret_cast<const uint4*>(&x.v[4]);
 }
 
+// Measured on B200 (profiles/r01_notes.md): the two radix-4 groups of a thread unrolled side by side (two
+// independent multiply chains per thread: the kernel stalls on fixed-latency dependencies, ncu "wait") at
+// >= 3 blocks per SM: 0.236 -> 0.220 ms at 2^20; capping registers for 6-7 blocks per SM instead: 0.226-0.229.
+#ifndef ZKB_NTT_MIN_BLOCKS
+#define ZKB_NTT_MIN_BLOCKS 3
+#endif
+#ifndef ZKB_NTT_NO_UNROLL
+#define ZKB_NTT_UNROLL2 1
+#endif
 template <bool DIT>
-__global__ void __launch_bounds__(128) k_ntt_pass(Fr* __restrict__ d, const Fr* __restrict__ tw, uint32_t log_n,
+__global__ void __launch_bounds__(128, ZKB_NTT_MIN_BLOCKS) k_ntt_pass(Fr* __restrict__ d, const Fr* __restrict__ tw, uint32_t log_n,
                                                   uint32_t hi, uint32_t lo, uint32_t logC) {
   extern __shared__ uint4 smem[];
   const uint32_t B = hi - lo;
@@ -165,6 +174,9 @@ __global__ void __launch_bounds__(128) k_ntt_pass(Fr* __restrict__ d, const Fr* 
       const uint32_t ls = 2 * r;  // lower stage of the round
       const uint32_t sh = ls + logC;
       const uint32_t h = 1u << sh;
+#ifdef ZKB_NTT_UNROLL2
+#pragma unroll 2
+#endif
       for (uint32_t q = t; q < (T >> 2); q += nthr) {
         const uint32_t e0 = ((q >> sh) << (sh + 2)) | (q & (h - 1));
         const uint32_t e1 = e0 + h, e2 = e0 + 2 * h, e3 = e0 + 3 * h;
