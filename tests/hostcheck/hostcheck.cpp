@@ -15,6 +15,13 @@ static G2Affine ldg2(const uint64_t* p) { G2Affine r; r.x = ld2(p); r.y = ld2(p 
 static void stg2(uint64_t* p, const G2Affine& a) { st2(p, a.x); st2(p + 8, a.y); }
 
 extern "C" {
+// n inverses at once, both ways: out = inverse(a) (safegcd), out2 = inverse_fermat(a); field: 0 Fr 1 Fq
+void hc_inverse_many(int field, int n, const uint64_t* a, uint64_t* out, uint64_t* out2) {
+  for (int i = 0; i < n; i++) {
+    if (field == 0) { Fr x = ld<Fr>(a + 4 * i); st(out + 4 * i, inverse(x)); st(out2 + 4 * i, inverse_fermat(x)); }
+    else { Fq x = ld<Fq>(a + 4 * i); st(out + 4 * i, inverse(x)); st(out2 + 4 * i, inverse_fermat(x)); }
+  }
+}
 // op: 0 mul 1 add 2 sub 3 inverse(a) ; field: 0 Fr 1 Fq
 void hc_field(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
   if (field == 0) {

@@ -120,3 +120,20 @@ def test_g2_group_law(hc):
         out = pack(0, 0, 0, 0)
         hc.hc_g2_mul(g2_pack(bn.G2_GEN), pack(k), out)
         assert g2_unpack(out) == bn.g2_mul(bn.G2_GEN, k)
+
+
+def test_fast_inverse_matches_fermat_and_bigint(hc):
+    """The safegcd inverse (ff.cuh: inverse) against the Fermat exponentiation and Python's pow on random and edge
+    inputs, for both moduli; inverse(0) = 0."""
+    rng = random.Random(99)
+    for field, p in ((0, FR.p), (1, Q_MODULUS)):
+        vals = [0, 1, 2, p - 1, p - 2, (p + 1) // 2, 1 << 253, (1 << 253) - 1, 3 << 200, p >> 1]
+        vals += [1 << k for k in range(0, 254, 7)] + [p - (1 << k) for k in range(0, 250, 11)]
+        vals += [rng.randrange(p) for _ in range(3000)] + [rng.randrange(1 << 64) for _ in range(100)]
+        n = len(vals)
+        out, out2 = (ctypes.c_uint64 * (4 * n))(), (ctypes.c_uint64 * (4 * n))()
+        hc.hc_inverse_many(field, n, pack(*vals), out, out2)
+        got, fermat = unpack(out, n), unpack(out2, n)
+        want = [pow(v, -1, p) if v else 0 for v in vals]
+        assert fermat == want
+        assert got == want
