@@ -184,9 +184,6 @@ static int msm_tail_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
 #ifndef ZKB_ACC_MIN_BLOCKS
 #define ZKB_ACC_MIN_BLOCKS 1
 #endif
-#ifndef ZKB_ACC_PAIRS_DEFAULT
-#define ZKB_ACC_PAIRS_DEFAULT 0
-#endif
 template <class F>
 __global__ void __launch_bounds__(128, ZKB_ACC_MIN_BLOCKS) k_accumulate_chunks(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
                                                            const uint32_t* __restrict__ sorted, uint32_t nbk, size_t nchunks,
@@ -218,129 +215,6 @@ __global__ void __launch_bounds__(128, ZKB_ACC_MIN_BLOCKS) k_accumulate_chunks(c
     Affine<F> P = pts[rec & 0x7fffffffu];
     if (rec >> 31) P = neg(P);
     acc = madd(acc, P);
-  }
-  if (is_head) heads[t] = acc; else buckets[g] = acc;
-}
-
-// Bucket accumulation with one level of batched affine additions in front of the XYZZ chain.
-// The records of a chunk are taken two at a time; a pair that lies in one bucket is first added in
-// AFFINE coordinates -- lambda = (y2 - y1)/(x2 - x1), three products plus three for its share of ONE
-// inversion per chunk (Montgomery's trick over the chunk's pairs, fast safegcd inverse, ff.cuh) --
-// and only the pair sums enter the 8M+2S mixed-addition chain: (6 + 10)/2 = 8 instead of 10 products
-// per G1 record, about 2 x 14.4 + 26 -> 20 instead of 26 product-equivalents per G2 record.  The price is
-// a second gather of the points (pass B recomputes what pass A saw: nothing but the prefix products is
-// kept between them) and 6 / 12 KB of local memory per thread for the prefix products and pair sums.
-// Pairs never straddle a bucket boundary; P + P, P + (-P) and identity operands are classified the
-// same way in both passes.  Same chunk plan, same heads / buckets contract as k_accumulate_chunks.
-template <class F>
-__device__ __forceinline__ Affine<F> load_signed(const Affine<F>* __restrict__ pts, uint32_t rec) {
-  Affine<F> P = pts[rec & 0x7fffffffu];
-  if (rec >> 31) P = neg(P);
-  return P;
-}
-// denominator of the chord / tangent through P and Q; kind 0: regular (den valid), 1: sum = Q, 2: sum = P, 3: sum = identity
-template <class F>
-__device__ __forceinline__ int pair_kind(const Affine<F>& P, const Affine<F>& Q, F& den) {
-  den = F::one();
-  if (P.is_inf()) return 1;
-  if (Q.is_inf()) return 2;
-  if (P.x == Q.x) {
-    if (!(P.y == Q.y) || P.y.is_zero()) return 3;
-    den = dbl(P.y);
-    return 0;
-  }
-  den = Q.x - P.x;
-  return 0;
-}
-static const int ZKB_PAIR_SMAX = 128;  // longest chunk (ChunkPlan::S1 <= 128)
-template <class F>
-__global__ void __launch_bounds__(128, ZKB_ACC_MIN_BLOCKS) k_accumulate_pairs(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
-                                                          const uint32_t* __restrict__ sorted, uint32_t nbk, size_t nchunks,
-                                                          ChunkPlan ch, XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nchunks) return;
-  const uint32_t total = offs[nbk];
-  const uint32_t start = ch.start((uint32_t)t);
-  if (start >= total) return;
-  const uint32_t S = ch.len((uint32_t)t);
-  const uint32_t end = (total - start > S) ? start + S : total;
-  uint32_t lo = 0, hi = nbk;
-  while (lo < hi) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (offs[mid] <= start) lo = mid + 1; else hi = mid;
-  }
-  const uint32_t g0 = lo - 1;
-  const uint32_t npairs = (end - start) >> 1;
-  F pre[ZKB_PAIR_SMAX / 2];
-  Affine<F> sum[ZKB_PAIR_SMAX / 2];
-  uint32_t paired[ZKB_PAIR_SMAX / 64] = {};
-  // pass A: which pairs share a bucket; prefix products of their denominators.  The two points of pair
-  // i + 1 are requested before pair i is worked on (the gathers are two dependent global loads: with one
-  // product of work per pair the pass would otherwise run at load latency).
-  F run = F::one();
-  {
-    uint32_t g = g0, bend = offs[g0 + 1];
-    Affine<F> Pn, Qn;
-    if (npairs) { Pn = load_signed(pts, sorted[start]); Qn = load_signed(pts, sorted[start + 1]); }
-    for (uint32_t i = 0; i < npairs; i++) {
-      const uint32_t p0 = start + 2 * i;
-      const Affine<F> P = Pn, Q = Qn;
-      if (i + 1 < npairs) { Pn = load_signed(pts, sorted[p0 + 2]); Qn = load_signed(pts, sorted[p0 + 3]); }
-      while (bend <= p0) { g++; bend = offs[g + 1]; }
-      if (p0 + 1 < bend) {
-        F den;
-        pair_kind(P, Q, den);
-        run = run * den;
-        paired[i >> 5] |= 1u << (i & 31);
-      }
-      pre[i] = run;
-    }
-  }
-  // pass B (backwards): inverse of every denominator from the one inversion, then the pair sums
-  run = inverse(run);
-  {
-    Affine<F> Pn, Qn;
-    if (npairs) { Pn = load_signed(pts, sorted[start + 2 * (npairs - 1)]); Qn = load_signed(pts, sorted[start + 2 * (npairs - 1) + 1]); }
-    for (uint32_t i = npairs; i-- > 0;) {
-      const Affine<F> P = Pn, Q = Qn;
-      if (i) { Pn = load_signed(pts, sorted[start + 2 * i - 2]); Qn = load_signed(pts, sorted[start + 2 * i - 1]); }
-      if (!((paired[i >> 5] >> (i & 31)) & 1u)) continue;
-      F den;
-      const int kind = pair_kind(P, Q, den);
-      if (kind != 0) {
-        sum[i] = kind == 1 ? Q : (kind == 2 ? P : Affine<F>::inf());
-        continue;
-      }
-      const F inv = i ? run * pre[i - 1] : run;
-      run = run * den;
-      F num;
-      if (P.x == Q.x) { F xx = sqr(P.x); num = dbl(xx) + xx; } else num = Q.y - P.y;
-      const F lambda = num * inv;
-      Affine<F> R;
-      R.x = sqr(lambda) - P.x - Q.x;
-      R.y = lambda * (P.x - R.x) - P.y;
-      sum[i] = R;
-    }
-  }
-  // pass C: the mixed-addition chain over pair sums and unpaired records, flushing at bucket boundaries
-  uint32_t g = g0;
-  bool is_head = offs[g] < start;
-  uint32_t bend = offs[g + 1];
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t p = start; p < end;) {
-    if (p == bend) {
-      if (is_head) { heads[t] = acc; is_head = false; } else buckets[g] = acc;
-      acc = XYZZ<F>::inf();
-      do { g++; bend = offs[g + 1]; } while (bend <= p);
-    }
-    const uint32_t i = (p - start) >> 1;
-    if (!((p - start) & 1u) && i < npairs && ((paired[i >> 5] >> (i & 31)) & 1u)) {
-      acc = madd(acc, sum[i]);
-      p += 2;
-    } else {
-      acc = madd(acc, load_signed(pts, sorted[p]));
-      p += 1;
-    }
   }
   if (is_head) heads[t] = acc; else buckets[g] = acc;
 }
@@ -492,13 +366,7 @@ __global__ void __launch_bounds__(128) k_expand_table(Affine<F>* __restrict__ ta
 template <class F>
 static int launch_accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
                              size_t nacc, ChunkPlan ch, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind) {
-  // ZKB_ACC_PAIRS: bit 0 = G1, bit 1 = G2 take the pair-sum variant (developer switch while it is being measured)
-  static const int pairs = getenv("ZKB_ACC_PAIRS") ? atoi(getenv("ZKB_ACC_PAIRS")) : ZKB_ACC_PAIRS_DEFAULT;
-  const bool use_pairs = (pairs >> (sizeof(F) == sizeof(Fq) ? 0 : 1)) & 1;
-  if (use_pairs && ch.S1 <= (uint32_t)ZKB_PAIR_SMAX && ch.S2 <= (uint32_t)ZKB_PAIR_SMAX)
-    ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_pairs<F>, cdiv(nacc, 128), 128, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
-  else
-    ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks<F>, cdiv(nacc, 128), 128, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
+  ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks<F>, cdiv(nacc, 128), 128, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
   return ZKB_OK;
 }
 template <class F>
