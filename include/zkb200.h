@@ -193,6 +193,14 @@ int zkb_pairing(zkb_ctx* ctx, const uint64_t* g1s, const uint64_t* g2s, size_t n
  * root = omega_{2^log_n} (forward) or its inverse with the 1/n scaling (inverse != 0).
  * coset_shift (host, 4 limbs, may be NULL): forward evaluates on shift*omega^i; inverse undoes it. */
 int zkb_ntt_fr(zkb_ctx* ctx, uint64_t* d_data, uint32_t log_n, int inverse, const uint64_t* coset_shift);
+/* Multi-GPU transform with the outer dimension sharded over G = 2^log_g ranks: rank g holds
+ * the decimated subsequence x[g], x[g+G], ... and transforms it with zkb_ntt_fr (size n/G, same `inverse`);
+ * the G partial transforms are all-gathered (NCCL) into d_parts (G x n/G x 4 limbs, canonical, device, rank
+ * order) and every rank evaluates its slice of `count` consecutive outputs from k0:
+ *   X[k] = sum_g root^(g k) * Y_g[k mod n/G]     (inverse: the inverse root and the remaining factor 1/G).
+ * d_out: count x 4 limbs, canonical, device.  The concatenated slices equal zkb_ntt_fr on the whole vector. */
+int zkb_ntt_combine(zkb_ctx* ctx, const uint64_t* d_parts, uint32_t log_n, uint32_t log_g, int inverse, uint64_t k0,
+                    uint64_t count, uint64_t* d_out);
 /* Kernel-only variant for measurement: data already in Montgomery form, natural order in,
  * bit-reversed order out (forward DIF) -- the form the prove pipeline uses internally. */
 int zkb_ntt_fr_raw(zkb_ctx* ctx, uint64_t* d_data_mont, uint32_t log_n, int inverse);

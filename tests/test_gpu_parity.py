@@ -109,6 +109,35 @@ def test_ntt_roundtrip_and_linearity_full_size(ctx, log_n):
         ctx.dev_free(d)
 
 
+@pytest.mark.parametrize("log_n,log_g", [(4, 1), (10, 2), (13, 3), (3, 3), (11, 0)])
+def test_ntt_outer_dimension_sharded(ctx, log_n, log_g):
+    """Multi-GPU transform (SURVEY 8e): G ranks transform the decimated subsequences x[g::G]; the all-gathered partial
+    transforms are combined slice by slice (zkb_ntt_combine).  One device plays every rank here; the exchange itself
+    is covered by tools/ntt_multi_gpu.py on real ranks.  Forward and inverse equal the single-device transform."""
+    rng = random.Random(900 + log_n)
+    n, G = 1 << log_n, 1 << log_g
+    sub = n // G
+    x = [rand_fr(rng) for _ in range(n)]
+    for inverse in (False, True):
+        want = zk.ntt(ctx, x, inverse=inverse)
+        parts = []
+        for g in range(G):
+            xs = x[g::G]
+            parts += zk.ntt(ctx, xs, inverse=inverse) if sub > 1 else xs
+        d_parts = ctx.dev_alloc(32 * n)
+        d_out = ctx.dev_alloc(32 * sub)
+        ctx.h2d(d_parts, zg.fr_limbs(parts))
+        got = []
+        for r in range(G):
+            zg.ntt_combine(ctx, d_parts, log_n, log_g, inverse, r * sub, sub, d_out)
+            buf = np.zeros((sub, 4), dtype=np.uint64)
+            ctx.d2h(buf, d_out)
+            got += zg.limbs_to_ints(buf)
+        ctx.dev_free(d_parts)
+        ctx.dev_free(d_out)
+        assert got == want
+
+
 # ------------------------------------------------------------------------------------------------
 # device field arithmetic (crate bn's Fr / Fq / Fq2 as reached through fr.rs:18-56)
 @pytest.mark.parametrize("field", [0, 1])

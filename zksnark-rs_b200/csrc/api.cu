@@ -298,6 +298,17 @@ int zkb_ntt_fr(zkb_ctx* ctx, uint64_t* d_data, uint32_t log_n, int inverse_, con
   return ZKB_OK;
 }
 
+int zkb_ntt_combine(zkb_ctx* ctx, const uint64_t* d_parts, uint32_t log_n, uint32_t log_g, int inverse, uint64_t k0,
+                    uint64_t count, uint64_t* d_out) {
+  if (!ctx || !d_parts || (!d_out && count)) return set_err(ctx, ZKB_ERR_ARG, "zkb_ntt_combine: NULL argument");
+  if (log_n < 1 || log_n > 27 || log_g > log_n || log_g > 6) return set_err(ctx, ZKB_ERR_ARG, "zkb_ntt_combine: bad sizes");
+  if (k0 + count > ((uint64_t)1 << log_n)) return set_err(ctx, ZKB_ERR_ARG, "zkb_ntt_combine: slice out of range");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZKB_TRY(ntt_combine(ctx, (const Fr*)d_parts, log_n, log_g, inverse != 0, k0, count, (Fr*)d_out, ctx->stream));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKB_OK;
+}
+
 // ---- bases / MSM --------------------------------------------------------------------------------
 static size_t pt_bytes(int group) { return group == 1 ? sizeof(G1Affine) : sizeof(G2Affine); }
 

@@ -129,6 +129,8 @@ int vec_to_mont(zkb_ctx* ctx, Fr* d, size_t n, bool to, cudaStream_t st);
 int vec_mul(zkb_ctx* ctx, Fr* out, const Fr* a, const Fr* b, size_t n, cudaStream_t st);
 // out[i] = first * base^i
 int fill_powers(zkb_ctx* ctx, Fr* out, const Fr& base, const Fr& first, size_t n, cudaStream_t st);
+int ntt_combine(zkb_ctx* ctx, const Fr* parts, uint32_t log_n, uint32_t log_g, bool inverse, uint64_t k0, uint64_t count, Fr* out,
+                cudaStream_t st);
 Fr host_omega(uint32_t log_n, bool inverse);  // Montgomery form
 int get_twiddles(zkb_ctx* ctx, uint32_t log_n, bool inverse, Fr** out);
 

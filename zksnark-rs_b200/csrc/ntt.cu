@@ -266,6 +266,35 @@ int ntt_dit(zkb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, cudaStream_t st) 
   return run_ntt<true>(ctx, d, log_n, inverse, st);
 }
 
+// Outer-dimension sharding across GPUs: rank g transforms the decimated subsequence
+// x[g], x[g+G], ... (a size-n/G transform, Y_g); after the all-gather of the Y_g every rank evaluates
+// its slice of  X[k] = sum_g w^(g k) Y_g[k mod n/G].  Inputs and outputs are canonical residues:
+// the twiddles are in Montgomery form, so the Montgomery product w * y is the canonical w y.
+__global__ void k_ntt_combine(const Fr* __restrict__ parts, const Fr* __restrict__ tw, uint32_t log_n, uint32_t log_g, Fr scale,
+                              int has_scale, uint64_t k0, uint64_t count, Fr* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint64_t n = (uint64_t)1 << log_n, sub = n >> log_g, k = k0 + i, kk = k & (sub - 1);
+  Fr acc = parts[kk];
+  for (uint64_t g = 1; g < ((uint64_t)1 << log_g); g++) {
+    const uint64_t e = (g * k) & (n - 1);
+    const Fr w = e < (n >> 1) ? tw[e] : neg(tw[e - (n >> 1)]);
+    acc = acc + w * parts[g * sub + kk];
+  }
+  if (has_scale) acc = scale * acc;
+  out[i] = acc;
+}
+int ntt_combine(zkb_ctx* ctx, const Fr* parts, uint32_t log_n, uint32_t log_g, bool inverse, uint64_t k0, uint64_t count, Fr* out,
+                cudaStream_t st) {
+  if (!count) return ZKB_OK;
+  Fr scale = Fr::one();
+  if (inverse) scale = inverse_fermat(fr_from_u64((uint64_t)1 << log_g));  // zkb_ntt_fr's inverse already divided by n/G
+  Fr* tw = nullptr;
+  if (log_g) ZKB_TRY(get_twiddles(ctx, log_n, inverse, &tw));
+  ZKB_LAUNCH(ctx, k_ntt_combine, cdiv(count, 256), 256, 0, st, parts, tw, log_n, log_g, scale, inverse ? 1 : 0, k0, count, out);
+  return ZKB_OK;
+}
+
 int bitrev_permute(zkb_ctx* ctx, Fr* out, const Fr* in, uint32_t log_n, const Fr* h_scale, cudaStream_t st) {
   size_t n = (size_t)1 << log_n;
   Fr sc = h_scale ? *h_scale : Fr::one();

@@ -34,3 +34,39 @@ def all_gather_partials(part: np.ndarray, device=None) -> np.ndarray:
     out = torch.empty(PARTIAL_LIMBS * world, dtype=torch.int64, device=src.device)
     dist.all_gather_into_tensor(out, src)
     return out.cpu().numpy().view(np.uint64).reshape(world, PARTIAL_LIMBS)
+
+
+def ntt_sharded(ctx, x_sub: np.ndarray, log_n: int, inverse: bool = False) -> np.ndarray:
+    """One size-2^log_n transform with its outer dimension sharded over the ranks (world a power of two).
+
+    x_sub: this rank's decimated subsequence x[rank::world] as (n/world, 4) uint64 canonical limbs.  Returns this
+    rank's slice X[rank*n/world : (rank+1)*n/world] (same layout).  Local size-n/world transform (zkb_ntt_fr), ONE
+    all-gather of the partial transforms (n*32 bytes arrive at every rank; NCCL on GPUs), then the
+    final coefficient reduction X[k] = sum_g w^(g k) Y_g[k mod n/world] on the device (zkb_ntt_combine).
+    """
+    import importlib
+
+    import torch
+    import torch.distributed as dist
+
+    zg = importlib.import_module(__package__ + ".groth16")
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    log_g = world.bit_length() - 1
+    assert 1 << log_g == world and log_g <= log_n
+    sub = (1 << log_n) >> log_g
+    assert x_sub.shape == (sub, 4)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mine = torch.from_numpy(np.ascontiguousarray(x_sub, dtype=np.uint64).view(np.int64)).to(dev)
+    if log_n - log_g >= 1:
+        zg.ntt_dev(ctx, mine.data_ptr(), log_n - log_g, inverse)
+    parts = torch.empty((world, sub, 4), dtype=torch.int64, device=dev)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.all_gather_into_tensor(parts.view(-1), mine.view(-1))
+        torch.cuda.synchronize()
+    else:
+        parts[0] = mine
+    out = torch.empty((sub, 4), dtype=torch.int64, device=dev)
+    zg.ntt_combine(ctx, parts.data_ptr(), log_n, log_g, inverse, rank * sub, sub, out.data_ptr())
+    return out.cpu().numpy().view(np.uint64)

@@ -82,6 +82,7 @@ ABI = {
     "zkb_prove_combine_batch": (C.c_int, [_P, _P, C.c_int, C.c_size_t, _P]),
     "zkb_qap_h": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "zkb_ntt_fr": (C.c_int, [_P, _P, C.c_uint32, C.c_int, _P]),
+    "zkb_ntt_combine": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, _P]),
     "zkb_ntt_fr_raw": (C.c_int, [_P, _P, C.c_uint32, C.c_int]),
     "zkb_fr_to_mont": (C.c_int, [_P, _P, C.c_size_t, C.c_int]),
     "zkb_bases_upload": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.POINTER(_P)]),
@@ -659,6 +660,17 @@ def ntt(ctx: Context, values, inverse=False, coset_shift=None) -> list:
     finally:
         ctx.dev_free(d)
     return limbs_to_ints(a)
+
+
+def ntt_dev(ctx: Context, d_data: int, log_n: int, inverse=False):
+    """zkb_ntt_fr in place on a device vector of canonical residues (natural order in and out)."""
+    ctx.check(ctx.lib.zkb_ntt_fr(ctx.h, C.c_void_p(d_data), log_n, 1 if inverse else 0, None), "zkb_ntt_fr")
+
+
+def ntt_combine(ctx: Context, d_parts: int, log_n: int, log_g: int, inverse: bool, k0: int, count: int, d_out: int):
+    """This rank's slice of a transform whose outer dimension is sharded over 2^log_g ranks (zkb_ntt_combine)."""
+    ctx.check(ctx.lib.zkb_ntt_combine(ctx.h, C.c_void_p(d_parts), log_n, log_g, 1 if inverse else 0, k0, count, C.c_void_p(d_out)),
+              "zkb_ntt_combine")
 
 
 class Bases:
