@@ -129,3 +129,45 @@ def test_all_gather_partials_world2_gloo(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+_GLOO_NTT_WORKER = """
+import importlib, os, sys, random
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+zd = importlib.import_module("zksnark-rs_b200.dist")
+zg = importlib.import_module("zksnark-rs_b200.groth16")
+from oracle import poly, synthetic          # the checker plays the two device steps (local transform, combine)
+from oracle.fields import FR
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+P, log_n = FR.p, 6
+n = 1 << log_n
+rng = random.Random(7)                      # the same vector on every rank
+x = [rng.randrange(P) for _ in range(n)]
+w = synthetic.omega(log_n)
+sl, k0, count = zd.ntt_shard_layout(log_n, rank, world)
+assert (k0, count) == (rank * n // world, n // world)
+y_mine = poly.dft(FR, x[sl], pow(w, world, P))                     # size n/G transform of the decimated subsequence
+parts = zd.all_gather_limbs(zg.fr_limbs(y_mine))                   # (world, n/G, 4), rank order
+ys = [zg.limbs_to_ints(parts[g]) for g in range(world)]
+mine = [sum(pow(w, g * k, P) * ys[g][k % count] for g in range(world)) % P for k in range(k0, k0 + count)]
+full = zd.all_gather_limbs(zg.fr_limbs(mine))
+got = [v for g in range(world) for v in zg.limbs_to_ints(full[g])]
+assert got == poly.dft(FR, x, w)
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_ntt_sharded_protocol_world2_gloo(tmp_path):
+    """The exchange and index conventions of the outer-dimension-sharded transform (dist.ntt_shard_layout,
+    all_gather_limbs) on CPU with world_size 2 over gloo; the oracle stands in for the two device steps."""
+    script = tmp_path / "worker_ntt.py"
+    script.write_text(_GLOO_NTT_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29612", str(script), ROOT]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

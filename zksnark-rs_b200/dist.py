@@ -36,6 +36,32 @@ def all_gather_partials(part: np.ndarray, device=None) -> np.ndarray:
     return out.cpu().numpy().view(np.uint64).reshape(world, PARTIAL_LIMBS)
 
 
+def all_gather_limbs(arr: np.ndarray, device=None) -> np.ndarray:
+    """(k, 4) uint64 limbs on every rank -> (world, k, 4), rank order (gloo on CPU tensors, NCCL on `device`)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    a = np.ascontiguousarray(arr, dtype=np.uint64)
+    if world == 1:
+        return a.reshape((1,) + a.shape).copy()
+    src = torch.from_numpy(a.view(np.int64).reshape(-1).copy())
+    if device is not None:
+        src = src.to(device)
+    out = torch.empty(src.numel() * world, dtype=torch.int64, device=src.device)
+    dist.all_gather_into_tensor(out, src)
+    return out.cpu().numpy().view(np.uint64).reshape((world,) + a.shape)
+
+
+def ntt_shard_layout(log_n: int, rank: int, world: int):
+    """Who holds what in the outer-dimension-sharded transform: (input = x[rank::world], output range [k0, k0 + count))."""
+    log_g = world.bit_length() - 1
+    if 1 << log_g != world or log_g > log_n:
+        raise ValueError("ntt_sharded: world must be a power of two not larger than the transform")
+    sub = (1 << log_n) >> log_g
+    return slice(rank, None, world), rank * sub, sub
+
+
 def ntt_sharded(ctx, x_sub: np.ndarray, log_n: int, inverse: bool = False) -> np.ndarray:
     """One size-2^log_n transform with its outer dimension sharded over the ranks (world a power of two).
 
@@ -53,8 +79,7 @@ def ntt_sharded(ctx, x_sub: np.ndarray, log_n: int, inverse: bool = False) -> np
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     log_g = world.bit_length() - 1
-    assert 1 << log_g == world and log_g <= log_n
-    sub = (1 << log_n) >> log_g
+    _, k0, sub = ntt_shard_layout(log_n, rank, world)
     assert x_sub.shape == (sub, 4)
     dev = torch.device("cuda", torch.cuda.current_device())
     mine = torch.from_numpy(np.ascontiguousarray(x_sub, dtype=np.uint64).view(np.int64)).to(dev)
@@ -68,5 +93,5 @@ def ntt_sharded(ctx, x_sub: np.ndarray, log_n: int, inverse: bool = False) -> np
     else:
         parts[0] = mine
     out = torch.empty((sub, 4), dtype=torch.int64, device=dev)
-    zg.ntt_combine(ctx, parts.data_ptr(), log_n, log_g, inverse, rank * sub, sub, out.data_ptr())
+    zg.ntt_combine(ctx, parts.data_ptr(), log_n, log_g, inverse, k0, sub, out.data_ptr())
     return out.cpu().numpy().view(np.uint64)
