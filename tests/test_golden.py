@@ -71,7 +71,8 @@ def test_device_matches_golden(c):
         n = len(c["rep"]["roots"])
         pad = lambda xs, k: list(xs) + [0] * (k - len(xs))
         assert u == pad(c["u_sum"], n) and v == pad(c["v_sum"], n)
-        assert h[:max(n - 1, 1)] == pad(c["h"], max(n - 1, 1)) or (n == 1 and h[0] == 0)
+        k = max(len(c["h"]), len(h))  # n = 1: the reference's quotient is [0], the device returns no coefficients
+        assert pad(h, k) == pad(c["h"], k)
         got = zk.prove(ctx, q, crs, c["weights"], c["r"], c["s"])
         assert (got.a, got.b, got.c) == (_pt(c["proof"]["a"]), _pt(c["proof"]["b"]), _pt(c["proof"]["c"]))
         assert zk.verify(ctx, crs, c["inputs"], got) == c["verify"]
