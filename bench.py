@@ -21,6 +21,8 @@ throughput under "other_mode", measured in the same run.
            the library around each launch during the timed region.
 `--impl reference`: the reference's own (single-threaded, O(n^2)) algorithm as restated in
            oracle/oracle_b.c, timed on bounded samples at full problem width and scaled to one proof.
+`cpu_best_effort`: context only -- one full proof with an NTT and Pippenger on all host threads
+           (oracle/oracle_fast.c); neither the reference's algorithm nor the reference arm.
 """
 
 import argparse
@@ -80,6 +82,21 @@ def reference_sample(log_n, scale=1.0, seed=1):
             f"breakdown s/proof: g1={t_g1 * g1_terms:.3g} g2={t_g2 * n:.3g} mul={t_mul * n:.3g} "
             f"div={t_div * (n - 1):.3g} wsum={t_ws * 3 * m:.3g}")
     return per_proof, desc
+
+
+def best_effort_cpu(log_n):
+    """SURVEY 8d "for context": ONE full proof with fast algorithms (NTT + Pippenger, oracle/oracle_fast.c) on every host
+    thread of this box.  Not the reference's algorithm and not the reference arm: a context number beside `cpu_baseline`."""
+    from oracle import oracle_fast as of
+    threads = of.threads_default()
+    ln = min(log_n, 20)  # one 2^20 proof is 10-30 s of wall clock on a typical host; larger sizes are scaled from it
+    sec, parts, _ = of.time_prove(ln, threads, seed=7)
+    sec *= float(1 << (log_n - ln))
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port-fast-algorithms",
+            "sample": (f"one full proof at 2^{ln}" + (f", scaled x{1 << (log_n - ln)} to 2^{log_n}" if ln != log_n else "") +
+                       f": inverse NTTs + size-2n NTT product, Pippenger MSMs (5n G1 + n G2 terms) over pthreads; seconds: "
+                       f"poly={parts['poly']:.3g} g1={parts['g1']:.3g} g2={parts['g2']:.3g}"),
+            "seconds_per_proof": sec}
 
 
 def run_reference(args):
@@ -283,6 +300,7 @@ def run_ours(args):
     if rank == 0 and world == 1:
         sec, desc = reference_sample(args.log_n, 6.0)  # ~12 s of single-core work
         cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
+        cpu_fast = best_effort_cpu(args.log_n)
 
     jobs = 1 if sw > 1 else world  # proofs completed per step by the whole job
     if rank == 0:
@@ -350,6 +368,7 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+            line["cpu_best_effort"] = cpu_fast
         if other:
             line["other_mode"] = other
         if world > 1:

@@ -13,8 +13,12 @@ Two restatements live here:
   ``dft``/``idft``, the ``.zk`` parser, ``setup``/``prove``/``verify``) over both
   back-ends the reference has: the toy field Z251 (its own test fixture) and
   BN254 (crate ``bn`` 0.4.3, restated from the published curve definition).
-* Oracle B (``oracle_b.cpp``): the same ``prove`` algorithm in C++ with 256-bit
+* Oracle B (``oracle_b.c``): the same ``prove`` algorithm in C with 256-bit
   Montgomery arithmetic, fast enough to be the timed CPU baseline.
+* Oracle F (``oracle_fast.c``): NOT the reference's algorithm -- the same proof
+  computed with an NTT and Pippenger on all host threads, pinned bit for bit
+  against A and B (``tests/test_oracle_fast.py``).  ``bench.py`` times it as the
+  ``cpu_best_effort`` context number; it is never the reference arm.
 
 Pinning status
 --------------

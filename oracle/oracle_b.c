@@ -43,6 +43,19 @@ static int ge4(const u64* a, const u64* b) {
   for (int i = 3; i >= 0; i--) { if (a[i] != b[i]) return a[i] > b[i]; }
   return 1;
 }
+#if defined(__x86_64__)
+#include <immintrin.h>
+static u64 add4(u64* r, const u64* a, const u64* b) {
+  unsigned long long t; unsigned char c = 0;
+  for (int i = 0; i < 4; i++) { c = _addcarry_u64(c, a[i], b[i], &t); r[i] = t; }
+  return c;
+}
+static u64 sub4(u64* r, const u64* a, const u64* b) {
+  unsigned long long t; unsigned char c = 0;
+  for (int i = 0; i < 4; i++) { c = _subborrow_u64(c, a[i], b[i], &t); r[i] = t; }
+  return c;
+}
+#else
 static u64 add4(u64* r, const u64* a, const u64* b) {
   u128 c = 0;
   for (int i = 0; i < 4; i++) { c += (u128)a[i] + b[i]; r[i] = (u64)c; c >>= 64; }
@@ -56,6 +69,7 @@ static u64 sub4(u64* r, const u64* a, const u64* b) {
   }
   return br;
 }
+#endif
 static fe fe_add(const field* F, fe a, fe b) {
   fe r; u64 c = add4(r.l, a.l, b.l);
   if (c || ge4(r.l, F->p)) sub4(r.l, r.l, F->p);
@@ -69,22 +83,26 @@ static int fe_is_zero(fe a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
 static int fe_eq(fe a, fe b) { return a.l[0] == b.l[0] && a.l[1] == b.l[1] && a.l[2] == b.l[2] && a.l[3] == b.l[3]; }
 static fe fe_neg(const field* F, fe a) { fe z = {{0, 0, 0, 0}}; return fe_sub(F, z, a); }
 
-/* Montgomery product (SOS): t = a*b; reduce */
+/* Montgomery product (CIOS, rows unrolled; both moduli are 254-bit, so five words hold every partial sum) */
 static fe fe_mul(const field* F, fe a, fe b) {
-  u64 t[9] = {0};
+  const u64 p0 = F->p[0], p1 = F->p[1], p2 = F->p[2], p3 = F->p[3], ninv = F->ninv;
+  u64 t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
   for (int i = 0; i < 4; i++) {
-    u128 c = 0;
-    for (int j = 0; j < 4; j++) { c += (u128)a.l[j] * b.l[i] + t[i + j]; t[i + j] = (u64)c; c >>= 64; }
-    t[i + 4] = (u64)c;
+    const u64 bi = b.l[i];
+    u128 c = (u128)a.l[0] * bi + t0; t0 = (u64)c; c >>= 64;
+    c += (u128)a.l[1] * bi + t1; t1 = (u64)c; c >>= 64;
+    c += (u128)a.l[2] * bi + t2; t2 = (u64)c; c >>= 64;
+    c += (u128)a.l[3] * bi + t3; t3 = (u64)c; c >>= 64;
+    t4 += (u64)c;
+    const u64 m = t0 * ninv;
+    c = (u128)m * p0 + t0; c >>= 64;
+    c += (u128)m * p1 + t1; t0 = (u64)c; c >>= 64;
+    c += (u128)m * p2 + t2; t1 = (u64)c; c >>= 64;
+    c += (u128)m * p3 + t3; t2 = (u64)c; c >>= 64;
+    c += t4; t3 = (u64)c; t4 = (u64)(c >> 64);
   }
-  for (int i = 0; i < 4; i++) {
-    u64 m = t[i] * F->ninv;
-    u128 c = 0;
-    for (int j = 0; j < 4; j++) { c += (u128)m * F->p[j] + t[i + j]; t[i + j] = (u64)c; c >>= 64; }
-    for (int k = i + 4; k < 9 && c; k++) { c += t[k]; t[k] = (u64)c; c >>= 64; }
-  }
-  fe r; memcpy(r.l, t + 4, 32);
-  if (t[8] || ge4(r.l, F->p)) sub4(r.l, r.l, F->p);
+  fe r = {{t0, t1, t2, t3}};
+  if (t4 || ge4(r.l, F->p)) sub4(r.l, r.l, F->p);
   return r;
 }
 static fe fe_sqr(const field* F, fe a) { return fe_mul(F, a, a); }

@@ -1,0 +1,102 @@
+"""ctypes front-end of Oracle F (oracle/oracle_fast.c): the prove() path with fast algorithms (NTT, Pippenger) on all
+host threads -- test infrastructure and bench.py's `cpu_best_effort` context number only."""
+
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+from . import oracle_b as ob
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "liboracle_fast.so")
+_lib = None
+
+
+def build() -> str:
+    """Compile oracle_fast.c (which #includes oracle_b.c); content-hash stamp over both sources."""
+    digest = hashlib.sha256(b"".join(open(os.path.join(HERE, f), "rb").read() for f in ("oracle_fast.c", "oracle_b.c"))).hexdigest()
+    stamp = SO + ".sha256"
+    if not (os.path.exists(SO) and os.path.exists(stamp) and open(stamp).read().strip() == digest):
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-Wall", "-Wno-unused-function", "-pthread", "-shared",
+                               "-o", SO, os.path.join(HERE, "oracle_fast.c")])
+        with open(stamp, "w") as f:
+            f.write(digest)
+    return SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.of_time_prove.restype = C.c_double
+        _lib.of_time_prove.argtypes = [C.c_uint, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def threads_default() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def ntt(values, inverse=False, threads=1):
+    """dft / idft of field/mod.rs:508-537 at the 2^k-th root of unity 5^((r-1)/2^k), natural order."""
+    n = len(values)
+    assert n and n & (n - 1) == 0
+    buf = ob._pack(values)
+    lib().of_ntt(buf, C.c_uint(n.bit_length() - 1), C.c_int(1 if inverse else 0), C.c_int(threads))
+    return ob._unpack(buf, n)
+
+
+def msm_g1(scalars, pts, threads=1):
+    out = (C.c_uint64 * 8)()
+    lib().of_msm_g1(ob._pack(scalars), ob.g1_pack(pts), C.c_size_t(len(scalars)), C.c_int(threads), out)
+    return ob.g1_unpack(out)
+
+
+def msm_g2(scalars, pts, threads=1):
+    out = (C.c_uint64 * 16)()
+    lib().of_msm_g2(ob._pack(scalars), ob.g2_pack(pts), C.c_size_t(len(scalars)), C.c_int(threads), out)
+    return ob.g2_unpack(out)
+
+
+class _ProveIn(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("n_input", C.c_size_t), ("n_sd", C.c_size_t),
+                ("alpha1", C.c_void_p), ("beta1", C.c_void_p), ("delta1", C.c_void_p), ("xi1", C.c_void_p),
+                ("xi_t", C.c_void_p), ("sum_delta", C.c_void_p), ("beta2", C.c_void_p), ("delta2", C.c_void_p),
+                ("xi2", C.c_void_p)]
+
+
+def prove(n, n_input, a_evals, b_evals, sigma, weights, r, s, threads=1):
+    """groth16::prove on the roots-of-unity domain from the evaluation vectors A_k = <weights, u(w^k)>, B_k likewise.
+    Returns (a, b, c, h) with h the n-1 quotient coefficients (trailing zeros kept)."""
+    s1, s2 = sigma
+    assert len(s1.xi) == n and len(s1.xi_t) == n - 1 and len(a_evals) == n and len(b_evals) == n
+    pin = _ProveIn()
+    pin.n, pin.n_input, pin.n_sd = n, n_input, len(s1.sum_delta)
+    bufs = {"alpha1": ob.g1_pack([s1.alpha]), "beta1": ob.g1_pack([s1.beta]), "delta1": ob.g1_pack([s1.delta]),
+            "xi1": ob.g1_pack(s1.xi), "xi_t": ob.g1_pack(s1.xi_t), "sum_delta": ob.g1_pack(s1.sum_delta),
+            "beta2": ob.g2_pack([s2.beta]), "delta2": ob.g2_pack([s2.delta]), "xi2": ob.g2_pack(s2.xi)}
+    for k, b in bufs.items():
+        setattr(pin, k, C.addressof(b))
+    proof = (C.c_uint64 * 32)()
+    hbuf = (C.c_uint64 * (4 * n))()
+    rc = lib().of_prove(C.byref(pin), ob._pack(a_evals), ob._pack(b_evals), ob._pack(weights), C.c_size_t(len(weights)),
+                        ob._pack([r]), ob._pack([s]), proof, hbuf, C.c_int(threads))
+    if rc != 0:
+        raise ValueError(f"of_prove rc={rc}")
+    return ob.g1_unpack(proof, 0), ob.g2_unpack(proof, 8), ob.g1_unpack(proof, 24), ob._unpack(hbuf, n - 1)
+
+
+def time_prove(log_n, threads=None, seed=1):
+    """Seconds for one full-size proof (synthetic shape m = 2n+2, input = 2) with fast algorithms on `threads` host threads.
+    Returns (seconds, {"poly": s, "g1": s, "g2": s}, check) -- check = proof.a.x, equal across thread counts."""
+    from .bn254 import G2_GEN
+    threads = threads or threads_default()
+    g2 = ob.g2_pack([G2_GEN])
+    tm = (C.c_double * 3)()
+    chk = (C.c_uint64 * 4)()
+    t = lib().of_time_prove(C.c_uint(log_n), C.c_int(threads), C.c_uint64(seed), C.addressof(g2), tm, chk)
+    return t, {"poly": tm[0], "g1": tm[1], "g2": tm[2]}, ob._unpack(chk, 1)[0]

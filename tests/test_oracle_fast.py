@@ -1,0 +1,77 @@
+"""Pin Oracle F (oracle/oracle_fast.c: NTT + Pippenger on host threads, bench.py's `cpu_best_effort` context number)
+against Oracle A (the literal restatement, itself pinned to the reference's golden vectors) and Oracle B.  CPU only."""
+
+import random
+
+import pytest
+
+from oracle import bn254 as bn, groth16 as g, oracle_b as ob, oracle_fast as of, poly, synthetic
+from oracle.fields import FR
+
+P = FR.p
+
+
+@pytest.mark.parametrize("log_n,threads", [(0, 1), (1, 1), (3, 1), (6, 3), (13, 4)])
+def test_ntt_is_the_reference_dft(log_n, threads):
+    rng = random.Random(log_n)
+    n = 1 << log_n
+    x = [rng.randrange(P) for _ in range(n)]
+    w = synthetic.omega(log_n)
+    y = of.ntt(x, threads=threads)
+    if n <= 64:
+        assert y == poly.dft(FR, x, w)  # field/mod.rs:508-523
+    else:
+        assert y[0] == sum(x) % P
+        for i in (1, n // 2, n - 1):
+            assert y[i] == sum(v * pow(w, i * j, P) for j, v in enumerate(x)) % P
+    assert of.ntt(y, inverse=True, threads=threads) == x  # idft, :525-537
+
+
+@pytest.mark.parametrize("n,threads", [(1, 1), (7, 2), (300, 1), (3000, 5)])
+def test_pippenger_matches_per_term_fold(n, threads):
+    rng = random.Random(n)
+    ks = [rng.randrange(P) for _ in range(max(n, 8))]
+    sc = [rng.choice([0, 1, P - 1, rng.randrange(P), rng.randrange(P)]) for _ in range(n)]
+    pts = [bn.g1_mul(bn.BASE_G1, k) for k in ks[:8]]
+    pts = (pts + [None, pts[0], bn.g1_neg(pts[0])] + pts * (n // 8 + 1))[:n]  # identity, repeated and opposite points
+    if n <= 300:
+        assert of.msm_g1(sc, pts, threads) == ob.msm_g1(sc, pts)
+    else:  # closed form: every point is a known multiple of the base point
+        kk = (ks[:8] + [0, ks[0], P - ks[0]] + ks[:8] * (n // 8 + 1))[:n]
+        assert of.msm_g1(sc, pts, threads) == bn.g1_mul(bn.BASE_G1, sum(a * b for a, b in zip(sc, kk)) % P)
+    m = min(n, 40)
+    p2 = [bn.g2_mul(bn.BASE_G2, k) for k in ks[:4]]
+    p2 = (p2 + [None, p2[1], bn.g2_neg(p2[1])] + p2 * (m // 4 + 1))[:m]
+    assert of.msm_g2(sc[:m], p2, threads) == ob.msm_g2(sc[:m], p2)
+
+
+@pytest.mark.parametrize("n,valid,threads", [(2, True, 1), (4, True, 2), (8, False, 3), (16, True, 8)])
+def test_prove_equals_the_literal_restatement(n, valid, threads):
+    log_n = n.bit_length() - 1
+    w = synthetic.omega(log_n)
+    roots = [pow(w, k, P) for k in range(n)]
+    rep = synthetic.horner_rep(FR, n, roots)
+    qap = g.qap_from_root_rep(FR, rep)
+    rng = random.Random(n)
+    wit = synthetic.horner_witness(FR, n, rng.randrange(1, P), [rng.randrange(P) for _ in range(n)])
+    if not valid:
+        wit[5] = (wit[5] + 3) % P
+    toxic = tuple(rng.randrange(1, P) for _ in range(5))
+    r, s = rng.randrange(1, P), rng.randrange(1, P)
+    B = g.BN254Backend()
+    sig = g.setup(B, qap, toxic)
+    want = g.prove(B, qap, sig, wit, r, s)
+    idx = {root: k for k, root in enumerate(roots)}
+    ev = lambda rows: [sum(wit[i] * val for i, row in enumerate(rows) for (root, val) in row if idx[root] == k) % P for k in range(n)]
+    a, b, c, h = of.prove(n, rep.input, ev(rep.u), ev(rep.v), sig, wit, r, s, threads)
+    assert (a, b, c) == (want.a, want.b, want.c)
+    u, v, ws = g.weighted_sums(FR, qap, wit)
+    hq = g.quotient_h(FR, qap, u, v, ws)
+    assert h[:len(hq)] == hq and not any(h[len(hq):])
+    assert ob.prove(qap, sig, wit, r, s)[:3] == (a, b, c)
+
+
+def test_timed_proof_is_deterministic_across_thread_counts():
+    t1, parts, chk1 = of.time_prove(6, 1, seed=3)
+    t2, _, chk2 = of.time_prove(6, 4, seed=3)
+    assert chk1 == chk2 and chk1 != 0 and t1 > 0 and t2 > 0 and set(parts) == {"poly", "g1", "g2"}
