@@ -138,6 +138,10 @@ void zkb_ctx_destroy(zkb_ctx* ctx) {
   for (auto& t : ctx->tw)
     for (auto& p : t)
       if (p) cudaFree(p);
+  for (auto& t : ctx->twt)
+    for (auto& d : t)
+      for (auto& p : d)
+        if (p) cudaFree(p);
   for (auto& b : ctx->scratch)
     if (b.p) cudaFree(b.p);
   prof_clear(ctx);

@@ -43,6 +43,9 @@ struct zkb_ctx {
   std::string err;
   // twiddle tables tw[log_n][inverse]: omega^k (k < n/2) in Montgomery form, built lazily
   zkb::Fr* tw[28][2] = {};
+  // per-pass twiddle TILES twt[log_n][inverse][pass]: what one block of k_ntt_pass needs, contiguous (two 16-byte
+  // planes), so the block fetches it with ONE bulk-async (TMA) copy into shared memory (ntt.cu); built with tw
+  uint4* twt[28][2][4] = {};
   // reusable scratch (grown on demand, never shrunk) for the non-pipelined entry points
   zkb::DevBuf scratch[16];
   // optional per-kernel-class CUDA-event timing (zkb_profile): pairs recorded around tracked launches

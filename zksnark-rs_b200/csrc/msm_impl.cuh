@@ -184,8 +184,11 @@ static int msm_tail_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
 #ifndef ZKB_ACC_MIN_BLOCKS
 #define ZKB_ACC_MIN_BLOCKS 1
 #endif
+#ifndef ZKB_ACC_THREADS
+#define ZKB_ACC_THREADS 128
+#endif
 template <class F>
-__global__ void __launch_bounds__(128, ZKB_ACC_MIN_BLOCKS) k_accumulate_chunks(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
+__global__ void __launch_bounds__(ZKB_ACC_THREADS, ZKB_ACC_MIN_BLOCKS) k_accumulate_chunks(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
                                                            const uint32_t* __restrict__ sorted, uint32_t nbk, size_t nchunks,
                                                            ChunkPlan ch, XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -211,6 +214,11 @@ __global__ void __launch_bounds__(128, ZKB_ACC_MIN_BLOCKS) k_accumulate_chunks(c
       acc = XYZZ<F>::inf();
       do { g++; bend = offs[g + 1]; } while (bend <= p);
     }
+#if defined(ZKB_ACC_PREFETCH) && ZKB_ACC_PREFETCH > 0
+    // developer variant: pull the table entry of a later record towards the SM while this addition runs
+    if (p + ZKB_ACC_PREFETCH < end)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pts + (sorted[p + ZKB_ACC_PREFETCH] & 0x7fffffffu)));
+#endif
     uint32_t rec = sorted[p];
     Affine<F> P = pts[rec & 0x7fffffffu];
     if (rec >> 31) P = neg(P);
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(128) k_expand_table(Affine<F>* __restrict__ ta
 template <class F>
 static int launch_accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
                              size_t nacc, ChunkPlan ch, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind) {
-  ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks<F>, cdiv(nacc, 128), 128, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
+  ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks<F>, cdiv(nacc, ZKB_ACC_THREADS), ZKB_ACC_THREADS, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
   return ZKB_OK;
 }
 template <class F>

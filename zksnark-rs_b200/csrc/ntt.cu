@@ -10,7 +10,11 @@
 // LDS.128), runs its stages there, and writes the tile back -- so HBM sees one read and one write
 // of the vector per pass (2-3 passes for 2^20..2^26).  Tiles of the strided passes are
 // (2^B rows) x (C = 2^(10-B) adjacent columns) so that every global access is a >=128-byte run.
-// Twiddles omega^k (k < n/2) live in a per-size table (L2-resident: 16 MB at 2^20).
+// Twiddles omega^k (k < n/2) live in a per-size table (L2-resident: 16 MB at 2^20).  Twiddle TILES: beside the flat
+// table every pass has a tiled copy in which the (2^B - 1) * C twiddles ONE block needs are contiguous (two 16-byte
+// planes, stage-major), so a block stages them with one bulk-async copy (TMA: cp.async.bulk + mbarrier) that
+// overlaps its data-tile loads, and the butterflies read them with conflict-free LDS.128 instead of 32-byte gathers
+// from L2 (ZKB_NTT_TMA=0/1 selects the path at run time; both are bit-identical).
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -64,6 +68,62 @@ __global__ void k_bitrev(Fr* out, const Fr* in, uint32_t log_n, Fr scale, int ha
   out[j] = v;
 }
 
+struct Pass { uint32_t lo, hi, logC; };
+
+static std::vector<Pass> plan(uint32_t log_n) {
+  std::vector<Pass> ps;  // ordered from the low stages up
+  uint32_t l0 = log_n < 10 ? log_n : 10;
+  ps.push_back({0, l0, 0});
+  uint32_t rem = log_n - l0;
+  if (rem) {
+    uint32_t np = (rem + 7) / 8;
+    uint32_t lo = l0;
+    for (uint32_t i = 0; i < np; i++) {
+      uint32_t b = rem / np + (i < rem % np ? 1 : 0);
+      ps.push_back({lo, lo + b, 10 - b});
+      lo += b;
+    }
+  }
+  return ps;
+}
+
+
+// ---- twiddle tiles ---------------------------------------------------------------------------------
+// Tile of group g (= column group Lbase / C of a pass) holds, for ls = 0..B-1, m0 < 2^ls, c < C:
+//   slot ((2^ls - 1) + m0) * C + c  =  omega_n^(((m0 << lo) + g*C + c) << (log_n - 1 - lo - ls))
+// as two planes of T uint4 (limbs 0..3 | limbs 4..7); slots >= T - C are padding.
+__global__ void k_fill_tw_tiles(uint4* __restrict__ out, const Fr* __restrict__ tw, uint32_t log_n, uint32_t lo, uint32_t B,
+                                uint32_t logC, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const uint32_t logT = B + logC, T = 1u << logT, C = 1u << logC;
+  const uint32_t slot = (uint32_t)(i & (T - 1));
+  const uint64_t g = i >> logT;
+  uint4 a = make_uint4(0, 0, 0, 0), b = a;
+  if (slot < T - C) {
+    const uint32_t idx = slot >> logC, c = slot & (C - 1);
+    const uint32_t ls = 31 - __clz(idx + 1), m0 = idx + 1 - (1u << ls);
+    const uint64_t j = ((uint64_t)m0 << lo) + (g << logC) + c;
+    const Fr w = tw[j << (log_n - 1 - lo - ls)];
+    a = *reinterpret_cast<const uint4*>(&w.v[0]);
+    b = *reinterpret_cast<const uint4*>(&w.v[4]);
+  }
+  out[(g * 2) * T + slot] = a;
+  out[(g * 2 + 1) * T + slot] = b;
+}
+
+template <bool DIT, bool TMA>
+__global__ void k_ntt_pass(Fr* __restrict__ d, const Fr* __restrict__ tw, const uint4* __restrict__ tiles, uint32_t log_n, uint32_t hi,
+                           uint32_t lo, uint32_t logC);
+
+#ifndef ZKB_NTT_TMA_DEFAULT
+#define ZKB_NTT_TMA_DEFAULT 0
+#endif
+static bool ntt_use_tma() {
+  static const int v = getenv("ZKB_NTT_TMA") ? atoi(getenv("ZKB_NTT_TMA")) : ZKB_NTT_TMA_DEFAULT;
+  return v != 0;
+}
+
 int get_twiddles(zkb_ctx* ctx, uint32_t log_n, bool inverse, Fr** out) {
   if (log_n < 1 || log_n > 27) return set_err(ctx, ZKB_ERR_ARG, "ntt size 2^%u unsupported", log_n);
   Fr*& t = ctx->tw[log_n][inverse ? 1 : 0];
@@ -71,6 +131,20 @@ int get_twiddles(zkb_ctx* ctx, uint32_t log_n, bool inverse, Fr** out) {
     size_t half = (size_t)1 << (log_n - 1);
     ZKB_CUDA(ctx, cudaMalloc(&t, half * sizeof(Fr)));
     ZKB_LAUNCH(ctx, k_fill_powers, cdiv(half, 256), 256, 0, ctx->stream, t, host_omega(log_n, inverse), Fr::one(), half);
+    if (ntt_use_tma()) {
+      std::vector<Pass> ps = plan(log_n);
+      for (size_t q = 0; q < ps.size() && q < 4; q++) {
+        const Pass& p = ps[q];
+        const uint32_t logT = p.hi - p.lo + p.logC;
+        const size_t groups = ((size_t)1 << p.lo) >> p.logC, total = groups << logT;
+        uint4*& tt = ctx->twt[log_n][inverse ? 1 : 0][q];
+        ZKB_CUDA(ctx, cudaMalloc(&tt, total * 32));
+        // 64 KB of dynamic shared memory (data tile + twiddle tile) needs the opt-in, per device
+        ZKB_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        ZKB_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        ZKB_LAUNCH(ctx, k_fill_tw_tiles, cdiv(total, 256), 256, 0, ctx->stream, tt, t, log_n, p.lo, p.hi - p.lo, p.logC, total);
+      }
+    }
     ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   *out = t;
@@ -109,10 +183,37 @@ __device__ __forceinline__ void sts_fr(uint4* p0, uint4* p1, uint32_t e, const F
 #ifndef ZKB_NTT_NO_UNROLL
 #define ZKB_NTT_UNROLL2 1
 #endif
-template <bool DIT>
-__global__ void __launch_bounds__(128, ZKB_NTT_MIN_BLOCKS) k_ntt_pass(Fr* __restrict__ d, const Fr* __restrict__ tw, uint32_t log_n,
+// bulk-async (TMA) staging of one contiguous global range into shared memory, completion on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the init visible to the async proxy
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+// TMA = true: `tiles` is this pass's tiled twiddle table (k_fill_tw_tiles); thread 0 issues one bulk copy of the
+// block's 32*T-byte tile into the upper half of shared memory before the data tile is loaded, every thread waits
+// on the mbarrier after the data barrier, and twiddles are LDS.128 pairs.  TMA = false: 32-byte gathers from `tw`.
+template <bool DIT, bool TMA>
+__global__ void __launch_bounds__(128, ZKB_NTT_MIN_BLOCKS) k_ntt_pass(Fr* __restrict__ d, const Fr* __restrict__ tw,
+                                                  const uint4* __restrict__ tiles, uint32_t log_n,
                                                   uint32_t hi, uint32_t lo, uint32_t logC) {
   extern __shared__ uint4 smem[];
+  __shared__ alignas(8) unsigned long long tw_bar;
   const uint32_t B = hi - lo;
   const uint32_t logT = B + logC;
   const uint32_t T = 1u << logT;
@@ -127,16 +228,28 @@ __global__ void __launch_bounds__(128, ZKB_NTT_MIN_BLOCKS) k_ntt_pass(Fr* __rest
   const uint64_t base = (H << hi) + Lbase;
   const uint4* g4 = reinterpret_cast<const uint4*>(d);
   uint4* gw4 = reinterpret_cast<uint4*>(d);
+  const uint4* tw0 = smem + 2 * T;  // TMA: twiddle planes
+  const uint4* tw1 = smem + 3 * T;
 
+  if (TMA) {
+    if (t == 0) mbar_init(&tw_bar, 1);
+    __syncthreads();
+    if (t == 0) bulk_load(smem + 2 * T, tiles + (size_t)(blockIdx.x % groups_per_H) * 2 * T, T * 32, &tw_bar);
+  }
   for (uint32_t e = t; e < T; e += nthr) {
     uint64_t gi = base + ((uint64_t)(e >> logC) << lo) + (e & (C - 1));
     p0[e] = g4[gi * 2];
     p1[e] = g4[gi * 2 + 1];
   }
   __syncthreads();
+  if (TMA) mbar_wait(&tw_bar, 0);
 
   // twiddle of the butterfly whose lower element is tile element e, in stage s = lo + ls
   auto twiddle = [&](uint32_t e, uint32_t ls) -> Fr {
+    if (TMA) {  // slot ((2^ls - 1) + m0) * C + c, with m0 * C + c = e & (2^(ls + logC) - 1)
+      const uint32_t slot = (((1u << ls) - 1) << logC) + (e & ((1u << (ls + logC)) - 1));
+      return lds_fr(tw0, tw1, slot);
+    }
     const uint32_t s = lo + ls;
     const uint64_t m0 = (e >> logC) & ((1u << ls) - 1);
     const uint64_t j = (m0 << lo) + Lbase + (e & (C - 1));
@@ -217,25 +330,6 @@ __global__ void __launch_bounds__(128, ZKB_NTT_MIN_BLOCKS) k_ntt_pass(Fr* __rest
   }
 }
 
-struct Pass { uint32_t lo, hi, logC; };
-
-static std::vector<Pass> plan(uint32_t log_n) {
-  std::vector<Pass> ps;  // ordered from the low stages up
-  uint32_t l0 = log_n < 10 ? log_n : 10;
-  ps.push_back({0, l0, 0});
-  uint32_t rem = log_n - l0;
-  if (rem) {
-    uint32_t np = (rem + 7) / 8;
-    uint32_t lo = l0;
-    for (uint32_t i = 0; i < np; i++) {
-      uint32_t b = rem / np + (i < rem % np ? 1 : 0);
-      ps.push_back({lo, lo + b, 10 - b});
-      lo += b;
-    }
-  }
-  return ps;
-}
-
 template <bool DIT>
 static int run_ntt(zkb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, cudaStream_t st) {
   if (log_n == 0) return ZKB_OK;
@@ -254,7 +348,13 @@ static int run_ntt(zkb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, cudaStream
     if (env_threads >= 32 && (unsigned)env_threads < block) block = (unsigned)env_threads;
     size_t smem = (size_t)T * 32;
     if (ctx->profile) ctx->prof_units[PK_NTT] += (uint64_t)1 << log_n;
-    ZKB_LAUNCH_K(ctx, PK_NTT, k_ntt_pass<DIT>, grid, block, smem, st, d, tw, log_n, p.hi, p.lo, p.logC);
+    const int pi = DIT ? q : np - 1 - q;  // index of the pass in plan order (= index of its tile table)
+    const uint4* tiles = (ntt_use_tma() && pi < 4) ? ctx->twt[log_n][inverse ? 1 : 0][pi] : nullptr;
+    if (tiles) {
+      ZKB_LAUNCH_K(ctx, PK_NTT, (k_ntt_pass<DIT, true>), grid, block, 2 * smem, st, d, tw, tiles, log_n, p.hi, p.lo, p.logC);
+    } else {
+      ZKB_LAUNCH_K(ctx, PK_NTT, (k_ntt_pass<DIT, false>), grid, block, smem, st, d, tw, tiles, log_n, p.hi, p.lo, p.logC);
+    }
   }
   return ZKB_OK;
 }
