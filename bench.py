@@ -297,7 +297,7 @@ def run_ours(args):
         assert (proof.a, proof.b, proof.c) == (single.a, single.b, single.c)
 
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.skip_cpu:
         sec, desc = reference_sample(args.log_n, 6.0)  # ~12 s of single-core work
         cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
         cpu_fast = best_effort_cpu(args.log_n)
@@ -423,6 +423,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true",
+                    help="profiling runs only (ncu replays): leave out the cpu_baseline / cpu_best_effort legs; the line is then not a bench line")
     ap.add_argument("--mode", default="replicas", choices=["shard", "replicas"],
                     help="N > 1: one proof stream per rank (default: throughput, weak scaling) or one proof sharded over the ranks (latency)")
     args = ap.parse_args()

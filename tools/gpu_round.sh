@@ -11,10 +11,10 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2>> gpurun_out/${tag}_bench.err
 timeout 300 python tools/verify_bench.py 10 1 1024 16384 > gpurun_out/${tag}_verify.log 2>&1
 timeout 600 python tools/msm_bench.py --g1 18 20 22 24 > gpurun_out/${tag}_msm_sweep.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu list exit $?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --skip-cpu --steps 2 --warmup 1 > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu list exit $?"
 for k in "acc_g1:k_accumulate_chunks.*FqParams" "acc_g2:k_accumulate_chunks.*Fq2" "ntt:k_ntt_pass"; do
   name=${k%%:*}; rx=${k#*:}
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s 8 -c 1 -f -o gpurun_out/${tag}_${name} python bench.py --steps 2 --warmup 1 > gpurun_out/${tag}_full_${name}.log 2>&1; echo "ncu full $name exit $?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s 8 -c 1 -f -o gpurun_out/${tag}_${name} python bench.py --skip-cpu --steps 2 --warmup 1 > gpurun_out/${tag}_full_${name}.log 2>&1; echo "ncu full $name exit $?"
 done
 : > gpurun_out/${tag}_sanitizer.txt
 for tool in memcheck racecheck synccheck; do

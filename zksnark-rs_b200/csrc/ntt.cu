@@ -14,7 +14,7 @@
 // table every pass has a tiled copy in which the (2^B - 1) * C twiddles ONE block needs are contiguous (two 16-byte
 // planes, stage-major), so a block stages them with one bulk-async copy (TMA: cp.async.bulk + mbarrier) that
 // overlaps its data-tile loads, and the butterflies read them with conflict-free LDS.128 instead of 32-byte gathers
-// from L2 (ZKB_NTT_TMA=0/1 selects the path at run time; both are bit-identical).
+// from L2 (ZKB_NTT_TMA=0..3 selects the policy at run time, see ntt_tma_mode; all are bit-identical).
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -117,11 +117,25 @@ __global__ void k_ntt_pass(Fr* __restrict__ d, const Fr* __restrict__ tw, const 
                            uint32_t lo, uint32_t logC);
 
 #ifndef ZKB_NTT_TMA_DEFAULT
-#define ZKB_NTT_TMA_DEFAULT 0
+#define ZKB_NTT_TMA_DEFAULT 3
 #endif
-static bool ntt_use_tma() {
+// 0: 32-byte gathers from the flat table in every pass; 1: tiles in every pass; 2: tiles only in passes whose whole
+// tile table is at most 4 MB (the low passes: few column groups, every block of a group re-reads the same tile from L2);
+// 3 (default): tiles in every pass of transforms up to 2^18 (two passes), gathers above.  Measured on B200
+// (profiles/r01_ntt_tma_modes.txt, ms per transform, modes 0 / 1 / 2): 2^12 .0431/.0409/.0409, 2^16 .0519/.0492/.0492,
+// 2^18 .0749/.0716/.0727, 2^20 .2200/.2218/.2211, 2^22 .8308/.8425/.8386, 2^24 3.494/3.541/3.539 -- staging wins 4-5 %
+// while the transform is latency-bound (two passes), and loses ~1 % once three passes keep the multiplier busy (the
+// 64 KB of shared memory per block instead of 32 KB leaves less L1 for the data tiles).
+static int ntt_tma_mode() {
   static const int v = getenv("ZKB_NTT_TMA") ? atoi(getenv("ZKB_NTT_TMA")) : ZKB_NTT_TMA_DEFAULT;
-  return v != 0;
+  return v;
+}
+static bool ntt_pass_uses_tiles(const Pass& p, uint32_t log_n) {
+  const int mode = ntt_tma_mode();
+  if (mode == 0) return false;
+  if (mode == 3) return log_n <= 18;
+  const size_t groups = ((size_t)1 << p.lo) >> p.logC;
+  return mode == 1 || (groups << (p.hi - p.lo + p.logC)) * 32 <= ((size_t)4 << 20);
 }
 
 int get_twiddles(zkb_ctx* ctx, uint32_t log_n, bool inverse, Fr** out) {
@@ -131,10 +145,11 @@ int get_twiddles(zkb_ctx* ctx, uint32_t log_n, bool inverse, Fr** out) {
     size_t half = (size_t)1 << (log_n - 1);
     ZKB_CUDA(ctx, cudaMalloc(&t, half * sizeof(Fr)));
     ZKB_LAUNCH(ctx, k_fill_powers, cdiv(half, 256), 256, 0, ctx->stream, t, host_omega(log_n, inverse), Fr::one(), half);
-    if (ntt_use_tma()) {
+    {
       std::vector<Pass> ps = plan(log_n);
       for (size_t q = 0; q < ps.size() && q < 4; q++) {
         const Pass& p = ps[q];
+        if (!ntt_pass_uses_tiles(p, log_n)) continue;
         const uint32_t logT = p.hi - p.lo + p.logC;
         const size_t groups = ((size_t)1 << p.lo) >> p.logC, total = groups << logT;
         uint4*& tt = ctx->twt[log_n][inverse ? 1 : 0][q];
@@ -349,7 +364,7 @@ static int run_ntt(zkb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, cudaStream
     size_t smem = (size_t)T * 32;
     if (ctx->profile) ctx->prof_units[PK_NTT] += (uint64_t)1 << log_n;
     const int pi = DIT ? q : np - 1 - q;  // index of the pass in plan order (= index of its tile table)
-    const uint4* tiles = (ntt_use_tma() && pi < 4) ? ctx->twt[log_n][inverse ? 1 : 0][pi] : nullptr;
+    const uint4* tiles = pi < 4 ? ctx->twt[log_n][inverse ? 1 : 0][pi] : nullptr;  // null: this pass gathers from the flat table
     if (tiles) {
       ZKB_LAUNCH_K(ctx, PK_NTT, (k_ntt_pass<DIT, true>), grid, block, 2 * smem, st, d, tw, tiles, log_n, p.hi, p.lo, p.logC);
     } else {
