@@ -6,7 +6,8 @@
 A step is ONE groth16::prove() (src/groth16/mod.rs:213-296): witness -> u_sum, v_sum, h (6 NTTs) ->
 three fixed-base MSMs over the window-expanded CRS tables (A and C over G1 as two jobs of one call,
 B over G2) -> Proof{a,b,c}.  N = 1: the K steps go through zkb_prove_batch, which keeps two proofs in
-flight (identical results to K zkb_prove calls; single-proof latency is reported in config).  N > 1
+flight at 2^20 (four up to 2^17, three up to 2^19: prove.cu batch_lane_count; identical results to K zkb_prove
+calls; single-proof latency is reported in config).  N > 1
 (torchrun, one rank per GPU): the MSM base vectors are sharded by points, every rank proves over its
 shard, the 32-limb partial sums are all-gathered over NCCL and folded -- one proof over all ranks, strong
 scaling (`--mode shard`: the latency-optimal layout).  `--mode replicas` (the default: the metric is
@@ -351,7 +352,7 @@ def run_ours(args):
             "scaling": "strong" if sw > 1 else "weak", "vs_baseline": None, "dtype": "u32x8 (256-bit modular integers)",
             "data": "synthetic",
             "config": {"workload": workload_name(args.log_n),
-                       "parallelism": ("1 GPU, zkb_prove_batch (two proofs in flight)" if world == 1 else
+                       "parallelism": (f"1 GPU, zkb_prove_batch ({4 if args.log_n <= 17 else 3 if args.log_n <= 19 else 2} proofs in flight)" if world == 1 else
                                        (f"msm-point-shard x{world}: one proof per step over all ranks" if sw > 1 else
                                         f"replicas x{world}: one proof per step on EVERY rank")),
                        "single_proof_latency_ms": latency_ms,

@@ -49,7 +49,7 @@ void prof_begin(zkb_ctx* ctx, int kind, cudaStream_t st, const char* name) {
   cudaEventCreate(&r.b);
   r.kind = kind;
   r.name = name;
-  r.stream_id = st == ctx->lanes[0].hi ? 1 : (st == ctx->lanes[0].lo ? 2 : (st == ctx->lanes[1].hi ? 3 : 4));
+  r.stream_id = st == ctx->lanes[0].hi ? 1 : (st == ctx->lanes[0].lo ? 2 : (st == ctx->lanes[0].hi2 ? 5 : (st == ctx->lanes[1].hi ? 3 : 4)));
   cudaEventRecord(r.a, st);
   ctx->prof.push_back(r);
 }
@@ -115,6 +115,7 @@ int zkb_ctx_create(zkb_ctx** out, int device_id) {
   for (auto& l : c->lanes) {
     cudaStreamCreateWithPriority(&l.hi, cudaStreamNonBlocking, prio_hi);
     cudaStreamCreateWithPriority(&l.lo, cudaStreamNonBlocking, prio_lo);
+    cudaStreamCreateWithPriority(&l.hi2, cudaStreamNonBlocking, prio_hi);
     for (auto& e : l.ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     if (cudaHostAlloc(&l.h_proof, 256, cudaHostAllocDefault) != cudaSuccess) {
       zkb_ctx_destroy(c);
@@ -152,6 +153,7 @@ void zkb_ctx_destroy(zkb_ctx* ctx) {
     for (auto& e : l.ev)
       if (e) cudaEventDestroy(e);
     if (l.hi) cudaStreamDestroy(l.hi);
+    if (l.hi2) cudaStreamDestroy(l.hi2);
     if (l.lo) cudaStreamDestroy(l.lo);
     if (l.h_proof) cudaFreeHost(l.h_proof);
   }

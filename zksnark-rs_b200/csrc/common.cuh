@@ -27,7 +27,8 @@ struct DevBuf {
 // the gaps of the accumulations instead of serially (zkb_prove_batch).
 struct zkb_lane {
   cudaStream_t hi = nullptr, lo = nullptr;
-  cudaEvent_t ev[4] = {};        // 0/1: G1 records sorted / accumulated; 2/3: same for G2
+  cudaStream_t hi2 = nullptr;    // second latency-class stream: the G1 tail runs beside the G2 tail (both low-occupancy)
+  cudaEvent_t ev[5] = {};        // 0/1: G1 records sorted / accumulated; 2/3: same for G2; 4: G1 tail done
   zkb::DevBuf scratch[16];       // per-lane scratch (MSM buffers, polynomial workspace, outputs)
   void* h_proof = nullptr;       // pinned staging for the 256-byte result
 };
@@ -35,7 +36,7 @@ struct zkb_lane {
 struct zkb_ctx {
   int device = 0;
   zkb_lane lanes[4];               // all created; zkb_prove_batch keeps `batch_lanes` proofs in flight
-  int batch_lanes = 2;             // ZKB_LANES=1..4 overrides (developer switch; 2 measured best, profiles/)
+  int batch_lanes = 0;             // 0 = by problem size (prove.cu: batch_lane_count); ZKB_LANES=1..4 overrides (developer switch)
   cudaStream_t stream = nullptr;   // = lanes[0].hi: everything outside the prove pipeline runs here
   cudaStream_t stream2 = nullptr;  // = lanes[0].lo
   int sm_count = 148;

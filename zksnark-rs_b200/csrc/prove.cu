@@ -475,8 +475,9 @@ static int prove_out(zkb_ctx* ctx, DevBuf* slots, ProveOut* o) {
 
 // Enqueue stages 1-7 over this rank's CRS shard on lane L; nothing waits on the host.  The 256-byte
 // result (proof for world 1, else the rank's partial sums) lands in L->h_proof when L->hi drains.
-//   L->hi: [H2D] polynomial stage, scalars, sort G2, sort G1 ... tail G2, tail G1, finish, D2H
-//   L->lo:                                   accumulate G2, accumulate G1
+//   L->hi:  [H2D] polynomial stage, scalars, sort G2, sort G1 ... tail G2 ........ finish, D2H
+//   L->lo:                                    accumulate G2, accumulate G1
+//   L->hi2:                                                                tail G1
 static int prove_enqueue(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights,
                          int on_device, const uint64_t* r, const uint64_t* s) {
   cudaStream_t hi = L->hi, lo = L->lo;
@@ -520,8 +521,12 @@ static int prove_enqueue(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, const zkb_
   ZKB_CUDA(ctx, cudaEventRecord(L->ev[1], lo));
   ZKB_CUDA(ctx, cudaStreamWaitEvent(hi, L->ev[3], 0));
   ZKB_TRY(msm_tail(ctx, P2, hi));
-  ZKB_CUDA(ctx, cudaStreamWaitEvent(hi, L->ev[1], 0));
-  ZKB_TRY(msm_tail(ctx, P1, hi));
+  // the G1 tail on its own latency-class stream: at small sizes the G2 tail is still running when the G1
+  // accumulation ends, and both are chains of low-occupancy kernels (2^16: single-proof latency 4.5 -> 3.8 ms)
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(L->hi2, L->ev[1], 0));
+  ZKB_TRY(msm_tail(ctx, P1, L->hi2));
+  ZKB_CUDA(ctx, cudaEventRecord(L->ev[4], L->hi2));
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(hi, L->ev[4], 0));
   ZKB_LAUNCH(ctx, k_finish, 1, 96, 0, hi, o.ac, o.b, o.proof);
   ZKB_CUDA(ctx, cudaMemcpyAsync(L->h_proof, o.proof, 256, cudaMemcpyDeviceToHost, hi));
   return ZKB_OK;
@@ -557,6 +562,14 @@ int zkb_prove_dev(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64
 // Throughput mode: `count` independent proofs over the same QAP / CRS, two in flight (one per lane),
 // so the latency-class stages of proof i+1 and the tails of proof i fill the gaps of the bucket
 // accumulations.  Same results as `count` zkb_prove calls.
+// Proofs in flight.  Measured on B200 (profiles/r01_lanes_by_size.txt, ms per proof for 1 / 2 / 3 / 4 lanes):
+// 2^16 4.27 / 2.82 / 2.34 / 2.19, 2^18 8.66 / 7.22 / 7.06 / 7.23, 2^20 23.8 / 23.2 / 23.2 / -- : small proofs are
+// dominated by the latency-bound tails (bucket hierarchy, head folding), which more proofs in flight hide.
+static size_t batch_lane_count(const zkb_ctx* ctx, const zkb_qap* q) {
+  if (ctx->batch_lanes >= 1 && ctx->batch_lanes <= 4) return (size_t)ctx->batch_lanes;
+  return q->n <= ((uint64_t)1 << 17) ? 4 : (q->n <= ((uint64_t)1 << 19) ? 3 : 2);
+}
+
 int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* const* weights, int on_device,
                     const uint64_t* r, const uint64_t* s, size_t count, zkb_proof* out) {
   if (!ctx || !q || !c || (count && (!weights || !r || !s || !out))) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_batch: NULL argument");
@@ -566,7 +579,7 @@ int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint
     if (!weights[i]) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_batch: weights[%zu] is NULL", i);
   int rc = ZKB_OK;
   size_t done = 0;
-  const size_t nl = (size_t)ctx->batch_lanes;
+  const size_t nl = batch_lane_count(ctx, q);
   for (size_t i = 0; i < count && rc == ZKB_OK; i++) {
     zkb_lane* L = &ctx->lanes[i % nl];
     if (i >= nl) {
