@@ -102,6 +102,23 @@ def test_bench_mirrors_of_library_plans():
     assert bench.msm_window(1 << 20) in (15, 16)
 
 
+def test_reference_arm_line_and_best_effort_leg():
+    """bench.py --impl reference (the reference's algorithm, Oracle B, sampled) prints the contract line without a GPU;
+    the cpu_best_effort leg (Oracle F) reports a full small proof.  Small size so the CPU suite stays short."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--log-n", "10", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "groth16_proofs_per_sec" and line["unit"] == "proofs/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["cpu_baseline"]["kind"] == "port"
+    assert line["cpu_baseline"]["cores"] == 1 and line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    fast = bench.best_effort_cpu(8)
+    assert fast["kind"] == "port-fast-algorithms" and fast["value"] > line["value"] and fast["cores"] >= 1
+
+
 _GLOO_WORKER = r"""
 import importlib, os, sys
 import numpy as np
