@@ -10,7 +10,7 @@ import os
 
 import pytest
 
-from oracle import circuit, groth16 as og, oracle_b as ob
+from oracle import circuit, groth16 as og, oracle_b as ob, oracle_fast as of
 from oracle.fields import FR
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -52,6 +52,13 @@ def test_oracles_reproduce_golden(c):
     assert (pr.a, pr.b, pr.c) == want
     a, b, cc, h = ob.prove(dense, sig, c["weights"], c["r"], c["s"])  # the C restatement
     assert (a, b, cc) == want and h == c["h"]
+    if c["name"].startswith("horner8_omega"):  # Oracle F (NTT + Pippenger) only knows the roots-of-unity domain
+        n, wts = len(rep.roots), c["weights"]
+        idx = {root: k for k, root in enumerate(rep.roots)}
+        ev = lambda rows: [sum(wts[i] * val for i, row in enumerate(rows) for (root, val) in row if idx[root] == k) % P
+                           for k in range(n)]
+        fa, fb, fc, fh = of.prove(n, rep.input, ev(rep.u), ev(rep.v), sig, wts, c["r"], c["s"], threads=2)
+        assert (fa, fb, fc) == want and fh[:len(c["h"])] == c["h"] and not any(fh[len(c["h"]):])
 
 
 @pytest.mark.gpu
