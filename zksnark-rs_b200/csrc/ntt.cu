@@ -87,7 +87,6 @@ static std::vector<Pass> plan(uint32_t log_n) {
   return ps;
 }
 
-
 // ---- twiddle tiles ---------------------------------------------------------------------------------
 // Tile of group g (= column group Lbase / C of a pass) holds, for ls = 0..B-1, m0 < 2^ls, c < C:
 //   slot ((2^ls - 1) + m0) * C + c  =  omega_n^(((m0 << lo) + g*C + c) << (log_n - 1 - lo - ls))
@@ -365,10 +364,12 @@ static int run_ntt(zkb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, cudaStream
     if (ctx->profile) ctx->prof_units[PK_NTT] += (uint64_t)1 << log_n;
     const int pi = DIT ? q : np - 1 - q;  // index of the pass in plan order (= index of its tile table)
     const uint4* tiles = pi < 4 ? ctx->twt[log_n][inverse ? 1 : 0][pi] : nullptr;  // null: this pass gathers from the flat table
+    auto* k_ntt_pass_tiles = &k_ntt_pass<DIT, true>;     // named so that traces (zkb_trace_dump) tell the two apart
+    auto* k_ntt_pass_gather = &k_ntt_pass<DIT, false>;
     if (tiles) {
-      ZKB_LAUNCH_K(ctx, PK_NTT, (k_ntt_pass<DIT, true>), grid, block, 2 * smem, st, d, tw, tiles, log_n, p.hi, p.lo, p.logC);
+      ZKB_LAUNCH_K(ctx, PK_NTT, k_ntt_pass_tiles, grid, block, 2 * smem, st, d, tw, tiles, log_n, p.hi, p.lo, p.logC);
     } else {
-      ZKB_LAUNCH_K(ctx, PK_NTT, (k_ntt_pass<DIT, false>), grid, block, smem, st, d, tw, tiles, log_n, p.hi, p.lo, p.logC);
+      ZKB_LAUNCH_K(ctx, PK_NTT, k_ntt_pass_gather, grid, block, smem, st, d, tw, tiles, log_n, p.hi, p.lo, p.logC);
     }
   }
   return ZKB_OK;
