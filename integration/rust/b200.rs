@@ -1,6 +1,8 @@
 //! Drop-in bodies for `groth16::{setup, prove, verify}` on one B200 (libzkb200.so), for the concrete BN254
-//! instantiation `T = FrLocal, U = G1Local, V = G2Local` (src/groth16/fr.rs:9-16).  Lives inside `groth16` because
-//! `SigmaG1`, `SigmaG2` and `Proof` have private fields and no accessors (src/groth16/mod.rs:105-128).
+//! instantiation `T = FrLocal, U = G1Local, V = G2Local` (src/groth16/fr.rs:9-16).  Lives at `src/groth16/fr/b200.rs`
+//! as a CHILD module of `groth16::fr` (`mod b200;` in fr.rs): `SigmaG1`, `SigmaG2` and `Proof` have private fields and
+//! no accessors (src/groth16/mod.rs:105-128) and `FrLocal(Fr)`, `G1Local(G1)`, `G2Local(G2)` have private tuple fields
+//! (fr.rs:8-14); a descendant module of both sees them, so nothing in the reference has to become `pub`.
 //!
 //! Contract kept from the reference: synchronous calls, borrowed inputs, owned outputs, and PANICS instead of
 //! `Result`s (fr.rs:54, field/mod.rs:440) -- every non-zero status of the C ABI becomes a panic with the library's text.
@@ -8,11 +10,11 @@
 //! NOT compiled in the zkb200 build image (no cargo / rustc there); see integration/rust/README.md.
 extern crate bn;
 
-use self::bn::{AffineG1, AffineG2, Fq, Fq2, Fr, Group, G1, G2};
-use super::circuit::RootRepresentation;
-use super::fr::{FrLocal, G1Local, G2Local};
-use super::zkb200_sys::*;
-use super::{Proof, Random, SigmaG1, SigmaG2};
+use self::bn::{AffineG1, AffineG2, Fq, Fq2, Group, G1, G2};
+use super::super::circuit::RootRepresentation;
+use super::super::zkb200_sys::*;
+use super::super::{Proof, Random, SigmaG1, SigmaG2};
+use super::{FrLocal, G1Local, G2Local};
 use std::collections::HashMap;
 
 // ---- element conversion: canonical residues, 4 x u64 little-endian limbs -----------------------------------------
@@ -105,7 +107,7 @@ impl B200 {
         let mut row_ptr: [Vec<u64>; 3] = [vec![0], vec![0], vec![0]];
         let mut gate: [Vec<u32>; 3] = [Vec::new(), Vec::new(), Vec::new()];
         let mut coeff: [Vec<u64>; 3] = [Vec::new(), Vec::new(), Vec::new()];
-        let mats = [rep.u(), rep.v(), rep.w()];
+        let mats = vec![rep.u(), rep.v(), rep.w()];  // (a Vec: by-value iteration on the 2015 edition)
         for (k, rows) in mats.into_iter().enumerate() {
             for row in rows {
                 for (root, value) in row {
@@ -255,8 +257,8 @@ impl<'a> Drop for DeviceCrs<'a> { fn drop(&mut self) { unsafe { zkb_crs_free(sel
 #[cfg(test)]
 mod tests {
     //! The reference's own end-to-end check (fr.rs:361-416, `verify == true`) through the device.
-    use super::super::circuit::dummy_rep::DummyRep;
-    use super::super::{setup, verify, CoefficientPoly, QAP};
+    use super::super::super::circuit::dummy_rep::DummyRep;
+    use super::super::super::{setup, verify, CoefficientPoly, QAP};
     use super::*;
 
     #[test]
