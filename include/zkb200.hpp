@@ -280,6 +280,30 @@ inline Proof prove(Context& ctx, const QAP& qap, const Sigma& sigma, const std::
   return prove_with_rs(ctx, qap, sigma, weights, Fr::random_elem(), Fr::random_elem());
 }
 
+// Throughput mode: one proof per (weights[i], rs[i]) against the same QAP / CRS, several in flight on the device
+// (zkb_prove_batch).  Same results as prove_with_rs in a loop.
+inline std::vector<Proof> prove_many(Context& ctx, const QAP& qap, const Sigma& sigma, const std::vector<std::vector<Fr>>& weights,
+                                     const std::vector<std::pair<Fr, Fr>>& rs) {
+  if (weights.size() != rs.size()) throw Error(ZKB_ERR_ARG, "prove_many: weights and (r, s) pairs differ in number");
+  const size_t count = weights.size();
+  std::vector<std::vector<uint64_t>> w(count, std::vector<uint64_t>(4 * qap.rows(), 0));
+  std::vector<const uint64_t*> ptrs(count);
+  std::vector<uint64_t> r(4 * count), s(4 * count);
+  for (size_t k = 0; k < count; k++) {
+    for (size_t i = 0; i < weights[k].size() && i < qap.rows(); i++) memcpy(&w[k][4 * i], weights[k][i].l.data(), 32);
+    ptrs[k] = w[k].data();
+    memcpy(&r[4 * k], rs[k].first.l.data(), 32);
+    memcpy(&s[4 * k], rs[k].second.l.data(), 32);
+  }
+  std::vector<zkb_proof> out(count);
+  if (count) ctx.check(zkb_prove_batch(ctx.get(), qap.get(), sigma.get(), ptrs.data(), 0, r.data(), s.data(), count, out.data()), "zkb_prove_batch");
+  std::vector<Proof> ps(count);
+  for (size_t k = 0; k < count; k++) {
+    memcpy(ps[k].a.v, out[k].a, sizeof out[k].a); memcpy(ps[k].b.v, out[k].b, sizeof out[k].b); memcpy(ps[k].c.v, out[k].c, sizeof out[k].c);
+  }
+  return ps;
+}
+
 // groth16::verify (mod.rs:299-320); the CRS is borrowed (the reference consumes it)
 inline bool verify(Context& ctx, const Sigma& sigma, const std::vector<Fr>& inputs, const Proof& proof) {
   std::vector<uint64_t> in(4 * inputs.size() + 4, 0);
@@ -289,6 +313,26 @@ inline bool verify(Context& ctx, const Sigma& sigma, const std::vector<Fr>& inpu
   int ok = 0;
   ctx.check(zkb_verify(ctx.get(), sigma.get(), in.data(), inputs.size(), &pc, &ok), "zkb_verify");
   return ok == 1;
+}
+
+// One verdict per (inputs[i], proofs[i]) against the same CRS, every inputs[i] of the same length (zkb_verify_batch).
+inline std::vector<bool> verify_many(Context& ctx, const Sigma& sigma, const std::vector<std::vector<Fr>>& inputs,
+                                     const std::vector<Proof>& proofs) {
+  if (inputs.size() != proofs.size()) throw Error(ZKB_ERR_ARG, "verify_many: inputs and proofs differ in number");
+  const size_t count = proofs.size(), k = count ? inputs[0].size() : 0;
+  std::vector<uint64_t> in(4 * k * count + 4, 0);
+  std::vector<zkb_proof> pcs(count);
+  for (size_t i = 0; i < count; i++) {
+    if (inputs[i].size() != k) throw Error(ZKB_ERR_ARG, "verify_many: every proof needs the same number of inputs");
+    for (size_t j = 0; j < k; j++) memcpy(&in[4 * (i * k + j)], inputs[i][j].l.data(), 32);
+    memcpy(pcs[i].a, proofs[i].a.v, sizeof pcs[i].a); memcpy(pcs[i].b, proofs[i].b.v, sizeof pcs[i].b);
+    memcpy(pcs[i].c, proofs[i].c.v, sizeof pcs[i].c);
+  }
+  std::vector<int> ok(count, 0);
+  if (count) ctx.check(zkb_verify_batch(ctx.get(), sigma.get(), in.data(), k, pcs.data(), count, ok.data()), "zkb_verify_batch");
+  std::vector<bool> res(count);
+  for (size_t i = 0; i < count; i++) res[i] = ok[i] == 1;
+  return res;
 }
 
 }  // namespace groth16

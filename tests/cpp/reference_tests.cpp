@@ -106,6 +106,33 @@ static int bn_encrypt_deg_15_test(Context& ctx) {
   return 0;
 }
 
+// throughput mode: prove_many == prove_with_rs in a loop, verify_many gives one verdict per proof
+static int batch_equals_single(Context& ctx) {
+  const size_t n = 16, count = 5;
+  QAP qap = QAP::from(ctx, horner_rep(n, 4));
+  Sigma sigma = groth16::setup(ctx, qap);
+  std::vector<std::vector<Fr>> weights, inputs;
+  std::vector<std::pair<Fr, Fr>> rs;
+  std::vector<Proof> single;
+  for (size_t i = 0; i < count; i++) {
+    std::vector<Fr> c(n);
+    for (auto& v : c) v = Fr::random_elem();
+    weights.push_back(horner_weights(n, Fr::random_elem(), c));
+    rs.push_back({Fr::random_elem(), Fr::random_elem()});
+    inputs.push_back({weights[i][1], weights[i][2]});
+    single.push_back(groth16::prove_with_rs(ctx, qap, sigma, weights[i], rs[i].first, rs[i].second));
+  }
+  std::vector<Proof> many = groth16::prove_many(ctx, qap, sigma, weights, rs);
+  CHECK(many.size() == count);
+  for (size_t i = 0; i < count; i++) CHECK(many[i].a == single[i].a && many[i].b == single[i].b && many[i].c == single[i].c);
+  inputs[3][1] = inputs[3][1] + Fr::one();  // one wrong public input
+  std::vector<bool> ok = groth16::verify_many(ctx, sigma, inputs, many);
+  for (size_t i = 0; i < count; i++) CHECK(ok[i] == (i != 3));
+  CHECK(groth16::prove_many(ctx, qap, sigma, {}, {}).empty() && groth16::verify_many(ctx, sigma, {}, {}).empty());
+  printf("ok batch_equals_single\n");
+  return 0;
+}
+
 // fixed secrets -> one proof, printed for the bit-exact comparison with the oracle (tests/test_cpp_host.py)
 static int parity_dump(Context& ctx) {
   const size_t n = 8;
@@ -133,6 +160,7 @@ int main() {
     if (int rc = single_mult_honest_bn(ctx)) return rc;
     if (int rc = qap_from_roots(ctx)) return rc;
     if (int rc = bn_encrypt_deg_15_test(ctx)) return rc;
+    if (int rc = batch_equals_single(ctx)) return rc;
     if (int rc = parity_dump(ctx)) return rc;
   } catch (const Error& e) {
     printf("zkb200::Error %d: %s\n", e.code, e.what());
