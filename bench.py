@@ -356,7 +356,8 @@ def run_ours(args):
                                        (f"msm-point-shard x{world}: one proof per step over all ranks" if sw > 1 else
                                         f"replicas x{world}: one proof per step on EVERY rank")),
                        "single_proof_latency_ms": latency_ms,
-                       "l2_policy": "inputs larger than L2 (CRS window tables ~5 GiB gathered at random + 64 MiB witness per proof; L2 is 126 MB)",
+                       "l2_policy": (f"inputs larger than L2 (CRS window tables {table_bytes(args.log_n) / 2**30:.2f} GiB gathered at random + "
+                                     f"{(2 * n + 2) * 32 / 2**20:.0f} MiB witness per proof; L2 is 126 MB)"),
                        "timing": "CUDA events on the library stream, max over ranks"},
             "e2e": {"value": jobs * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(w_np.nbytes) * world,
                     "d2h_bytes_per_step": 256 * world if sw == 1 else 256 * world + 256 * world, "ms_per_step": ms_e2e / args.steps},
@@ -392,14 +393,21 @@ def ncu_traffic(tag):
 
 
 def msm_window(npts):
-    """Mirror of pick_c in csrc/msm_impl.cuh (for the roofline bookkeeping only)."""
-    best, best_cost = 4, float("inf")
-    for c in range(4, 19):
+    """Mirror of pick_c in csrc/msm_impl.cuh: window bits of a fixed-base table over npts points."""
+    best, best_cost = 2, float("inf")
+    for c in range(2, 23):
         W = 254 // c + 1
-        cost = W * (10.0 * npts + 56.0 * (1 << (c - 1)))
+        cost = W * 10.0 * max(npts, 1) + 56.0 * (1 << (c - 1))
         if cost < best_cost:
             best, best_cost = c, cost
     return best
+
+
+def table_bytes(log_n):
+    """Bytes of the window-expanded CRS tables of the synthetic QAP (crs.cu: g1_cnt = 4n + 1 incl. the fixed points, g2_cnt = n + 2)."""
+    n = 1 << log_n
+    g1, g2 = 4 * n + 1, n + 2
+    return (254 // msm_window(g1) + 1) * g1 * 64 + (254 // msm_window(g2) + 1) * g2 * 128
 
 
 def ntt_plan(log_n):

@@ -99,7 +99,8 @@ def test_bench_mirrors_of_library_plans():
     bench = importlib.import_module("bench")
     assert bench.ntt_plan(20) == [(0, 10), (10, 15), (15, 20)]
     assert bench.ntt_plan(8) == [(0, 8)]
-    assert bench.msm_window(1 << 20) in (15, 16)
+    assert bench.msm_window((1 << 22) + 1) == 20 and bench.msm_window((1 << 20) + 2) == 17  # c1, c2 at 2^20
+    assert 5.0 < bench.table_bytes(20) / 2**30 < 6.5 and bench.table_bytes(16) > 126e6
 
 
 def test_reference_arm_line_and_best_effort_leg():
