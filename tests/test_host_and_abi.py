@@ -189,3 +189,37 @@ def test_ntt_sharded_protocol_world2_gloo(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_ntt_twiddle_tile_layout_matches_flat_table_index():
+    """ntt.cu: the slot a butterfly reads from its block's TMA-staged twiddle tile (k_ntt_pass<.., true>) holds the same
+    power of omega as the flat-table gather (k_ntt_pass<.., false>), for every pass of every plan (Python restatement
+    of k_fill_tw_tiles and of the two branches of the `twiddle` lambda; the GPU suite checks the transforms bit for bit)."""
+    import random
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    rng = random.Random(3)
+    for log_n in (1, 2, 3, 5, 10, 11, 13, 16, 18, 20, 22, 26):
+        for (lo, hi) in bench.ntt_plan(log_n):
+            B = hi - lo
+            logC = 0 if lo == 0 else 10 - B
+            T, C = 1 << (B + logC), 1 << logC
+            groups = (1 << lo) >> logC
+
+            def tile_exponent(g, slot):  # k_fill_tw_tiles
+                assert slot < T - C
+                idx, c = slot >> logC, slot & (C - 1)
+                ls = (idx + 1).bit_length() - 1
+                m0 = idx + 1 - (1 << ls)
+                e = (((m0 << lo) + (g << logC) + c) << (log_n - 1 - lo - ls))
+                assert e < 1 << (log_n - 1)
+                return e
+            for _ in range(300):
+                g, ls, e = rng.randrange(groups), rng.randrange(B), rng.randrange(T)
+                e &= ~(1 << (ls + logC))  # lower element of a butterfly of stage ls: row bit ls clear
+                s = lo + ls
+                m0 = (e >> logC) & ((1 << ls) - 1)
+                j = (m0 << lo) + (g << logC) + (e & (C - 1))
+                flat = (0 if s == 0 else j & ((1 << s) - 1)) << (log_n - 1 - s)
+                slot = (((1 << ls) - 1) << logC) + (e & ((1 << (ls + logC)) - 1))
+                assert tile_exponent(g, slot) == flat
