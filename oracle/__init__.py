@@ -1,8 +1,10 @@
 """CPU oracle for the groth16::prove() hot path of republicprotocol/zksnark-rs.
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the shipped
-product: only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
-``--impl reference`` legs of ``bench.py`` may import or execute it, and only as
+product: only ``tests/`` (incl. its helper scripts ``gen_golden.py``,
+``check_full_size.py``, ``sanitize_case.py``), ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``cpu_best_effort`` / ``--impl reference`` legs of ``bench.py``
+may import or execute it, and only as
 the checker / the timed CPU baseline, never as the thing that produces a result
 the product returns.
 

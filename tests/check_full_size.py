@@ -1,5 +1,5 @@
 """One-off full-size parity check: device setup + prove at 2^log_n against the closed-form proof from the
-toxic waste (oracle/closed_form.py), single and batch.  Usage: python tools/check_full_size.py [log_n]"""
+toxic waste (oracle/closed_form.py), single and batch.  Usage: python tests/check_full_size.py [log_n]"""
 import importlib
 import os
 import random

@@ -5,7 +5,7 @@ image (Rust, no cargo).  The fixtures pin BOTH sides: `-m "not gpu"` tests re-de
 Cases: BASELINE config #1 (test_programs/simple.zk text, parser row order, roots 1..=n), the single-gate QAP of
 fr.rs:248-271, a Horner circuit on the roots of unity (valid and invalid witness), the quadratic share of
 mod.rs:635-690.
-Usage: python tools/gen_golden.py   (rewrites tests/golden/proofs.json; ~1 min)"""
+Usage: python tests/gen_golden.py   (rewrites tests/golden/proofs.json; ~1 min)"""
 import json
 import os
 import random
@@ -75,7 +75,7 @@ def main():
     cases.append(case("quad_share_roots_123", rep, wit, 5, "groth16/mod.rs:635-690 (qap_from_roots)"))
     out = os.path.join(ROOT, "tests", "golden", "proofs.json")
     with open(out, "w") as f:
-        json.dump({"generator": "tools/gen_golden.py (Oracle A)", "field_modulus": P, "cases": cases}, f, indent=0)
+        json.dump({"generator": "tests/gen_golden.py (Oracle A)", "field_modulus": P, "cases": cases}, f, indent=0)
     print(out, os.path.getsize(out), "bytes;", [(c["name"], c["verify"]) for c in cases])
 
 

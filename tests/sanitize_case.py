@@ -3,7 +3,7 @@ multi-pass NTT (2^13: three shared-memory passes incl. strided tiles), the MSM w
 head folding on both paths (skewed scalars -> one huge bucket -> warp-cooperative fold), the
 warp-level bucket hierarchy, batch proving on two lanes and the sharded fold, at sizes a sanitizer
 finishes in a minute.  Results are checked against the oracle's closed forms.
-Usage: compute-sanitizer --tool memcheck python tools/sanitize_case.py"""
+Usage: compute-sanitizer --tool memcheck python tests/sanitize_case.py"""
 import importlib
 import os
 import random

@@ -1,4 +1,4 @@
-"""Committed golden fixtures (tests/golden/proofs.json, made by tools/gen_golden.py from Oracle A).
+"""Committed golden fixtures (tests/golden/proofs.json, made by tests/gen_golden.py from Oracle A).
 
 CPU (`-m "not gpu"`): Oracle A and Oracle B (C) re-derive every fixture -- the oracle cannot drift without this
 failing -- and the pinned facts of the reference hold (config #1: h = [r - 64]; every honest proof verifies).

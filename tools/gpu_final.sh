@@ -15,8 +15,8 @@ full acc_g1 "k_accumulate_chunks.*FqParams" ""
 full ntt_tma "k_ntt_pass" "--log-n 16"
 : > gpurun_out/${tag}_sanitizer.txt
 for tool in racecheck memcheck; do
-  echo "== compute-sanitizer --tool $tool python tools/sanitize_case.py" >> gpurun_out/${tag}_sanitizer.txt
-  timeout 240 compute-sanitizer --tool $tool python tools/sanitize_case.py 2>&1 | grep -v "^=========     \|^$" | tail -6 >> gpurun_out/${tag}_sanitizer.txt
+  echo "== compute-sanitizer --tool $tool python tests/sanitize_case.py" >> gpurun_out/${tag}_sanitizer.txt
+  timeout 240 compute-sanitizer --tool $tool python tests/sanitize_case.py 2>&1 | grep -v "^=========     \|^$" | tail -6 >> gpurun_out/${tag}_sanitizer.txt
 done
 tail -8 gpurun_out/${tag}_sanitizer.txt
 full acc_g2 "k_accumulate_chunks.*Fq2" ""

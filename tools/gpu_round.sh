@@ -20,8 +20,8 @@ done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ntt_pass -s 8 -c 1 -f -o gpurun_out/${tag}_ntt_tma python bench.py --skip-cpu --log-n 16 --steps 2 --warmup 1 > gpurun_out/${tag}_full_ntt_tma.log 2>&1; echo "ncu full ntt_tma exit $?"
 : > gpurun_out/${tag}_sanitizer.txt
 for tool in memcheck racecheck synccheck; do
-  echo "== compute-sanitizer --tool $tool python tools/sanitize_case.py" >> gpurun_out/${tag}_sanitizer.txt
-  timeout 900 compute-sanitizer --tool $tool python tools/sanitize_case.py 2>&1 | grep -v "^=========     \|^$" | tail -6 >> gpurun_out/${tag}_sanitizer.txt
+  echo "== compute-sanitizer --tool $tool python tests/sanitize_case.py" >> gpurun_out/${tag}_sanitizer.txt
+  timeout 900 compute-sanitizer --tool $tool python tests/sanitize_case.py 2>&1 | grep -v "^=========     \|^$" | tail -6 >> gpurun_out/${tag}_sanitizer.txt
 done
 tail -12 gpurun_out/${tag}_sanitizer.txt
 ls -la gpurun_out/ | tail -20
