@@ -150,14 +150,20 @@ static void ob_init(void) {
 typedef struct { fe c0, c1; } fe2;
 static fe2 f2_add(fe2 a, fe2 b) { fe2 r = {fe_add(&FQ, a.c0, b.c0), fe_add(&FQ, a.c1, b.c1)}; return r; }
 static fe2 f2_sub(fe2 a, fe2 b) { fe2 r = {fe_sub(&FQ, a.c0, b.c0), fe_sub(&FQ, a.c1, b.c1)}; return r; }
-static fe2 f2_mul(fe2 a, fe2 b) {
+static fe2 f2_mul(fe2 a, fe2 b) { /* Karatsuba: 3 base-field products (as crate bn's Fq2 does) */
   fe aa = fe_mul(&FQ, a.c0, b.c0), bb = fe_mul(&FQ, a.c1, b.c1);
   fe2 r;
   r.c0 = fe_sub(&FQ, aa, bb);
-  r.c1 = fe_add(&FQ, fe_mul(&FQ, a.c0, b.c1), fe_mul(&FQ, a.c1, b.c0));
+  r.c1 = fe_sub(&FQ, fe_sub(&FQ, fe_mul(&FQ, fe_add(&FQ, a.c0, a.c1), fe_add(&FQ, b.c0, b.c1)), aa), bb);
   return r;
 }
-static fe2 f2_sqr(fe2 a) { return f2_mul(a, a); }
+static fe2 f2_sqr(fe2 a) { /* complex squaring: (a0 + a1)(a0 - a1) + 2 a0 a1 u */
+  fe ab = fe_mul(&FQ, a.c0, a.c1);
+  fe2 r;
+  r.c0 = fe_mul(&FQ, fe_add(&FQ, a.c0, a.c1), fe_sub(&FQ, a.c0, a.c1));
+  r.c1 = fe_add(&FQ, ab, ab);
+  return r;
+}
 static int f2_is_zero(fe2 a) { return fe_is_zero(a.c0) && fe_is_zero(a.c1); }
 static int f2_eq(fe2 a, fe2 b) { return fe_eq(a.c0, b.c0) && fe_eq(a.c1, b.c1); }
 static fe2 f2_inv(fe2 a) {
