@@ -559,7 +559,7 @@ int zkb_prove_dev(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64
   return prove_common(ctx, q, c, d_weights, 1, r, s, (uint64_t*)out);
 }
 
-// Throughput mode: `count` independent proofs over the same QAP / CRS, two in flight (one per lane),
+// Throughput mode: `count` independent proofs over the same QAP / CRS, several in flight (one per lane: batch_lane_count),
 // so the latency-class stages of proof i+1 and the tails of proof i fill the gaps of the bucket
 // accumulations.  Same results as `count` zkb_prove calls.
 // Proofs in flight.  Measured on B200 (profiles/r01_lanes_by_size.txt, ms per proof for 1 / 2 / 3 / 4 lanes):

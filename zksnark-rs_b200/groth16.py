@@ -521,7 +521,7 @@ def prove_dev(ctx: Context, qap: QAP, crs: CRS, d_weights: int, r: int, s: int) 
 
 
 def prove_batch(ctx: Context, qap: QAP, crs: CRS, weights, rs, ss, on_device=False) -> list:
-    """`len(weights)` proofs with two in flight (zkb_prove_batch).  weights: list of witness vectors
+    """`len(weights)` proofs with several in flight (two at 2^20, up to four at small sizes) (zkb_prove_batch).  weights: list of witness vectors
     (host: anything _weights_array accepts, ideally pinned (m, 4) uint64 arrays; device: pointers)."""
     k = len(weights)
     if on_device:
