@@ -75,3 +75,47 @@ def test_timed_proof_is_deterministic_across_thread_counts():
     t1, parts, chk1 = of.time_prove(6, 1, seed=3)
     t2, _, chk2 = of.time_prove(6, 4, seed=3)
     assert chk1 == chk2 and chk1 != 0 and t1 > 0 and t2 > 0 and set(parts) == {"poly", "g1", "g2"}
+
+
+def test_prove_512_gates_equals_closed_form():
+    """Beyond the sizes the literal restatement reaches: a 512-gate Horner proof on 4 threads (several windows x point
+    slices per MSM, block-local + global NTT stages) against the closed form from the toxic waste."""
+    import types
+
+    from oracle import closed_form as cf
+
+    n, log_n, threads = 512, 9, 4
+    w = synthetic.omega(log_n)
+    roots = [pow(w, k, P) for k in range(n)]
+    rep = synthetic.horner_rep(FR, n, roots)
+    rng = random.Random(512)
+    wit = synthetic.horner_witness(FR, n, rng.randrange(1, P), [rng.randrange(P) for _ in range(n)])
+    alpha, beta, gamma, delta, x = toxic = tuple(rng.randrange(1, P) for _ in range(5))
+    r, s = rng.randrange(1, P), rng.randrange(1, P)
+    idx = {root: k for k, root in enumerate(roots)}
+    by_gate = lambda rows: [[(idx[root], val) for (root, val) in row] for row in rows]
+    ru, rv, rw = by_gate(rep.u), by_gate(rep.v), by_gate(rep.w)
+    # the CRS of groth16/mod.rs:134-197 from its defining scalars (C scalar multiplications)
+    L = cf.lagrange_at(n, w, x)
+    ux, vx, wx = cf.row_evals(ru, L), cf.row_evals(rv, L), cf.row_evals(rw, L)
+    dinv, tx = pow(delta, -1, P), (pow(x, n, P) - 1) % P
+    g1 = lambda k: ob.g1_mul(bn.BASE_G1, k % P)
+    g2 = lambda k: ob.g2_mul(bn.BASE_G2, k % P)
+    xs = [pow(x, j, P) for j in range(n)]
+    m = len(ru)
+    s1 = types.SimpleNamespace(alpha=g1(alpha), beta=g1(beta), delta=g1(delta), xi=[g1(v) for v in xs],
+                               xi_t=[g1(v * tx % P * dinv) for v in xs[:n - 1]],
+                               sum_delta=[g1((beta * ux[i] + alpha * vx[i] + wx[i]) % P * dinv) for i in range(rep.input + 1, m)])
+    s2 = types.SimpleNamespace(beta=g2(beta), delta=g2(delta), xi=[g2(v) for v in xs])
+    ev = lambda rows: [sum(wit[i] * val for i, val in per_gate) % P for per_gate in rows]
+    gates_u, gates_v = [[] for _ in range(n)], [[] for _ in range(n)]
+    for i, row in enumerate(ru):
+        for k, val in row:
+            gates_u[k].append((i, val))
+    for i, row in enumerate(rv):
+        for k, val in row:
+            gates_v[k].append((i, val))
+    a, b, c, h = of.prove(n, rep.input, ev(gates_u), ev(gates_v), (s1, s2), wit, r, s, threads)
+    assert (a, b, c) == cf.expected_proof(n, w, ru, rv, rw, rep.input, wit, toxic, r, s)
+    assert len(h) == n - 1 and sum(hk * pow(x, k, P) for k, hk in enumerate(h)) % P * tx % P == \
+        (sum(ai * e for ai, e in zip(wit, ux)) * sum(ai * e for ai, e in zip(wit, vx)) - sum(ai * e for ai, e in zip(wit, wx))) % P
