@@ -20,8 +20,12 @@
 // reference's tests do with FrLocal): plain 256-bit modular arithmetic, never used by the library.
 #pragma once
 #include <array>
+#include <cerrno>
+#include <cstdio>
 #include <cstring>
-#include <random>
+#if defined(__linux__)
+#include <sys/random.h>
+#endif
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -52,12 +56,36 @@ struct Fr {
     }
     return r;
   }
-  // uniform and never zero (fr.rs:90-99)
+  // uniform and never zero (fr.rs:90-99).  The reference draws from rand::thread_rng (an OS-seeded CSPRNG); these
+  // values are the toxic waste of setup() and the blinding r, s of prove(), so every candidate comes straight from
+  // the kernel CSPRNG (getrandom(2), /dev/urandom as the fallback) -- never from a seeded userspace generator --
+  // with rejection sampling on the 254-bit candidates.  Throws when the OS source is unavailable.
+  static void os_random(void* buf, size_t len) {
+    unsigned char* p = static_cast<unsigned char*>(buf);
+    size_t got = 0;
+#if defined(__linux__)
+    while (got < len) {
+      ssize_t k = ::getrandom(p + got, len - got, 0);
+      if (k < 0) {
+        if (errno == EINTR) continue;
+        break;  // ENOSYS etc.: try /dev/urandom
+      }
+      got += (size_t)k;
+    }
+#endif
+    if (got < len) {
+      std::FILE* f = std::fopen("/dev/urandom", "rb");
+      if (f) {
+        got += std::fread(p + got, 1, len - got, f);
+        std::fclose(f);
+      }
+    }
+    if (got < len) throw Error(ZKB_ERR_UNSUPPORTED, "Fr::random_elem: no OS random source (getrandom, /dev/urandom)");
+  }
   static Fr random_elem() {
-    static thread_local std::mt19937_64 gen{std::random_device{}()};
     for (;;) {
       Fr r;
-      for (auto& w : r.l) w = gen();
+      os_random(r.l.data(), sizeof r.l);
       r.l[3] &= 0x3fffffffffffffffull;
       if (!geq(r.l, R) && !r.is_zero()) return r;
     }

@@ -303,6 +303,58 @@ int of_prove(const of_prove_in* in, const u64* A_evals, const u64* B_evals, cons
   return 0;
 }
 
+/* ---- array-level entry points for the full-size parity tests (tests/test_gpu_parity_large.py) ----
+ * The weighted sums of mod.rs:233-253 on the root domain: A_k = sum_i a_i u_i(w^k), B_k likewise, from the by-wire CSR rows
+ * (row_ptr[m+1], gate[nnz], coeff[nnz x 4] canonical) and nw weights; wires >= nw count as zero (zip truncation). */
+void of_qap_evals(size_t m, size_t n, const u64* ptr_u, const uint32_t* gate_u, const u64* coef_u, const u64* ptr_v,
+                  const uint32_t* gate_v, const u64* coef_v, const u64* weights, size_t nw, u64* A_out, u64* B_out) {
+  ob_init();
+  const u64* ptr[2] = {ptr_u, ptr_v}; const uint32_t* gate[2] = {gate_u, gate_v}; const u64* coef[2] = {coef_u, coef_v};
+  u64* out[2] = {A_out, B_out};
+  fe* acc = malloc(n * sizeof(fe));
+  for (int t = 0; t < 2; t++) {
+    memset(acc, 0, n * sizeof(fe));
+    for (size_t i = 0; i < m && i < nw; i++) {
+      fe w = fe_from_canon(&FR, weights + 4 * i);
+      for (u64 e = ptr[t][i]; e < ptr[t][i + 1]; e++)
+        acc[gate[t][e]] = fe_add(&FR, acc[gate[t][e]], fe_mul(&FR, fe_from_canon(&FR, coef[t] + 4 * e), w));
+    }
+    for (size_t k = 0; k < n; k++) fe_to_canon(&FR, acc[k], out[t] + 4 * k);
+  }
+  free(acc);
+}
+/* u_sum, v_sum (n coefficients each) and h = quotient of u_sum * v_sum by x^n - 1 (n - 1 coefficients, h_out[n-1] = 0):
+ * inverse NTTs + one size-2n product, the polynomial stage of prove_core.  All arrays n x 4 canonical limbs. */
+int of_qap_h(const u64* A_evals, const u64* B_evals, unsigned log_n, u64* u_out, u64* v_out, u64* h_out, int threads) {
+  ob_init();
+  size_t n = (size_t)1 << log_n;
+  if (log_n < 1) return -1;
+  fe* A = malloc(n * sizeof(fe)); fe* B = malloc(n * sizeof(fe));
+  for (size_t i = 0; i < n; i++) { A[i] = fe_from_canon(&FR, A_evals + 4 * i); B[i] = fe_from_canon(&FR, B_evals + 4 * i); }
+  ntt_mont(A, log_n, 1, threads); ntt_mont(B, log_n, 1, threads);
+  fe* pu = calloc(2 * n, sizeof(fe)); fe* pv = calloc(2 * n, sizeof(fe));
+  memcpy(pu, A, n * sizeof(fe)); memcpy(pv, B, n * sizeof(fe));
+  ntt_mont(pu, log_n + 1, 0, threads); ntt_mont(pv, log_n + 1, 0, threads);
+  mulv_ctx mc = {pu, pv}; par_for(threads, 2 * n, mulv_range, &mc);
+  ntt_mont(pu, log_n + 1, 1, threads);
+  for (size_t i = 0; i < n; i++) {
+    if (u_out) fe_to_canon(&FR, A[i], u_out + 4 * i);
+    if (v_out) fe_to_canon(&FR, B[i], v_out + 4 * i);
+    if (h_out) fe_to_canon(&FR, pu[n + i], h_out + 4 * i);  /* index 2n-1 is zero: deg(u v) <= 2n-2 */
+  }
+  free(A); free(B); free(pu); free(pv);
+  return 0;
+}
+/* data[i] *= g^i (the coset shift of a forward transform) */
+void of_scale_powers(u64* data, size_t n, const u64* g_) {
+  ob_init();
+  fe g = fe_from_canon(&FR, g_), p = FR.one;
+  for (size_t i = 0; i < n; i++) {
+    fe_to_canon(&FR, fe_mul(&FR, fe_from_canon(&FR, data + 4 * i), p), data + 4 * i);
+    p = fe_mul(&FR, p, g);
+  }
+}
+
 /* ---- timing of one full-size proof (bench.py: cpu_best_effort) ----
  * The bases are n distinct points P0 + i*D (batch-normalised), not a real CRS: the cost of an MSM
  * does not depend on which points it folds.  Scalars, evaluations and weights are uniform in Fr. */

@@ -90,6 +90,91 @@ def prove(n, n_input, a_evals, b_evals, sigma, weights, r, s, threads=1):
     return ob.g1_unpack(proof, 0), ob.g2_unpack(proof, 8), ob.g1_unpack(proof, 24), ob._unpack(hbuf, n - 1)
 
 
+# ---- array-level (numpy uint64 limbs) entry points for full-size parity tests --------------------------------
+def _np():
+    import numpy as np
+    return np
+
+
+def _arr(a, cols=4):
+    np = _np()
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, cols)
+    return a
+
+
+def ntt_np(data, inverse=False, threads=None, coset_shift=None):
+    """dft / idft of an (n, 4) uint64 limb array (canonical residues), natural order; returns a new array.
+    coset_shift g: forward evaluates on g*w^i (input scaled by g^i); inverse undoes it (output scaled by g^-i)."""
+    np = _np()
+    a = _arr(data).copy()
+    n = a.shape[0]
+    assert n and n & (n - 1) == 0
+    threads = threads or threads_default()
+    L = lib()
+    if coset_shift is not None and not inverse:
+        L.of_scale_powers(a.ctypes.data_as(C.c_void_p), C.c_size_t(n), ob._pack([coset_shift]))
+    L.of_ntt(a.ctypes.data_as(C.c_void_p), C.c_uint(n.bit_length() - 1), C.c_int(1 if inverse else 0), C.c_int(threads))
+    if coset_shift is not None and inverse:
+        from .fields import FR
+        L.of_scale_powers(a.ctypes.data_as(C.c_void_p), C.c_size_t(n), ob._pack([pow(coset_shift, FR.p - 2, FR.p)]))
+    return a
+
+
+def qap_evals_np(m, n, rows, weights):
+    """A_k = sum_i a_i u_i(w^k), B_k likewise (mod.rs:233-246 on the root domain) from the by-wire CSR rows
+    [(row_ptr u64[m+1], gate u32[nnz], coeff u64[nnz, 4])] for u, v(, w) and an (nw, 4) limb array of weights."""
+    np = _np()
+    w = _arr(weights)
+    A = np.zeros((n, 4), dtype=np.uint64)
+    B = np.zeros((n, 4), dtype=np.uint64)
+    keep = []
+    args = [C.c_size_t(m), C.c_size_t(n)]
+    for ptr, gate, coef in rows[:2]:
+        ptr = np.ascontiguousarray(ptr, dtype=np.uint64)
+        gate = np.ascontiguousarray(gate, dtype=np.uint32)
+        coef = _arr(coef) if len(gate) else np.zeros((1, 4), dtype=np.uint64)
+        assert len(ptr) == m + 1
+        keep += [ptr, gate, coef]
+        args += [ptr.ctypes.data_as(C.c_void_p), gate.ctypes.data_as(C.c_void_p), coef.ctypes.data_as(C.c_void_p)]
+    args += [w.ctypes.data_as(C.c_void_p), C.c_size_t(w.shape[0]), A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p)]
+    lib().of_qap_evals(*args)
+    return A, B
+
+
+def qap_h_np(A, B, threads=None):
+    """(u_sum, v_sum, h) as (n, 4) limb arrays from the evaluation vectors; h[n-1] = 0 (n - 1 quotient coefficients)."""
+    np = _np()
+    A, B = _arr(A), _arr(B)
+    n = A.shape[0]
+    assert n >= 2 and n & (n - 1) == 0 and B.shape[0] == n
+    u, v, h = (np.zeros((n, 4), dtype=np.uint64) for _ in range(3))
+    rc = lib().of_qap_h(A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), C.c_uint(n.bit_length() - 1),
+                        u.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p),
+                        C.c_int(threads or threads_default()))
+    assert rc == 0
+    return u, v, h
+
+
+def prove_np(n, n_input, A, B, crs, weights, r, s, threads=None):
+    """prove() from limb arrays: crs = dict of uint64 arrays in the zkb_crs_host layout (alpha1, beta1, delta1 (1, 8); xi1 (n, 8);
+    xi_t (n-1, 8); sum_delta (k, 8); beta2, delta2 (1, 16); xi2 (n, 16)).  Returns the proof as a 32-limb array (a | b | c)."""
+    np = _np()
+    A, B, w = _arr(A), _arr(B), _arr(weights)
+    pin = _ProveIn()
+    pin.n, pin.n_input, pin.n_sd = n, n_input, crs["sum_delta"].shape[0]
+    keep = {}
+    for k in ("alpha1", "beta1", "delta1", "xi1", "xi_t", "sum_delta", "beta2", "delta2", "xi2"):
+        keep[k] = np.ascontiguousarray(crs[k], dtype=np.uint64)
+        setattr(pin, k, keep[k].ctypes.data if keep[k].size else None)
+    proof = np.zeros(32, dtype=np.uint64)
+    rc = lib().of_prove(C.byref(pin), A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p),
+                        C.c_size_t(w.shape[0]), ob._pack([r]), ob._pack([s]), proof.ctypes.data_as(C.c_void_p), None,
+                        C.c_int(threads or threads_default()))
+    if rc != 0:
+        raise ValueError(f"of_prove rc={rc}")
+    return proof
+
+
 def time_prove(log_n, threads=None, seed=1):
     """Seconds for one full-size proof (synthetic shape m = 2n+2, input = 2) with fast algorithms on `threads` host threads.
     Returns (seconds, {"poly": s, "g1": s, "g2": s}, check) -- check = proof.a.x, equal across thread counts."""

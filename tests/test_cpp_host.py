@@ -68,3 +68,25 @@ def test_cpp_reference_tests_on_gpu(exe):
     assert got["proof.a"] == list(want.a)
     assert got["proof.b"] == [want.b[0][0], want.b[0][1], want.b[1][0], want.b[1][1]]
     assert got["proof.c"] == list(want.c)
+
+
+def test_random_elem_comes_from_the_os_csprng(tmp_path):
+    """The toxic waste of setup() and the blinding r, s of prove() are drawn with Fr::random_elem (fr.rs:90-99; the
+    reference uses rand::thread_rng, an OS-seeded CSPRNG).  The host mirror must read the kernel CSPRNG directly: no
+    seeded userspace generator anywhere in the header, values uniform below r, never zero, no repeats."""
+    hdr = open(os.path.join(ROOT, "include", "zkb200.hpp")).read()
+    for banned in ("mt19937", "random_device", "minstd", "srand(", "rand()", "<random>"):
+        assert banned not in hdr, f"zkb200.hpp uses {banned}"
+    assert "getrandom" in hdr and "/dev/urandom" in hdr
+    src = tmp_path / "rnd.cpp"
+    src.write_text('#include <cstdio>\n#include "zkb200.hpp"\nint main() { for (int i = 0; i < 2000; i++) { zkb200::Fr r = zkb200::Fr::random_elem();'
+                   ' std::printf("%016lx%016lx%016lx%016lx\\n", (unsigned long)r.l[3], (unsigned long)r.l[2], (unsigned long)r.l[1], (unsigned long)r.l[0]); } }\n')
+    exe = tmp_path / "rnd"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", PKG, "-lzkb200", f"-Wl,-rpath,{PKG}"])
+    vals = [int(x, 16) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    r = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    assert len(vals) == 2000 and len(set(vals)) == 2000 and all(0 < v < r for v in vals)
+    assert max(vals) > r * 3 // 4 and min(vals) < r // 4  # spread over the whole range
+    ones = sum(bin(v & ((1 << 250) - 1)).count("1") for v in vals) / (2000 * 250)
+    assert 0.48 < ones < 0.52

@@ -664,3 +664,91 @@ def test_verify_batch_and_edge_cases(ctx):
     # a sharded CRS verifies on every rank (fixed points and sum_gamma are replicated)
     crs1 = zk.CRS.upload(ctx, sig[0], sig[1], rank=1, world=2)
     assert zk.verify(ctx, crs1, pub, good) and not zk.verify(ctx, crs1, pub, tampered)
+
+
+# ------------------------------------------------------------------------------------------------
+# raw coordinates over the ABI: curve and subgroup membership (the reference can only hold bn-constructed group elements)
+def _f2_pow(a, e):
+    r = bn.F2_ONE
+    while e:
+        if e & 1:
+            r = bn.f2_mul(r, a)
+        a = bn.f2_mul(a, a)
+        e >>= 1
+    return r
+
+
+def _f2_sqrt(a):
+    """Square root in Fq2 = Fq[u]/(u^2 + 1), q = 3 mod 4 (complex method); None if a is not a square."""
+    q = bn.Q
+    a1 = _f2_pow(a, (q - 3) // 4)
+    alpha = bn.f2_mul(a1, bn.f2_mul(a1, a))
+    x0 = bn.f2_mul(a1, a)
+    if alpha == ((q - 1) % q, 0):
+        x = bn.f2_mul((0, 1), x0)
+    else:
+        b = _f2_pow(bn.f2_add(bn.F2_ONE, alpha), (q - 1) // 2)
+        x = bn.f2_mul(b, x0)
+    return x if bn.f2_mul(x, x) == (a[0] % q, a[1] % q) else None
+
+
+def _twist_point_outside_g2(seed):
+    """A point of the twist E'(Fq2) that is NOT in the order-r subgroup (the cofactor is ~2^254, so a random twist point
+    almost never is): on the curve, but [r]P != O."""
+    rng = random.Random(seed)
+    while True:
+        x = (rng.randrange(bn.Q), rng.randrange(bn.Q))
+        y = _f2_sqrt(bn.f2_add(bn.f2_mul(x, bn.f2_mul(x, x)), bn.G2_B))
+        if y is None:
+            continue
+        Pt = (x, y)
+        assert bn.g2_is_on_curve(Pt)
+        if bn.g2_add(bn.g2_mul(Pt, bn.R_ORDER - 1), Pt) is not None:  # [r]P != O (g2_mul reduces its scalar mod r)
+            return Pt
+
+
+def test_g2_points_outside_the_subgroup_are_rejected(ctx):
+    """zkb_pairing / zkb_verify / zkb_crs_upload / zkb_bases_upload take raw coordinates; a twist point outside the
+    order-r subgroup (on the curve!) must be refused, as EIP-197 demands of alt_bn128 verifiers."""
+    bad = _twist_point_outside_g2(5)
+    Pa = bn.g1_mul(bn.BASE_G1, 7)
+    with pytest.raises(zk.ZkbError, match="subgroup"):
+        zk.pairing(ctx, [(Pa, bad)])
+    with pytest.raises(zk.ZkbError, match="subgroup"):
+        zk.pairing(ctx, [(Pa, bn.BASE_G2), (Pa, bad)])
+    with pytest.raises(zk.ZkbError, match="subgroup"):
+        zk.Bases.upload(ctx, 2, [bn.BASE_G2, bad])
+    with pytest.raises(zk.ZkbError, match="not on its curve"):
+        zk.Bases.upload(ctx, 1, [bn.BASE_G1, (5, 7)])
+    assert zk.Bases.upload(ctx, 2, [bn.BASE_G2, None, bn.g2_mul(bn.BASE_G2, 5)]).download()[2] == bn.g2_mul(bn.BASE_G2, 5)
+    n = 4
+    rep, wit, toxic, r, s = _horner_case(n, 606)
+    B = og.BN254Backend()
+    dense = og.qap_from_root_rep(FR, rep)
+    s1, s2 = og.setup(B, dense, toxic)
+    q = zk.QAP.from_root_representation(ctx, rep)
+    crs = zk.CRS.upload(ctx, s1, s2)
+    good = zk.prove(ctx, q, crs, wit, r, s)
+    pub = wit[1:rep.input + 1]
+    assert zk.verify(ctx, crs, pub, good)
+    assert not zk.verify(ctx, crs, pub, zg.Proof(good.a, bad, good.c))
+    got = zg.verify_batch(ctx, crs, [pub, pub, pub], [good, zg.Proof(good.a, bad, good.c), good])
+    assert got == [True, False, True]
+    import copy
+    for field, val in (("xi", bad), ("beta", bad), ("gamma", bad), ("delta", bad)):
+        t2 = copy.deepcopy(s2)
+        if field == "xi":
+            t2.xi[1] = val
+        else:
+            setattr(t2, field, val)
+        with pytest.raises(zk.ZkbError, match="subgroup"):
+            zk.CRS.upload(ctx, s1, t2)
+    t1 = copy.deepcopy(s1)
+    t1.sum_delta[0] = (t1.sum_delta[0][0], (t1.sum_delta[0][1] + 1) % bn.Q)
+    with pytest.raises(zk.ZkbError, match="not on its curve"):
+        zk.CRS.upload(ctx, t1, s2)
+    # a CRS whose vectors do not fit the QAP (check_pair): one sum_delta entry short
+    t1 = copy.deepcopy(s1)
+    t1.sum_delta = t1.sum_delta[:-1]
+    with pytest.raises(zk.ZkbError, match="does not belong"):
+        zk.prove(ctx, q, zk.CRS.upload(ctx, t1, s2), wit, r, s)

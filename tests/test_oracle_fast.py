@@ -119,3 +119,56 @@ def test_prove_512_gates_equals_closed_form():
     assert (a, b, c) == cf.expected_proof(n, w, ru, rv, rw, rep.input, wit, toxic, r, s)
     assert len(h) == n - 1 and sum(hk * pow(x, k, P) for k, hk in enumerate(h)) % P * tx % P == \
         (sum(ai * e for ai, e in zip(wit, ux)) * sum(ai * e for ai, e in zip(wit, vx)) - sum(ai * e for ai, e in zip(wit, wx))) % P
+
+
+@pytest.mark.parametrize("n,valid", [(4, True), (16, False), (64, True)])
+def test_array_level_entry_points_equal_the_list_level_ones(n, valid):
+    """of.qap_evals_np / qap_h_np / prove_np / ntt_np (uint64 limb arrays: what tests/test_gpu_parity_large.py compares the
+    device with at 2^12 .. 2^22) against the list-level functions pinned above and the literal restatement."""
+    import importlib
+
+    import numpy as np
+    zg = importlib.import_module("zksnark-rs_b200.groth16")
+    log_n = n.bit_length() - 1
+    w = synthetic.omega(log_n)
+    roots = [pow(w, k, P) for k in range(n)]
+    rep = synthetic.horner_rep(FR, n, roots)
+    qap = g.qap_from_root_rep(FR, rep)
+    rng = random.Random(7 * n)
+    wit = synthetic.horner_witness(FR, n, rng.randrange(1, P), [rng.randrange(P) for _ in range(n)])
+    if not valid:
+        wit[3] = (wit[3] + 1) % P
+        wit[-1] = rng.randrange(P)
+    m, n_input, rows = zg.horner_qap_rows(n)
+    assert m == len(rep.u) and n_input == rep.input
+    wl = zg.fr_limbs(wit)
+    A, B = of.qap_evals_np(m, n, rows, wl)
+    idx = {root: k for k, root in enumerate(roots)}
+    ev = lambda rws: [sum(wit[i] * val for i, row in enumerate(rws) for (root, val) in row if idx[root] == k) % P for k in range(n)]
+    assert zg.limbs_to_ints(A) == ev(rep.u) and zg.limbs_to_ints(B) == ev(rep.v)
+    u, v, h = of.qap_h_np(A, B, threads=3)
+    uu, vv, ws = g.weighted_sums(FR, qap, wit)
+    hq = g.quotient_h(FR, qap, uu, vv, ws)  # literal schoolbook Mul + long division, remainder discarded
+    pad = lambda p, k: (list(p) + [0] * k)[:k]
+    assert zg.limbs_to_ints(u) == pad(uu, n) and zg.limbs_to_ints(v) == pad(vv, n) and zg.limbs_to_ints(h) == pad(hq, n)
+    # short witness: zip truncation
+    A2, _ = of.qap_evals_np(m, n, rows, wl[: m - 2])
+    assert zg.limbs_to_ints(A2) == ev([row if i < m - 2 else [] for i, row in enumerate(rep.u)])
+    if n <= 16:
+        toxic = tuple(rng.randrange(1, P) for _ in range(5))
+        r, s = rng.randrange(1, P), rng.randrange(1, P)
+        Bk = g.BN254Backend()
+        s1, s2 = g.setup(Bk, qap, toxic)
+        want = g.prove(Bk, qap, (s1, s2), wit, r, s)
+        crs = {"alpha1": zg.g1_pack([s1.alpha]), "beta1": zg.g1_pack([s1.beta]), "delta1": zg.g1_pack([s1.delta]),
+               "xi1": zg.g1_pack(s1.xi), "xi_t": zg.g1_pack(s1.xi_t), "sum_delta": zg.g1_pack(s1.sum_delta),
+               "beta2": zg.g2_pack([s2.beta]), "delta2": zg.g2_pack([s2.delta]), "xi2": zg.g2_pack(s2.xi)}
+        got = of.prove_np(n, n_input, A, B, crs, wl, r, s, threads=2)
+        assert zg.g1_unpack(got[0:8])[0] == want.a and zg.g2_unpack(got[8:24])[0] == want.b and zg.g1_unpack(got[24:32])[0] == want.c
+    x = [rng.randrange(P) for _ in range(n)]
+    xl = zg.fr_limbs(x)
+    assert zg.limbs_to_ints(of.ntt_np(xl, threads=2)) == poly.dft(FR, x, w)
+    assert zg.limbs_to_ints(of.ntt_np(xl, inverse=True, threads=2)) == poly.idft(FR, x, w)
+    sh = 7
+    assert zg.limbs_to_ints(of.ntt_np(xl, coset_shift=sh)) == poly.dft(FR, [a * pow(sh, i, P) % P for i, a in enumerate(x)], w)
+    assert np.array_equal(of.ntt_np(of.ntt_np(xl, coset_shift=sh), inverse=True, coset_shift=sh), xl)

@@ -371,12 +371,25 @@ int zkb_bases_upload(zkb_ctx* ctx, int group, const uint64_t* h_points, size_t n
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   zkb_bases* b;
   ZKB_TRY(bases_new(ctx, group, n, &b));
-  int rc = ZKB_OK;
+  int rc = ZKB_OK, bad = 0;
   if (n) {
-    cudaMemcpyAsync(b->d, h_points, n * pt_bytes(group), cudaMemcpyHostToDevice, ctx->stream);
-    rc = fq_to_mont(ctx, (Fq*)b->d, n * (group == 1 ? 2 : 4), true, ctx->stream);
+    void* p = nullptr;
+    if (cudaMemcpyAsync(b->d, h_points, n * pt_bytes(group), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+      rc = set_err(ctx, ZKB_ERR_CUDA, "bases upload: copy failed");
+    if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)b->d, n * (group == 1 ? 2 : 4), true, ctx->stream);
+    // raw coordinates from outside: on the curve (or identity), G2 additionally in the order-r subgroup (see zkb_crs_upload)
+    if (rc == ZKB_OK) rc = scratch_get(ctx, 9, sizeof(int), &p);
+    if (rc == ZKB_OK) {
+      const char* tr = getenv("ZKB_CRS_TRUSTED");
+      cudaMemsetAsync(p, 0, sizeof(int), ctx->stream);
+      rc = group == 1 ? check_points_g1(ctx, (const G1Affine*)b->d, n, (int*)p, ctx->stream)
+                      : check_points_g2(ctx, (const G2Affine*)b->d, n, !(tr && atoi(tr) == 1), (int*)p, ctx->stream);
+      if (rc == ZKB_OK) cudaMemcpyAsync(&bad, p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    }
   }
   if (rc == ZKB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(ctx, ZKB_ERR_CUDA, "bases upload failed");
+  if (rc == ZKB_OK && (bad & 1)) rc = set_err(ctx, ZKB_ERR_ARG, "zkb_bases_upload: a point is not on its curve");
+  if (rc == ZKB_OK && (bad & 2)) rc = set_err(ctx, ZKB_ERR_ARG, "zkb_bases_upload: a G2 point is not in the order-r subgroup");
   if (rc == ZKB_OK) rc = bases_expand(ctx, b, msm_pick_c(n));
   if (rc != ZKB_OK) { zkb_bases_free(ctx, b); return rc; }
   *out = b;

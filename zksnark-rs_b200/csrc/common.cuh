@@ -204,6 +204,10 @@ int fixed_base_g2(zkb_ctx* ctx, G2Affine* out, const Fr* scalars_mont, size_t n,
 int fq_to_mont(zkb_ctx* ctx, Fq* d, size_t n, bool to, cudaStream_t st);
 int xyzz_to_affine_g1(zkb_ctx* ctx, G1Affine* out, const G1XYZZ* in, size_t n, cudaStream_t st);
 int xyzz_to_affine_g2(zkb_ctx* ctx, G2Affine* out, const G2XYZZ* in, size_t n, cudaStream_t st);
+// points supplied over the ABI (Montgomery form, device): *d_bad |= 1 if one is off its curve, |= 2 if a G2 point is
+// outside the order-r subgroup (checked only when `subgroup`); d_bad must be zeroed by the caller
+int check_points_g1(zkb_ctx* ctx, const G1Affine* pts, size_t n, int* d_bad, cudaStream_t st);
+int check_points_g2(zkb_ctx* ctx, const G2Affine* pts, size_t n, bool subgroup, int* d_bad, cudaStream_t st);
 int sum_affine_g1(zkb_ctx* ctx, const G1Affine* pts, size_t n, G1XYZZ* d_out, cudaStream_t st);
 int sum_affine_g2(zkb_ctx* ctx, const G2Affine* pts, size_t n, G2XYZZ* d_out, cudaStream_t st);
 

@@ -123,22 +123,54 @@ int zkb_crs_upload(zkb_ctx* ctx, const zkb_crs_host* h, int rank, int world, zkb
   cudaStream_t st = ctx->stream;
   const size_t nxi = c->nxi(), nxt = c->nxt(), nsd = c->nsd();
   G1Affine* fx = c->g1 + c->off_fixed();
-  cudaMemcpyAsync(fx + 0, h->alpha1, 64, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(fx + 1, h->beta1, 64, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(fx + 2, h->delta1, 64, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(c->g2 + nxi + 0, h->beta2, 128, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(c->g2 + nxi + 1, h->delta2, 128, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(c->gamma2, h->gamma2, 128, cudaMemcpyHostToDevice, st);
-  if (nxi) cudaMemcpyAsync(c->g1, h->xi1 + c->xi_lo * 8, nxi * 64, cudaMemcpyHostToDevice, st);
-  if (nxt) cudaMemcpyAsync(c->g1 + c->off_xit(), h->xi_t + c->xit_lo * 8, nxt * 64, cudaMemcpyHostToDevice, st);
-  if (nsd) cudaMemcpyAsync(c->g1 + c->off_sd(), h->sum_delta + c->sd_lo * 8, nsd * 64, cudaMemcpyHostToDevice, st);
-  if (c->n_sum_gamma) cudaMemcpyAsync(c->sum_gamma, h->sum_gamma, c->n_sum_gamma * 64, cudaMemcpyHostToDevice, st);
-  if (nxi) cudaMemcpyAsync(c->g2, h->xi2 + c->xi_lo * 16, nxi * 128, cudaMemcpyHostToDevice, st);
-  int rc = fq_to_mont(ctx, (Fq*)c->g1, c->g1_cnt * 2, true, st);
+  if (!h->alpha1 || !h->beta1 || !h->delta1 || !h->beta2 || !h->gamma2 || !h->delta2 || !h->xi1 || !h->xi2 ||
+      (h->n > 1 && !h->xi_t) || (h->n_sum_gamma && !h->sum_gamma) || (h->n_sum_delta && !h->sum_delta)) {
+    zkb_crs_free(ctx, c);
+    return set_err(ctx, ZKB_ERR_ARG, "zkb_crs_upload: NULL vector in zkb_crs_host");
+  }
+  cudaError_t ce = cudaSuccess;
+  auto cp = [&](void* dst, const void* src, size_t bytes) {
+    if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  };
+  cp(fx + 0, h->alpha1, 64);
+  cp(fx + 1, h->beta1, 64);
+  cp(fx + 2, h->delta1, 64);
+  cp(c->g2 + nxi + 0, h->beta2, 128);
+  cp(c->g2 + nxi + 1, h->delta2, 128);
+  cp(c->gamma2, h->gamma2, 128);
+  cp(c->g1, h->xi1 + c->xi_lo * 8, nxi * 64);
+  cp(c->g1 + c->off_xit(), h->xi_t + c->xit_lo * 8, nxt * 64);
+  cp(c->g1 + c->off_sd(), h->sum_delta + c->sd_lo * 8, nsd * 64);
+  cp(c->sum_gamma, h->sum_gamma, c->n_sum_gamma * 64);
+  cp(c->g2, h->xi2 + c->xi_lo * 16, nxi * 128);
+  int rc = ce == cudaSuccess ? ZKB_OK : set_err(ctx, ZKB_ERR_CUDA, "crs upload: copy failed: %s", cudaGetErrorString(ce));
+  if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->g1, c->g1_cnt * 2, true, st);
   if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->g2, c->g2_cnt * 4, true, st);
   if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->gamma2, 4, true, st);
   if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->sum_gamma, c->n_sum_gamma * 2, true, st);
-  if (rc == ZKB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = set_err(ctx, ZKB_ERR_CUDA, "crs upload failed");
+  // Raw coordinates from outside: every point must be the identity or on its curve, and every G2 point in the order-r
+  // subgroup (the reference's SigmaG1 / SigmaG2 can only hold bn-constructed group elements, mod.rs:105-121; a point
+  // outside the subgroup would make the proofs and the verifier's pairings meaningless).  ZKB_CRS_TRUSTED=1 skips the
+  // subgroup scalar multiplications (one per G2 point: ~0.2 s at 2^20) for a CRS the caller produced itself.
+  int bad = 0;
+  if (rc == ZKB_OK) {
+    void* p;
+    rc = scratch_get(ctx, 9, sizeof(int), &p);
+    int* d_bad = (int*)p;
+    const char* tr = getenv("ZKB_CRS_TRUSTED");
+    const bool sub = !(tr && atoi(tr) == 1);
+    if (rc == ZKB_OK && cudaMemsetAsync(d_bad, 0, sizeof(int), st) != cudaSuccess) rc = set_err(ctx, ZKB_ERR_CUDA, "crs upload: memset failed");
+    if (rc == ZKB_OK) rc = check_points_g1(ctx, c->g1, c->g1_cnt, d_bad, st);
+    if (rc == ZKB_OK) rc = check_points_g1(ctx, c->sum_gamma, c->n_sum_gamma, d_bad, st);
+    if (rc == ZKB_OK) rc = check_points_g2(ctx, c->g2, c->g2_cnt, sub, d_bad, st);
+    if (rc == ZKB_OK) rc = check_points_g2(ctx, c->gamma2, 1, sub, d_bad, st);
+    if (rc == ZKB_OK && cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      rc = set_err(ctx, ZKB_ERR_CUDA, "crs upload: copy failed");
+  }
+  if (rc == ZKB_OK && cudaStreamSynchronize(st) != cudaSuccess)
+    rc = set_err(ctx, ZKB_ERR_CUDA, "crs upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc == ZKB_OK && (bad & 1)) rc = set_err(ctx, ZKB_ERR_ARG, "zkb_crs_upload: a CRS point is not on its curve");
+  if (rc == ZKB_OK && (bad & 2)) rc = set_err(ctx, ZKB_ERR_ARG, "zkb_crs_upload: a G2 point of the CRS is not in the order-r subgroup");
   if (rc == ZKB_OK) rc = crs_expand(ctx, c, st);
   if (rc != ZKB_OK) { zkb_crs_free(ctx, c); return rc; }
   *out = c;

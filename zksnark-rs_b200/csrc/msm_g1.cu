@@ -177,6 +177,9 @@ int fixed_base_g1(zkb_ctx* ctx, G1Affine* out, const Fr* scalars_mont, size_t n,
 int xyzz_to_affine_g1(zkb_ctx* ctx, G1Affine* out, const G1XYZZ* in, size_t n, cudaStream_t st) {
   return to_affine_impl<Fq>(ctx, out, in, n, st);
 }
+int check_points_g1(zkb_ctx* ctx, const G1Affine* pts, size_t n, int* d_bad, cudaStream_t st) {
+  return check_points_impl<Fq>(ctx, pts, n, false, d_bad, st);
+}
 int sum_affine_g1(zkb_ctx* ctx, const G1Affine* pts, size_t n, G1XYZZ* d_out, cudaStream_t st) {
   return sum_affine_impl<Fq>(ctx, pts, n, d_out, st);
 }

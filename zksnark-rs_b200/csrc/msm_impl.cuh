@@ -481,6 +481,52 @@ __global__ void k_sum_affine(const Affine<F>* pts, size_t n, XYZZ<F>* out) {
   if (threadIdx.x == 0) *out = sh[0];
 }
 
+// ---- validation of points that arrive over the ABI -------------------------------------------------
+// The reference can only hold group elements that crate `bn` constructed (fr.rs:102-123), so it never meets a point
+// off the curve or -- on G2, whose curve has a cofactor != 1 -- outside the order-r subgroup.  Raw coordinates can:
+// bit 0 of *bad: a point is neither the identity nor on y^2 = x^3 + b; bit 1: a G2 point with [r]P != O (the Miller
+// loop / bucket sums are only meaningful on the r-torsion; EIP-197 mandates the same check).  G1 has cofactor 1.
+template <class F> __device__ __forceinline__ F curve_b();
+template <> __device__ __forceinline__ Fq curve_b<Fq>() {
+  const uint32_t b[8] = ZKB_G1_B;
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = b[i];
+  return r;
+}
+template <> __device__ __forceinline__ Fq2 curve_b<Fq2>() {
+  const uint32_t b0[8] = ZKB_G2_B0, b1[8] = ZKB_G2_B1;
+  Fq2 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { r.c0.v[i] = b0[i]; r.c1.v[i] = b1[i]; }
+  return r;
+}
+template <class F>
+__device__ __forceinline__ bool on_curve(const Affine<F>& p) {
+  return p.is_inf() || sqr(p.y) == sqr(p.x) * p.x + curve_b<F>();
+}
+template <class F>
+__device__ bool in_subgroup(const Affine<F>& p) {  // [r]P == O by double-and-add with the complete formulas
+  const Fr m = Fr::modulus();
+  return scalar_mul(p, m.v).is_inf();
+}
+template <class F>
+__global__ void __launch_bounds__(128) k_check_points(const Affine<F>* __restrict__ pts, size_t n, int subgroup, int* __restrict__ bad) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Affine<F> p = pts[i];
+  int f = 0;
+  if (!on_curve(p)) f = 1;
+  else if (subgroup && !p.is_inf() && !in_subgroup(p)) f = 2;
+  if (f) atomicOr(bad, f);
+}
+template <class F>
+static int check_points_impl(zkb_ctx* ctx, const Affine<F>* pts, size_t n, bool subgroup, int* d_bad, cudaStream_t st) {
+  if (!n) return ZKB_OK;
+  ZKB_LAUNCH(ctx, k_check_points<F>, cdiv(n, 128), 128, 0, st, pts, n, subgroup ? 1 : 0, d_bad);
+  return ZKB_OK;
+}
+
 template <class F>
 static int fixed_base_impl(zkb_ctx* ctx, Affine<F>* out, const Fr* scalars_mont, size_t n, cudaStream_t st) {
   if (!n) return ZKB_OK;

@@ -139,29 +139,43 @@ static bool ntt_pass_uses_tiles(const Pass& p, uint32_t log_n) {
 
 int get_twiddles(zkb_ctx* ctx, uint32_t log_n, bool inverse, Fr** out) {
   if (log_n < 1 || log_n > 27) return set_err(ctx, ZKB_ERR_ARG, "ntt size 2^%u unsupported", log_n);
-  Fr*& t = ctx->tw[log_n][inverse ? 1 : 0];
-  if (!t) {
-    size_t half = (size_t)1 << (log_n - 1);
-    ZKB_CUDA(ctx, cudaMalloc(&t, half * sizeof(Fr)));
-    ZKB_LAUNCH(ctx, k_fill_powers, cdiv(half, 256), 256, 0, ctx->stream, t, host_omega(log_n, inverse), Fr::one(), half);
-    {
+  Fr*& slot = ctx->tw[log_n][inverse ? 1 : 0];
+  if (!slot) {
+    // Built into locals and published to ctx->tw / ctx->twt only after the fill kernels have completed: a failed
+    // allocation or launch leaves the cache untouched (and frees what was allocated), so a later call cannot take a
+    // half-built table for a finished one or race the fill on another lane's stream.
+    const size_t half = (size_t)1 << (log_n - 1);
+    Fr* t = nullptr;
+    uint4* tiles[4] = {nullptr, nullptr, nullptr, nullptr};
+    auto build = [&]() -> int {
+      ZKB_CUDA(ctx, cudaMalloc(&t, half * sizeof(Fr)));
+      ZKB_LAUNCH(ctx, k_fill_powers, cdiv(half, 256), 256, 0, ctx->stream, t, host_omega(log_n, inverse), Fr::one(), half);
       std::vector<Pass> ps = plan(log_n);
       for (size_t q = 0; q < ps.size() && q < 4; q++) {
         const Pass& p = ps[q];
         if (!ntt_pass_uses_tiles(p, log_n)) continue;
         const uint32_t logT = p.hi - p.lo + p.logC;
         const size_t groups = ((size_t)1 << p.lo) >> p.logC, total = groups << logT;
-        uint4*& tt = ctx->twt[log_n][inverse ? 1 : 0][q];
-        ZKB_CUDA(ctx, cudaMalloc(&tt, total * 32));
+        ZKB_CUDA(ctx, cudaMalloc(&tiles[q], total * 32));
         // 64 KB of dynamic shared memory (data tile + twiddle tile) needs the opt-in, per device
         ZKB_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         ZKB_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        ZKB_LAUNCH(ctx, k_fill_tw_tiles, cdiv(total, 256), 256, 0, ctx->stream, tt, t, log_n, p.lo, p.hi - p.lo, p.logC, total);
+        ZKB_LAUNCH(ctx, k_fill_tw_tiles, cdiv(total, 256), 256, 0, ctx->stream, tiles[q], t, log_n, p.lo, p.hi - p.lo, p.logC, total);
       }
+      ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      return ZKB_OK;
+    };
+    const int rc = build();
+    if (rc != ZKB_OK) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(t);
+      for (auto& p : tiles) cudaFree(p);
+      return rc;
     }
-    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < 4; q++) ctx->twt[log_n][inverse ? 1 : 0][q] = tiles[q];
+    slot = t;
   }
-  *out = t;
+  *out = slot;
   return ZKB_OK;
 }
 

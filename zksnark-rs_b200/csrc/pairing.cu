@@ -92,7 +92,20 @@ __global__ void k_pairs_load(const uint32_t* __restrict__ g1s, const uint32_t* _
   if (i >= n) return;
   bool ok = g1_load_checked(g1s + i * 16, &P[i]);
   ok = g2_load_checked(g2s + i * 32, &Q[i]) && ok;
-  if (!ok) *bad = 1;
+  if (!ok) atomicOr(bad, 1);
+}
+
+// proof.b / pairing arguments must lie in the order-r subgroup of the twist (cofactor != 1): [r]Q == O by double-and-add.
+// The reference's G2Local values are always bn-constructed subgroup elements; raw coordinates over the ABI are not.
+// One thread per point Q[i * stride]; per_item: bad[i] |= 2, else *bad |= 2.  Runs beside the Miller loops.
+__global__ void __launch_bounds__(32) k_g2_subgroup(const G2Affine* __restrict__ Q, size_t stride, size_t count, int* __restrict__ bad,
+                                                    int per_item) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const G2Affine q = Q[i * stride];
+  if (q.is_inf()) return;
+  const Fr m = Fr::modulus();
+  if (!scalar_mul(q, m.v).is_inf()) atomicOr(per_item ? bad + i : bad, 2);
 }
 
 __global__ void __launch_bounds__(32) k_miller(const G1Affine* __restrict__ P, const G2Affine* __restrict__ Q, size_t n,
@@ -153,7 +166,14 @@ int zkb_verify_batch(zkb_ctx* ctx, const zkb_crs* crs, const uint64_t* inputs, s
   if (terms) ZKB_LAUNCH(ctx, k_verify_terms, cdiv(terms * count, 64), 64, 0, st, crs->sum_gamma, d_in, n_inputs, terms, count, term);
   ZKB_LAUNCH(ctx, k_verify_pairs, cdiv(count, 32), 32, 0, st, crs->g1 + crs->off_fixed(), crs->g2 + crs->nxi(), crs->gamma2,
              crs->g2 + crs->nxi() + 1, d_pr, term, terms, count, P, Q, d_bad);
+  // subgroup membership of proof.b on the second stream, beside the Miller loops
+  cudaEvent_t ev_pairs = ctx->lanes[0].ev[0], ev_sub = ctx->lanes[0].ev[1];
+  ZKB_CUDA(ctx, cudaEventRecord(ev_pairs, st));
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ev_pairs, 0));
+  ZKB_LAUNCH(ctx, k_g2_subgroup, cdiv(count, 32), 32, 0, ctx->stream2, Q, (size_t)4, count, d_bad, 1);
+  ZKB_CUDA(ctx, cudaEventRecord(ev_sub, ctx->stream2));
   ZKB_LAUNCH(ctx, k_miller, cdiv(4 * count, 32), 32, 0, st, P, Q, 4 * count, ml);
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(st, ev_sub, 0));
   ZKB_LAUNCH(ctx, k_final_exp, cdiv(count, 32), 32, 0, st, ml, (size_t)4, count, d_bad, (uint32_t*)nullptr, d_ok);
   ZKB_CUDA(ctx, cudaMemcpyAsync(ok, d_ok, count * sizeof(int), cudaMemcpyDeviceToHost, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -184,14 +204,21 @@ int zkb_pairing(zkb_ctx* ctx, const uint64_t* g1s, const uint64_t* g2s, size_t n
     ZKB_CUDA(ctx, cudaMemcpyAsync(d_g1, g1s, n * 64, cudaMemcpyHostToDevice, st));
     ZKB_CUDA(ctx, cudaMemcpyAsync(d_g2, g2s, n * 128, cudaMemcpyHostToDevice, st));
     ZKB_LAUNCH(ctx, k_pairs_load, cdiv(n, 32), 32, 0, st, d_g1, d_g2, n, P, Q, d_bad);
+    cudaEvent_t ev_pairs = ctx->lanes[0].ev[0], ev_sub = ctx->lanes[0].ev[1];
+    ZKB_CUDA(ctx, cudaEventRecord(ev_pairs, st));
+    ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ev_pairs, 0));
+    ZKB_LAUNCH(ctx, k_g2_subgroup, cdiv(n, 32), 32, 0, ctx->stream2, Q, (size_t)1, n, d_bad, 0);
+    ZKB_CUDA(ctx, cudaEventRecord(ev_sub, ctx->stream2));
     ZKB_LAUNCH(ctx, k_miller, cdiv(n, 32), 32, 0, st, P, Q, n, ml);
+    ZKB_CUDA(ctx, cudaStreamWaitEvent(st, ev_sub, 0));
   }
   ZKB_LAUNCH(ctx, k_final_exp, 1, 32, 0, st, ml, n, (size_t)1, (const int*)nullptr, d_gt, (int*)nullptr);
   int bad = 0;
   ZKB_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   ZKB_CUDA(ctx, cudaMemcpyAsync(gt, d_gt, 48 * 8, cudaMemcpyDeviceToHost, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));
-  if (bad) return set_err(ctx, ZKB_ERR_ARG, "zkb_pairing: a point is not on its curve (or a coordinate is not a canonical residue)");
+  if (bad & 1) return set_err(ctx, ZKB_ERR_ARG, "zkb_pairing: a point is not on its curve (or a coordinate is not a canonical residue)");
+  if (bad & 2) return set_err(ctx, ZKB_ERR_ARG, "zkb_pairing: a G2 point is not in the order-r subgroup");
   return ZKB_OK;
 }
 

@@ -453,9 +453,16 @@ static int poly_stage(zkb_ctx* ctx, const zkb_qap* q, const Work& w, const Fr* d
   return ZKB_OK;
 }
 
+// The reference's prove() zips whatever it is given (mod.rs:237..288); a CRS made for another QAP would silently give a
+// proof that cannot verify.  setup() fixes n = qap.degree, sum_gamma = input + 1 and sum_delta = m - input - 1 entries
+// (mod.rs:146-168), so all three must agree with the QAP.
 static int check_pair(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c) {
   if (c->n != q->n) return set_err(ctx, ZKB_ERR_ARG, "CRS (n=%llu) does not belong to QAP (n=%llu)",
                                    (unsigned long long)c->n, (unsigned long long)q->n);
+  if (c->n_sum_gamma != q->n_input + 1 || c->n_sum_gamma + c->n_sum_delta != q->m)
+    return set_err(ctx, ZKB_ERR_ARG, "CRS (sum_gamma %llu + sum_delta %llu entries) does not belong to QAP (m=%llu wires, %llu inputs)",
+                   (unsigned long long)c->n_sum_gamma, (unsigned long long)c->n_sum_delta, (unsigned long long)q->m,
+                   (unsigned long long)q->n_input);
   return ZKB_OK;
 }
 

@@ -433,7 +433,8 @@ class CRS:
         self.ctx.check(self.ctx.lib.zkb_crs_dims(self.h, C.byref(n), C.byref(g), C.byref(d)), "zkb_crs_dims")
         return n.value, g.value, d.value
 
-    def download(self) -> dict:
+    def download_raw(self) -> dict:
+        """The CRS as uint64 limb arrays in the zkb_crs_host layout (canonical affine coordinates)."""
         n, ng, nd = self.dims()
         host = _CrsHost()
         host.n, host.n_sum_gamma, host.n_sum_delta = n, ng, nd
@@ -444,6 +445,10 @@ class CRS:
         for k, a in arrs.items():
             setattr(host, k, a.ctypes.data if a.size else None)
         self.ctx.check(self.ctx.lib.zkb_crs_download(self.ctx.h, self.h, C.byref(host)), "zkb_crs_download")
+        return arrs
+
+    def download(self) -> dict:
+        arrs = self.download_raw()
         out = {}
         for k, a in arrs.items():
             pts = g2_unpack(a) if a.shape[1] == 16 else g1_unpack(a)
@@ -635,12 +640,17 @@ def prove_combine_batch(ctx: Context, partials: np.ndarray) -> list:
     return [_proof(out[i]) for i in range(count)]
 
 
-def qap_h(ctx: Context, qap: QAP, weights):
-    """(u_sum, v_sum, h) coefficient lists: mod.rs:233-246 and :277."""
+def qap_h_raw(ctx: Context, qap: QAP, weights):
+    """(u_sum, v_sum, h) as (n, 4) uint64 limb arrays (h[n-1] = 0): mod.rs:233-246 and :277."""
     w = _weights_array(qap, weights)
     outs = [np.zeros((qap.n, 4), dtype=np.uint64) for _ in range(3)]
     ctx.check(ctx.lib.zkb_qap_h(ctx.h, qap.h, _ptr(w), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2])), "zkb_qap_h")
-    u, v, h = (limbs_to_ints(o) for o in outs)
+    return outs
+
+
+def qap_h(ctx: Context, qap: QAP, weights):
+    """(u_sum, v_sum, h) coefficient lists: mod.rs:233-246 and :277."""
+    u, v, h = (limbs_to_ints(o) for o in qap_h_raw(ctx, qap, weights))
     return u, v, h[: qap.n - 1]
 
 
