@@ -202,10 +202,14 @@ def run_ours(args):
     m = qap.m
     rng = random.Random(3)
     toxic = tuple(rng.randrange(1, FR) for _ in range(5))
-    # shard: ONE proof per step over all ranks (MSM bases sharded by points, NCCL all-gather of the partial
-    # sums).  replicas: every rank proves its own stream with a full CRS (no data-path collective).
-    sw = world if args.mode == "shard" else 1
-    crs = zk.setup(ctx, qap, toxic, rank=rank if sw > 1 else 0, world=sw)
+    # shard (default at N > 1): ONE proof per step over all ranks -- the NTT's outer dimension and the MSM points sharded,
+    # the exchanges (3 all-to-alls of the polynomial stage + the partial sums) done by the library's kernels over NVLink
+    # peer memory, per proof, no host bounce.  replicas: every rank proves its own stream with a full CRS (no exchange).
+    zd = importlib.import_module("zksnark-rs_b200.dist")
+    mode = args.mode or ("shard" if world > 1 else "replicas")
+    sw = world if (mode == "shard" and world > 1) else 1
+    comm = zd.connect(ctx, args.log_n, device=torch.device("cuda", local)) if world > 1 else None
+    crs = zk.setup_shard(ctx, comm, qap, toxic) if sw > 1 else zk.setup(ctx, qap, toxic)
     crs_by_sw = {sw: crs}
     r, s = rng.randrange(1, FR), rng.randrange(1, FR)
     w_np = make_witness(zg, n, 2)
@@ -226,14 +230,9 @@ def run_ours(args):
         if sw == 1:
             ws = [d_w] * steps if on_device else [pins[i & 1] for i in range(steps)]
             return zk.prove_batch(ctx, qap, crs, ws, [r] * steps, [s] * steps, on_device=on_device)[-1]
-        # sharded: K partial records per rank (two proofs in flight), ONE all-gather, one fold kernel
+        # sharded: every proof runs over all ranks (up to four in flight, one exchange channel each); every rank gets it
         ws = [d_w] * steps if on_device else [pins[i & 1] for i in range(steps)]
-        parts = zk.prove_batch(ctx, qap, crs, ws, [r] * steps, [s] * steps, on_device=on_device)  # (steps, 32) limbs
-        gin = torch.from_numpy(parts.view(np.int64).reshape(-1)).to("cuda", non_blocking=False)
-        gout = torch.empty(world * gin.numel(), dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(gout, gin)
-        allp = gout.cpu().numpy().view(np.uint64).reshape(world, steps, 32)
-        return zk.prove_combine_batch(ctx, allp)[-1]
+        return zk.prove_shard_batch(ctx, comm, qap, crs, ws, [r] * steps, [s] * steps, on_device=on_device)[-1]
 
     def barrier():
         torch.cuda.synchronize()
@@ -261,9 +260,10 @@ def run_ours(args):
     run_steps(False, max(args.warmup, 3))
     # single-proof latency (zkb_prove_dev, one proof in flight), for context
     lat0 = time.perf_counter()
+    single = None
     for _ in range(3):
-        single = zg.prove_dev(ctx, qap, crs, d_w, r, s) if sw == 1 else None
-    latency_ms = (time.perf_counter() - lat0) / 3 * 1e3 if sw == 1 else None
+        single = zg.prove_dev(ctx, qap, crs, d_w, r, s) if sw == 1 else zk.prove_shard(ctx, comm, qap, crs, d_w, r, s, on_device=True)
+    latency_ms = (time.perf_counter() - lat0) / 3 * 1e3
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -278,7 +278,7 @@ def run_ours(args):
         if sw == 1:
             zg.prove_dev(ctx, qap, crs, d_w, r, s)
         else:
-            zk.prove_partial(ctx, qap, crs, d_w, r, s, on_device=True)
+            zk.prove_shard(ctx, comm, qap, crs, d_w, r, s, on_device=True)
     prof_step_ms = (time.perf_counter() - t_prof0) / args.steps * 1e3
     prof = {k: ctx.profile_read(k) for k in (1, 2, 3)}
     ctx.profile(False)
@@ -287,7 +287,9 @@ def run_ours(args):
     other = None
     if world > 1:  # the other layout, device-resident witnesses, same K steps (context for the headline number)
         osw = 1 if sw > 1 else world
-        crs_by_sw[osw] = zk.setup(ctx, qap, toxic, rank=rank if osw > 1 else 0, world=osw)
+        if sw > 1:
+            crs.free()  # the two layouts' window tables need not be resident together (2^22: tens of GiB)
+        crs_by_sw[osw] = zk.setup_shard(ctx, comm, qap, toxic) if osw > 1 else zk.setup(ctx, qap, toxic)
         run_steps(True, max(args.warmup, 3), osw)
         ms_o, _, proof_o = timed(True, args.steps, osw)
         assert (proof_o.a, proof_o.b, proof_o.c) == (proof.a, proof.b, proof.c)  # sharded == replicated, bit for bit
@@ -353,14 +355,15 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args.log_n),
                        "parallelism": (f"1 GPU, zkb_prove_batch ({4 if args.log_n <= 17 else 3 if args.log_n <= 19 else 2} proofs in flight)" if world == 1 else
-                                       (f"msm-point-shard x{world}: one proof per step over all ranks" if sw > 1 else
+                                       (f"one proof per step over all {world} ranks: NTT outer dimension + MSM points sharded, 4 exchanges per proof by kernel "
+                                        f"stores into peer HBM over NVLink (in-library, per proof, no host bounce), several proofs in flight" if sw > 1 else
                                         f"replicas x{world}: one proof per step on EVERY rank")),
                        "single_proof_latency_ms": latency_ms,
                        "l2_policy": (f"inputs larger than L2 (CRS window tables {table_bytes(args.log_n) / 2**30:.2f} GiB gathered at random + "
                                      f"{(2 * n + 2) * 32 / 2**20:.0f} MiB witness per proof; L2 is 126 MB)"),
                        "timing": "CUDA events on the library stream, max over ranks"},
             "e2e": {"value": jobs * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(w_np.nbytes) * world,
-                    "d2h_bytes_per_step": 256 * world if sw == 1 else 256 * world + 256 * world, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 256 * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_ntt": roofline_ntt,
             "msm_g2": {"kernel": "k_accumulate_chunks<Fq2>", "total_ms": g2_ms, "launches": g2_cnt, "records": g2_recs,
@@ -434,8 +437,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true",
                     help="profiling runs only (ncu replays): leave out the cpu_baseline / cpu_best_effort legs; the line is then not a bench line")
-    ap.add_argument("--mode", default="replicas", choices=["shard", "replicas"],
-                    help="N > 1: one proof stream per rank (default: throughput, weak scaling) or one proof sharded over the ranks (latency)")
+    ap.add_argument("--mode", default=None, choices=["shard", "replicas"],
+                    help="N > 1: ONE proof over all ranks per step (default: strong scaling; NTT outer dimension + MSM points sharded, "
+                         "exchanges over NVLink peer memory inside the library) or one independent proof stream per rank (weak scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -35,11 +35,13 @@ extern "C" {
 #define ZKB_ERR_ALLOC (-3)       /* device or host allocation failed */
 #define ZKB_ERR_UNSUPPORTED (-4) /* valid request this build does not implement */
 #define ZKB_ERR_DIV_ZERO (-5)    /* the reference would panic: inverse of zero (fr.rs:54,69) */
+#define ZKB_ERR_COMM (-6)        /* multi-GPU exchange: a peer did not arrive within the timeout */
 
 typedef struct zkb_ctx zkb_ctx;
 typedef struct zkb_qap zkb_qap;     /* device-resident QAP<CoefficientPoly<FrLocal>> (sparse evaluation rows) */
 typedef struct zkb_crs zkb_crs;     /* device-resident (SigmaG1<G1Local>, SigmaG2<G2Local>) */
 typedef struct zkb_bases zkb_bases; /* device-resident vector of G1 or G2 affine points */
+typedef struct zkb_comm zkb_comm;   /* one rank's end of a multi-GPU communicator (exchange window in HBM, mapped by the peers) */
 
 /* ---- context ------------------------------------------------------------------------------- */
 int zkb_ctx_create(zkb_ctx** out, int device_id);
@@ -164,6 +166,50 @@ int zkb_prove_combine(zkb_ctx* ctx, const uint64_t* partials /* world x 32, host
  * kernel launch folds into `count` proofs. */
 int zkb_prove_combine_batch(zkb_ctx* ctx, const uint64_t* partials /* world x count x 32, host */, int world,
                             size_t count, zkb_proof* out);
+/* ---- ONE proof over several GPUs, exchanges inside the library (replaces the single-threaded
+ * groth16/mod.rs:213-296 as a whole -- the reference has no process or device boundary, so this surface is new).
+ * One process (or one context) per GPU, world = 2^k ranks.  Every rank owns an exchange window in its HBM that the
+ * peers map (CUDA IPC between processes; the raw pointer between contexts of one process) and the kernels write
+ * into directly over NVLink: no NCCL call and no host bounce on the data path.
+ *   1. zkb_comm_create on every rank -> a 128-byte handle; 2. the host side gathers the `world` handles in rank order
+ *   (any transport: torch.distributed / MPI / a file -- once, at start-up); 3. zkb_comm_connect maps the peers.
+ * The polynomial stage shards the NTT's outer dimension: rank r evaluates gates r, r+G, ..., each of the six
+ * transforms is a local size-n/G transform plus ONE all-to-all plus log G butterfly stages (three exchanges per
+ * proof: 3 + 2 + 1 vectors of n/G elements per rank), and u_sum, v_sum, h come out in the "strided block" layout
+ * (local index k1*q + t <-> coefficient (r*q + t) + (n/G)*k1, q = n/G^2).  zkb_setup_shard / zkb_crs_upload_shard
+ * shard sigma_g1.xi, sigma_g1.xi_t and sigma_g2.xi the same way (sum_delta by contiguous ranges; the fixed points on
+ * rank 0), so every rank's MSMs run over 1/G of the points; the 256-byte partial sums of A, B, C are written into
+ * every peer's window and folded on the device ("allreduce" = all-to-all stores + local fold: EC addition is not a
+ * reduction operator of NCCL).  Every rank returns the complete proof, bit-identical to zkb_prove on one GPU.
+ * Requirements: roots-of-unity domain, n >= 2 * world^2, world <= 16.  Collective semantics: every rank must make the
+ * same sequence of zkb_prove_shard* / zkb_ntt_shard calls; a rank that never arrives makes the others fail with
+ * ZKB_ERR_COMM after ZKB_COMM_TIMEOUT_MS (default 20000) instead of hanging. */
+#define ZKB_COMM_HANDLE_BYTES 128
+int zkb_comm_create(zkb_ctx* ctx, int rank, int world, uint32_t max_log_n, zkb_comm** out, uint8_t* handle /* 128 bytes */);
+int zkb_comm_connect(zkb_comm* comm, const uint8_t* handles /* world x 128 bytes, rank order */);
+void zkb_comm_destroy(zkb_comm* comm);
+/* rank / world of the communicator and its sticky status word (0 ok, 1 = an exchange timed out); any may be NULL */
+int zkb_comm_info(const zkb_comm* comm, int* rank, int* world, int* status);
+/* groth16::setup (mod.rs:134-197) / upload of a reference-made CRS for this rank's shard in the layout above */
+int zkb_setup_shard(zkb_ctx* ctx, const zkb_comm* comm, const zkb_qap* qap, const uint64_t* toxic, zkb_crs** out);
+int zkb_crs_upload_shard(zkb_ctx* ctx, const zkb_comm* comm, const zkb_crs_host* crs, zkb_crs** out);
+/* groth16::prove over all ranks.  weights: the full witness (m x 4 limbs) on every rank, host or device. */
+int zkb_prove_shard(zkb_ctx* ctx, zkb_comm* comm, const zkb_qap* qap, const zkb_crs* crs, const uint64_t* weights,
+                    int weights_on_device, const uint64_t r[4], const uint64_t s[4], zkb_proof* out);
+/* The same split in two so that several proofs (lanes 0..3, one exchange channel each) can be in flight, or several
+ * ranks can be driven from one host thread: enqueue returns as soon as the work is queued, collect waits for it. */
+int zkb_prove_shard_enqueue(zkb_ctx* ctx, zkb_comm* comm, const zkb_qap* qap, const zkb_crs* crs, const uint64_t* weights,
+                            int weights_on_device, const uint64_t r[4], const uint64_t s[4], int lane);
+int zkb_prove_shard_collect(zkb_ctx* ctx, zkb_comm* comm, int lane, zkb_proof* out);
+/* `count` proofs, each over all ranks, up to four in flight (zkb_prove_batch's pipelining; same results). */
+int zkb_prove_shard_batch(zkb_ctx* ctx, zkb_comm* comm, const zkb_qap* qap, const zkb_crs* crs, const uint64_t* const* weights,
+                          int weights_on_device, const uint64_t* r, const uint64_t* s, size_t count, zkb_proof* out);
+/* One size-2^log_n transform (zkb_ntt_fr's convention) with its outer dimension sharded over the ranks: d_local holds
+ * n/G canonical residues, x[rank + G*i] on entry and X[(rank*q + t) + (n/G)*k1] at index k1*q + t on return.
+ * One all-to-all of n*32*(G-1)/G bytes in total and log G butterfly stages.  async != 0: return once queued
+ * (zkb_sync completes it). */
+int zkb_ntt_shard(zkb_ctx* ctx, zkb_comm* comm, uint64_t* d_local, uint32_t log_n, int inverse, int async);
+
 /* h(x) alone: h = (u_sum * v_sum - w_sum) / t  (mod.rs:277; coefficient_poly.rs:93-157;
  * field/mod.rs:428-469).  Outputs (host, canonical, n x 4 limbs each; any may be NULL):
  * u_sum, v_sum coefficient vectors and h (n-1 meaningful coefficients, h[n-1] = 0). */

@@ -49,7 +49,7 @@ void prof_begin(zkb_ctx* ctx, int kind, cudaStream_t st, const char* name) {
   cudaEventCreate(&r.b);
   r.kind = kind;
   r.name = name;
-  r.stream_id = st == ctx->lanes[0].hi ? 1 : (st == ctx->lanes[0].lo ? 2 : (st == ctx->lanes[0].hi2 ? 5 : (st == ctx->lanes[1].hi ? 3 : 4)));
+  r.stream_id = st == ctx->lanes[0].hi ? 1 : (st == ctx->lanes[0].lo ? 2 : (st == ctx->lanes[0].hi2 ? 5 : (ctx->lanes[1].hi && st == ctx->lanes[1].hi ? 3 : 4)));
   cudaEventRecord(r.a, st);
   ctx->prof.push_back(r);
 }
@@ -57,6 +57,28 @@ void prof_end(zkb_ctx* ctx, cudaStream_t st) { cudaEventRecord(ctx->prof.back().
 void prof_clear(zkb_ctx* ctx) {
   for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   ctx->prof.clear();
+}
+
+// per lane: latency-class streams at high priority, throughput-class (bucket accumulation) at low
+int lane_get(zkb_ctx* c, int idx, zkb_lane** out) {
+  if (idx < 0 || idx >= 4) return set_err(c, ZKB_ERR_ARG, "lane %d out of range", idx);
+  zkb_lane& l = c->lanes[idx];
+  if (!l.hi) {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (const char* e = getenv("ZKB_PRIO")) {  // developer switch: 0 = no priorities, -1 = reversed
+      if (atoi(e) == 0) prio_hi = prio_lo;
+      if (atoi(e) < 0) std::swap(prio_lo, prio_hi);
+    }
+    if (cudaStreamCreateWithPriority(&l.hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&l.lo, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&l.hi2, cudaStreamNonBlocking, prio_hi) != cudaSuccess)
+      return set_err(c, ZKB_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    for (auto& e : l.ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (cudaHostAlloc(&l.h_proof, 512, cudaHostAllocDefault) != cudaSuccess) return set_err(c, ZKB_ERR_ALLOC, "cudaHostAlloc failed");
+  }
+  if (out) *out = &l;
+  return ZKB_OK;
 }
 
 Fr fr_from_limbs(const uint64_t* l) {  // canonical limbs -> Montgomery (host)
@@ -111,22 +133,12 @@ int zkb_ctx_create(zkb_ctx** out, int device_id) {
     int v = atoi(e);
     if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
   }
-  // per lane: latency-class stream at high priority, throughput-class (bucket accumulation) at low
-  int prio_lo = 0, prio_hi = 0;
-  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  if (const char* e = getenv("ZKB_PRIO")) {  // developer switch: 0 = no priorities, -1 = reversed
-    if (atoi(e) == 0) prio_hi = prio_lo;
-    if (atoi(e) < 0) std::swap(prio_lo, prio_hi);
-  }
-  for (auto& l : c->lanes) {
-    cudaStreamCreateWithPriority(&l.hi, cudaStreamNonBlocking, prio_hi);
-    cudaStreamCreateWithPriority(&l.lo, cudaStreamNonBlocking, prio_lo);
-    cudaStreamCreateWithPriority(&l.hi2, cudaStreamNonBlocking, prio_hi);
-    for (auto& e : l.ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    if (cudaHostAlloc(&l.h_proof, 256, cudaHostAllocDefault) != cudaSuccess) {
-      zkb_ctx_destroy(c);
-      return set_err(nullptr, ZKB_ERR_ALLOC, "cudaHostAlloc failed");
-    }
+  // lane 0 now, the others on first use (lane_get): streams share a small number of hardware queues
+  // (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default), and work queued behind another stream's exchange wait in the same
+  // queue would be held up with it -- so no more streams than proofs in flight need
+  if (lane_get(c, 0, nullptr) != ZKB_OK) {
+    zkb_ctx_destroy(c);
+    return set_err(nullptr, ZKB_ERR_ALLOC, "stream / pinned staging creation failed");
   }
   c->stream = c->lanes[0].hi;
   c->stream2 = c->lanes[0].lo;
@@ -254,8 +266,10 @@ int zkb_memcpy_d2h(zkb_ctx* ctx, void* dst, const void* src, size_t bytes) {
 int zkb_sync(zkb_ctx* ctx) {
   if (!ctx) return ZKB_ERR_ARG;
   for (auto& l : ctx->lanes) {
+    if (!l.hi) continue;
     ZKB_CUDA(ctx, cudaStreamSynchronize(l.hi));
     ZKB_CUDA(ctx, cudaStreamSynchronize(l.lo));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(l.hi2));
   }
   return ZKB_OK;
 }

@@ -30,12 +30,12 @@ struct zkb_lane {
   cudaStream_t hi2 = nullptr;    // second latency-class stream: the G1 tail runs beside the G2 tail (both low-occupancy)
   cudaEvent_t ev[5] = {};        // 0/1: G1 records sorted / accumulated; 2/3: same for G2; 4: G1 tail done
   zkb::DevBuf scratch[16];       // per-lane scratch (MSM buffers, polynomial workspace, outputs)
-  void* h_proof = nullptr;       // pinned staging for the 256-byte result
+  void* h_proof = nullptr;       // pinned staging for the 256-byte result (+ the exchange status word of a sharded proof)
 };
 
 struct zkb_ctx {
   int device = 0;
-  zkb_lane lanes[4];               // all created; zkb_prove_batch keeps `batch_lanes` proofs in flight
+  zkb_lane lanes[4];               // lane 0 always, the others created on first use (lane_get); zkb_prove_batch keeps `batch_lanes` proofs in flight
   int batch_lanes = 0;             // 0 = by problem size (prove.cu: batch_lane_count); ZKB_LANES=1..4 overrides (developer switch)
   cudaStream_t stream = nullptr;   // = lanes[0].hi: everything outside the prove pipeline runs here
   cudaStream_t stream2 = nullptr;  // = lanes[0].lo
@@ -63,6 +63,8 @@ namespace zkb {
 extern thread_local std::string g_err;
 
 int set_err(zkb_ctx* ctx, int code, const char* fmt, ...);
+// lane `idx` of the context, its streams / events / pinned staging created on first use (api.cu)
+int lane_get(zkb_ctx* ctx, int idx, zkb_lane** out);
 
 #define ZKB_CUDA(ctx, expr)                                                                     \
   do {                                                                                          \
@@ -213,6 +215,63 @@ int sum_affine_g2(zkb_ctx* ctx, const G2Affine* pts, size_t n, G2XYZZ* d_out, cu
 
 }  // namespace zkb
 
+// ---- shard.cu: one proof over several GPUs, exchanges over NVLink peer memory -----------------------
+// Every rank owns an exchange WINDOW in its HBM that all peers map (CUDA IPC between processes, the raw
+// pointer inside one process).  Ranks only ever WRITE into peers' windows (kernel stores over NVLink) and
+// READ their own; a transfer is: remote stores, __threadfence_system, then a remote store of the channel's
+// epoch into the peer's flag word, which the consumer kernel polls.  Layout (identical on every rank):
+//   [0, 2048)        flags[channel][step][src rank] (u32 epochs)     [2048]  status word (1 = a wait timed out)
+//   [4096, 24576)    partial-sum slots[channel][src rank][64 u32]
+//   [32768, ...)     per channel 6 * m_max Fr: R0 (3 vectors) | R1 (2) | R2 (1), each [vector][src rank][q]
+static const int ZKB_COMM_MAX_WORLD = 16;
+static const int ZKB_COMM_CHANNELS = 5;  // one per proof lane + one for stand-alone transforms
+static const int ZKB_COMM_STEPS = 4;     // three all-to-alls of the polynomial stage + the partial sums
+namespace zkb {
+struct CommView {  // by-value kernel argument
+  char* base[ZKB_COMM_MAX_WORLD];  // base[g]: rank g's window as mapped into this process (base[rank]: own)
+  int rank, world, lg;
+  unsigned long long timeout_ns;
+};
+struct ShardTables {  // per (comm, log_n): this rank's slices of the cross-rank twiddles and coset tables
+  Fr *Tinv = nullptr, *Tfwd = nullptr, *cosS = nullptr, *QS = nullptr;
+};
+}  // namespace zkb
+struct zkb_comm {
+  zkb_ctx* ctx = nullptr;
+  int rank = 0, world = 1, lg = 0;
+  uint32_t max_log_n = 0;
+  size_t m_max = 0, window_bytes = 0;
+  char* window = nullptr;  // own
+  bool connected = false;
+  bool peer_is_ipc[ZKB_COMM_MAX_WORLD] = {};
+  zkb::CommView view;
+  uint32_t epoch[ZKB_COMM_CHANNELS] = {};
+  zkb::ShardTables tabs[28];
+};
+
+namespace zkb {
+// shard.cu internals used by prove.cu
+static inline size_t comm_flag_off(int ch, int step, int src) { return (((size_t)ch * ZKB_COMM_STEPS + step) * ZKB_COMM_MAX_WORLD + src) * 4; }
+static const size_t COMM_STATUS_OFF = 2048, COMM_SLOTS_OFF = 4096, COMM_DATA_OFF = 32768;
+static inline size_t comm_slot_off(int ch, int src) { return COMM_SLOTS_OFF + ((size_t)ch * ZKB_COMM_MAX_WORLD + src) * 256; }
+static inline size_t comm_region_off(const zkb_comm* c, int ch, int region /*0,1,2*/) {
+  static const size_t first[3] = {0, 3, 5};
+  return COMM_DATA_OFF + ((size_t)ch * 6 + first[region]) * c->m_max * sizeof(Fr);
+}
+int shard_check(zkb_ctx* ctx, const zkb_comm* c, uint32_t log_n);
+// builds (once) the cross-rank tables and the local transforms' twiddles of a size-2^log_n sharded transform
+int shard_prepare(zkb_ctx* ctx, zkb_comm* c, uint32_t log_n);
+int matvec_launch(zkb_ctx* ctx, const zkb_qap* q, const Fr* wmont, size_t k0, size_t kstride, size_t count, Fr* A, Fr* B, Fr* AB,
+                  cudaStream_t st);
+int combine_partials_launch(zkb_ctx* ctx, const uint32_t* d_partials, int world, size_t count, uint32_t* d_out, cudaStream_t st);
+// polynomial stage of a sharded proof on channel `ch`: ws = 7 * (n / world) Fr; on return (stream order) un, vn, hn
+// (Montgomery, layout S: local index s = k1 * q + t <-> coefficient (rank * q + t) + (n / world) * k1) are ws + 3m, 4m, 6m
+int shard_poly_stage(zkb_ctx* ctx, zkb_comm* c, int ch, uint32_t epoch, const zkb_qap* q, Fr* ws, const Fr* wmont, cudaStream_t st);
+// partial sums: `partial` (64 u32, device) -> every rank's slot; then wait for all ranks' records and fold them into `out`
+int shard_exchange_partials(zkb_ctx* ctx, zkb_comm* c, int ch, uint32_t epoch, const uint32_t* partial, uint32_t* out, int* d_status_copy,
+                            cudaStream_t st);
+}  // namespace zkb
+
 struct zkb_bases {
   int group = 1;
   size_t n = 0;
@@ -252,7 +311,8 @@ struct zkb_qap {
 struct zkb_crs {
   uint64_t n = 0, n_sum_gamma = 0, n_sum_delta = 0;
   int rank = 0, world = 1;
-  // shard ranges [lo, hi) into the logical vectors
+  int layout = 0;  // 0: contiguous index ranges; 1: xi / xi_t in the sharded transform's output layout S (shard.cu)
+  // shard ranges [lo, hi) into the logical vectors (layout 1: xi / xi_t are LOCAL ranges [0, count))
   uint64_t xi_lo = 0, xi_hi = 0, xit_lo = 0, xit_hi = 0, sd_lo = 0, sd_hi = 0;
   // G1 table, row 0 = [xi1 shard | alpha1 beta1 delta1 | xi_t shard | sum_delta shard], rows j>0 = 2^(c1*j) multiples
   zkb::G1Affine* g1 = nullptr;

@@ -60,6 +60,14 @@ __global__ void k_lin(const uint32_t* ru, const uint32_t* gu, const Fr* cu, cons
   if (lane == 0) out[i] = (beta * u + alpha * v + w) * (i <= n_input ? inv_gamma : inv_delta);
 }
 
+// layout 1 (shard.cu, layout S): local index s = k1*q + t <-> global index (rank*q + t) + m*k1
+__global__ void k_gather_S(Fr* __restrict__ dst, const Fr* __restrict__ src, uint64_t rank, uint64_t q, uint64_t m, uint64_t count) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= count) return;
+  const uint64_t k1 = s / q, t = s - k1 * q;
+  dst[s] = src[rank * q + t + m * k1];
+}
+
 }  // namespace zkb
 
 using namespace zkb;
@@ -78,12 +86,18 @@ static void shard(uint64_t len, int rank, int world, uint64_t* lo, uint64_t* hi)
   *hi = len * (uint64_t)(rank + 1) / (uint64_t)world;
 }
 
-static int crs_new(zkb_ctx* ctx, uint64_t n, uint64_t nsg, uint64_t nsd, int rank, int world, zkb_crs** out) {
+static int crs_new(zkb_ctx* ctx, uint64_t n, uint64_t nsg, uint64_t nsd, int rank, int world, int layout, zkb_crs** out) {
   zkb_crs* c = new zkb_crs();
   c->n = n; c->n_sum_gamma = nsg; c->n_sum_delta = nsd;
-  c->rank = rank; c->world = world;
-  shard(n, rank, world, &c->xi_lo, &c->xi_hi);
-  shard(n - 1, rank, world, &c->xit_lo, &c->xit_hi);
+  c->rank = rank; c->world = world; c->layout = layout;
+  if (layout == 1) {  // xi / xi_t in the sharded transform's output layout: n / world entries, local indices
+    if (n % ((uint64_t)world * world)) { delete c; return set_err(ctx, ZKB_ERR_ARG, "crs: n = %llu is not a multiple of world^2", (unsigned long long)n); }
+    c->xi_lo = 0; c->xi_hi = n / world;
+    c->xit_lo = 0; c->xit_hi = n / world - (rank == world - 1 ? 1 : 0);  // xi_t has n - 1 entries: the last index belongs to the last rank
+  } else {
+    shard(n, rank, world, &c->xi_lo, &c->xi_hi);
+    shard(n - 1, rank, world, &c->xit_lo, &c->xit_hi);
+  }
   shard(nsd, rank, world, &c->sd_lo, &c->sd_hi);
   c->g1_cnt = c->nxi() + 3 + c->nxt() + c->nsd();
   c->g2_cnt = c->nxi() + 2;
@@ -112,14 +126,14 @@ static int crs_expand(zkb_ctx* ctx, zkb_crs* c, cudaStream_t st) {
   return ZKB_OK;
 }
 
-int zkb_crs_upload(zkb_ctx* ctx, const zkb_crs_host* h, int rank, int world, zkb_crs** out) {
+static int crs_upload_impl(zkb_ctx* ctx, const zkb_crs_host* h, int rank, int world, int layout, zkb_crs** out) {
   if (!ctx || !h || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_crs_upload: NULL argument");
   *out = nullptr;
   if (world < 1 || rank < 0 || rank >= world) return set_err(ctx, ZKB_ERR_ARG, "bad rank/world");
   if (h->n < 1) return set_err(ctx, ZKB_ERR_ARG, "crs.n must be >= 1");
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   zkb_crs* c;
-  ZKB_TRY(crs_new(ctx, h->n, h->n_sum_gamma, h->n_sum_delta, rank, world, &c));
+  ZKB_TRY(crs_new(ctx, h->n, h->n_sum_gamma, h->n_sum_delta, rank, world, layout, &c));
   cudaStream_t st = ctx->stream;
   const size_t nxi = c->nxi(), nxt = c->nxt(), nsd = c->nsd();
   G1Affine* fx = c->g1 + c->off_fixed();
@@ -138,11 +152,22 @@ int zkb_crs_upload(zkb_ctx* ctx, const zkb_crs_host* h, int rank, int world, zkb
   cp(c->g2 + nxi + 0, h->beta2, 128);
   cp(c->g2 + nxi + 1, h->delta2, 128);
   cp(c->gamma2, h->gamma2, 128);
-  cp(c->g1, h->xi1 + c->xi_lo * 8, nxi * 64);
-  cp(c->g1 + c->off_xit(), h->xi_t + c->xit_lo * 8, nxt * 64);
+  if (layout == 1) {  // world runs of q consecutive entries: local [k1*q, (k1+1)*q) <-> global [m*k1 + rank*q, ...)
+    const uint64_t m = h->n / world, q = m / world;
+    for (uint64_t k1 = 0; k1 < (uint64_t)world; k1++) {
+      const uint64_t g0 = m * k1 + (uint64_t)rank * q;
+      const uint64_t cnt_t = k1 * q + q <= nxt ? q : (nxt > k1 * q ? nxt - k1 * q : 0);
+      cp(c->g1 + k1 * q, h->xi1 + g0 * 8, q * 64);
+      cp(c->g2 + k1 * q, h->xi2 + g0 * 16, q * 128);
+      cp(c->g1 + c->off_xit() + k1 * q, h->xi_t + g0 * 8, cnt_t * 64);
+    }
+  } else {
+    cp(c->g1, h->xi1 + c->xi_lo * 8, nxi * 64);
+    cp(c->g1 + c->off_xit(), h->xi_t + c->xit_lo * 8, nxt * 64);
+    cp(c->g2, h->xi2 + c->xi_lo * 16, nxi * 128);
+  }
   cp(c->g1 + c->off_sd(), h->sum_delta + c->sd_lo * 8, nsd * 64);
   cp(c->sum_gamma, h->sum_gamma, c->n_sum_gamma * 64);
-  cp(c->g2, h->xi2 + c->xi_lo * 16, nxi * 128);
   int rc = ce == cudaSuccess ? ZKB_OK : set_err(ctx, ZKB_ERR_CUDA, "crs upload: copy failed: %s", cudaGetErrorString(ce));
   if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->g1, c->g1_cnt * 2, true, st);
   if (rc == ZKB_OK) rc = fq_to_mont(ctx, (Fq*)c->g2, c->g2_cnt * 4, true, st);
@@ -177,10 +202,17 @@ int zkb_crs_upload(zkb_ctx* ctx, const zkb_crs_host* h, int rank, int world, zkb
   return ZKB_OK;
 }
 
-int zkb_setup(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* toxic, int rank, int world, zkb_crs** out) {
+int zkb_crs_upload(zkb_ctx* ctx, const zkb_crs_host* h, int rank, int world, zkb_crs** out) {
+  return crs_upload_impl(ctx, h, rank, world, 0, out);
+}
+int zkb_crs_upload_shard(zkb_ctx* ctx, const zkb_comm* comm, const zkb_crs_host* h, zkb_crs** out) {
+  if (!comm) return set_err(ctx, ZKB_ERR_ARG, "zkb_crs_upload_shard: NULL communicator");
+  return crs_upload_impl(ctx, h, comm->rank, comm->world, 1, out);
+}
+
+static int setup_impl(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* toxic, int rank, int world, int layout, zkb_crs** out) {
   if (!ctx || !q || !toxic || !out) return set_err(ctx, ZKB_ERR_ARG, "zkb_setup: NULL argument");
   *out = nullptr;
-  if (world < 1 || rank < 0 || rank >= world) return set_err(ctx, ZKB_ERR_ARG, "bad rank/world");
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   Fr alpha = fr_from_limbs(toxic), beta = fr_from_limbs(toxic + 4), gamma = fr_from_limbs(toxic + 8),
      delta = fr_from_limbs(toxic + 12), x = fr_from_limbs(toxic + 16);
@@ -188,18 +220,20 @@ int zkb_setup(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* toxic, int rank, i
     return set_err(ctx, ZKB_ERR_DIV_ZERO, "setup: toxic values must be non-zero (random_elem, fr.rs:90-99)");
   const uint64_t n = q->n, m = q->m;
   zkb_crs* c;
-  ZKB_TRY(crs_new(ctx, n, q->n_input + 1, m - q->n_input - 1, rank, world, &c));
+  if (layout == 1 && q->generic) return set_err(ctx, ZKB_ERR_UNSUPPORTED, "sharded setup needs the roots-of-unity domain");
+  ZKB_TRY(crs_new(ctx, n, q->n_input + 1, m - q->n_input - 1, rank, world, layout, &c));
   int rc;
   auto fail = [&](int code) { zkb_crs_free(ctx, c); return code; };
   cudaStream_t st = ctx->stream;
   const size_t nxi = c->nxi(), nxt = c->nxt(), nsd = c->nsd();
   // scalars
   void* p;
-  if ((rc = scratch_get(ctx, 8, (n + n + m + 8) * sizeof(Fr), &p)) != ZKB_OK) return fail(rc);
+  if ((rc = scratch_get(ctx, 8, (n + n + m + 8 + 2 * (n / world + 1)) * sizeof(Fr), &p)) != ZKB_OK) return fail(rc);
   Fr* d_L = (Fr*)p;           // n   Lagrange basis at x; later reused for xi_t scalars
   Fr* d_pow = d_L + n;        // n   x^i
   Fr* d_lin = d_pow + n;      // m
   Fr* d_six = d_lin + m;      // alpha, beta, delta | beta, delta | gamma
+  Fr* d_gat = d_six + 8;      // layout 1: this rank's xi scalars | xi_t scalars, gathered into local order
   if ((rc = scratch_get(ctx, 9, sizeof(int), &p)) != ZKB_OK) return fail(rc);
   int* d_bad = (int*)p;
   cudaMemsetAsync(d_bad, 0, sizeof(int), st);
@@ -234,15 +268,33 @@ int zkb_setup(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* toxic, int rank, i
   if ((rc = fixed_base_g1(ctx, c->g1 + c->off_fixed(), d_six, 3, st)) != ZKB_OK) return fail(rc);
   if ((rc = fixed_base_g2(ctx, c->g2 + nxi, d_six + 3, 2, st)) != ZKB_OK) return fail(rc);
   if ((rc = fixed_base_g2(ctx, c->gamma2, d_six + 5, 1, st)) != ZKB_OK) return fail(rc);
-  if ((rc = fixed_base_g1(ctx, c->g1, d_pow + c->xi_lo, nxi, st)) != ZKB_OK) return fail(rc);
-  if ((rc = fixed_base_g2(ctx, c->g2, d_pow + c->xi_lo, nxi, st)) != ZKB_OK) return fail(rc);
-  if ((rc = fixed_base_g1(ctx, c->g1 + c->off_xit(), d_L + c->xit_lo, nxt, st)) != ZKB_OK) return fail(rc);
+  const Fr *xi_scal = d_pow + c->xi_lo, *xit_scal = d_L + c->xit_lo;
+  if (layout == 1) {
+    const uint64_t ml = n / world, ql = ml / world;
+    k_gather_S<<<cdiv(nxi, 256), 256, 0, st>>>(d_gat, d_pow, (uint64_t)rank, ql, ml, nxi);
+    if (nxt) k_gather_S<<<cdiv(nxt, 256), 256, 0, st>>>(d_gat + ml, d_L, (uint64_t)rank, ql, ml, nxt);
+    ctx->launches += 2;
+    if (cudaGetLastError() != cudaSuccess) return launch_fail("k_gather_S");
+    xi_scal = d_gat; xit_scal = d_gat + ml;
+  }
+  if ((rc = fixed_base_g1(ctx, c->g1, xi_scal, nxi, st)) != ZKB_OK) return fail(rc);
+  if ((rc = fixed_base_g2(ctx, c->g2, xi_scal, nxi, st)) != ZKB_OK) return fail(rc);
+  if ((rc = fixed_base_g1(ctx, c->g1 + c->off_xit(), xit_scal, nxt, st)) != ZKB_OK) return fail(rc);
   if ((rc = fixed_base_g1(ctx, c->sum_gamma, d_lin, c->n_sum_gamma, st)) != ZKB_OK) return fail(rc);
   if ((rc = fixed_base_g1(ctx, c->g1 + c->off_sd(), d_lin + c->n_sum_gamma + c->sd_lo, nsd, st)) != ZKB_OK) return fail(rc);
   if (cudaStreamSynchronize(st) != cudaSuccess) return launch_fail("fixed-base");
   if ((rc = crs_expand(ctx, c, st)) != ZKB_OK) return fail(rc);
   *out = c;
   return ZKB_OK;
+}
+
+int zkb_setup(zkb_ctx* ctx, const zkb_qap* q, const uint64_t* toxic, int rank, int world, zkb_crs** out) {
+  if (world < 1 || rank < 0 || rank >= world) return set_err(ctx, ZKB_ERR_ARG, "bad rank/world");
+  return setup_impl(ctx, q, toxic, rank, world, 0, out);
+}
+int zkb_setup_shard(zkb_ctx* ctx, const zkb_comm* comm, const zkb_qap* q, const uint64_t* toxic, zkb_crs** out) {
+  if (!comm) return set_err(ctx, ZKB_ERR_ARG, "zkb_setup_shard: NULL communicator");
+  return setup_impl(ctx, q, toxic, comm->rank, comm->world, 1, out);
 }
 
 int zkb_crs_dims(const zkb_crs* c, uint64_t* n, uint64_t* nsg, uint64_t* nsd) {

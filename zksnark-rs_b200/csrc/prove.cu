@@ -31,9 +31,12 @@ namespace zkb {
 // kernels of the polynomial stage
 __global__ void k_matvec(const uint32_t* __restrict__ gptr_u, const uint32_t* __restrict__ wire_u, const Fr* __restrict__ coef_u,
                          const uint32_t* __restrict__ gptr_v, const uint32_t* __restrict__ wire_v, const Fr* __restrict__ coef_v,
-                         const Fr* __restrict__ a, size_t m, size_t n, Fr* __restrict__ A, Fr* __restrict__ B, Fr* __restrict__ AB) {
-  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
+                         const Fr* __restrict__ a, size_t m, size_t k0, size_t kstride, size_t count, Fr* __restrict__ A,
+                         Fr* __restrict__ B, Fr* __restrict__ AB) {
+  // output i <-> gate k = k0 + kstride * i (one GPU: all gates; a sharded proof: the gates rank, rank + G, ...)
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const size_t k = k0 + kstride * i;
   Fr su = Fr::zero(), sv = Fr::zero();
   for (uint32_t p = gptr_u[k], e = gptr_u[k + 1]; p < e; p++) {
     uint32_t w = wire_u[p];
@@ -43,9 +46,9 @@ __global__ void k_matvec(const uint32_t* __restrict__ gptr_u, const uint32_t* __
     uint32_t w = wire_v[p];
     if (w < m) sv = sv + coef_v[p] * a[w];
   }
-  A[k] = su;
-  B[k] = sv;
-  AB[k] = su * sv;
+  A[i] = su;
+  B[i] = sv;
+  AB[i] = su * sv;
 }
 
 __global__ void k_mul2(Fr* __restrict__ o1, const Fr* __restrict__ a1, Fr* __restrict__ o2, const Fr* __restrict__ a2,
@@ -270,6 +273,17 @@ __global__ void __launch_bounds__(96) k_combine_partials(const uint32_t* __restr
   }
 }
 
+int matvec_launch(zkb_ctx* ctx, const zkb_qap* q, const Fr* wmont, size_t k0, size_t kstride, size_t count, Fr* A, Fr* B, Fr* AB,
+                  cudaStream_t st) {
+  ZKB_LAUNCH(ctx, k_matvec, cdiv(count, 128), 128, 0, st, q->d_gptr[0], q->d_wire[0], q->d_coeff[0], q->d_gptr[1], q->d_wire[1],
+             q->d_coeff[1], wmont, (size_t)q->m, k0, kstride, count, A, B, AB);
+  return ZKB_OK;
+}
+int combine_partials_launch(zkb_ctx* ctx, const uint32_t* d_partials, int world, size_t count, uint32_t* d_out, cudaStream_t st) {
+  ZKB_LAUNCH(ctx, k_combine_partials, (unsigned)count, 96, 0, st, d_partials, world, count, d_out);
+  return ZKB_OK;
+}
+
 }  // namespace zkb
 
 using namespace zkb;
@@ -410,9 +424,9 @@ int zkb_qap_upload(zkb_ctx* ctx, const zkb_qap_host* h, zkb_qap** out) {
 struct Work {
   Fr *ws, *wcanon, *wmont;
 };
-static int work_get(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, Work* w) {
+static int work_get(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, Work* w, size_t ws_elems = 0) {
   void* p;
-  ZKB_TRY(scratch_get_in(ctx, L->scratch, 11, 8 * q->n * sizeof(Fr), &p));
+  ZKB_TRY(scratch_get_in(ctx, L->scratch, 11, (ws_elems ? ws_elems : 8 * q->n) * sizeof(Fr), &p));
   w->ws = (Fr*)p;
   ZKB_TRY(scratch_get_in(ctx, L->scratch, 12, q->m * sizeof(Fr), &p));
   w->wcanon = (Fr*)p;
@@ -428,8 +442,7 @@ static int poly_stage(zkb_ctx* ctx, const zkb_qap* q, const Work& w, const Fr* d
      *hn = ws + 7 * n;
   ZKB_CUDA(ctx, cudaMemcpyAsync(w.wmont, d_w_canon, m * 32, cudaMemcpyDeviceToDevice, st));
   ZKB_TRY(vec_to_mont(ctx, w.wmont, m, true, st));
-  ZKB_LAUNCH(ctx, k_matvec, cdiv(n, 128), 128, 0, st, q->d_gptr[0], q->d_wire[0], q->d_coeff[0], q->d_gptr[1],
-             q->d_wire[1], q->d_coeff[1], w.wmont, m, n, A, B, AB);
+  ZKB_TRY(matvec_launch(ctx, q, w.wmont, 0, 1, n, A, B, AB, st));
   if (q->generic) {  // dense path: interpolate, high half of the product, quotient by t
     ZKB_LAUNCH(ctx, k_gen_interp, cdiv(n, 64), 64, 0, st, A, B, q->d_Lc, n, un, vn);
     if (n > 1) ZKB_LAUNCH(ctx, k_gen_prod_high, cdiv(n, 64), 64, 0, st, un, vn, n, AB);
@@ -473,7 +486,7 @@ struct ProveOut {
 };
 static int prove_out(zkb_ctx* ctx, DevBuf* slots, ProveOut* o) {
   void* p;
-  ZKB_TRY(scratch_get_in(ctx, slots, 6, 2 * sizeof(G1XYZZ) + sizeof(G2XYZZ) + 256, &p));
+  ZKB_TRY(scratch_get_in(ctx, slots, 6, 2 * sizeof(G1XYZZ) + sizeof(G2XYZZ) + 1024, &p));  // + partial | proof | status
   o->ac = (G1XYZZ*)p;
   o->b = (G2XYZZ*)(o->ac + 2);
   o->proof = (uint32_t*)(o->b + 1);
@@ -485,19 +498,16 @@ static int prove_out(zkb_ctx* ctx, DevBuf* slots, ProveOut* o) {
 //   L->hi:  [H2D] polynomial stage, scalars, sort G2, sort G1 ... tail G2 ........ finish, D2H
 //   L->lo:                                    accumulate G2, accumulate G1
 //   L->hi2:                                                                tail G1
+// comm != NULL: ONE proof over all ranks of `comm` (CRS in layout 1): the polynomial stage is sharded (shard.cu, three
+// exchanges over peer memory on channel `ch`), the partial sums are exchanged and folded on the device, and every rank
+// ends up with the complete proof.
 static int prove_enqueue(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights,
-                         int on_device, const uint64_t* r, const uint64_t* s) {
+                         int on_device, const uint64_t* r, const uint64_t* s, zkb_comm* comm = nullptr, int ch = 0) {
   cudaStream_t hi = L->hi, lo = L->lo;
+  // Every allocation, table and plan first, launches after: scratch growth synchronises the device and the first use of a
+  // twiddle table synchronises a stream, and neither may happen behind a kernel that is waiting for a peer.
   Work w;
-  ZKB_TRY(work_get(ctx, L, q, &w));
-  const Fr* d_w = (const Fr*)weights;
-  if (!on_device) {
-    ZKB_CUDA(ctx, cudaMemcpyAsync(w.wcanon, weights, q->m * 32, cudaMemcpyHostToDevice, hi));
-    d_w = w.wcanon;
-  }
-  ZKB_TRY(poly_stage(ctx, q, w, d_w, hi));
-  const size_t n = q->n;
-  Fr *un = w.ws + 5 * n, *vn = w.ws + 6 * n, *hn = w.ws + 7 * n;
+  ZKB_TRY(work_get(ctx, L, q, &w, comm ? 7 * (q->n >> comm->lg) : 0));
   ScalarPlan sp;
   sp.nxi = c->nxi(); sp.nxt = c->nxt(); sp.nsd = c->nsd();
   sp.xi_lo = c->xi_lo; sp.xit_lo = c->xit_lo; sp.sd_lo = c->sd_lo;
@@ -507,8 +517,6 @@ static int prove_enqueue(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, const zkb_
   Fr* SC = (Fr*)p;
   Fr* SA = SC + c->g1_cnt;
   Fr* SB = SA + sp.nxi + 3;
-  ZKB_LAUNCH(ctx, k_msm_scalars, cdiv(c->g1_cnt, 256), 256, 0, hi, un, vn, hn, w.wmont, sp, fr_from_limbs(r), fr_from_limbs(s), SA,
-             SB, SC);
   ProveOut o;
   ZKB_TRY(prove_out(ctx, L->scratch, &o));
   MsmJob jb = {SB, c->g2_cnt};
@@ -516,6 +524,27 @@ static int prove_enqueue(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, const zkb_
   MsmPlan P2, P1;
   ZKB_TRY(msm_prepare(ctx, L->scratch, 3, 2, c->g2, c->g2_cnt, c->c2, &jb, 1, o.b, &P2));
   ZKB_TRY(msm_prepare(ctx, L->scratch, 0, 1, c->g1, c->g1_cnt, c->c1, j1, 2, o.ac, &P1));
+  if (comm) ZKB_TRY(shard_prepare(ctx, comm, q->log_n));
+  const Fr* d_w = (const Fr*)weights;
+  if (!on_device) {
+    ZKB_CUDA(ctx, cudaMemcpyAsync(w.wcanon, weights, q->m * 32, cudaMemcpyHostToDevice, hi));
+    d_w = w.wcanon;
+  }
+  const size_t n = q->n;
+  Fr *un = w.ws + 5 * n, *vn = w.ws + 6 * n, *hn = w.ws + 7 * n;
+  uint32_t epoch = 0;
+  if (comm) {
+    const size_t ml = n >> comm->lg;
+    epoch = ++comm->epoch[ch];
+    ZKB_CUDA(ctx, cudaMemcpyAsync(w.wmont, d_w, q->m * 32, cudaMemcpyDeviceToDevice, hi));
+    ZKB_TRY(vec_to_mont(ctx, w.wmont, q->m, true, hi));
+    ZKB_TRY(shard_poly_stage(ctx, comm, ch, epoch, q, w.ws, w.wmont, hi));
+    un = w.ws + 3 * ml; vn = w.ws + 4 * ml; hn = w.ws + 6 * ml;
+  } else {
+    ZKB_TRY(poly_stage(ctx, q, w, d_w, hi));
+  }
+  ZKB_LAUNCH(ctx, k_msm_scalars, cdiv(c->g1_cnt, 256), 256, 0, hi, un, vn, hn, w.wmont, sp, fr_from_limbs(r), fr_from_limbs(s), SA,
+             SB, SC);
   ZKB_TRY(msm_sort(ctx, P2, hi));
   ZKB_CUDA(ctx, cudaEventRecord(L->ev[2], hi));
   ZKB_TRY(msm_sort(ctx, P1, hi));
@@ -535,13 +564,23 @@ static int prove_enqueue(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, const zkb_
   ZKB_CUDA(ctx, cudaEventRecord(L->ev[4], L->hi2));
   ZKB_CUDA(ctx, cudaStreamWaitEvent(hi, L->ev[4], 0));
   ZKB_LAUNCH(ctx, k_finish, 1, 96, 0, hi, o.ac, o.b, o.proof);
+  if (comm) {  // partial sums -> every rank's window; wait for all of them; fold; the proof replaces the partial record
+    int* d_status = reinterpret_cast<int*>(o.proof + 128);
+    ZKB_TRY(shard_exchange_partials(ctx, comm, ch, epoch, o.proof, o.proof + 64, d_status, hi));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(L->h_proof, o.proof + 64, 256, cudaMemcpyDeviceToHost, hi));
+    ZKB_CUDA(ctx, cudaMemcpyAsync((char*)L->h_proof + 256, d_status, sizeof(int), cudaMemcpyDeviceToHost, hi));
+    return ZKB_OK;
+  }
   ZKB_CUDA(ctx, cudaMemcpyAsync(L->h_proof, o.proof, 256, cudaMemcpyDeviceToHost, hi));
   return ZKB_OK;
 }
 
-static int prove_collect(zkb_ctx* ctx, zkb_lane* L, void* out) {
+static int prove_collect(zkb_ctx* ctx, zkb_lane* L, void* out, bool sharded = false) {
   ZKB_CUDA(ctx, cudaStreamSynchronize(L->hi));
   memcpy(out, L->h_proof, 256);
+  if (sharded && *reinterpret_cast<const int*>((const char*)L->h_proof + 256) != 0)
+    return set_err(ctx, ZKB_ERR_COMM, "sharded proof: a peer did not arrive within the exchange timeout (ZKB_COMM_TIMEOUT_MS); "
+                                      "the communicator is unusable from here on");
   return ZKB_OK;
 }
 
@@ -587,6 +626,7 @@ int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint
   int rc = ZKB_OK;
   size_t done = 0;
   const size_t nl = batch_lane_count(ctx, q);
+  for (size_t l = 0; l < nl && l < count; l++) ZKB_TRY(lane_get(ctx, (int)l, nullptr));
   for (size_t i = 0; i < count && rc == ZKB_OK; i++) {
     zkb_lane* L = &ctx->lanes[i % nl];
     if (i >= nl) {
@@ -598,6 +638,66 @@ int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint
   }
   for (size_t i = done; i < count && rc == ZKB_OK; i++) rc = prove_collect(ctx, &ctx->lanes[i % nl], &out[i]);
   if (rc != ZKB_OK) cudaDeviceSynchronize();  // leave no work in flight behind an error
+  return rc;
+}
+
+// ---- one proof over all ranks of a communicator ------------------------------------------------------
+static int check_shard(zkb_ctx* ctx, zkb_comm* comm, const zkb_qap* q, const zkb_crs* c) {
+  ZKB_TRY(check_pair(ctx, q, c));
+  if (q->generic) return set_err(ctx, ZKB_ERR_UNSUPPORTED, "sharded proofs need the roots-of-unity domain");
+  ZKB_TRY(shard_check(ctx, comm, q->log_n));
+  if (c->layout != 1 || c->world != comm->world || c->rank != comm->rank)
+    return set_err(ctx, ZKB_ERR_ARG, "sharded proof: the CRS was not made by zkb_setup_shard / zkb_crs_upload_shard for this communicator");
+  return ZKB_OK;
+}
+
+int zkb_prove_shard_enqueue(zkb_ctx* ctx, zkb_comm* comm, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights, int on_device,
+                            const uint64_t r[4], const uint64_t s[4], int lane) {
+  if (!ctx || !comm || !q || !c || !weights || !r || !s) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_shard_enqueue: NULL argument");
+  if (lane < 0 || lane >= 4) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_shard_enqueue: lane %d out of range [0, 4)", lane);
+  ZKB_TRY(check_shard(ctx, comm, q, c));
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZKB_TRY(lane_get(ctx, lane, nullptr));
+  return prove_enqueue(ctx, &ctx->lanes[lane], q, c, weights, on_device, r, s, comm, lane);
+}
+int zkb_prove_shard_collect(zkb_ctx* ctx, zkb_comm* comm, int lane, zkb_proof* out) {
+  if (!ctx || !comm || !out || lane < 0 || lane >= 4 || !ctx->lanes[lane].hi) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_shard_collect: bad argument");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return prove_collect(ctx, &ctx->lanes[lane], out, true);
+}
+int zkb_prove_shard(zkb_ctx* ctx, zkb_comm* comm, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights, int on_device,
+                    const uint64_t r[4], const uint64_t s[4], zkb_proof* out) {
+  if (!out) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_shard: NULL argument");
+  ZKB_TRY(zkb_prove_shard_enqueue(ctx, comm, q, c, weights, on_device, r, s, 0));
+  return zkb_prove_shard_collect(ctx, comm, 0, out);
+}
+// `count` proofs, each over all ranks, several in flight (one per lane / exchange channel).  Every rank must make the
+// same sequence of calls with the same count.
+int zkb_prove_shard_batch(zkb_ctx* ctx, zkb_comm* comm, const zkb_qap* q, const zkb_crs* c, const uint64_t* const* weights, int on_device,
+                          const uint64_t* r, const uint64_t* s, size_t count, zkb_proof* out) {
+  if (!ctx || !comm || !q || !c || (count && (!weights || !r || !s || !out))) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_shard_batch: NULL argument");
+  ZKB_TRY(check_shard(ctx, comm, q, c));
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (size_t i = 0; i < count; i++)
+    if (!weights[i]) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_shard_batch: weights[%zu] is NULL", i);
+  size_t nl = 4;
+  if (ctx->batch_lanes >= 1 && ctx->batch_lanes <= 4) nl = (size_t)ctx->batch_lanes;
+  else if ((q->n >> comm->lg) > ((uint64_t)1 << 19)) nl = 2;
+  else if ((q->n >> comm->lg) > ((uint64_t)1 << 17)) nl = 3;
+  for (size_t l = 0; l < nl && l < count; l++) ZKB_TRY(lane_get(ctx, (int)l, nullptr));
+  int rc = ZKB_OK;
+  size_t done = 0;
+  for (size_t i = 0; i < count && rc == ZKB_OK; i++) {
+    const int lane = (int)(i % nl);
+    if (i >= nl) {
+      rc = prove_collect(ctx, &ctx->lanes[lane], &out[i - nl], true);
+      done = i - nl + 1;
+      if (rc != ZKB_OK) break;
+    }
+    rc = prove_enqueue(ctx, &ctx->lanes[lane], q, c, weights[i], on_device, r + 4 * i, s + 4 * i, comm, lane);
+  }
+  for (size_t i = done; i < count && rc == ZKB_OK; i++) rc = prove_collect(ctx, &ctx->lanes[i % nl], &out[i], true);
+  if (rc != ZKB_OK) cudaDeviceSynchronize();
   return rc;
 }
 
@@ -619,7 +719,7 @@ int zkb_prove_combine_batch(zkb_ctx* ctx, const uint64_t* partials, int world, s
   uint32_t* d_in = (uint32_t*)p;
   uint32_t* d_out = d_in + in_bytes / 4;
   ZKB_CUDA(ctx, cudaMemcpyAsync(d_in, partials, in_bytes, cudaMemcpyHostToDevice, st));
-  ZKB_LAUNCH(ctx, k_combine_partials, (unsigned)count, 96, 0, st, d_in, world, count, d_out);
+  ZKB_TRY(combine_partials_launch(ctx, d_in, world, count, d_out, st));
   ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));
   return ZKB_OK;

@@ -1,4 +1,12 @@
-"""Multi-GPU plumbing for a sharded proof: one process per GPU, torch.distributed for the exchange.
+"""Multi-GPU plumbing: one process per GPU.
+
+ONE PROOF OVER ALL RANKS (the default layout of bench.py at N > 1): `connect` builds the in-library communicator
+(zkb_comm_*: every rank's exchange window in HBM is mapped by its peers, and the kernels exchange the sharded
+transforms' columns and the partial sums by direct stores over NVLink) -- torch.distributed only carries the
+128-byte window handles once at start-up.  `layout_s_index` is the host-side mirror of the device's "strided block"
+ownership (csrc/shard.cu).
+
+Older host-driven helpers, kept for the stand-alone sweeps (tools/msm_multi_gpu.py, tools/ntt_multi_gpu.py):
 
 The MSM base vectors (sigma_g1.xi / xi_t / sum_delta, sigma_g2.xi) are sharded by contiguous point
 ranges; each rank produces its partial sums of A, B, C (32 limbs, `zkb_prove_partial`), the records are
@@ -95,3 +103,47 @@ def ntt_sharded(ctx, x_sub: np.ndarray, log_n: int, inverse: bool = False) -> np
     out = torch.empty((sub, 4), dtype=torch.int64, device=dev)
     zg.ntt_combine(ctx, parts.data_ptr(), log_n, log_g, inverse, k0, sub, out.data_ptr())
     return out.cpu().numpy().view(np.uint64)
+
+
+# ------------------------------------------------------------------------------------------------
+# in-library communicator (csrc/shard.cu)
+def layout_s_index(n: int, rank: int, world: int) -> np.ndarray:
+    """Global coefficient index of every local index of layout S on `rank`: s = k1*q + t <-> (rank*q + t) + (n/world)*k1.
+    This is how u_sum, v_sum, h come out of a sharded proof's polynomial stage and how zkb_setup_shard /
+    zkb_crs_upload_shard shard sigma_g1.xi, sigma_g1.xi_t (minus index n-1) and sigma_g2.xi."""
+    m = n // world
+    q = m // world
+    if q * world * world != n:
+        raise ValueError("layout S needs n to be a multiple of world^2")
+    s = np.arange(m, dtype=np.int64)
+    k1, t = s // q, s % q
+    return rank * q + t + m * k1
+
+
+def layout_d_index(n: int, rank: int, world: int) -> np.ndarray:
+    """Layout D (decimated): local index i <-> global index rank + world*i (the gates a rank evaluates)."""
+    return rank + world * np.arange(n // world, dtype=np.int64)
+
+
+def connect(ctx, max_log_n: int, device=None):
+    """Create this rank's communicator end and connect it to all ranks of the default torch.distributed group
+    (any backend: only `world` x 128 bytes of window handles travel, once)."""
+    import importlib
+
+    import torch
+    import torch.distributed as dist
+
+    zg = importlib.import_module(__package__ + ".groth16")
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    comm = zg.Comm.create(ctx, rank, world, max_log_n)
+    if world == 1:
+        return comm.connect(comm.handle)
+    mine = torch.frombuffer(bytearray(comm.handle), dtype=torch.uint8)
+    if device is not None:
+        mine = mine.to(device)
+    out = torch.empty(world * zg.COMM_HANDLE_BYTES, dtype=torch.uint8, device=mine.device)
+    dist.all_gather_into_tensor(out, mine)
+    comm.connect(bytes(out.cpu().numpy().tobytes()))
+    dist.barrier()  # nobody starts writing into a window before every rank has mapped it
+    return comm

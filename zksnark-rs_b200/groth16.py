@@ -96,7 +96,19 @@ ABI = {
     "zkb_verify_batch": (C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     "zkb_pairing": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "zkb_bench_modmul": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "zkb_comm_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint32, C.POINTER(_P), _P]),
+    "zkb_comm_connect": (C.c_int, [_P, _P]),
+    "zkb_comm_destroy": (None, [_P]),
+    "zkb_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "zkb_setup_shard": (C.c_int, [_P, _P, _P, _P, C.POINTER(_P)]),
+    "zkb_crs_upload_shard": (C.c_int, [_P, _P, C.POINTER(_CrsHost), C.POINTER(_P)]),
+    "zkb_prove_shard": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, C.POINTER(_ProofC)]),
+    "zkb_prove_shard_enqueue": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, C.c_int]),
+    "zkb_prove_shard_collect": (C.c_int, [_P, _P, C.c_int, C.POINTER(_ProofC)]),
+    "zkb_prove_shard_batch": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
+    "zkb_ntt_shard": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_int, C.c_int]),
 }
+COMM_HANDLE_BYTES = 128
 
 _lib = None
 
@@ -403,6 +415,22 @@ class QAP:
             pass
 
 
+def _crs_host(sigma_g1, sigma_g2):
+    """zkb_crs_host over packed copies of the reference-shaped objects; returns (struct, arrays to keep alive)."""
+    host = _CrsHost()
+    host.n, host.n_sum_gamma, host.n_sum_delta = len(sigma_g1.xi), len(sigma_g1.sum_gamma), len(sigma_g1.sum_delta)
+    arrs = {
+        "alpha1": g1_pack([sigma_g1.alpha]), "beta1": g1_pack([sigma_g1.beta]), "delta1": g1_pack([sigma_g1.delta]),
+        "xi1": g1_pack(sigma_g1.xi), "xi_t": g1_pack(sigma_g1.xi_t), "sum_gamma": g1_pack(sigma_g1.sum_gamma),
+        "sum_delta": g1_pack(sigma_g1.sum_delta),
+        "beta2": g2_pack([sigma_g2.beta]), "gamma2": g2_pack([sigma_g2.gamma]), "delta2": g2_pack([sigma_g2.delta]),
+        "xi2": g2_pack(sigma_g2.xi),
+    }
+    for k, a in arrs.items():
+        setattr(host, k, a.ctypes.data if a.size else None)
+    return host, arrs
+
+
 class CRS:
     """Device-resident (SigmaG1, SigmaG2) (groth16/mod.rs:105-121)."""
 
@@ -413,19 +441,10 @@ class CRS:
     def upload(cls, ctx: Context, sigma_g1, sigma_g2, rank=0, world=1) -> "CRS":
         """From the reference-shaped objects (attributes alpha, beta, delta, xi, sum_gamma, sum_delta,
         xi_t / beta, gamma, delta, xi)."""
-        host = _CrsHost()
-        host.n, host.n_sum_gamma, host.n_sum_delta = len(sigma_g1.xi), len(sigma_g1.sum_gamma), len(sigma_g1.sum_delta)
-        arrs = {
-            "alpha1": g1_pack([sigma_g1.alpha]), "beta1": g1_pack([sigma_g1.beta]), "delta1": g1_pack([sigma_g1.delta]),
-            "xi1": g1_pack(sigma_g1.xi), "xi_t": g1_pack(sigma_g1.xi_t), "sum_gamma": g1_pack(sigma_g1.sum_gamma),
-            "sum_delta": g1_pack(sigma_g1.sum_delta),
-            "beta2": g2_pack([sigma_g2.beta]), "gamma2": g2_pack([sigma_g2.gamma]), "delta2": g2_pack([sigma_g2.delta]),
-            "xi2": g2_pack(sigma_g2.xi),
-        }
-        for k, a in arrs.items():
-            setattr(host, k, a.ctypes.data if a.size else None)
+        host, keep = _crs_host(sigma_g1, sigma_g2)
         h = C.c_void_p()
         ctx.check(ctx.lib.zkb_crs_upload(ctx.h, C.byref(host), rank, world, C.byref(h)), "zkb_crs_upload")
+        del keep
         return cls(ctx, h, rank, world)
 
     def dims(self):
@@ -748,3 +767,115 @@ def points_sum(ctx: Context, group: int, points):
     ctx.check(ctx.lib.zkb_points_sum(ctx.h, group, _ptr(arr) if arr.size else None, len(points), _ptr(out)),
               "zkb_points_sum")
     return (g1_unpack(out) if group == 1 else g2_unpack(out))[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# one proof over several GPUs (include/zkb200.h: zkb_comm_*, zkb_prove_shard*)
+class Comm:
+    """One rank's end of a multi-GPU communicator.  `Comm.create` allocates the exchange window and returns the
+    128-byte handle; after the host side has gathered all handles in rank order (dist.connect does it over
+    torch.distributed), `connect` maps the peers' windows."""
+
+    def __init__(self, ctx: Context, h, rank: int, world: int, handle: bytes):
+        self.ctx, self.h, self.rank, self.world, self.handle = ctx, h, rank, world, handle
+
+    @classmethod
+    def create(cls, ctx: Context, rank: int, world: int, max_log_n: int) -> "Comm":
+        h = C.c_void_p()
+        buf = (C.c_uint8 * COMM_HANDLE_BYTES)()
+        ctx.check(ctx.lib.zkb_comm_create(ctx.h, rank, world, max_log_n, C.byref(h), buf), "zkb_comm_create")
+        return cls(ctx, h, rank, world, bytes(buf))
+
+    def connect(self, handles):
+        """handles: the `world` 128-byte handles in rank order (list of bytes or one bytes object)."""
+        blob = handles if isinstance(handles, (bytes, bytearray)) else b"".join(handles)
+        assert len(blob) == self.world * COMM_HANDLE_BYTES
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self.ctx.check(self.ctx.lib.zkb_comm_connect(self.h, buf), "zkb_comm_connect")
+        return self
+
+    def status(self) -> int:
+        st = C.c_int(0)
+        self.ctx.check(self.ctx.lib.zkb_comm_info(self.h, None, None, C.byref(st)), "zkb_comm_info")
+        return st.value
+
+    def free(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.zkb_comm_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def setup_shard(ctx: Context, comm: Comm, qap: QAP, toxic) -> CRS:
+    """groth16::setup for this rank's shard of a proof that runs over all ranks of `comm` (zkb_setup_shard)."""
+    t = fr_limbs(toxic)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.zkb_setup_shard(ctx.h, comm.h, qap.h, _ptr(t), C.byref(h)), "zkb_setup_shard")
+    return CRS(ctx, h, comm.rank, comm.world)
+
+
+def crs_upload_shard(ctx: Context, comm: Comm, sigma_g1, sigma_g2) -> CRS:
+    """This rank's shard of a reference-shaped CRS (zkb_crs_upload_shard)."""
+    host, keep = _crs_host(sigma_g1, sigma_g2)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.zkb_crs_upload_shard(ctx.h, comm.h, C.byref(host), C.byref(h)), "zkb_crs_upload_shard")
+    del keep
+    return CRS(ctx, h, comm.rank, comm.world)
+
+
+def _wptr(qap, weights, on_device):
+    if on_device:
+        return C.c_void_p(weights), None
+    w = _weights_array(qap, weights)
+    return _ptr(w), w
+
+
+def prove_shard_enqueue(ctx: Context, comm: Comm, qap: QAP, crs: CRS, weights, r: int, s: int, lane=0, on_device=False):
+    wp, keep = _wptr(qap, weights, on_device)
+    rl, sl = fr_limbs([r]), fr_limbs([s])
+    ctx.check(ctx.lib.zkb_prove_shard_enqueue(ctx.h, comm.h, qap.h, crs.h, wp, 1 if on_device else 0, _ptr(rl), _ptr(sl), lane),
+              "zkb_prove_shard_enqueue")
+    return keep  # the caller keeps host weights alive until collect
+
+
+def prove_shard_collect(ctx: Context, comm: Comm, lane=0) -> Proof:
+    out = _ProofC()
+    ctx.check(ctx.lib.zkb_prove_shard_collect(ctx.h, comm.h, lane, C.byref(out)), "zkb_prove_shard_collect")
+    return _proof(out)
+
+
+def prove_shard(ctx: Context, comm: Comm, qap: QAP, crs: CRS, weights, r: int, s: int, on_device=False) -> Proof:
+    """groth16::prove (mod.rs:213-296) as ONE proof over all ranks of `comm`; every rank gets the complete proof."""
+    wp, keep = _wptr(qap, weights, on_device)
+    rl, sl = fr_limbs([r]), fr_limbs([s])
+    out = _ProofC()
+    ctx.check(ctx.lib.zkb_prove_shard(ctx.h, comm.h, qap.h, crs.h, wp, 1 if on_device else 0, _ptr(rl), _ptr(sl), C.byref(out)),
+              "zkb_prove_shard")
+    del keep
+    return _proof(out)
+
+
+def prove_shard_batch(ctx: Context, comm: Comm, qap: QAP, crs: CRS, weights, rs, ss, on_device=False) -> list:
+    k = len(weights)
+    if on_device:
+        keep = None
+        ptrs = (C.c_void_p * k)(*[C.c_void_p(w) for w in weights])
+    else:
+        keep = [_weights_array(qap, w) for w in weights]
+        ptrs = (C.c_void_p * k)(*[a.ctypes.data for a in keep])
+    rl, sl = fr_limbs(list(rs)), fr_limbs(list(ss))
+    out = (_ProofC * k)()
+    ctx.check(ctx.lib.zkb_prove_shard_batch(ctx.h, comm.h, qap.h, crs.h, ptrs, 1 if on_device else 0, _ptr(rl), _ptr(sl), k, out),
+              "zkb_prove_shard_batch")
+    del keep
+    return [_proof(out[i]) for i in range(k)]
+
+
+def ntt_shard(ctx: Context, comm: Comm, d_local: int, log_n: int, inverse=False, wait=True):
+    """zkb_ntt_shard on this rank's n/world canonical residues (layout D in, layout S out)."""
+    ctx.check(ctx.lib.zkb_ntt_shard(ctx.h, comm.h, C.c_void_p(d_local), log_n, 1 if inverse else 0, 0 if wait else 1), "zkb_ntt_shard")
