@@ -40,6 +40,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# before CUDA starts: one hardware queue per stream (default 8), so the streams of the proofs in flight do not share queues
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "groth16_proofs_per_sec"
 UNIT = "proofs/s"

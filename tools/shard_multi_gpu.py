@@ -16,6 +16,7 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before CUDA starts: one hardware queue per stream
 FR = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 
 
@@ -26,6 +27,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--ntt", type=int, nargs="*", default=[])
+    ap.add_argument("--trace", default=None, help="rank 0: per-kernel timeline of one sharded proof (zkb_trace_dump) to this path")
     ap.add_argument("--skip-single", action="store_true", help="do not build the full CRS on rank 0 for the one-GPU comparison")
     args = ap.parse_args()
     zk = importlib.import_module("zksnark-rs_b200")
@@ -93,6 +95,14 @@ def main():
     out["batch_ms_per_proof"] = float(t.item()) / args.steps * 1e3
     out["batch_equal"] = all((p.a, p.b, p.c) == (proof.a, proof.b, proof.c) for p in ps)
     out["comm_status"] = comm.status()
+    if args.trace:
+        dist.barrier()
+        if rank == 0:
+            ctx.profile(2)
+        zk.prove_shard(ctx, comm, qap, crs, d_w, r, s, on_device=True)
+        if rank == 0:
+            ctx.trace_dump(args.trace)
+            ctx.profile(0)
     # the transform alone
     ntt = []
     for lg in args.ntt:

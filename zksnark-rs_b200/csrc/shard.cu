@@ -17,8 +17,8 @@
 //                             rank k1 receives Z[.][k1] = W_k1; then X[k1 + G*k2] = local size-m transform of W_k1
 // The proof chains them: gate evaluations A, B, A.B (layout D: rank r evaluates gates r, r+G, ...) -iNTT-> u_sum,
 // v_sum, c = p_lo + p_hi (S) -coset NTT-> u, v on the coset (D) -product, iNTT-> d (S) -> h (S).  Three exchanges per
-// proof (3, 2 and 1 vectors of m elements per rank), fused with the kernels on both sides: k_shard_mid waits for
-// exchange 0, finishes three inverse transforms, starts two forward ones and stores their results straight into the
+// proof (3, 2 and 1 vectors of m elements per rank), fused with the kernels on both sides: k_shard_mid finishes three
+// inverse transforms from what exchange 0 delivered, starts two forward ones and stores their results straight into the
 // peers' windows.  u_sum, v_sum and h come out in layout S, so the CRS vectors xi / xi_t are sharded the same way
 // (crs.cu, layout 1): any partition of an MSM's terms gives the same sum, and results are compared in affine form.
 // tests/shard_model.py is the CPU model of exactly these steps (checked against the reference restatement).
@@ -43,9 +43,11 @@ __device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
 __device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// All threads of the block call this; threads g < world poll flags[ch][step][g] of the own window until every rank has
-// published `epoch`.  A wait that outlives the timeout sets the sticky status word instead of hanging the GPU: the
-// proof then comes out wrong and the host reports ZKB_ERR_COMM.
+// Threads g < world poll flags[ch][step][g] of the own window until every rank has published `epoch`.  A wait that outlives
+// the timeout sets the sticky status word instead of hanging the GPU: the proof then comes out wrong and the host reports
+// ZKB_ERR_COMM.  Waits are ALWAYS their own one-block kernel (k_comm_wait) in front of the consumer, never a prologue of the
+// consumer's blocks: with several proofs in flight, a grid of waiting blocks could fill every SM while the kernels that
+// would release it -- another lane's sends, here and on the peer -- find no SM to run on (seen on 2 GPUs: both ranks timed out).
 __device__ __forceinline__ void comm_wait_all(const CommView& cv, size_t flag_off0, uint32_t epoch) {
   if ((int)threadIdx.x < cv.world) {
     char* own = cv.base[cv.rank];
@@ -132,8 +134,8 @@ __device__ __forceinline__ void combine_column(const Fr* __restrict__ R /* [G][q
 }
 
 struct MidArgs {
-  size_t r0_off, r1_off, flag0_off;  // own window: exchange-0 region, flags of exchange 0; peers' windows: exchange-1 region
-  uint32_t epoch, q;
+  size_t r0_off, r1_off;  // own window: exchange-0 region; peers' windows: exchange-1 region
+  uint32_t q;
   const Fr *Tinv, *Tfwd, *cosS;
   Fr *un, *vn, *cS;  // layout S outputs (Montgomery): u_sum, v_sum, c = iNTT(A.B)
 };
@@ -141,7 +143,6 @@ struct MidArgs {
 // 2: A.B -> c (stays local)
 template <int LG>
 __global__ void __launch_bounds__(128) k_shard_mid(CommView cv, MidArgs a, SmallTw tw_inv, SmallTw tw_fwd) {
-  comm_wait_all(cv, a.flag0_off, a.epoch);
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.q) return;
   constexpr int G = 1 << LG;
@@ -170,10 +171,9 @@ __global__ void __launch_bounds__(128) k_shard_mid(CommView cv, MidArgs a, Small
 
 // last exchange: d = iNTT(coset product) (layout S), h = c / 2 - d * g^-j / 2
 template <int LG>
-__global__ void __launch_bounds__(128) k_shard_fin(CommView cv, size_t r2_off, size_t flag2_off, uint32_t epoch, uint32_t q,
+__global__ void __launch_bounds__(128) k_shard_fin(CommView cv, size_t r2_off, uint32_t q,
                                                    const Fr* __restrict__ Tinv, const Fr* __restrict__ QS, const Fr* __restrict__ cS, Fr inv2,
                                                    SmallTw tw_inv, Fr* __restrict__ hn) {
-  comm_wait_all(cv, flag2_off, epoch);
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= q) return;
   constexpr int G = 1 << LG;
@@ -188,9 +188,8 @@ __global__ void __launch_bounds__(128) k_shard_fin(CommView cv, size_t r2_off, s
 
 // stand-alone distributed transform, receiver side: out (layout S, canonical residues)
 template <int LG>
-__global__ void __launch_bounds__(128) k_shard_combine(CommView cv, size_t r_off, size_t flag_off, uint32_t epoch, uint32_t q,
+__global__ void __launch_bounds__(128) k_shard_combine(CommView cv, size_t r_off, uint32_t q,
                                                        const Fr* __restrict__ T, SmallTw tw, Fr* __restrict__ out) {
-  comm_wait_all(cv, flag_off, epoch);
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= q) return;
   constexpr int G = 1 << LG;
@@ -274,7 +273,8 @@ int shard_check(zkb_ctx* ctx, const zkb_comm* c, uint32_t log_n) {
 }
 
 template <int LG>
-static int launch_mid(zkb_ctx* ctx, const zkb_comm* c, const MidArgs& a, cudaStream_t st) {
+static int launch_mid(zkb_ctx* ctx, const zkb_comm* c, const MidArgs& a, size_t flag0_off, uint32_t epoch, cudaStream_t st) {
+  ZKB_LAUNCH(ctx, k_comm_wait, 1, 32, 0, st, c->view, flag0_off, epoch);
   dim3 grid(cdiv(a.q, 128), 3);
   ZKB_LAUNCH(ctx, k_shard_mid<LG>, grid, 128, 0, st, c->view, a, small_tw(0, LG, true), small_tw(0, LG, false));
   return ZKB_OK;
@@ -282,14 +282,16 @@ static int launch_mid(zkb_ctx* ctx, const zkb_comm* c, const MidArgs& a, cudaStr
 template <int LG>
 static int launch_fin(zkb_ctx* ctx, const zkb_comm* c, size_t r2, size_t f2, uint32_t epoch, uint32_t q, const ShardTables& T, Fr* cS,
                       Fr* hn, cudaStream_t st) {
-  ZKB_LAUNCH(ctx, k_shard_fin<LG>, cdiv(q, 128), 128, 0, st, c->view, r2, f2, epoch, q, T.Tinv, T.QS, cS, inverse(fr_from_u64(2)),
+  ZKB_LAUNCH(ctx, k_comm_wait, 1, 32, 0, st, c->view, f2, epoch);
+  ZKB_LAUNCH(ctx, k_shard_fin<LG>, cdiv(q, 128), 128, 0, st, c->view, r2, q, T.Tinv, T.QS, cS, inverse(fr_from_u64(2)),
              small_tw(0, LG, true), hn);
   return ZKB_OK;
 }
 template <int LG>
 static int launch_combine(zkb_ctx* ctx, const zkb_comm* c, size_t r_off, size_t f_off, uint32_t epoch, uint32_t q, const Fr* T, bool inv,
                           Fr* out, cudaStream_t st) {
-  ZKB_LAUNCH(ctx, k_shard_combine<LG>, cdiv(q, 128), 128, 0, st, c->view, r_off, f_off, epoch, q, T, small_tw(0, LG, inv), out);
+  ZKB_LAUNCH(ctx, k_comm_wait, 1, 32, 0, st, c->view, f_off, epoch);
+  ZKB_LAUNCH(ctx, k_shard_combine<LG>, cdiv(q, 128), 128, 0, st, c->view, r_off, q, T, small_tw(0, LG, inv), out);
   return ZKB_OK;
 }
 #define ZKB_BY_LG(lg, call)                                                                                          \
@@ -317,11 +319,11 @@ int shard_poly_stage(zkb_ctx* ctx, zkb_comm* c, int ch, uint32_t epoch, const zk
   ZKB_LAUNCH(ctx, k_shard_send<true>, cdiv(3 * m, 256), 256, 0, st, A, m, 3, log_m, (uint32_t)q, c->view, comm_region_off(c, ch, 0));
   ZKB_TRY(signal(ctx, c, ch, 0, epoch, st));
   MidArgs a;
-  a.r0_off = comm_region_off(c, ch, 0); a.r1_off = comm_region_off(c, ch, 1); a.flag0_off = comm_flag_off(ch, 0, 0);
-  a.epoch = epoch; a.q = (uint32_t)q;
+  a.r0_off = comm_region_off(c, ch, 0); a.r1_off = comm_region_off(c, ch, 1);
+  a.q = (uint32_t)q;
   a.Tinv = T->Tinv; a.Tfwd = T->Tfwd; a.cosS = T->cosS;
   a.un = un; a.vn = vn; a.cS = cS;
-  ZKB_TRY(ZKB_BY_LG(c->lg, launch_mid)(ctx, c, a, st));
+  ZKB_TRY(ZKB_BY_LG(c->lg, launch_mid)(ctx, c, a, comm_flag_off(ch, 0, 0), epoch, st));
   ZKB_TRY(signal(ctx, c, ch, 1, epoch, st));
   ZKB_LAUNCH(ctx, k_comm_wait, 1, 32, 0, st, c->view, comm_flag_off(ch, 1, 0), epoch);
   Fr* Wu = reinterpret_cast<Fr*>(c->window + comm_region_off(c, ch, 1));  // [vector][src rank][q] = W in natural order
