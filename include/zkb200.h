@@ -206,9 +206,9 @@ int zkb_prove_shard_batch(zkb_ctx* ctx, zkb_comm* comm, const zkb_qap* qap, cons
                           int weights_on_device, const uint64_t* r, const uint64_t* s, size_t count, zkb_proof* out);
 /* One size-2^log_n transform (zkb_ntt_fr's convention) with its outer dimension sharded over the ranks: d_local holds
  * n/G canonical residues, x[rank + G*i] on entry and X[(rank*q + t) + (n/G)*k1] at index k1*q + t on return.
- * One all-to-all of n*32*(G-1)/G bytes in total and log G butterfly stages.  async != 0: return once queued
+ * One all-to-all of n*32*(G-1)/G bytes in total and log G butterfly stages.  no_wait != 0: return once queued
  * (zkb_sync completes it). */
-int zkb_ntt_shard(zkb_ctx* ctx, zkb_comm* comm, uint64_t* d_local, uint32_t log_n, int inverse, int async);
+int zkb_ntt_shard(zkb_ctx* ctx, zkb_comm* comm, uint64_t* d_local, uint32_t log_n, int inverse, int no_wait);
 
 /* h(x) alone: h = (u_sum * v_sum - w_sum) / t  (mod.rs:277; coefficient_poly.rs:93-157;
  * field/mod.rs:428-469).  Outputs (host, canonical, n x 4 limbs each; any may be NULL):

@@ -453,6 +453,87 @@ int ob_prove(const ob_prove_in* in, const u64* weights, size_t nw, const u64* r_
   return 0;
 }
 
+/* ---- the reference's prove() run IN FULL on a roots-of-unity QAP given as sparse evaluation rows (bench.py:
+ * cpu_baseline_measured).  The dense QAP<CoefficientPoly<Fr>> the reference holds (mod.rs:60-67: 3*m coefficient
+ * vectors of n entries) is built here first, OUTSIDE the timed region -- in the reference that is `QAP::from`
+ * (fr.rs:140-173), a separate call -- from L_k(x) = (1/n) sum_j w^(-kj) x^j; the timed region is ob_prove alone, i.e.
+ * exactly mod.rs:213-296 with the reference's algorithms.  row_ptr: m+1 offsets; gate: 0-based gate indices;
+ * coeff: 4 limbs each.  omega_inv: w^-1 (canonical).  Returns seconds of ob_prove, or a negative value on failure. */
+typedef struct {
+  size_t log_n, m, n_input;
+  const u64* row_ptr[3];
+  const uint32_t* gate[3];
+  const u64* coeff[3];
+  const u64* omega_inv;
+  size_t n_sd;
+  const u64 *alpha1, *beta1, *delta1, *xi1, *xi_t, *sum_delta, *beta2, *delta2, *xi2;
+} ob_full_in;
+
+static double now(void);
+double ob_prove_full_omega(const ob_full_in* in, const u64* weights, size_t nw, const u64* r_, const u64* s_, u64* proof,
+                           double* dense_build_s) {
+  ob_init();
+  const size_t n = (size_t)1 << in->log_n, m = in->m;
+  double t0 = now();
+  fe winv = fe_from_canon(&FR, in->omega_inv);
+  fe* pw = malloc(n * sizeof(fe)); /* w^-e, e < n */
+  pw[0] = FR.one;
+  for (size_t e = 1; e < n; e++) pw[e] = fe_mul(&FR, pw[e - 1], winv);
+  u64 ncan[4] = {(u64)n, 0, 0, 0};
+  fe ninv = fe_inv(&FR, fe_from_canon(&FR, ncan));
+  u64* dense[3];
+  size_t* lens[3];
+  for (int t = 0; t < 3; t++) {
+    dense[t] = calloc(m * n * 4, sizeof(u64));
+    lens[t] = malloc(m * sizeof(size_t));
+    if (!dense[t] || !lens[t]) return -1.0;
+    fe* acc = malloc(n * sizeof(fe));
+    for (size_t i = 0; i < m; i++) {
+      size_t e0 = in->row_ptr[t][i], e1 = in->row_ptr[t][i + 1];
+      if (e0 == e1) { lens[t][i] = 1; continue; } /* the sum of no basis polynomials: [0] (coefficient_poly.rs:84-89) */
+      memset(acc, 0, n * sizeof(fe)); /* Montgomery form of 0 is 0 */
+      for (size_t e = e0; e < e1; e++) {
+        fe c = fe_mul(&FR, fe_from_canon(&FR, in->coeff[t] + 4 * e), ninv);
+        size_t k = in->gate[t][e], idx = 0;
+        for (size_t j = 0; j < n; j++) {
+          acc[j] = fe_add(&FR, acc[j], fe_mul(&FR, c, pw[idx]));
+          idx = (idx + k) & (n - 1);
+        }
+      }
+      for (size_t j = 0; j < n; j++) fe_to_canon(&FR, acc[j], dense[t] + 4 * (i * n + j));
+      lens[t][i] = n;
+    }
+    free(acc);
+  }
+  u64* tc = calloc((n + 1) * 4, sizeof(u64)); /* t = x^n - 1 */
+  fe_to_canon(&FR, fe_neg(&FR, FR.one), tc);
+  tc[4 * n] = 1;
+  ob_prove_in pin;
+  pin.m = m; pin.stride = n; pin.nt = n + 1; pin.n_input = in->n_input;
+  pin.u = dense[0]; pin.v = dense[1]; pin.w = dense[2]; pin.t = tc;
+  pin.ulen = lens[0]; pin.vlen = lens[1]; pin.wlen = lens[2];
+  pin.n_xi = n; pin.n_xit = n - 1; pin.n_sd = in->n_sd;
+  pin.alpha1 = in->alpha1; pin.beta1 = in->beta1; pin.delta1 = in->delta1; pin.xi1 = in->xi1; pin.xi_t = in->xi_t;
+  pin.sum_delta = in->sum_delta; pin.beta2 = in->beta2; pin.delta2 = in->delta2; pin.xi2 = in->xi2;
+  if (dense_build_s) *dense_build_s = now() - t0;
+  t0 = now();
+  int rc = ob_prove(&pin, weights, nw, r_, s_, proof, NULL, NULL);
+  double dt = now() - t0;
+  for (int t = 0; t < 3; t++) { free(dense[t]); free(lens[t]); }
+  free(tc); free(pw);
+  return rc == 0 ? dt : -2.0;
+}
+
+/* valid, pairwise distinct points for timing runs that have no device to make a CRS: P_i = (i + 1) * G by repeated addition */
+void ob_fill_points(u64* g1_out, size_t n1, u64* g2_out, size_t n2, const u64* g2gen) {
+  ob_init();
+  u64 g1gen[8] = {1, 0, 0, 0, 2, 0, 0, 0};
+  g1 G = g1_from_affine(g1gen), acc = G;
+  for (size_t i = 0; i < n1; i++) { g1_store(acc, g1_out + 8 * i); acc = g1_add(acc, G); }
+  g2 H = g2_from_affine(g2gen), acc2 = H;
+  for (size_t i = 0; i < n2; i++) { g2_store(acc2, g2_out + 16 * i); acc2 = g2_add(acc2, H); }
+}
+
 /* ---- bounded timing samples of the reference algorithm at full problem width (bench.py) ----
  * Each returns seconds for the sampled work; bench.py scales to one proof. */
 static double now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }

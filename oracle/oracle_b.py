@@ -191,3 +191,101 @@ def prove(qap, sigma, weights, r, s):
     if rc != 0:
         raise ZeroDivisionError(f"ob_prove rc={rc}")
     return g1_unpack(proof, 0), g2_unpack(proof, 8), g1_unpack(proof, 24), _unpack(hbuf, hlen.value)
+
+
+class _FullIn(C.Structure):
+    _fields_ = [("log_n", C.c_size_t), ("m", C.c_size_t), ("n_input", C.c_size_t),
+                ("row_ptr", C.c_void_p * 3), ("gate", C.c_void_p * 3), ("coeff", C.c_void_p * 3), ("omega_inv", C.c_void_p),
+                ("n_sd", C.c_size_t),
+                ("alpha1", C.c_void_p), ("beta1", C.c_void_p), ("delta1", C.c_void_p), ("xi1", C.c_void_p),
+                ("xi_t", C.c_void_p), ("sum_delta", C.c_void_p), ("beta2", C.c_void_p), ("delta2", C.c_void_p),
+                ("xi2", C.c_void_p)]
+
+
+def prove_full_omega(log_n, m, n_input, rows, crs_raw, weights_limbs, r, s):
+    """The reference's prove() (mod.rs:213-296, its own O(m n + n^2) algorithms, one thread) run IN FULL and timed, on a
+    roots-of-unity QAP given as sparse rows -- numpy (row_ptr u64, gate u32, coeff (nnz, 4) u64) for u, v, w -- and a
+    CRS as uint64 limb arrays in the zkb_crs_host layout.  Returns (seconds of prove, seconds of building the dense QAP
+    (not part of prove: QAP::from, fr.rs:140-173), proof limbs (32,) a | b | c)."""
+    import numpy as np
+    L = lib()
+    L.ob_prove_full_omega.restype = C.c_double
+    fin = _FullIn()
+    fin.log_n, fin.m, fin.n_input = log_n, m, n_input
+    keep = []
+    for t, (ptr, gate, coeff) in enumerate(rows):
+        a = [np.ascontiguousarray(ptr, dtype=np.uint64), np.ascontiguousarray(gate, dtype=np.uint32),
+             np.ascontiguousarray(coeff, dtype=np.uint64)]
+        keep += a
+        fin.row_ptr[t], fin.gate[t], fin.coeff[t] = (x.ctypes.data for x in a)
+    p = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    winv = _pack([pow(pow(5, (p - 1) >> log_n, p), -1, p)])
+    fin.omega_inv = C.addressof(winv)
+    arrs = {k: np.ascontiguousarray(v, dtype=np.uint64) for k, v in crs_raw.items()}
+    for k in ("alpha1", "beta1", "delta1", "xi1", "xi_t", "sum_delta", "beta2", "delta2", "xi2"):
+        setattr(fin, k, arrs[k].ctypes.data)
+    fin.n_sd = arrs["sum_delta"].shape[0]
+    w = np.ascontiguousarray(weights_limbs, dtype=np.uint64)
+    proof = np.zeros(32, dtype=np.uint64)
+    build = C.c_double()
+    sec = L.ob_prove_full_omega(C.byref(fin), C.c_void_p(w.ctypes.data), C.c_size_t(w.shape[0]), _pack([r]), _pack([s]),
+                                C.c_void_p(proof.ctypes.data), C.byref(build))
+    if sec < 0:
+        raise RuntimeError(f"ob_prove_full_omega failed ({sec})")
+    del keep
+    return sec, build.value, proof
+
+
+G2_GEN = [10857046999023057135944570762232829481370756359578518086990519993285655852781,
+          11559732032986387107991004021392285783925812861821192530917403151452391805634,
+          8495653923123431417604973247489272438418190587263600148770280649306958101930,
+          4082367875863433681332203403145435568316851327593401208105741076214120093531]
+
+
+def horner_rows_np(n):
+    """Sparse rows (by wire) of the n-gate Horner circuit of SURVEY.md 8d (row order of ASTParser, circuit/mod.rs:230-526:
+    0 unity, 1 x, 2 y, t_k -> 2k+1, c_k -> 2k+2, c_n -> 2n+1), as (row_ptr, gate, coeff) numpy triples for u, v, w."""
+    import numpy as np
+    m = 2 * n + 2
+    rows_u = {0: [n - 1], 1: list(range(n - 1))}
+    rows_v, rows_w = {}, {2: [n - 1]}
+    for k in range(1, n + 1):
+        c_row = 2 * k + 2 if k < n else 2 * n + 1
+        rows_v.setdefault(c_row, []).append(k - 1)
+        if k > 1:
+            rows_v.setdefault(2 * (k - 1) + 1, []).append(k - 1)
+        if k < n:
+            rows_w.setdefault(2 * k + 1, []).append(k - 1)
+    out = []
+    for d in (rows_u, rows_v, rows_w):
+        ptr = np.zeros(m + 1, dtype=np.uint64)
+        gates = []
+        for i in range(m):
+            gates += d.get(i, [])
+            ptr[i + 1] = len(gates)
+        coeff = np.zeros((len(gates), 4), dtype=np.uint64)
+        coeff[:, 0] = 1
+        out.append((ptr, np.asarray(gates, dtype=np.uint32), coeff))
+    return m, 2, out
+
+
+def time_full_prove(log_n, seed=1):
+    """One complete run of the reference's prove() at n = 2^log_n on the Horner QAP with stand-in CRS points (valid curve
+    points; the running time does not depend on which) and a random witness.  Returns (seconds, seconds to build the dense QAP)."""
+    import random
+
+    import numpy as np
+    n = 1 << log_n
+    m, n_input, rows = horner_rows_np(n)
+    L = lib()
+    n1 = 3 + n + (n - 1) + (m - n_input - 1)
+    g1 = np.zeros((n1, 8), dtype=np.uint64)
+    g2 = np.zeros((2 + n, 16), dtype=np.uint64)
+    L.ob_fill_points(C.c_void_p(g1.ctypes.data), C.c_size_t(n1), C.c_void_p(g2.ctypes.data), C.c_size_t(2 + n), _pack(G2_GEN))
+    crs = {"alpha1": g1[0:1], "beta1": g1[1:2], "delta1": g1[2:3], "xi1": g1[3:3 + n], "xi_t": g1[3 + n:2 + 2 * n],
+           "sum_delta": g1[2 + 2 * n:], "beta2": g2[0:1], "delta2": g2[1:2], "xi2": g2[2:]}
+    rng = random.Random(seed)
+    p = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    w = np.frombuffer(b"".join(rng.randrange(p).to_bytes(32, "little") for _ in range(m)), dtype="<u8").reshape(m, 4).copy()
+    sec, build, _ = prove_full_omega(log_n, m, n_input, rows, crs, w, rng.randrange(1, p), rng.randrange(1, p))
+    return sec, build

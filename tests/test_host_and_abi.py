@@ -35,6 +35,21 @@ def test_library_exports_every_declared_symbol(lib):
         assert getattr(lib, name) is not None
 
 
+def test_rust_extern_block_covers_the_whole_header():
+    """integration/rust/zkb200_sys.rs is generated from include/zkb200.h (tools/gen_rust_sys.py): the committed file is
+    up to date and declares exactly the header's functions, with as many parameters each."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    gen = importlib.import_module("gen_rust_sys")
+    text, names = gen.generate()
+    assert open(os.path.join(ROOT, "integration", "rust", "zkb200_sys.rs")).read() == text, "run python tools/gen_rust_sys.py"
+    header = open(os.path.join(ROOT, "include", "zkb200.h")).read()
+    declared = set(re.findall(r"\b(zkb_[a-z0-9_]+)\s*\(", gen.strip_comments(header)))
+    rust = dict(re.findall(r"pub fn (zkb_[a-z0-9_]+)\(([^)]*)\)", text))
+    assert set(rust) == declared == set(zg.ABI)
+    for name, args in rust.items():
+        assert len([a for a in args.split(",") if a.strip()]) == len(zg.ABI[name][1]), name
+
+
 def test_no_cpu_fallback(lib):
     """Without a device every computing entry point must fail loudly, not fall back."""
     import torch
@@ -118,6 +133,8 @@ def test_reference_arm_line_and_best_effort_leg():
     assert line["impl"] == "reference" and line["metric"] == "groth16_proofs_per_sec" and line["unit"] == "proofs/s"
     assert line["value"] > 0 and line["higher_is_better"] is True and line["cpu_baseline"]["kind"] == "port"
     assert line["cpu_baseline"]["cores"] == 1 and line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    full = line["config"]["measured_full"]  # the same port run to completion at a size where it finishes
+    assert full["log_n"] == 10 and 0.2 < full["seconds_per_proof"] < 120
     sys.path.insert(0, ROOT)
     bench = importlib.import_module("bench")
     fast = bench.best_effort_cpu(8)

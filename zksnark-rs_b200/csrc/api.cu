@@ -127,12 +127,6 @@ int zkb_ctx_create(zkb_ctx** out, int device_id) {
   zkb_ctx* c = new zkb_ctx();
   c->device = device_id;
   c->sm_count = prop.multiProcessorCount;
-  if (const char* e = getenv("ZKB_L2_FETCH")) {  // developer switch (unmeasured): L2 fetch granularity hint, 32 / 64 / 128 bytes.
-    // The G1 accumulation gathers 64-byte table entries and ncu shows 135 B of DRAM reads per record (128-byte
-    // fetches); the kernel is multiplier-bound (DRAM 11 %), so this only trims HBM traffic.
-    int v = atoi(e);
-    if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
-  }
   // lane 0 now, the others on first use (lane_get): streams share a small number of hardware queues
   // (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default), and work queued behind another stream's exchange wait in the same
   // queue would be held up with it -- so no more streams than proofs in flight need

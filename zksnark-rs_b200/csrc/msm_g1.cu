@@ -78,26 +78,37 @@ __global__ void k_scan_block(const uint32_t* __restrict__ in, uint32_t* __restri
   if (threadIdx.x == 255) sums[blockIdx.x] = sh[255];
 }
 
-__global__ void k_scan_sums(uint32_t* sums, size_t nblocks, uint32_t* total) {
-  // single block, sequential over chunks of 1024
-  __shared__ uint32_t sh[1024];
+__global__ void __launch_bounds__(256) k_scan_sums(uint32_t* sums, size_t nblocks, uint32_t* total) {
+  // single block of 256 threads (it has to find room on an SM that bucket accumulations of another proof fill: a
+  // 1024-thread block waited ~0.5 ms for that), four entries per thread, sequential over chunks of 1024
+  __shared__ uint32_t sh[256];
   __shared__ uint32_t carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (size_t base = 0; base < nblocks; base += 1024) {
-    size_t i = base + threadIdx.x;
-    uint32_t v = i < nblocks ? sums[i] : 0;
-    sh[threadIdx.x] = v;
+    const size_t i0 = base + threadIdx.x * 4;
+    uint32_t v[4], tot = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      v[q] = i0 + q < nblocks ? sums[i0 + q] : 0;
+      tot += v[q];
+    }
+    sh[threadIdx.x] = tot;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
+    for (int off = 1; off < 256; off <<= 1) {
       uint32_t x = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
       __syncthreads();
       sh[threadIdx.x] += x;
       __syncthreads();
     }
-    if (i < nblocks) sums[i] = carry + sh[threadIdx.x] - v;
+    uint32_t excl = carry + sh[threadIdx.x] - tot;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (i0 + q < nblocks) sums[i0 + q] = excl;
+      excl += v[q];
+    }
     __syncthreads();
-    if (threadIdx.x == 1023) carry += sh[1023];
+    if (threadIdx.x == 255) carry += sh[255];
     __syncthreads();
   }
   if (threadIdx.x == 0) *total = carry;
@@ -123,7 +134,7 @@ int msm_sort_records(zkb_ctx* ctx, const MsmJob* jobs, int njobs, size_t stride,
     if (jobs[j].n)
       ZKB_LAUNCH(ctx, k_digits_count, cdiv(jobs[j].n, 256), 256, 0, st, jobs[j].scalars, jobs[j].n, pl, hist + (size_t)j * pl.nb);
   ZKB_LAUNCH(ctx, k_scan_block, (unsigned)nscan_blocks, 256, 0, st, hist, offs, sums, nbk);
-  ZKB_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, st, sums, nscan_blocks, sums + nscan_blocks);
+  ZKB_LAUNCH(ctx, k_scan_sums, 1, 256, 0, st, sums, nscan_blocks, sums + nscan_blocks);
   ZKB_LAUNCH(ctx, k_scan_add, cdiv(nbk + 1, 256), 256, 0, st, offs, cursor, sums, nbk, sums + nscan_blocks);
   for (int j = 0; j < njobs; j++)
     if (jobs[j].n)

@@ -187,6 +187,26 @@ static int msm_tail_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
 #ifndef ZKB_ACC_THREADS
 #define ZKB_ACC_THREADS 128
 #endif
+// Gather of one table entry.  A G1 entry is 64 bytes and 64-byte aligned, but the L2 fills 128-byte lines by default
+// (ncu: 134.7 B of DRAM reads per record, profiles/r02_l2_fetch_granularity.txt; cudaLimitMaxL2FetchGranularity changed
+// nothing): the loads carry the L2::64B prefetch-size qualifier instead (-DZKB_ACC_NO_L2_HINT builds the plain loads).
+template <class F>
+__device__ __forceinline__ Affine<F> ld_table_entry(const Affine<F>* p) {
+#if !defined(ZKB_ACC_NO_L2_HINT)
+  if (sizeof(Affine<F>) == 64) {
+    Affine<F> r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      asm volatile("ld.global.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(w[4 * k]), "=r"(w[4 * k + 1]), "=r"(w[4 * k + 2]), "=r"(w[4 * k + 3])
+                   : "l"(reinterpret_cast<const char*>(p) + 16 * k));
+    return r;
+  }
+#endif
+  return *p;
+}
+
 template <class F>
 __global__ void __launch_bounds__(ZKB_ACC_THREADS, ZKB_ACC_MIN_BLOCKS) k_accumulate_chunks(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
                                                            const uint32_t* __restrict__ sorted, uint32_t nbk, size_t nchunks,
@@ -220,7 +240,7 @@ __global__ void __launch_bounds__(ZKB_ACC_THREADS, ZKB_ACC_MIN_BLOCKS) k_accumul
       asm volatile("prefetch.global.L1 [%0];" ::"l"(pts + (sorted[p + ZKB_ACC_PREFETCH] & 0x7fffffffu)));
 #endif
     uint32_t rec = sorted[p];
-    Affine<F> P = pts[rec & 0x7fffffffu];
+    Affine<F> P = ld_table_entry(pts + (rec & 0x7fffffffu));
     if (rec >> 31) P = neg(P);
     acc = madd(acc, P);
   }

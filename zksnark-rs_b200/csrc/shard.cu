@@ -473,7 +473,7 @@ int zkb_comm_info(const zkb_comm* c, int* rank, int* world, int* status) {
 // One size-2^log_n transform over all ranks of `comm` (reference convention, field/mod.rs:508-537).  d_local holds this
 // rank's m = n / world elements, canonical: in layout D (x[rank + world * i]) on entry, in layout S on return
 // (index s = k1 * q + t <-> X[(rank * q + t) + m * k1], q = m / world).
-int zkb_ntt_shard(zkb_ctx* ctx, zkb_comm* c, uint64_t* d_local, uint32_t log_n, int inverse_, int async) {
+int zkb_ntt_shard(zkb_ctx* ctx, zkb_comm* c, uint64_t* d_local, uint32_t log_n, int inverse_, int no_wait) {
   if (!ctx || !c || !d_local) return set_err(ctx, ZKB_ERR_ARG, "zkb_ntt_shard: NULL argument");
   ZKB_TRY(shard_check(ctx, c, log_n));
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -495,7 +495,7 @@ int zkb_ntt_shard(zkb_ctx* ctx, zkb_comm* c, uint64_t* d_local, uint32_t log_n, 
   ZKB_TRY(signal(ctx, c, ch, 0, epoch, st));
   ZKB_TRY(ZKB_BY_LG(c->lg, launch_combine)(ctx, c, roff, comm_flag_off(ch, 0, 0), epoch, (uint32_t)q,
                                            inverse_ ? T->Tinv : T->Tfwd, inverse_ != 0, d, st));
-  if (!async) {
+  if (!no_wait) {
     ZKB_CUDA(ctx, cudaStreamSynchronize(st));
     int status = 0;
     ZKB_TRY(zkb_comm_info(c, nullptr, nullptr, &status));
