@@ -49,15 +49,28 @@ __host__ __device__ inline DigitPlan make_plan(int c) {
   return p;
 }
 
+#ifndef ZKB_ACC_MIN_BLOCKS
+#define ZKB_ACC_MIN_BLOCKS 1
+#endif
+#ifndef ZKB_ACC_THREADS
+#define ZKB_ACC_THREADS 128
+#endif
 static const int MSM_MAX_JOBS = 4;
-// chunk plan for max_recs records: long chunks for the first ~7/8, short ones for the rest
+// Chunk plan for max_recs records: long chunks for the first ~7/8, short ones (a quarter as long) for the rest, so that
+// the grid drains in a fraction of a long chunk's duration.  Long-chunk size by record count (measured, r01).  A plan that
+// sizes the long chunks to fill the machine a whole number of times (S1 = 7/8 records / (resident threads x rounds)) was
+// measured in round 2 and is NOT better: 2^20 on one GPU G2 7.55 -> 8.68 ms, a rank of an 8-GPU proof G1 1.81 -> 1.92 ms
+// (profiles/r02_chunk_plan.txt) -- blocks do not run in lock-step rounds (bucket flushes and head pieces make chunk
+// times uneven and the scheduler backfills), so full rounds followed by the short chunks only add a partial round.
+// ZKB_ACC_S1 / ZKB_ACC_FRAC: developer switches for sweeps.
 template <class F>
-static inline ChunkPlan chunk_plan(size_t max_recs) {
+static inline ChunkPlan chunk_plan(size_t max_recs, int sm_count) {
+  (void)sm_count;
   const bool g1 = sizeof(F) == sizeof(Fq);
   uint32_t S1 = g1 ? (max_recs >= ((size_t)1 << 25) ? 128 : (max_recs >= ((size_t)1 << 23) ? 64 : 32)) : (max_recs >= ((size_t)1 << 23) ? 128 : 32);
-  if (const char* e = getenv("ZKB_ACC_S")) {
+  if (const char* e = getenv(g1 ? "ZKB_ACC_S1" : "ZKB_ACC_S1_G2")) {
     int v = atoi(e);
-    if (v == 16 || v == 32 || v == 64 || v == 128 || v == 256) S1 = v;
+    if (v >= 4 && v <= 1024) S1 = (uint32_t)v;
   }
   ChunkPlan ch;
   ch.S1 = S1;
@@ -131,7 +144,7 @@ static int msm_prepare_t(zkb_ctx* ctx, DevBuf* slots, int slot, const Affine<F>*
   P->nbk = (size_t)njobs * pl.nb;
   const size_t nscan_blocks = (P->nbk + 1023) / 1024;
   P->max_recs = (size_t)pl.W * total_n;
-  P->ch = chunk_plan<F>(P->max_recs);
+  P->ch = chunk_plan<F>(P->max_recs, ctx->sm_count);
   P->nacc = P->ch.count(P->max_recs);
   P->lvl_elems = msm_level_elems(pl.nb, njobs);
   void* p;
@@ -181,12 +194,6 @@ static int msm_tail_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
 // A bucket that begins inside the chunk is written to buckets[g]; the leading piece of a bucket
 // that began in an earlier chunk goes to heads[t] and is folded in by k_fix_heads.  buckets[] is
 // zero-filled (= identity) beforehand, empty buckets are never touched.
-#ifndef ZKB_ACC_MIN_BLOCKS
-#define ZKB_ACC_MIN_BLOCKS 1
-#endif
-#ifndef ZKB_ACC_THREADS
-#define ZKB_ACC_THREADS 128
-#endif
 // Gather of one table entry.  A G1 entry is 64 bytes and 64-byte aligned, but the L2 fills 128-byte lines by default
 // (ncu: 134.7 B of DRAM reads per record, profiles/r02_l2_fetch_granularity.txt; cudaLimitMaxL2FetchGranularity changed
 // nothing): the loads carry the L2::64B prefetch-size qualifier instead (-DZKB_ACC_NO_L2_HINT builds the plain loads).
