@@ -84,7 +84,10 @@ void* zkb_stream(zkb_ctx* ctx);
  * Generic domain (roots != NULL): what `QAP::from(DummyRep)` accepts for parser-produced circuits
  * (fr.rs:140-173): same results as the reference's Lagrange interpolation (coefficient_poly.rs:159-190),
  * schoolbook product (:93-130) and long division (field/mod.rs:428-469), computed with dense O(n^2)
- * device kernels, n <= 4096. */
+ * device kernels, n <= 32768 (the n x n table of Lagrange coefficients takes n^2 * 32 bytes of HBM: 2 GiB at 8192,
+ * 32 GiB at 32768).  Larger parser circuits: re-index the gates onto the roots of unity (gate k <-> omega^k, padded to a
+ * power of two with empty gates) -- a different but equivalent QAP of the same circuit, which the reference permits
+ * (DummyRep.roots is a public field; CircuitInstance::new takes the root assignment as a closure, circuit/mod.rs:99-104). */
 typedef struct {
   uint64_t n;         /* number of gates = qap.degree                                   */
   uint64_t m;         /* number of rows (wires incl. the unity wire) = qap.u.len()      */
@@ -94,7 +97,7 @@ typedef struct {
   const uint64_t* coeff[3];    /* nnz x 4 limbs, canonical                              */
   const uint64_t* roots;       /* NULL: the n-th roots of unity (n a power of two).  Else n x 4 limbs:
                                   explicit pairwise-distinct roots, gate k <-> roots[k] (the reference's
-                                  ASTParser uses 1..=n, circuit/mod.rs:517); any n in [1, 4096]; dense
+                                  ASTParser uses 1..=n, circuit/mod.rs:517); any n in [1, 32768]; dense
                                   O(n^2) interpolation / product / division on the device            */
 } zkb_qap_host;
 int zkb_qap_upload(zkb_ctx* ctx, const zkb_qap_host* qap, zkb_qap** out);
@@ -215,6 +218,25 @@ int zkb_ntt_shard(zkb_ctx* ctx, zkb_comm* comm, uint64_t* d_local, uint32_t log_
  * u_sum, v_sum coefficient vectors and h (n-1 meaningful coefficients, h[n-1] = 0). */
 int zkb_qap_h(zkb_ctx* ctx, const zkb_qap* qap, const uint64_t* weights, uint64_t* u_sum,
               uint64_t* v_sum, uint64_t* h);
+
+/* ---- wire format: flat little-endian layout of QAP, CRS and Proof (host-only; no device is touched) -------------
+ * The reference cannot serialise anything: QAP, SigmaG1, SigmaG2, Proof have private fields and no accessors
+ * (groth16/mod.rs:60-128).  A prover service needs to (setup once, ship CRS + QAP to the GPU box, get proofs back), so:
+ * 64-byte header (magic "ZKB200W", version, kind 1 QAP / 2 CRS / 3 Proof, total length, four size fields, FNV-1a-64 of
+ * the payload) followed by the arrays of the zkb_*_host structs in declaration order, each padded to 8 bytes (layout
+ * in csrc/wire.cu).  Writers fill a caller buffer of zkb_wire_size_* bytes.  Readers check magic, version, kind, length
+ * and checksum and return VIEWS: the pointers of *out point into `buf`, which must be 8-byte aligned and outlive them
+ * (pass the struct straight to zkb_qap_upload / zkb_crs_upload*).  ctx-less: errors via zkb_last_error(NULL). */
+#define ZKB_WIRE_PROOF_BYTES 320
+int zkb_wire_kind(const uint8_t* buf, uint64_t len, int* kind, uint64_t* total_bytes);
+int zkb_wire_size_qap(const zkb_qap_host* qap, uint64_t* bytes);
+int zkb_wire_write_qap(const zkb_qap_host* qap, uint8_t* buf, uint64_t cap);
+int zkb_wire_read_qap(const uint8_t* buf, uint64_t len, zkb_qap_host* out);
+int zkb_wire_size_crs(const zkb_crs_host* crs, uint64_t* bytes);
+int zkb_wire_write_crs(const zkb_crs_host* crs, uint8_t* buf, uint64_t cap);
+int zkb_wire_read_crs(const uint8_t* buf, uint64_t len, zkb_crs_host* out);
+int zkb_wire_write_proof(const zkb_proof* proof, uint8_t* buf, uint64_t cap);
+int zkb_wire_read_proof(const uint8_t* buf, uint64_t len, zkb_proof* out);
 
 /* ---- groth16::verify (groth16/mod.rs:299-320) ----------------------------------------------- */
 /* *ok = 1 iff  e(alpha1, beta2) * e(sum_term, gamma2) * e(proof.c, delta2) == e(proof.a, proof.b)

@@ -200,7 +200,7 @@ class QAP {
  public:
   // `impl From<RootRepresentation> for QAP` (fr.rs:140-173).  Roots omega^0 .. omega^(n-1) in order (n a power of
   // two >= 2) take the NTT path; any other pairwise-distinct roots (ASTParser's 1..=n, circuit/mod.rs:517) the
-  // dense device path (n <= 4096).
+  // dense device path (n <= 32768).
   static QAP from(Context& ctx, const RootRepresentation& rep) {
     const size_t n = rep.roots.size(), m = rep.u.size();
     if (rep.v.size() != m || rep.w.size() != m) throw Error(ZKB_ERR_ARG, "QAP: u, v, w must have the same number of rows");  // fr.rs:157-158

@@ -100,7 +100,7 @@ impl B200 {
     /// `QAP::from(root_rep)` (fr.rs:140-173) without densifying: the sparse (root, value) rows go to the device as
     /// CSR by wire.  `omega_domain`: the caller asserts that `roots` are w^0 .. w^(n-1) for the n-th root of unity
     /// w = 5^((r-1)/n) (n a power of two): NTT path, any n up to 2^27.  Otherwise the roots are passed explicitly
-    /// (the ASTParser's 1..=n, circuit/mod.rs:517) and the dense O(n^2) path serves n <= 4096.
+    /// (the ASTParser's 1..=n, circuit/mod.rs:517) and the dense O(n^2) path serves n <= 32768.
     pub fn upload_qap<R: RootRepresentation<FrLocal>>(&self, rep: &R, omega_domain: bool) -> DeviceQap {
         let roots: Vec<FrLocal> = rep.roots().collect();
         let index: HashMap<[u64; 4], u32> = roots.iter().enumerate().map(|(k, r)| (fr_limbs(r), k as u32)).collect();

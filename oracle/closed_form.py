@@ -44,6 +44,25 @@ def lagrange_at(n: int, omega: int, x: int) -> list:
     return [tx * w % P * d % P for w, d in zip(ws, den)]
 
 
+def lagrange_at_1_to_n(n: int, x: int):
+    """([L_0(x), ..., L_{n-1}(x)], t(x)) on the parser's domain: gate k (0-based) <-> root k + 1 (circuit/mod.rs:517).
+    L_k(x) = t(x) / ((x - r_k) t'(r_k)) with t'(k + 1) = k! (n - 1 - k)! (-1)^(n - 1 - k): O(n)."""
+    fact = [1] * (n + 1)
+    for i in range(1, n + 1):
+        fact[i] = fact[i - 1] * i % P
+    tx = 1
+    for k in range(1, n + 1):
+        tx = tx * (x - k) % P
+    dens = []
+    for k in range(n):
+        tp = fact[k] * fact[n - 1 - k] % P
+        if (n - 1 - k) & 1:
+            tp = P - tp
+        dens.append((x - (k + 1)) * tp % P)
+    inv = batch_inverse(dens)
+    return [tx * d % P for d in inv], tx
+
+
 def row_evals(rows, L, index_of_root=None):
     """rows: per wire list of (gate index, coeff) -> [row_i(x)]."""
     return [sum(c * L[g] for g, c in row) % P for row in rows]
@@ -51,18 +70,20 @@ def row_evals(rows, L, index_of_root=None):
 
 def expected_proof_scalars(n, omega, rows_u, rows_v, rows_w, n_input, weights, toxic, r, s):
     """Scalars (a, b, c) with A = a*BASE_G1, B = b*BASE_G2, C = c*BASE_G1.  rows_*: per wire list of
-    (gate index, coeff).  Valid witnesses only (see module docstring)."""
+    (gate index, coeff).  Valid witnesses only (see module docstring).  omega = None: the parser's domain 1..=n."""
     alpha, beta, gamma, delta, x = toxic
-    L = lagrange_at(n, omega, x)
+    if omega is None:
+        L, tx_generic = lagrange_at_1_to_n(n, x)
+    else:
+        L = lagrange_at(n, omega, x)
     ux, vx, wx = row_evals(rows_u, L), row_evals(rows_v, L), row_evals(rows_w, L)
     m = len(rows_u)
     a = list(weights) + [0] * max(0, m - len(weights))
     U = sum(ai * e for ai, e in zip(a, ux)) % P
     V = sum(ai * e for ai, e in zip(a, vx)) % P
     W = sum(ai * e for ai, e in zip(a, wx)) % P
-    tx = (pow(x, n, P) - 1) % P
     dinv = pow(delta, -1, P)
-    hx_t = (U * V - W) % P  # h(x) * t(x)
+    hx_t = (U * V - W) % P  # h(x) * t(x): t(x) itself is not needed
     lin = [(beta * u + alpha * v + w) % P for u, v, w in zip(ux, vx, wx)]
     wit = sum(a[i] * lin[i] for i in range(n_input + 1, m)) % P * dinv % P
     A = (U + alpha + r * delta) % P

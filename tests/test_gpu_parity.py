@@ -514,7 +514,7 @@ def test_parser_circuits_generic_domain(ctx, name, text, n_inputs, valid):
 
 def test_generic_domain_random_roots_and_limits(ctx):
     """Arbitrary pairwise-distinct roots (not 1..n, n not a power of two); repeated roots are refused
-    (the reference's lagrange_basis would divide by zero); n > 4096 on an explicit domain is refused."""
+    (the reference's lagrange_basis would divide by zero); n > 32768 on an explicit domain is refused."""
     rng = random.Random(33)
     n = 11
     roots = rng.sample(range(2, 10 ** 6), n)
@@ -532,9 +532,72 @@ def test_generic_domain_random_roots_and_limits(ctx):
     bad = synthetic.horner_rep(FR, 4, [5, 6, 5, 7])
     with pytest.raises(zk.ZkbError):
         zk.QAP.from_root_representation(ctx, bad)
-    m, n_input, rows = zg.horner_qap_rows(8192)
+    m, n_input, rows = zg.horner_qap_rows(32769)
     with pytest.raises(zk.ZkbError):
-        zk.QAP(ctx, 8192, m, n_input, rows, roots=list(range(1, 8193)))
+        zk.QAP(ctx, 32769, m, n_input, rows, roots=list(range(1, 32770)))
+
+
+def test_generic_domain_6000_gates_parser_numbering(ctx):
+    """Past toy sizes on the parser's own domain (roots 1..=n, circuit/mod.rs:517; n = 6000, not a power of two): the dense
+    device path against (1) the closed-form proof from the toxic waste, (2) u_sum / v_sum interpolating the gate
+    evaluations at sampled roots (the defining property of mod.rs:233-246 + coefficient_poly.rs:159-190), (3) the division
+    identity u(z) v(z) - w(z) = h(z) t(z) at a random point (field/mod.rs:428-469, remainder 0 for a satisfying witness),
+    (4) verify == true / false on the device."""
+    n = 6000
+    rng = random.Random(6000)
+    m, n_input, rows = zg.horner_qap_rows(n)
+    wit = zg.horner_witness(n, rand_fr(rng, True), [rand_fr(rng) for _ in range(n)])
+    toxic = tuple(rand_fr(rng, True) for _ in range(5))
+    r, s = rand_fr(rng, True), rand_fr(rng, True)
+    q = zk.QAP(ctx, n, m, n_input, rows, roots=list(range(1, n + 1)))
+    crs = zk.setup(ctx, q, toxic)
+    got = zk.prove(ctx, q, crs, wit, r, s)
+    ru, rv, rw = _rows_from_csr(rows)
+    assert (got.a, got.b, got.c) == cf.expected_proof(n, None, ru, rv, rw, n_input, wit, toxic, r, s)
+    assert zk.verify(ctx, crs, wit[1:3], got) and not zk.verify(ctx, crs, [wit[1], (wit[2] + 1) % P], got)
+    u, v, h = zk.qap_h(ctx, q, wit)
+
+    def gate_evals(rows_):
+        out = [0] * n
+        for i, row in enumerate(rows_):
+            for g, c in row:
+                out[g] = (out[g] + c * wit[i]) % P
+        return out
+    A, Bv, Cw = gate_evals(ru), gate_evals(rv), gate_evals(rw)
+
+    def horner(cs, x):
+        acc = 0
+        for c in reversed(cs):
+            acc = (acc * x + c) % P
+        return acc
+    for k in [0, 1, n - 1] + rng.sample(range(n), 29):
+        assert horner(u, k + 1) == A[k] and horner(v, k + 1) == Bv[k]
+    z = rand_fr(rng, True)
+    L, tz = cf.lagrange_at_1_to_n(n, z)
+    wz = sum(c * l for c, l in zip(Cw, L)) % P
+    assert (horner(u, z) * horner(v, z) - wz) % P == horner(h, z) * tz % P
+    assert len(h) == n - 1
+
+
+def test_reindexed_parser_circuit_on_the_fast_domain(ctx):
+    """QAP.from_root_representation(rep, reindex=True): a parser-numbered circuit moved onto the roots of unity (next power
+    of two, empty gates appended) proves and verifies under the CRS of that QAP; accepted / rejected as the reference's
+    acceptance tests do (lib.rs:156-190)."""
+    rng = random.Random(5)
+    rep = circuit.try_parse(FR, MIXED)
+    wit = circuit.weights(FR, MIXED, [rand_fr(rng, True) for _ in range(3)])
+    q = zk.QAP.from_root_representation(ctx, rep, reindex=True)
+    assert q.n == 4 and len(rep.roots) == 4
+    rep5 = synthetic.horner_rep(FR, 5, [1, 2, 3, 4, 5])
+    q5 = zk.QAP.from_root_representation(ctx, rep5, reindex=True)
+    assert q5.n == 8
+    for qq, ww, npub in ((q, wit, rep.input), (q5, synthetic.horner_witness(FR, 5, 3, [4, 5, 6, 7, 8]), 2)):
+        crs = zk.setup(ctx, qq, tuple(rand_fr(rng, True) for _ in range(5)))
+        pr = zk.prove(ctx, qq, crs, ww)
+        assert zk.verify(ctx, crs, ww[1:1 + npub], pr)
+        bad = list(ww[1:1 + npub])
+        bad[-1] = (bad[-1] + 1) % P
+        assert not zk.verify(ctx, crs, bad, pr)
 
 
 def test_prove_batch_sharded_equals_single(ctx):

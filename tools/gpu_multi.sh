@@ -7,7 +7,7 @@ N=${2:-8}
 sizes=${3:-"20 22"}
 mkdir -p gpurun_out
 run() { timeout "$1" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port "$2" "${@:3}"; }
-run 600 29655 tools/shard_multi_gpu.py --log-n 20 --steps 20 --ntt 20 22 24 --trace gpurun_out/${tag}_trace_shard_2pow20.csv \
+[ -n "$SKIP_TOOL" ] || run 600 29655 tools/shard_multi_gpu.py --log-n 20 --steps 20 --ntt 20 22 24 --trace gpurun_out/${tag}_trace_shard_2pow20.csv \
   > gpurun_out/${tag}_shard.json 2> gpurun_out/${tag}_shard.err
 echo "shard tool exit $?"; tail -c 1800 gpurun_out/${tag}_shard.json; grep -v "^\*\|OMP_NUM\|^$\|NCCL version" gpurun_out/${tag}_shard.err | tail -5
 port=29660

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--ntt", type=int, nargs="*", default=[])
     ap.add_argument("--trace", default=None, help="rank 0: per-kernel timeline of one sharded proof (zkb_trace_dump) to this path")
+    ap.add_argument("--trace-batch", default=None, help="rank 0: timeline of a batch of 12 sharded proofs in flight")
     ap.add_argument("--skip-single", action="store_true", help="do not build the full CRS on rank 0 for the one-GPU comparison")
     args = ap.parse_args()
     zk = importlib.import_module("zksnark-rs_b200")
@@ -102,6 +103,14 @@ def main():
         zk.prove_shard(ctx, comm, qap, crs, d_w, r, s, on_device=True)
         if rank == 0:
             ctx.trace_dump(args.trace)
+            ctx.profile(0)
+    if args.trace_batch:
+        dist.barrier()
+        if rank == 0:
+            ctx.profile(2)
+        zk.prove_shard_batch(ctx, comm, qap, crs, [d_w] * 12, [r] * 12, [s] * 12, on_device=True)
+        if rank == 0:
+            ctx.trace_dump(args.trace_batch)
             ctx.profile(0)
     # the transform alone
     ntt = []

@@ -279,7 +279,7 @@ struct zkb_bases {
   void* d = nullptr;  // G1Affine* or G2Affine*, Montgomery form: row 0 = the points, rows 1..W-1 = 2^(c*j) multiples
 };
 
-static const uint64_t ZKB_GENERIC_MAX_N = 4096;
+static const uint64_t ZKB_GENERIC_MAX_N = 32768;  // the n x n Lagrange table is 32 GiB there (180 GB of HBM)
 struct zkb_qap {
   uint64_t n = 0, m = 0, n_input = 0;
   uint32_t log_n = 0;

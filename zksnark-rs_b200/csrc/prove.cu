@@ -80,7 +80,7 @@ __global__ void k_coset_tables(Fr* P, Fr* Q, Fr g, Fr ginv, Fr invn, Fr inv2n, u
 
 
 // ------------------------------------------------------------------------------------------------
-// Generic root domain (explicit roots, n <= 4096): the reference's own algorithms restated as dense
+// Generic root domain (explicit roots, n <= 32768): the reference's own algorithms restated as dense
 // O(n^2) kernels.  Upload builds t(x) = prod (x - r_k) (root_poly, coefficient_poly.rs:192-200), the
 // coefficient rows of the Lagrange basis L_k = t / ((x - r_k) t'(r_k)) (lagrange_basis, :173-190)
 // and g = 1 / rev(t) mod x^(n-1); a proof then needs u = sum_k A_k L_k, v likewise (the unique

@@ -107,7 +107,17 @@ ABI = {
     "zkb_prove_shard_collect": (C.c_int, [_P, _P, C.c_int, C.POINTER(_ProofC)]),
     "zkb_prove_shard_batch": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "zkb_ntt_shard": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_int, C.c_int]),
+    "zkb_wire_kind": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
+    "zkb_wire_size_qap": (C.c_int, [C.POINTER(_QapHost), C.POINTER(C.c_uint64)]),
+    "zkb_wire_write_qap": (C.c_int, [C.POINTER(_QapHost), _P, C.c_uint64]),
+    "zkb_wire_read_qap": (C.c_int, [_P, C.c_uint64, C.POINTER(_QapHost)]),
+    "zkb_wire_size_crs": (C.c_int, [C.POINTER(_CrsHost), C.POINTER(C.c_uint64)]),
+    "zkb_wire_write_crs": (C.c_int, [C.POINTER(_CrsHost), _P, C.c_uint64]),
+    "zkb_wire_read_crs": (C.c_int, [_P, C.c_uint64, C.POINTER(_CrsHost)]),
+    "zkb_wire_write_proof": (C.c_int, [C.POINTER(_ProofC), _P, C.c_uint64]),
+    "zkb_wire_read_proof": (C.c_int, [_P, C.c_uint64, C.POINTER(_ProofC)]),
 }
+WIRE_PROOF_BYTES = 320
 COMM_HANDLE_BYTES = 128
 
 _lib = None
@@ -371,11 +381,16 @@ class QAP:
         self.h = h
 
     @classmethod
-    def from_root_representation(cls, ctx: Context, rep) -> "QAP":
+    def from_root_representation(cls, ctx: Context, rep, reindex: bool = False) -> "QAP":
         """`From<RootRepresentation> for QAP` (fr.rs:140-173).  ``rep`` has u, v, w (per wire: list of
         (root, value)), roots, input -- the DummyRep data model (circuit/dummy_rep.rs:7-13).  Roots that
         are omega_n^0 .. omega_n^(n-1) in order take the NTT path; any other pairwise-distinct roots (the
-        parser's 1..=n, circuit/mod.rs:517) take the dense O(n^2) device path (n <= 4096)."""
+        parser's 1..=n, circuit/mod.rs:517) take the dense O(n^2) device path (n <= 32768), bit-identical to the
+        reference on that QAP.  ``reindex=True`` instead moves gate k (whatever its root) to omega^k on the next power
+        of two (extra gates are empty: 0 * 0 = 0), i.e. builds the QAP the reference would build for the SAME circuit
+        had its gates been numbered with roots of unity (the reference lets the caller choose the roots:
+        dummy_rep.rs:11, circuit/mod.rs:99-104): O(n log n) proofs at any size, verifying under the CRS of THAT
+        QAP -- not bit-identical to proofs over the 1..=n numbering."""
         n = len(rep.roots)
         if not (len(rep.u) == len(rep.v) == len(rep.w)):
             raise ZkbError("QAP: u, v, w must have the same number of rows")  # assert at fr.rs:157-158
@@ -396,6 +411,9 @@ class QAP:
                 rows.append(_csr([[(index[r % FR_MODULUS], c % FR_MODULUS) for r, c in row] for row in mat], m))
             except KeyError as e:  # the reference's Lagrange interpolation would silently ignore nothing: a point off the domain is a bug
                 raise ZkbError(f"QAP: row entry at {e} is not one of the roots") from None
+        if reindex and not fast:
+            n2 = max(2, 1 << (n - 1).bit_length())
+            return cls(ctx, n2, m, rep.input, rows, roots=None)
         return cls(ctx, n, m, rep.input, rows, roots=None if fast else roots)
 
     @classmethod
@@ -879,3 +897,151 @@ def prove_shard_batch(ctx: Context, comm: Comm, qap: QAP, crs: CRS, weights, rs,
 def ntt_shard(ctx: Context, comm: Comm, d_local: int, log_n: int, inverse=False, wait=True):
     """zkb_ntt_shard on this rank's n/world canonical residues (layout D in, layout S out)."""
     ctx.check(ctx.lib.zkb_ntt_shard(ctx.h, comm.h, C.c_void_p(d_local), log_n, 1 if inverse else 0, 0 if wait else 1), "zkb_ntt_shard")
+
+
+# ------------------------------------------------------------------------------------------------
+# wire format (include/zkb200.h: zkb_wire_*; layout in csrc/wire.cu).  Host-only: works without a GPU.
+def _wire_check(rc: int, what: str):
+    if rc != 0:
+        raise ZkbError(f"{what} = {rc}: {load_library().zkb_last_error(None).decode()}")
+
+
+def _aligned_copy(data: bytes) -> np.ndarray:
+    """8-byte aligned copy of `data` (the readers return views into the buffer)."""
+    arr = np.zeros((len(data) + 7) // 8, dtype=np.uint64)
+    arr.view(np.uint8)[: len(data)] = np.frombuffer(data, dtype=np.uint8)
+    return arr
+
+
+def _qap_host(n, m, n_input, rows, roots=None):
+    host, keep = _QapHost(), []
+    host.n, host.m, host.n_input = n, m, n_input
+    if roots is not None:
+        ra = roots if isinstance(roots, np.ndarray) else fr_limbs([r % FR_MODULUS for r in roots])
+        ra = np.ascontiguousarray(ra, dtype=np.uint64).reshape(n, 4)
+        keep.append(ra)
+        host.roots = ra.ctypes.data
+    else:
+        host.roots = None
+    for t, (ptr, gate, coeff) in enumerate(rows):
+        a = [np.ascontiguousarray(ptr, dtype=np.uint64), np.ascontiguousarray(gate, dtype=np.uint32),
+             np.ascontiguousarray(coeff, dtype=np.uint64)]
+        keep += a
+        host.row_ptr[t], host.gate[t], host.coeff[t] = (x.ctypes.data for x in a)
+    return host, keep
+
+
+def qap_to_bytes(n: int, m: int, n_input: int, rows, roots=None) -> bytes:
+    """Serialise a QAP given as CSR rows (the arguments of QAP(...)): kind 1 record."""
+    lib = load_library()
+    host, keep = _qap_host(n, m, n_input, rows, roots)
+    size = C.c_uint64()
+    _wire_check(lib.zkb_wire_size_qap(C.byref(host), C.byref(size)), "zkb_wire_size_qap")
+    buf = np.zeros(size.value, dtype=np.uint8)
+    _wire_check(lib.zkb_wire_write_qap(C.byref(host), _ptr(buf), size.value), "zkb_wire_write_qap")
+    del keep
+    return buf.tobytes()
+
+
+def qap_from_bytes(data: bytes):
+    """-> (n, m, n_input, rows, roots or None) with numpy arrays copied out of the record."""
+    lib = load_library()
+    buf = _aligned_copy(data)
+    host = _QapHost()
+    _wire_check(lib.zkb_wire_read_qap(_ptr(buf), len(data), C.byref(host)), "zkb_wire_read_qap")
+    n, m = int(host.n), int(host.m)
+    rows = []
+    for t in range(3):
+        ptr = np.ctypeslib.as_array(C.cast(host.row_ptr[t], C.POINTER(C.c_uint64)), shape=(m + 1,)).copy()
+        nnz = int(ptr[m])
+        gate = np.ctypeslib.as_array(C.cast(host.gate[t], C.POINTER(C.c_uint32)), shape=(max(nnz, 1),))[:nnz].copy()
+        coeff = np.ctypeslib.as_array(C.cast(host.coeff[t], C.POINTER(C.c_uint64)), shape=(max(nnz, 1) * 4,))[: nnz * 4].reshape(nnz, 4).copy()
+        rows.append((ptr, gate, coeff))
+    roots = None
+    if host.roots:
+        roots = np.ctypeslib.as_array(C.cast(host.roots, C.POINTER(C.c_uint64)), shape=(n * 4,)).reshape(n, 4).copy()
+    return n, m, int(host.n_input), rows, roots
+
+
+def qap_upload_bytes(ctx: Context, data: bytes) -> QAP:
+    """Upload a serialised QAP (zkb_wire_read_qap view -> zkb_qap_upload, no intermediate copies of the arrays)."""
+    buf = _aligned_copy(data)
+    host = _QapHost()
+    _wire_check(ctx.lib.zkb_wire_read_qap(_ptr(buf), len(data), C.byref(host)), "zkb_wire_read_qap")
+    q = QAP.__new__(QAP)
+    q.ctx, q.n, q.m, q.input, q.degree = ctx, int(host.n), int(host.m), int(host.n_input), int(host.n)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.zkb_qap_upload(ctx.h, C.byref(host), C.byref(h)), "zkb_qap_upload")
+    q.h = h
+    return q
+
+
+_CRS_SHAPES = (("alpha1", 8), ("beta1", 8), ("delta1", 8), ("xi1", 8), ("xi_t", 8), ("sum_gamma", 8), ("sum_delta", 8),
+               ("beta2", 16), ("gamma2", 16), ("delta2", 16), ("xi2", 16))
+
+
+def crs_raw_to_bytes(raw: dict) -> bytes:
+    """Serialise a CRS given as limb arrays in the zkb_crs_host layout (CRS.download_raw()): kind 2 record."""
+    lib = load_library()
+    host = _CrsHost()
+    host.n, host.n_sum_gamma, host.n_sum_delta = raw["xi1"].shape[0], raw["sum_gamma"].shape[0], raw["sum_delta"].shape[0]
+    keep = {k: np.ascontiguousarray(raw[k], dtype=np.uint64) for k, _ in _CRS_SHAPES}
+    for k, a in keep.items():
+        setattr(host, k, a.ctypes.data if a.size else None)
+    size = C.c_uint64()
+    _wire_check(lib.zkb_wire_size_crs(C.byref(host), C.byref(size)), "zkb_wire_size_crs")
+    buf = np.zeros(size.value, dtype=np.uint8)
+    _wire_check(lib.zkb_wire_write_crs(C.byref(host), _ptr(buf), size.value), "zkb_wire_write_crs")
+    return buf.tobytes()
+
+
+def crs_raw_from_bytes(data: bytes) -> dict:
+    lib = load_library()
+    buf = _aligned_copy(data)
+    host = _CrsHost()
+    _wire_check(lib.zkb_wire_read_crs(_ptr(buf), len(data), C.byref(host)), "zkb_wire_read_crs")
+    n, ng, nd = int(host.n), int(host.n_sum_gamma), int(host.n_sum_delta)
+    counts = {"alpha1": 1, "beta1": 1, "delta1": 1, "xi1": n, "xi_t": max(n - 1, 0), "sum_gamma": ng, "sum_delta": nd,
+              "beta2": 1, "gamma2": 1, "delta2": 1, "xi2": n}
+    out = {}
+    for k, w in _CRS_SHAPES:
+        c = counts[k]
+        p = getattr(host, k)
+        out[k] = (np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(c * w,)).reshape(c, w).copy() if c
+                  else np.zeros((0, w), dtype=np.uint64))
+    return out
+
+
+def crs_upload_bytes(ctx: Context, data: bytes, rank=0, world=1, comm=None) -> CRS:
+    """Upload a serialised CRS (whole, a contiguous shard, or -- with `comm` -- this rank's shard of a sharded proof)."""
+    buf = _aligned_copy(data)
+    host = _CrsHost()
+    _wire_check(ctx.lib.zkb_wire_read_crs(_ptr(buf), len(data), C.byref(host)), "zkb_wire_read_crs")
+    h = C.c_void_p()
+    if comm is not None:
+        ctx.check(ctx.lib.zkb_crs_upload_shard(ctx.h, comm.h, C.byref(host), C.byref(h)), "zkb_crs_upload_shard")
+        return CRS(ctx, h, comm.rank, comm.world)
+    ctx.check(ctx.lib.zkb_crs_upload(ctx.h, C.byref(host), rank, world, C.byref(h)), "zkb_crs_upload")
+    return CRS(ctx, h, rank, world)
+
+
+def proof_to_bytes(proof: Proof) -> bytes:
+    pc = _proof_c(proof)
+    buf = np.zeros(WIRE_PROOF_BYTES, dtype=np.uint8)
+    _wire_check(load_library().zkb_wire_write_proof(C.byref(pc), _ptr(buf), WIRE_PROOF_BYTES), "zkb_wire_write_proof")
+    return buf.tobytes()
+
+
+def proof_from_bytes(data: bytes) -> Proof:
+    buf = _aligned_copy(data)
+    pc = _ProofC()
+    _wire_check(load_library().zkb_wire_read_proof(_ptr(buf), len(data), C.byref(pc)), "zkb_wire_read_proof")
+    return _proof(pc)
+
+
+def wire_kind(data: bytes) -> int:
+    """1 QAP, 2 CRS, 3 Proof (after the header / length / checksum checks)."""
+    buf = _aligned_copy(data)
+    k, total = C.c_int(), C.c_uint64()
+    _wire_check(load_library().zkb_wire_kind(_ptr(buf), len(data), C.byref(k), C.byref(total)), "zkb_wire_kind")
+    return k.value
