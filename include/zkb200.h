@@ -219,6 +219,35 @@ int zkb_ntt_shard(zkb_ctx* ctx, zkb_comm* comm, uint64_t* d_local, uint32_t log_
 int zkb_qap_h(zkb_ctx* ctx, const zkb_qap* qap, const uint64_t* weights, uint64_t* u_sum,
               uint64_t* v_sum, uint64_t* h);
 
+/* ---- witness generation on the device: replaces `weights()` and `evaluate()`
+ * (groth16/circuit/mod.rs:529-656) and the builder's memoised `Circuit::evaluate` (circuit/builder/mod.rs:535-580).
+ * The reference evaluates `(= var (* lhs rhs))` assignment by assignment; on the QAP that is, per gate k,
+ *   a[out_k] = <u row of gate k, a> * <v row of gate k, a> / (w coefficient),   out_k = the single wire in gate k's w row.
+ * A plan levelises the gates once per circuit (level = 1 + the deepest producer of an input; free wires and the
+ * unity wire are level 0); zkb_witness_generate then runs one launch per wide level (one thread per gate) and one
+ * single-block launch per run of narrow levels.  Gates with an empty w row assign nothing and are skipped (padding
+ * gates of a re-indexed QAP).  free_wires: the wires whose values the caller supplies -- the `(in ...)` variables of
+ * the program (circuit/mod.rs:543-567), as indices into the weight vector (1 .. m-1; wire 0 is the constant 1).
+ * Errors (ZKB_ERR_ARG, message as in the reference): a wire assigned twice ("Attempted to assign to an already assigned
+ * variable", :601-606), a gate reading a wire nothing produces -- with ZKB_WITNESS_PROGRAM_ORDER also one only a LATER
+ * gate produces, which is what the sequential walk rejects -- ("Under constrained expression", :608-616), a wire
+ * nothing assigns ("Every variable should have an assignment", :630), "Wrong number of values supplied" (:553-558).
+ * Without the flag any topological order is accepted (the builder's demand-driven evaluate).  A gate with several
+ * wires in its w row is ZKB_ERR_UNSUPPORTED.  The plan borrows the QAP's device arrays: free it before the QAP. */
+typedef struct zkb_witness_plan zkb_witness_plan;
+#define ZKB_WITNESS_PROGRAM_ORDER 1
+int zkb_witness_plan_create(zkb_ctx* ctx, const zkb_qap* qap, const uint32_t* free_wires, size_t n_free, int flags,
+                            zkb_witness_plan** out);
+/* gates that assign a wire, levels (circuit depth), widest level, kernel launches per zkb_witness_generate; any may be NULL */
+int zkb_witness_plan_info(const zkb_witness_plan* plan, uint64_t* n_gates, uint64_t* n_levels, uint64_t* max_width,
+                          uint64_t* n_launches);
+/* values: n_values x 4 limbs canonical (host or device), in free_wires order.  weights_out: m x 4 limbs canonical --
+ * `[1] ++ assignments in wire order` (circuit/mod.rs:634-636) -- in host memory, or (out_on_device) in device memory
+ * where zkb_prove_dev / zkb_prove_batch(weights_on_device) read it without a host round trip. */
+int zkb_witness_generate(zkb_ctx* ctx, const zkb_witness_plan* plan, const uint64_t* values, size_t n_values,
+                         int values_on_device, uint64_t* weights_out, int out_on_device);
+void zkb_witness_plan_free(zkb_ctx* ctx, zkb_witness_plan* plan);
+
 /* ---- wire format: flat little-endian layout of QAP, CRS and Proof (host-only; no device is touched) -------------
  * The reference cannot serialise anything: QAP, SigmaG1, SigmaG2, Proof have private fields and no accessors
  * (groth16/mod.rs:60-128).  A prover service needs to (setup once, ship CRS + QAP to the GPU box, get proofs back), so:

@@ -342,3 +342,86 @@ def dummy_rep_from_legacy(F: Field, code: str) -> DummyRep:
             v[names.index(tok) + 1].append((g, one))
     roots = [F.from_usize(k) for k in range(1, count + 1)]
     return DummyRep(u=u, v=v, w=w, roots=roots, input=len(inputs))
+
+
+def input_wires(F: Field, code: str) -> list:
+    """Indices (into the weight vector) of the program's `(in ...)` variables, in their order of declaration:
+    weights()[i] belongs to variable_order()[i - 1] (circuit/mod.rs:625-636), so `in` variable v sits at
+    1 + variable_order().index(v)."""
+    exps = expressions(F, code)
+    order = variable_order(try_to_list(F, code))
+    return [1 + order.index(name) for (_, name) in exps[0][1]]
+
+
+def weights_from_rows(p: int, n: int, m: int, by_gate, free_wires: list, values: list, program_order: bool = True) -> list:
+    """The same walk as ``weights()`` / ``evaluate()`` (circuit/mod.rs:598-656), restated on the DummyRep rows instead
+    of the expression tree: gate k (= the k-th assignment `(= var (* lhs rhs))`) computes
+        a[out_k] = (sum of coeff * a[wire] over gate k's u entries) * (same over its v entries) / (w coefficient),
+    out_k the single wire of gate k's w row.  ``by_gate``: for u, v, w a list (per gate) of [(wire, coeff)].  Errors as
+    the reference's: assigning twice, reading a wire without a value ("Under constrained expression"), a wire nothing
+    assigns, wrong number of values.  ``program_order=False``: gates may appear in any order (the builder's demand-driven
+    ``evaluate``, builder/mod.rs:556-580); evaluated by repeated sweeps."""
+    if len(free_wires) != len(values):
+        raise ParseErr("Wrong number of values supplied")
+    a = [None] * m
+    a[0] = 1
+    for w, val in zip(free_wires, values):
+        if a[w] is not None:
+            raise ParseErr("Attempted to assign to an already assigned variable")
+        a[w] = val % p
+    gu, gv, gw = by_gate
+    outs = set()
+    for k in range(n):
+        if len(gw[k]) == 1:
+            w = gw[k][0][0]
+            if a[w] is not None or w in outs:
+                raise ParseErr("Attempted to assign to an already assigned variable")
+            outs.add(w)
+        elif len(gw[k]) > 1:
+            raise ParseErr("more than one output wire")
+    pending = [k for k in range(n) if len(gw[k]) == 1]
+    while pending:
+        later = []
+        for k in pending:
+            terms = [a[w] for w, _ in gu[k]] + [a[w] for w, _ in gv[k]]
+            if any(t is None for t in terms):
+                if program_order:
+                    raise ParseErr("Under constrained expression")
+                later.append(k)
+                continue
+            su = sum(c * a[w] for w, c in gu[k]) % p
+            sv = sum(c * a[w] for w, c in gv[k]) % p
+            w, c = gw[k][0]
+            a[w] = su * sv * pow(c, -1, p) % p
+        if len(later) == len(pending):
+            raise ParseErr("Under constrained expression")
+        pending = later
+    if any(x is None for x in a):
+        raise ParseErr("Every variable should have an assignment")
+    return a
+
+
+def rep_by_gate(rep: DummyRep) -> tuple:
+    """DummyRep rows (per wire: [(root, value)]) -> per gate [(wire, value)], gate k <-> rep.roots[k]."""
+    index = {r: k for k, r in enumerate(rep.roots)}
+    out = []
+    for mat in (rep.u, rep.v, rep.w):
+        g = [[] for _ in rep.roots]
+        for wire, row in enumerate(mat):
+            for r, c in row:
+                g[index[r]].append((wire, c))
+        out.append(g)
+    return tuple(out)
+
+
+def csr_by_gate(n: int, m: int, rows) -> tuple:
+    """CSR triples by wire (row_ptr, gate, coeff limbs) x (u, v, w) -> per gate [(wire, coeff int)]."""
+    out = []
+    for ptr, gate, coeff in rows:
+        g = [[] for _ in range(n)]
+        for wire in range(m):
+            for e in range(int(ptr[wire]), int(ptr[wire + 1])):
+                c = sum(int(coeff[e][j]) << (64 * j) for j in range(4))
+                g[int(gate[e])].append((wire, c))
+        out.append(g)
+    return tuple(out)

@@ -9,8 +9,10 @@ computes raises ``ZkbError`` unless the CUDA library is built and a B200 is pres
 
 from .groth16 import (CRS, QAP, Bases, Context, Proof, ZkbError, fr_limbs, horner_qap_rows, lib_path,
                       load_library, msm, ntt, prove, prove_batch, prove_partial, prove_combine, prove_combine_batch, qap_h, setup, verify, verify_batch, pairing,
-                      Comm, setup_shard, crs_upload_shard, prove_shard, prove_shard_batch, prove_shard_enqueue, prove_shard_collect, ntt_shard)
+                      Comm, setup_shard, crs_upload_shard, prove_shard, prove_shard_batch, prove_shard_enqueue, prove_shard_collect, ntt_shard,
+                      WitnessPlan, weights, witness_generate_raw, witness_generate_dev, layered_qap_rows)
 
 __all__ = ["CRS", "QAP", "Bases", "Context", "Proof", "ZkbError", "fr_limbs", "horner_qap_rows", "lib_path",
            "load_library", "msm", "ntt", "prove", "prove_batch", "prove_partial", "prove_combine", "prove_combine_batch", "qap_h", "setup", "verify", "verify_batch", "pairing",
-           "Comm", "setup_shard", "crs_upload_shard", "prove_shard", "prove_shard_batch", "prove_shard_enqueue", "prove_shard_collect", "ntt_shard"]
+           "Comm", "setup_shard", "crs_upload_shard", "prove_shard", "prove_shard_batch", "prove_shard_enqueue", "prove_shard_collect", "ntt_shard",
+           "WitnessPlan", "weights", "witness_generate_raw", "witness_generate_dev", "layered_qap_rows"]

@@ -292,6 +292,8 @@ struct zkb_qap {
   uint32_t* d_gate[3] = {};
   zkb::Fr* d_rcoeff[3] = {};  // Montgomery, in row order
   uint64_t nnz[3] = {};
+  // host copy of the by-gate structure (offsets and wires, no coefficients): the witness planner levelises it (witness.cu)
+  std::vector<uint32_t> h_gptr[3], h_wire[3];
   // coset tables in bit-reversed position order: P[i] = g^br(i) / n, Q[i] = g^-br(i) / (2n), g = omega_2n
   zkb::Fr* d_cosP = nullptr;
   zkb::Fr* d_cosQ = nullptr;

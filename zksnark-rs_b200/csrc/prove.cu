@@ -370,6 +370,8 @@ int zkb_qap_upload(zkb_ctx* ctx, const zkb_qap_host* h, zkb_qap** out) {
     if (e != cudaSuccess) return fail(set_err(ctx, ZKB_ERR_CUDA, "qap upload copy: %s", cudaGetErrorString(e)));
     rc = vec_to_mont(ctx, q->d_coeff[t], nnz, true, st);
     if (rc == ZKB_OK) rc = vec_to_mont(ctx, q->d_rcoeff[t], nnz, true, st);
+    q->h_gptr[t] = std::move(gptr);
+    q->h_wire[t] = std::move(wire);
   }
   if (rc != ZKB_OK) return fail(rc);
   q->generic = generic;

@@ -1,0 +1,334 @@
+// Witness generation on the device: replaces `weights()` + `evaluate()`
+// (/root/reference/src/groth16/circuit/mod.rs:529-656) and the builder's memoised `Circuit::evaluate`
+// (circuit/builder/mod.rs:535-580).
+//
+// The reference walks the program's `(= var (* lhs rhs))` assignments one after the other, each side a
+// literal / variable / `+` list of literal-weighted variables (circuit/mod.rs:639-656).  In the QAP data
+// model that is, per gate k:   a[out_k] = <u row of gate k, a> * <v row of gate k, a>   with out_k the
+// single wire of gate k's w row -- the by-gate CSR rows that k_matvec (prove.cu) reads anyway.  Gates
+// whose inputs are all known are independent, so the device evaluates the circuit LEVEL BY LEVEL:
+//   plan (host, once per circuit and choice of free wires): level(k) = 1 + max level of the gates that
+//     produce k's inputs (free wires and the unity wire: level 0); gates counting-sorted by level; the
+//     u / v entries of the gates copied into a level-ordered CSR on the device (one contiguous read per
+//     level instead of three dependent gathers per gate);
+//   generate (device, per witness): scatter the free values, then one launch per WIDE level (one thread
+//     per gate) and one single-block launch per RUN of consecutive narrow levels (block-wide barrier
+//     between levels: a depth-d chain costs d barriers instead of d launches).
+// Error behaviour mirrors the reference: assigning a wire twice, reading a wire no gate has produced
+// ("Under constrained expression"; with ZKB_WITNESS_PROGRAM_ORDER also a wire only a LATER gate produces,
+// which is what the sequential walk of circuit/mod.rs:598-621 rejects), a wire nothing assigns, the wrong
+// number of values.
+#include <string.h>
+#include <algorithm>
+#include "common.cuh"
+
+struct zkb_witness_plan {
+  uint64_t m = 0, n_gates = 0, n_free = 0, n_levels = 0, max_width = 0, nnz = 0;
+  uint32_t* d_free = nullptr;   // n_free wire indices
+  uint32_t* d_ptr = nullptr;    // 2 * n_gates + 1: [2g] start of the u entries of plan gate g, [2g+1] start of its v entries
+  uint32_t* d_wire = nullptr;   // nnz
+  zkb::Fr* d_coef = nullptr;    // nnz, Montgomery
+  uint32_t* d_out = nullptr;    // n_gates: output wire
+  zkb::Fr* d_winv = nullptr;    // n_gates: 1 / (w coefficient), only when some coefficient != 1
+  uint32_t* d_lptr = nullptr;   // n_levels + 1: plan-gate range of every level
+  struct Seg { uint32_t l0, l1; bool wide; };
+  std::vector<Seg> segs;        // launch schedule
+  std::vector<uint32_t> h_lptr;
+};
+
+namespace zkb {
+
+static const uint32_t WIT_NARROW = 512;  // levels up to this many gates are chained inside one block
+
+__device__ __forceinline__ void wit_gate(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ wire,
+                                         const Fr* __restrict__ coef, const uint32_t* __restrict__ out,
+                                         const Fr* __restrict__ winv, Fr* a, uint32_t g) {
+  const uint32_t pu = ptr[2 * g], pv = ptr[2 * g + 1], pe = ptr[2 * g + 2];
+  Fr su = Fr::zero(), sv = Fr::zero();
+  for (uint32_t p = pu; p < pv; p++) su = su + coef[p] * a[wire[p]];
+  for (uint32_t p = pv; p < pe; p++) sv = sv + coef[p] * a[wire[p]];
+  Fr r = su * sv;
+  if (winv) r = r * winv[g];
+  a[out[g]] = r;
+}
+
+// one wide level: plan gates [g0, g1), one thread each
+__global__ void k_wit_level(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ wire, const Fr* __restrict__ coef,
+                            const uint32_t* __restrict__ out, const Fr* __restrict__ winv, Fr* a, uint32_t g0, uint32_t g1) {
+  const uint32_t g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < g1) wit_gate(ptr, wire, coef, out, winv, a, g);
+}
+
+// a run of narrow levels [l0, l1) in ONE block: the stores of level l are visible to the block after the barrier
+__global__ void __launch_bounds__(WIT_NARROW) k_wit_run(const uint32_t* __restrict__ lptr, const uint32_t* __restrict__ ptr,
+                                                        const uint32_t* __restrict__ wire, const Fr* __restrict__ coef,
+                                                        const uint32_t* __restrict__ out, const Fr* __restrict__ winv, Fr* a,
+                                                        uint32_t l0, uint32_t l1) {
+  uint32_t lo = lptr[l0];
+  for (uint32_t l = l0; l < l1; l++) {
+    const uint32_t hi = lptr[l + 1];
+    const uint32_t g = lo + threadIdx.x;
+    if (g < hi) wit_gate(ptr, wire, coef, out, winv, a, g);
+    lo = hi;
+    __syncthreads();
+  }
+}
+
+// a[] = 0 except the unity wire; the caller's values (canonical) go to the free wires
+__global__ void k_wit_init(Fr* __restrict__ a, size_t m, const uint32_t* __restrict__ free_w, const Fr* __restrict__ vals, size_t n_free) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_free) a[free_w[i]] = to_mont(vals[i]);
+  if (i == 0) a[0] = Fr::one();
+}
+
+// plan construction: entries of plan gate g <- the by-gate rows of QAP gate order[g]
+__global__ void k_wit_gather(const uint32_t* __restrict__ order, const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ gptr_u,
+                             const uint32_t* __restrict__ wire_u, const Fr* __restrict__ coef_u, const uint32_t* __restrict__ gptr_v,
+                             const uint32_t* __restrict__ wire_v, const Fr* __restrict__ coef_v, const uint32_t* __restrict__ gptr_w,
+                             const Fr* __restrict__ coef_w, uint32_t* __restrict__ wire, Fr* __restrict__ coef, Fr* __restrict__ winv,
+                             size_t n_gates) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_gates) return;
+  const uint32_t k = order[g];
+  uint32_t o = ptr[2 * g];
+  for (uint32_t p = gptr_u[k], e = gptr_u[k + 1]; p < e; p++, o++) { wire[o] = wire_u[p]; coef[o] = coef_u[p]; }
+  for (uint32_t p = gptr_v[k], e = gptr_v[k + 1]; p < e; p++, o++) { wire[o] = wire_v[p]; coef[o] = coef_v[p]; }
+  if (winv) winv[g] = inverse(coef_w[gptr_w[k]]);
+}
+
+__global__ void k_wit_any_not_one(const Fr* __restrict__ c, size_t n, int* flag) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(c[i] == Fr::one())) *flag = 1;
+}
+
+}  // namespace zkb
+
+using namespace zkb;
+
+extern "C" {
+
+void zkb_witness_plan_free(zkb_ctx* ctx, zkb_witness_plan* p) {
+  if (!p) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(p->d_free); cudaFree(p->d_ptr); cudaFree(p->d_wire); cudaFree(p->d_coef);
+  cudaFree(p->d_out); cudaFree(p->d_winv); cudaFree(p->d_lptr);
+  delete p;
+}
+
+int zkb_witness_plan_create(zkb_ctx* ctx, const zkb_qap* q, const uint32_t* free_wires, size_t n_free, int flags,
+                            zkb_witness_plan** out) {
+  if (!ctx || !q || !out || (n_free && !free_wires)) return set_err(ctx, ZKB_ERR_ARG, "zkb_witness_plan_create: NULL argument");
+  *out = nullptr;
+  const uint64_t n = q->n, m = q->m;
+  const bool program_order = (flags & ZKB_WITNESS_PROGRAM_ORDER) != 0;
+  const std::vector<uint32_t>*gp = q->h_gptr, *gw = q->h_wire;
+  if (gp[0].size() != n + 1 || gp[1].size() != n + 1 || gp[2].size() != n + 1)
+    return set_err(ctx, ZKB_ERR_ARG, "zkb_witness_plan_create: the QAP carries no host copy of its by-gate rows");
+  // wire state: NONE = nothing assigns it (yet); otherwise the level at which its value exists
+  const uint32_t NONE = 0xffffffffu;
+  std::vector<uint32_t> wlevel(m, NONE), producer(m, NONE);
+  wlevel[0] = 0;  // the unity wire (`once(F::one())`, circuit/mod.rs:634)
+  for (size_t i = 0; i < n_free; i++) {
+    uint32_t w = free_wires[i];
+    if (w == 0 || w >= m) return set_err(ctx, ZKB_ERR_ARG, "witness plan: free wire %u out of range [1, %llu)", w, (unsigned long long)m);
+    if (wlevel[w] != NONE) return set_err(ctx, ZKB_ERR_ARG, "witness plan: free wire %u listed twice", w);
+    wlevel[w] = 0;
+  }
+  // output wire of every gate: the single entry of its w row.  Gates without a w entry assign nothing (padding gates
+  // 0 * 0 = 0 of a re-indexed QAP, or pure constraints) and are skipped.
+  std::vector<uint32_t> outw(n, NONE);
+  uint64_t n_gates = 0;
+  for (uint64_t k = 0; k < n; k++) {
+    uint32_t cnt = gp[2][k + 1] - gp[2][k];
+    if (cnt == 0) continue;
+    if (cnt != 1)
+      return set_err(ctx, ZKB_ERR_UNSUPPORTED, "witness plan: gate %llu has %u wires in its w row; evaluation needs exactly one output "
+                     "wire per gate (the form `(= var (* lhs rhs))` produces, circuit/mod.rs:300-340)", (unsigned long long)k, cnt);
+    uint32_t w = gw[2][gp[2][k]];
+    if (wlevel[w] != NONE || producer[w] != NONE)  // circuit/mod.rs:601-606
+      return set_err(ctx, ZKB_ERR_ARG, "witness plan: gate %llu: Attempted to assign to an already assigned variable (wire %u)",
+                     (unsigned long long)k, w);
+    producer[w] = (uint32_t)k;
+    outw[k] = w;
+    n_gates++;
+  }
+  // levels
+  std::vector<uint32_t> glevel(n, NONE);
+  auto input_level = [&](uint64_t k, uint32_t w, uint32_t* lv) -> int {  // level at which wire w exists, for gate k
+    if (wlevel[w] != NONE) { *lv = wlevel[w]; return ZKB_OK; }
+    return set_err(ctx, ZKB_ERR_ARG, "witness plan: gate %llu: Under constrained expression (wire %u has no value%s)",
+                   (unsigned long long)k, w, producer[w] != NONE ? " yet: a later gate assigns it" : "");
+  };
+  if (program_order) {
+    for (uint64_t k = 0; k < n; k++) {
+      if (outw[k] == NONE) continue;
+      uint32_t lv = 0;
+      for (int t = 0; t < 2; t++)
+        for (uint32_t p = gp[t][k]; p < gp[t][k + 1]; p++) {
+          uint32_t l;
+          ZKB_TRY(input_level(k, gw[t][p], &l));
+          lv = std::max(lv, l);
+        }
+      glevel[k] = lv + 1;
+      wlevel[outw[k]] = lv + 1;
+    }
+  } else {
+    // any topological order (the builder's demand-driven evaluate, builder/mod.rs:556-580): depth-first with an explicit stack
+    std::vector<uint8_t> state(n, 0);  // 0 new, 1 on the stack, 2 done
+    std::vector<uint64_t> stack;
+    for (uint64_t k0 = 0; k0 < n; k0++) {
+      if (outw[k0] == NONE || state[k0] == 2) continue;
+      stack.push_back(k0);
+      while (!stack.empty()) {
+        uint64_t k = stack.back();
+        if (state[k] == 2) { stack.pop_back(); continue; }
+        state[k] = 1;
+        uint32_t lv = 0;
+        bool ready = true;
+        for (int t = 0; t < 2 && ready; t++)
+          for (uint32_t p = gp[t][k]; p < gp[t][k + 1]; p++) {
+            uint32_t w = gw[t][p];
+            if (wlevel[w] != NONE) { lv = std::max(lv, wlevel[w]); continue; }
+            uint32_t pk = producer[w];
+            if (pk == NONE) { uint32_t l; return input_level(k, w, &l); }
+            if (state[pk] == 1)
+              return set_err(ctx, ZKB_ERR_ARG, "witness plan: gates %llu and %u depend on each other (Under constrained expression)",
+                             (unsigned long long)k, pk);
+            stack.push_back(pk);
+            ready = false;
+            break;
+          }
+        if (!ready) continue;
+        glevel[k] = lv + 1;
+        wlevel[outw[k]] = lv + 1;
+        state[k] = 2;
+        stack.pop_back();
+      }
+    }
+  }
+  for (uint64_t w = 1; w < m; w++)
+    if (wlevel[w] == NONE)  // `.expect("Every variable should have an assignment")`, circuit/mod.rs:630
+      return set_err(ctx, ZKB_ERR_ARG, "witness plan: Every variable should have an assignment (wire %llu has none)", (unsigned long long)w);
+  // counting sort of the gates by level
+  uint32_t n_levels = 0;
+  for (uint64_t k = 0; k < n; k++)
+    if (glevel[k] != NONE) n_levels = std::max(n_levels, glevel[k]);
+  std::vector<uint32_t> lptr(n_levels + 1, 0);
+  for (uint64_t k = 0; k < n; k++)
+    if (glevel[k] != NONE) lptr[glevel[k]]++;  // level l (1-based) -> slot l; prefix sums below shift it to [l-1]
+  for (uint32_t l = 1; l <= n_levels; l++) lptr[l] += lptr[l - 1];
+  // now lptr[l] = number of gates with level <= l, i.e. END of level l (1-based) = start of plan level index l
+  std::vector<uint32_t> order(n_gates ? n_gates : 1), cur(lptr.begin(), lptr.end());
+  for (uint64_t k = 0; k < n; k++)
+    if (glevel[k] != NONE) order[cur[glevel[k] - 1]++] = (uint32_t)k;
+  std::vector<uint32_t> ptr(2 * n_gates + 1), outs(n_gates ? n_gates : 1);
+  uint64_t nnz = 0;
+  for (uint64_t g = 0; g < n_gates; g++) {
+    uint32_t k = order[g];
+    ptr[2 * g] = (uint32_t)nnz;
+    nnz += gp[0][k + 1] - gp[0][k];
+    ptr[2 * g + 1] = (uint32_t)nnz;
+    nnz += gp[1][k + 1] - gp[1][k];
+    outs[g] = outw[k];
+  }
+  ptr[2 * n_gates] = (uint32_t)nnz;
+  if (nnz >= ((uint64_t)1 << 32)) return set_err(ctx, ZKB_ERR_ARG, "witness plan: too many entries");
+
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  zkb_witness_plan* p = new zkb_witness_plan();
+  p->m = m; p->n_gates = n_gates; p->n_free = n_free; p->n_levels = n_levels; p->nnz = nnz;
+  p->h_lptr = lptr;
+  for (uint32_t l = 0; l < n_levels; l++) p->max_width = std::max<uint64_t>(p->max_width, lptr[l + 1] - lptr[l]);
+  // launch schedule: runs of narrow levels share one single-block launch
+  for (uint32_t l = 0; l < n_levels;) {
+    if (lptr[l + 1] - lptr[l] > WIT_NARROW) { p->segs.push_back({l, l + 1, true}); l++; continue; }
+    uint32_t e = l;
+    while (e < n_levels && lptr[e + 1] - lptr[e] <= WIT_NARROW) e++;
+    p->segs.push_back({l, e, false});
+    l = e;
+  }
+  cudaStream_t st = ctx->stream;
+  auto fail = [&](int code) { zkb_witness_plan_free(ctx, p); return code; };
+  void* vp;
+  int rc = scratch_get(ctx, 12, (n_gates + 1) * 4 + sizeof(int), &vp);
+  if (rc != ZKB_OK) return fail(rc);
+  uint32_t* d_order = (uint32_t*)vp;
+  int* d_flag = (int*)(d_order + n_gates + 1);
+  if (cudaMalloc(&p->d_free, (n_free + 1) * 4) || cudaMalloc(&p->d_ptr, (2 * n_gates + 1) * 4) || cudaMalloc(&p->d_wire, (nnz + 1) * 4) ||
+      cudaMalloc(&p->d_coef, (nnz + 1) * 32) || cudaMalloc(&p->d_out, (n_gates + 1) * 4) || cudaMalloc(&p->d_lptr, (n_levels + 1) * 4))
+    return fail(set_err(ctx, ZKB_ERR_ALLOC, "witness plan: cudaMalloc failed"));
+  if (n_free) cudaMemcpyAsync(p->d_free, free_wires, n_free * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(p->d_ptr, ptr.data(), (2 * n_gates + 1) * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(p->d_lptr, lptr.data(), (n_levels + 1) * 4, cudaMemcpyHostToDevice, st);
+  if (n_gates) {
+    cudaMemcpyAsync(p->d_out, outs.data(), n_gates * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_order, order.data(), n_gates * 4, cudaMemcpyHostToDevice, st);
+  }
+  cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+  int flag = 0;
+  if (q->nnz[2]) {
+    k_wit_any_not_one<<<cdiv(q->nnz[2], 256), 256, 0, st>>>(q->d_coeff[2], q->nnz[2], d_flag);
+    ctx->launches++;
+  }
+  cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);  // host vectors go out of scope; flag decides the allocation below
+  if (e != cudaSuccess) return fail(set_err(ctx, ZKB_ERR_CUDA, "witness plan upload: %s", cudaGetErrorString(e)));
+  if (flag && cudaMalloc(&p->d_winv, (n_gates + 1) * 32)) return fail(set_err(ctx, ZKB_ERR_ALLOC, "witness plan: cudaMalloc failed"));
+  if (n_gates) {
+    k_wit_gather<<<cdiv(n_gates, 128), 128, 0, st>>>(d_order, p->d_ptr, q->d_gptr[0], q->d_wire[0], q->d_coeff[0], q->d_gptr[1],
+                                                     q->d_wire[1], q->d_coeff[1], q->d_gptr[2], q->d_coeff[2], p->d_wire, p->d_coef,
+                                                     p->d_winv, (size_t)n_gates);
+    ctx->launches++;
+  }
+  e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(set_err(ctx, ZKB_ERR_CUDA, "witness plan gather: %s", cudaGetErrorString(e)));
+  *out = p;
+  return ZKB_OK;
+}
+
+int zkb_witness_plan_info(const zkb_witness_plan* p, uint64_t* n_gates, uint64_t* n_levels, uint64_t* max_width, uint64_t* n_launches) {
+  if (!p) return set_err(nullptr, ZKB_ERR_ARG, "zkb_witness_plan_info: NULL plan");
+  if (n_gates) *n_gates = p->n_gates;
+  if (n_levels) *n_levels = p->n_levels;
+  if (max_width) *max_width = p->max_width;
+  if (n_launches) *n_launches = p->segs.size() + 2;  // + k_wit_init and the Montgomery -> canonical conversion
+  return ZKB_OK;
+}
+
+int zkb_witness_generate(zkb_ctx* ctx, const zkb_witness_plan* p, const uint64_t* values, size_t n_values, int values_on_device,
+                         uint64_t* weights_out, int out_on_device) {
+  if (!ctx || !p || !weights_out || (p->n_free && !values)) return set_err(ctx, ZKB_ERR_ARG, "zkb_witness_generate: NULL argument");
+  if (n_values != p->n_free)  // circuit/mod.rs:553-558
+    return set_err(ctx, ZKB_ERR_ARG, "zkb_witness_generate: Wrong number of values supplied (%zu for %llu free wires)", n_values,
+                   (unsigned long long)p->n_free);
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t m = p->m;
+  Fr* a;
+  void* vp;
+  if (out_on_device) a = (Fr*)weights_out;
+  else { ZKB_TRY(scratch_get(ctx, 11, m * sizeof(Fr), &vp)); a = (Fr*)vp; }
+  const Fr* d_vals = (const Fr*)values;
+  if (!values_on_device && p->n_free) {
+    ZKB_TRY(scratch_get(ctx, 12, p->n_free * sizeof(Fr), &vp));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(vp, values, p->n_free * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    d_vals = (const Fr*)vp;
+  }
+  ZKB_CUDA(ctx, cudaMemsetAsync(a, 0, m * sizeof(Fr), st));
+  ZKB_LAUNCH(ctx, k_wit_init, cdiv(std::max<size_t>(p->n_free, 1), 256), 256, 0, st, a, m, p->d_free, d_vals, (size_t)p->n_free);
+  for (const auto& s : p->segs) {
+    if (s.wide) {
+      const uint32_t g0 = p->h_lptr[s.l0], g1 = p->h_lptr[s.l1];
+      ZKB_LAUNCH(ctx, k_wit_level, cdiv(g1 - g0, 128), 128, 0, st, p->d_ptr, p->d_wire, p->d_coef, p->d_out, p->d_winv, a, g0, g1);
+    } else {
+      ZKB_LAUNCH(ctx, k_wit_run, 1, WIT_NARROW, 0, st, p->d_lptr, p->d_ptr, p->d_wire, p->d_coef, p->d_out, p->d_winv, a, s.l0, s.l1);
+    }
+  }
+  ZKB_TRY(vec_to_mont(ctx, a, m, false, st));
+  if (!out_on_device) ZKB_CUDA(ctx, cudaMemcpyAsync(weights_out, a, m * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
+}  // extern "C"

@@ -116,7 +116,12 @@ ABI = {
     "zkb_wire_read_crs": (C.c_int, [_P, C.c_uint64, C.POINTER(_CrsHost)]),
     "zkb_wire_write_proof": (C.c_int, [C.POINTER(_ProofC), _P, C.c_uint64]),
     "zkb_wire_read_proof": (C.c_int, [_P, C.c_uint64, C.POINTER(_ProofC)]),
+    "zkb_witness_plan_create": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int, C.POINTER(_P)]),
+    "zkb_witness_plan_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "zkb_witness_generate": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int, _P, C.c_int]),
+    "zkb_witness_plan_free": (None, [_P, _P]),
 }
+WITNESS_PROGRAM_ORDER = 1
 WIRE_PROOF_BYTES = 320
 COMM_HANDLE_BYTES = 128
 
@@ -1045,3 +1050,94 @@ def wire_kind(data: bytes) -> int:
     k, total = C.c_int(), C.c_uint64()
     _wire_check(load_library().zkb_wire_kind(_ptr(buf), len(data), C.byref(k), C.byref(total)), "zkb_wire_kind")
     return k.value
+
+
+# ------------------------------------------------------------------------------------------------
+# witness generation on the device: `weights()` / `evaluate()` (circuit/mod.rs:529-656)
+class WitnessPlan:
+    """Levelised evaluation plan of a circuit: which wires the caller supplies (``free_wires``: the program's
+    ``(in ...)`` variables as indices into the weight vector) and, per level, the gates whose inputs are known.
+    ``program_order=True`` mirrors `weights()` exactly (a gate may only read wires assigned by EARLIER gates,
+    circuit/mod.rs:598-621); False accepts any topological order (the builder's `evaluate`, builder/mod.rs:556-580)."""
+
+    def __init__(self, ctx: Context, qap: QAP, free_wires, program_order: bool = True):
+        self.ctx, self.qap = ctx, qap  # the plan borrows the QAP's device arrays
+        fw = np.ascontiguousarray(np.asarray(list(free_wires), dtype=np.int64).astype(np.uint32))
+        self.n_free = int(fw.size)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.zkb_witness_plan_create(ctx.h, qap.h, fw.ctypes.data if fw.size else None, fw.size,
+                                                  WITNESS_PROGRAM_ORDER if program_order else 0, C.byref(h)), "zkb_witness_plan_create")
+        self.h = h
+
+    def info(self) -> dict:
+        v = [C.c_uint64() for _ in range(4)]
+        self.ctx.check(self.ctx.lib.zkb_witness_plan_info(self.h, *[C.byref(x) for x in v]), "zkb_witness_plan_info")
+        return dict(zip(("n_gates", "n_levels", "max_width", "n_launches"), (int(x.value) for x in v)))
+
+    def free(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.zkb_witness_plan_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def witness_generate_raw(ctx: Context, plan: WitnessPlan, values) -> np.ndarray:
+    """-> (m, 4) uint64 canonical limbs (host)."""
+    vals = values if isinstance(values, np.ndarray) else fr_limbs([v % FR_MODULUS for v in values])
+    vals = np.ascontiguousarray(vals, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty((plan.qap.m, 4), dtype=np.uint64)
+    ctx.check(ctx.lib.zkb_witness_generate(ctx.h, plan.h, vals.ctypes.data if vals.size else None, vals.shape[0], 0,
+                                           out.ctypes.data, 0), "zkb_witness_generate")
+    return out
+
+
+def weights(ctx: Context, plan: WitnessPlan, values) -> list:
+    """`groth16::weights(code, values)` (circuit/mod.rs:529-637) with the parse already done: values of the `in`
+    variables in plan order -> [1, every wire's assignment] as ints."""
+    return limbs_to_ints(witness_generate_raw(ctx, plan, values))
+
+
+def witness_generate_dev(ctx: Context, plan: WitnessPlan, d_values: int, n_values: int, d_out: int):
+    """Values and result in device memory (canonical limbs); d_out feeds prove_dev / prove_batch(on_device=True)."""
+    ctx.check(ctx.lib.zkb_witness_generate(ctx.h, plan.h, d_values, n_values, 1, d_out, 1), "zkb_witness_generate")
+
+
+def layered_qap_rows(width: int, depth: int, fan_in: int = 2, seed: int = 1):
+    """Synthetic WIDE circuit for witness generation (the Horner family is a depth-n chain): `depth` layers of `width`
+    gates; gate j of layer l multiplies two sums of `fan_in` wires each, drawn (seeded) from the previous layer's
+    outputs -- layer 0 from the `width` free input wires -- with small literal weights.  Wire order: 0 unity,
+    1..width inputs, then the gate outputs in gate order (gate k -> wire width + 1 + k); n = width * depth gates.
+    Returns (n, m, n_input, rows, free_wires).  Vectorised: builds 2^20 gates in about a second."""
+    rng = np.random.default_rng(seed)
+    n = width * depth
+    m = 1 + width + n
+    gate = np.repeat(np.arange(n, dtype=np.int64), fan_in)
+    layer = gate // width
+    base = np.where(layer == 0, 1, 1 + width + (layer - 1) * width)  # first wire of the previous layer
+    rows = []
+    for _ in range(2):  # u, v
+        wire = base + rng.integers(0, width, size=n * fan_in)
+        coef = rng.integers(1, 8, size=n * fan_in).astype(np.uint64)
+        # merge duplicate (wire, gate) pairs: a by-wire row holds one entry per gate
+        key = wire * n + gate
+        uniq, inv = np.unique(key, return_inverse=True)
+        csum = np.zeros(uniq.size, dtype=np.uint64)
+        np.add.at(csum, inv, coef)
+        w_u, g_u = uniq // n, uniq % n  # sorted by wire, then gate
+        ptr = np.zeros(m + 1, dtype=np.uint64)
+        np.add.at(ptr, w_u + 1, 1)
+        ptr = np.cumsum(ptr).astype(np.uint64)
+        limbs = np.zeros((uniq.size, 4), dtype=np.uint64)
+        limbs[:, 0] = csum
+        rows.append((ptr, g_u.astype(np.uint32), limbs))
+    pw = np.zeros(m + 1, dtype=np.uint64)
+    pw[1 + width + 1:] = np.arange(1, n + 1, dtype=np.uint64)
+    one = np.zeros((n, 4), dtype=np.uint64)
+    one[:, 0] = 1
+    rows.append((pw, np.arange(n, dtype=np.uint32), one))
+    return n, m, width, rows, list(range(1, width + 1))
