@@ -343,6 +343,37 @@ inline bool verify(Context& ctx, const Sigma& sigma, const std::vector<Fr>& inpu
   return ok == 1;
 }
 
+// `weights()` / `evaluate()` (circuit/mod.rs:529-656) on the device, the parse already done: `input_wires` are the
+// positions of the program's `(in ...)` variables in the weight vector, in declaration order.  The plan levelises the
+// circuit once; weights(values) evaluates it for one assignment of the inputs -> [1, every wire's value in wire order].
+// program_order = true rejects what the reference's sequential walk rejects (a gate reading a wire a later gate assigns).
+class WitnessPlan {
+ public:
+  WitnessPlan(Context& ctx, const QAP& qap, const std::vector<uint32_t>& input_wires, bool program_order = true)
+      : ctx_(&ctx), m_(qap.rows()), n_in_(input_wires.size()) {
+    ctx.check(zkb_witness_plan_create(ctx.get(), qap.get(), input_wires.data(), input_wires.size(),
+                                      program_order ? ZKB_WITNESS_PROGRAM_ORDER : 0, &h_), "zkb_witness_plan_create");
+  }
+  WitnessPlan(WitnessPlan&& o) noexcept : ctx_(o.ctx_), h_(o.h_), m_(o.m_), n_in_(o.n_in_) { o.h_ = nullptr; }
+  WitnessPlan(const WitnessPlan&) = delete;
+  ~WitnessPlan() { if (h_) zkb_witness_plan_free(ctx_->get(), h_); }
+  std::vector<Fr> weights(const std::vector<Fr>& values) const {
+    std::vector<uint64_t> in(4 * values.size() + 4, 0), out(4 * m_);
+    for (size_t i = 0; i < values.size(); i++) memcpy(&in[4 * i], values[i].l.data(), 32);
+    ctx_->check(zkb_witness_generate(ctx_->get(), h_, in.data(), values.size(), 0, out.data(), 0), "zkb_witness_generate");
+    std::vector<Fr> w(m_);
+    for (size_t i = 0; i < m_; i++) memcpy(w[i].l.data(), &out[4 * i], 32);
+    return w;
+  }
+  uint64_t levels() const { uint64_t l = 0; zkb_witness_plan_info(h_, nullptr, &l, nullptr, nullptr); return l; }
+  const zkb_witness_plan* get() const { return h_; }
+
+ private:
+  Context* ctx_;
+  zkb_witness_plan* h_ = nullptr;
+  size_t m_, n_in_;
+};
+
 // One verdict per (inputs[i], proofs[i]) against the same CRS, every inputs[i] of the same length (zkb_verify_batch).
 inline std::vector<bool> verify_many(Context& ctx, const Sigma& sigma, const std::vector<std::vector<Fr>>& inputs,
                                      const std::vector<Proof>& proofs) {

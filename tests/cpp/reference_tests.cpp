@@ -154,6 +154,31 @@ static int parity_dump(Context& ctx) {
   return 0;
 }
 
+// circuit/mod.rs:746-769 (weights_test) on the rows its program parses to (roots 1, 2; wires 1 b x temp a c), then
+// weights -> prove -> verify as lib.rs:156-190 does for the same program
+static int weights_test(Context& ctx) {
+  Fr one = Fr::one(), r1 = 1, r2 = 2;
+  RootRepresentation rep;
+  rep.u = {{{r2, one}}, {}, {}, {}, {{r1, one}}, {}};                  // gate 1: a * b ; gate 2: 1 * (4 temp + c + 6)
+  rep.v = {{{r2, Fr(6)}}, {{r1, one}}, {}, {{r2, Fr(4)}}, {}, {{r2, one}}};
+  rep.w = {{}, {}, {{r2, one}}, {{r1, one}}, {}, {}};
+  rep.roots = {r1, r2};
+  rep.input = 2;
+  QAP qap = QAP::from(ctx, rep);
+  groth16::WitnessPlan plan(ctx, qap, {4, 1, 5});  // (in a b c)
+  std::vector<Fr> w = plan.weights({Fr(3), Fr(2), Fr(4)});
+  std::vector<Fr> expected = {1, 2, 34, 6, 3, 4};
+  CHECK(w == expected && plan.levels() == 2);
+  Sigma sigma = groth16::setup(ctx, qap);
+  Proof proof = groth16::prove(ctx, qap, sigma, w);
+  CHECK(groth16::verify(ctx, sigma, {w[1], w[2]}, proof));
+  bool threw = false;
+  try { plan.weights({Fr(3), Fr(2)}); } catch (const Error& e) { threw = e.code == ZKB_ERR_ARG; }  // "Wrong number of values supplied"
+  CHECK(threw);
+  printf("ok weights_test\n");
+  return 0;
+}
+
 int main() {
   try {
     Context ctx(0);
@@ -161,6 +186,7 @@ int main() {
     if (int rc = qap_from_roots(ctx)) return rc;
     if (int rc = bn_encrypt_deg_15_test(ctx)) return rc;
     if (int rc = batch_equals_single(ctx)) return rc;
+    if (int rc = weights_test(ctx)) return rc;
     if (int rc = parity_dump(ctx)) return rc;
   } catch (const Error& e) {
     printf("zkb200::Error %d: %s\n", e.code, e.what());

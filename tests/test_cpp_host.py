@@ -47,7 +47,7 @@ def test_cpp_reference_tests_on_gpu(exe):
     from oracle.fields import FR
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
-    for name in ("single_mult_honest_bn", "qap_from_roots", "bn_encrypt_deg_15_test", "batch_equals_single", "parity_dump"):
+    for name in ("single_mult_honest_bn", "qap_from_roots", "bn_encrypt_deg_15_test", "batch_equals_single", "weights_test", "parity_dump"):
         assert f"ok {name}" in r.stdout
     got = {}
     for line in r.stdout.splitlines():

@@ -36,10 +36,17 @@ def main():
         rows = list(csv.DictReader(open(path)))
         acc = [float(r["dur_ms"]) for r in rows if "accumulate" in r["kernel"]]
         heads = [float(r["dur_ms"]) for r in rows if "fix_heads" in r["kernel"]]
-        lv = sum(float(r["dur_ms"]) for r in rows if "bucket_" in r["kernel"])
+        lv = sum(float(r["dur_ms"]) for r in rows if any(s in r["kernel"] for s in ("bucket_", "level_quad", "horner")))
         end = max(float(r["end_ms"]) for r in rows)
         print(f"2^{lg} rank 0 of {world}: accumulate G2 {acc[0]:.3f} ms, G1 {acc[1]:.3f} ms (x{world}: {acc[0] * world:.2f} / {acc[1] * world:.2f}); "
               f"fix_heads {heads[0]:.3f} / {heads[1]:.3f}; bucket levels total {lv:.3f}; one proof {end:.3f} ms", flush=True)
+        if os.environ.get("PROBE_BATCH"):
+            import time
+            k = int(os.environ["PROBE_BATCH"])
+            zk.prove_batch(ctx, q, crs, [d_w] * 4, [17] * 4, [19] * 4, on_device=True)
+            t0 = time.perf_counter()
+            zk.prove_batch(ctx, q, crs, [d_w] * k, [17] * k, [19] * k, on_device=True)
+            print(f"2^{lg} rank 0 of {world}: batch of {k} (proxy: full polynomial stage on this rank): {(time.perf_counter() - t0) / k * 1e3:.3f} ms/proof", flush=True)
         crs.free()
 
 

@@ -180,6 +180,8 @@ struct MsmPlan {
   int c = 0, njobs = 0;
   ChunkPlan ch;  // how the sorted records are cut into per-thread chunks
   int win_rank = 0, win_world = 1;  // window sharding: only table rows j = win_rank (mod win_world) emit records
+  int tail = 0;  // bucket hierarchy: 0 = quad plan (latency: the caller waits for this proof), 2 = quad plan with quads from 2048 elements
+                 // (several small proofs in flight), 1 = v1 plan (least multiplier work: long accumulations of other proofs hide it)
   MsmJob jobs[4];
   bool empty = true;
   size_t nbk = 0, max_recs = 0, nacc = 0, lvl_elems = 0;

@@ -134,6 +134,84 @@ template <class F> ZKB_HD XYZZ<F> add(const XYZZ<F>& a, const XYZZ<F>& b) {
 #if defined(__CUDACC__)
 template <class F> __device__ __noinline__ XYZZ<F> add_ool(const XYZZ<F>& a, const XYZZ<F>& b) { return add(a, b); }
 template <class F> __device__ __noinline__ XYZZ<F> dbl_ool(const XYZZ<F>& a) { return dbl(a); }
+
+// ---- one addition on FOUR lanes (a "quad": lanes 4k .. 4k+3 of a warp) ----------------------------------------------
+// The bucket hierarchy is a dependent chain of additions executed by a handful of warps: its duration is the latency
+// of ONE thread's addition -- 14 field multiplications back to back, each a carry chain through the single CC flag
+// (~25 us for an Fq2 addition) -- not the machine's throughput.  The 14 products of add-2008-s form 4 dependency
+// levels of <= 4 independent products, so a quad that holds the operands replicated computes one level per step,
+// every lane one product, and exchanges the results with shuffles: 4 multiplications deep instead of 14 (doubling:
+// 3 instead of 9).  All 32 lanes of the warp must call these together (full-mask shuffles); the special cases
+// (identity operands, P + P, P + (-P)) are resolved by selection after the arithmetic, never by early exit.
+template <class F>
+__device__ __forceinline__ F quad_get(const F& v, int k) {  // the value lane k of this lane's quad holds
+  F r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+  const int src = (threadIdx.x & 28) | k;
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = __shfl_sync(0xffffffffu, s[i], src);
+  return r;
+}
+template <class F>
+__device__ __forceinline__ F sel4(int q, const F& a0, const F& a1, const F& a2, const F& a3) {
+  F r;
+  const uint32_t *p0 = reinterpret_cast<const uint32_t*>(&a0), *p1 = reinterpret_cast<const uint32_t*>(&a1),
+                 *p2 = reinterpret_cast<const uint32_t*>(&a2), *p3 = reinterpret_cast<const uint32_t*>(&a3);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = q == 0 ? p0[i] : (q == 1 ? p1[i] : (q == 2 ? p2[i] : p3[i]));
+  return r;
+}
+// 2 * p (dbl-2008-s-1) on a quad
+template <class F>
+__device__ __noinline__ XYZZ<F> qdbl(const XYZZ<F>& p) {
+  const int q = threadIdx.x & 3;
+  const F u = dbl(p.y);
+  F t = sel4(q, u, p.x, u, p.x);
+  t = sqr(t);
+  const F v = quad_get(t, 0), xx = quad_get(t, 1);
+  const F m = dbl(xx) + xx;
+  t = sel4(q, u, p.x, m, v) * sel4(q, v, v, m, p.zz);
+  const F w = quad_get(t, 0), s = quad_get(t, 1), m2 = quad_get(t, 2);
+  XYZZ<F> r;
+  r.zz = quad_get(t, 3);
+  r.x = m2 - dbl(s);
+  t = sel4(q, m, w, w, w) * sel4(q, s - r.x, p.y, p.zzz, p.zzz);
+  r.y = quad_get(t, 0) - quad_get(t, 1);
+  r.zzz = quad_get(t, 2);
+  if (p.is_inf()) return XYZZ<F>::inf();
+  return r;
+}
+// a + b (add-2008-s) on a quad, complete
+template <class F>
+__device__ __noinline__ XYZZ<F> qadd(const XYZZ<F>& a, const XYZZ<F>& b) {
+  const int q = threadIdx.x & 3;
+  F t = sel4(q, a.x, b.x, a.y, b.y) * sel4(q, b.zz, a.zz, b.zzz, a.zzz);
+  const F u1 = quad_get(t, 0), s1 = quad_get(t, 2);
+  const F pp_ = quad_get(t, 1) - u1, rr = quad_get(t, 3) - s1;
+  t = sel4(q, pp_, rr, a.zz, a.zzz) * sel4(q, pp_, rr, b.zz, b.zzz);
+  const F pp = quad_get(t, 0), rr2 = quad_get(t, 1), zzab = quad_get(t, 2), zzzab = quad_get(t, 3);
+  t = sel4(q, pp_, u1, zzab, s1) * pp;
+  const F ppp = quad_get(t, 0), qq = quad_get(t, 1), s1pp = quad_get(t, 3);
+  XYZZ<F> r;
+  r.zz = quad_get(t, 2);
+  r.x = rr2 - ppp - dbl(qq);
+  t = sel4(q, rr, s1pp, zzzab, zzzab) * sel4(q, qq - r.x, pp_, ppp, ppp);
+  r.y = quad_get(t, 0) - quad_get(t, 1);
+  r.zzz = quad_get(t, 2);
+  const bool ai = a.is_inf(), bi = b.is_inf();
+  const bool same_x = !ai && !bi && pp_.is_zero();
+  const bool twice = same_x && rr.is_zero();
+  if (__any_sync(0xffffffffu, twice)) {  // P + P somewhere in the warp: every lane takes the doubling together
+    const XYZZ<F> d = qdbl(a);
+    if (twice) r = d;
+  }
+  if (same_x && !twice) r = XYZZ<F>::inf();
+  if (bi) r = a;
+  else if (ai) r = b;
+  return r;
+}
 #endif
 
 template <class F> ZKB_HD Affine<F> to_affine(const XYZZ<F>& p) {

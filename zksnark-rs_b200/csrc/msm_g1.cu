@@ -155,8 +155,8 @@ template <> int MsmLaunch<Fq>::fix_heads(zkb_ctx* ctx, const uint32_t* offs, uin
   return launch_fix_heads<Fq>(ctx, offs, nbk, ch, buckets, heads, st);
 }
 template <> int MsmLaunch<Fq>::reduce(zkb_ctx* ctx, const G1XYZZ* buckets, uint32_t nb, int njobs, G1XYZZ* lvlS, G1XYZZ* lvlA,
-                                      G1XYZZ* d_out, cudaStream_t st) {
-  return launch_reduce<Fq>(ctx, buckets, nb, njobs, lvlS, lvlA, d_out, st);
+                                      G1XYZZ* d_out, cudaStream_t st, int tail) {
+  return launch_reduce<Fq>(ctx, buckets, nb, njobs, lvlS, lvlA, d_out, st, tail);
 }
 template <> int MsmLaunch<Fq>::expand_table(zkb_ctx* ctx, G1Affine* tab, size_t stride, size_t n, int c, cudaStream_t st) {
   return launch_expand_table<Fq>(ctx, tab, stride, n, c, st);

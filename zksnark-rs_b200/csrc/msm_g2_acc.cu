@@ -3,6 +3,7 @@
 // mixed addition is ~100 KB of code and ran instruction-fetch bound (ncu: no_instruction 1.2 per issue,
 // fmaheavy pipe 64 %); out of line it reaches 0.89 of the modmul peak (profiles/r01_*).
 #define ZKB_FQ2_OOL 1
+#define ZKB_ACC_SM_VARIANT 1  // 1: built, off by default (ZKB_ACC_SM=1 selects it); 2: on by default
 #include "msm_impl.cuh"
 namespace zkb {
 template <> int MsmLaunch<Fq2>::accumulate(zkb_ctx* ctx, const G2Affine* tab, const uint32_t* offs, const uint32_t* sorted,

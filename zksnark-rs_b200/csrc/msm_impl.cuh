@@ -108,7 +108,7 @@ struct MsmLaunch {
                        cudaStream_t st);
   // full hierarchy: buckets[njobs][nb] -> d_out[njobs]; lvlS / lvlA hold the intermediate levels
   static int reduce(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int njobs, XYZZ<F>* lvlS, XYZZ<F>* lvlA, XYZZ<F>* d_out,
-                    cudaStream_t st);
+                    cudaStream_t st, int tail);
   static int expand_table(zkb_ctx* ctx, Affine<F>* tab, size_t stride, size_t n, int c, cudaStream_t st);
   static int set_inf(zkb_ctx* ctx, XYZZ<F>* out, int n, cudaStream_t st);
 };
@@ -118,8 +118,10 @@ int msm_sort_records(zkb_ctx* ctx, const MsmJob* jobs, int njobs, size_t stride,
                      uint32_t* cursor, uint32_t* sums, uint32_t* sorted, cudaStream_t st);
 
 static inline size_t msm_level_elems(uint32_t nb, int njobs) {
-  // upper bound for any level plan with fan-in >= 4: nb/4 + nb/16 + ... < nb/3 (+ one per level)
-  return ((size_t)nb / 3 + 40) * njobs;
+  // lvlS and lvlA are contiguous: 2 * (nb/2 + 128) elements per job.  The v1 plan (fan-in >= 4) needs nb/4 + nb/16 + ...
+  // < nb/3 (+ one per level) in each; the quad plan (launch_reduce_quad) at most 2 nb/4 + 3 nb/16 + 4 nb/64 + ... < 0.78 nb
+  // (+ a few per level) in total, checked there.
+  return ((size_t)nb / 2 + 128) * njobs;
 }
 
 // phases of one MSM call (see MsmPlan in common.cuh); F-typed views of the plan's buffers
@@ -181,7 +183,7 @@ static int msm_tail_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
   if (P.empty) return MsmLaunch<F>::set_inf(ctx, (XYZZ<F>*)P.d_out, P.njobs, st);
   ZKB_TRY(MsmLaunch<F>::fix_heads(ctx, P.offs, (uint32_t)P.nbk, P.ch, (XYZZ<F>*)P.buckets, (const XYZZ<F>*)P.heads, st));
   return MsmLaunch<F>::reduce(ctx, (const XYZZ<F>*)P.buckets, make_plan(P.c).nb, P.njobs, (XYZZ<F>*)P.lvlS, (XYZZ<F>*)P.lvlA,
-                              (XYZZ<F>*)P.d_out, st);
+                              (XYZZ<F>*)P.d_out, st, P.tail);
 }
 
 // ================================================================================================
@@ -254,6 +256,98 @@ __global__ void __launch_bounds__(ZKB_ACC_THREADS, ZKB_ACC_MIN_BLOCKS) k_accumul
   if (is_head) heads[t] = acc; else buckets[g] = acc;
 }
 
+// ---- variant: the accumulator in SHARED memory (G2) ----------------------------------------------------------------
+// k_accumulate_chunks<Fq2> needs 230 registers: two blocks of 128 threads per SM, 8 warps, and the multiplier pipe idles
+// ~20 % of the time on fixed-latency dependencies that two warps per scheduler cannot cover.  A third block needs
+// <= 168 registers.  Here the 64-register XYZZ accumulator lives in shared memory (32 KB per block, 16-byte word k of
+// thread t at [k][t]: conflict-free LDS.128 / STS.128) and the mixed addition loads each coordinate where it is used.
+template <class F>
+struct SmAcc {
+  uint4* base;  // &smem[threadIdx.x]
+  static constexpr int WORDS = sizeof(F) / 16;
+  __device__ __forceinline__ F ld(int coord) const {
+    F r;
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < WORDS; k++) {
+      const uint32_t addr = (uint32_t)__cvta_generic_to_shared(base + (coord * WORDS + k) * ZKB_ACC_THREADS);
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d[4 * k]), "=r"(d[4 * k + 1]), "=r"(d[4 * k + 2]), "=r"(d[4 * k + 3]) : "r"(addr));
+    }
+    return r;
+  }
+  __device__ __forceinline__ void st(int coord, const F& v) const {
+    const uint32_t* d = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int k = 0; k < WORDS; k++) {
+      const uint32_t addr = (uint32_t)__cvta_generic_to_shared(base + (coord * WORDS + k) * ZKB_ACC_THREADS);
+      asm volatile("st.shared.v4.u32 [%4], {%0, %1, %2, %3};" ::"r"(d[4 * k]), "r"(d[4 * k + 1]), "r"(d[4 * k + 2]), "r"(d[4 * k + 3]), "r"(addr) : "memory");
+    }
+  }
+  __device__ __forceinline__ XYZZ<F> get() const { XYZZ<F> r; r.x = ld(0); r.y = ld(1); r.zz = ld(2); r.zzz = ld(3); return r; }
+  __device__ __forceinline__ void put(const XYZZ<F>& v) const { st(0, v.x); st(1, v.y); st(2, v.zz); st(3, v.zzz); }
+};
+// acc += p (madd-2008-s, complete); `inf` tracks acc == identity in a register
+template <class F>
+__device__ __forceinline__ void madd_sm(const SmAcc<F>& a, bool& inf, const Affine<F>& p) {
+  if (p.is_inf()) return;
+  if (inf) { a.st(0, p.x); a.st(1, p.y); a.st(2, F::one()); a.st(3, F::one()); inf = false; return; }
+  const F u2 = p.x * a.ld(2);
+  const F s2 = p.y * a.ld(3);
+  const F pp_ = u2 - a.ld(0);
+  const F rr = s2 - a.ld(1);
+  if (pp_.is_zero()) {
+    if (rr.is_zero()) a.put(dbl_affine(p)); else inf = true;
+    return;
+  }
+  const F pp = sqr(pp_);
+  const F ppp = pp_ * pp;
+  const F q = a.ld(0) * pp;
+  const F x3 = sqr(rr) - ppp - dbl(q);
+  a.st(0, x3);
+  a.st(1, mul_sub_mul(rr, q - x3, a.ld(1), ppp));
+  a.st(2, a.ld(2) * pp);
+  a.st(3, a.ld(3) * ppp);
+}
+template <class F>
+__global__ void __launch_bounds__(ZKB_ACC_THREADS, 3) k_accumulate_chunks_sm(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
+                                                                             const uint32_t* __restrict__ sorted, uint32_t nbk, size_t nchunks,
+                                                                             ChunkPlan ch, XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads) {
+  __shared__ uint4 sm[sizeof(XYZZ<F>) / 16 * ZKB_ACC_THREADS];
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  const uint32_t total = offs[nbk];
+  const uint32_t start = ch.start((uint32_t)t);
+  if (start >= total) return;
+  const uint32_t S = ch.len((uint32_t)t);
+  const uint32_t end = (total - start > S) ? start + S : total;
+  uint32_t lo = 0, hi = nbk;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (offs[mid] <= start) lo = mid + 1; else hi = mid;
+  }
+  uint32_t g = lo - 1;
+  bool is_head = offs[g] < start;
+  uint32_t bend = offs[g + 1];
+  SmAcc<F> acc;
+  acc.base = sm + threadIdx.x;
+  bool inf = true;
+  for (uint32_t p = start; p < end; p++) {
+    if (p == bend) {
+      XYZZ<F>* dst = is_head ? heads + t : buckets + g;
+      *dst = inf ? XYZZ<F>::inf() : acc.get();
+      is_head = false;
+      inf = true;
+      do { g++; bend = offs[g + 1]; } while (bend <= p);
+    }
+    uint32_t rec = sorted[p];
+    Affine<F> P = ld_table_entry(pts + (rec & 0x7fffffffu));
+    if (rec >> 31) P = neg(P);
+    madd_sm(acc, inf, P);
+  }
+  XYZZ<F>* dst = is_head ? heads + t : buckets + g;
+  *dst = inf ? XYZZ<F>::inf() : acc.get();
+}
+
 template <class F>
 __device__ __forceinline__ XYZZ<F> shfl_down_xyzz(const XYZZ<F>& p, int off) {
   XYZZ<F> r;
@@ -320,11 +414,12 @@ __global__ void __launch_bounds__(128) k_fix_heads(const uint32_t* __restrict__ 
 template <class F>
 __global__ void __launch_bounds__(128) k_bucket_level(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ A_in,
                                                       uint32_t n_in, uint32_t n_out, uint32_t L, int shift,
-                                                      XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ A_out) {
+                                                      XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ A_out, size_t in_stride,
+                                                      size_t out_stride) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_out) return;
   const size_t job = blockIdx.y;
-  const XYZZ<F>* s = S_in + job * n_in + (size_t)t * L;
+  const XYZZ<F>* s = S_in + job * in_stride + (size_t)t * L;
   const uint32_t cnt = n_in - t * L < L ? n_in - t * L : L;
   XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
   for (int i = (int)cnt - 1; i >= 1; i--) {
@@ -334,11 +429,92 @@ __global__ void __launch_bounds__(128) k_bucket_level(const XYZZ<F>* __restrict_
   run = add_ool(run, s[0]);
   for (int q = 0; q < shift; q++) acc = dbl_ool(acc);
   if (A_in) {
-    const XYZZ<F>* a = A_in + job * n_in + (size_t)t * L;
+    const XYZZ<F>* a = A_in + job * in_stride + (size_t)t * L;
     for (uint32_t i = 0; i < cnt; i++) acc = add_ool(acc, a[i]);
   }
-  S_out[job * n_out + t] = run;
-  A_out[job * n_out + t] = acc;
+  S_out[job * out_stride + t] = run;
+  A_out[job * out_stride + t] = acc;
+}
+
+// plain L:1 sums of the vectors 1 .. nvec-1 of a level (the partial sums of D_0 .. D_{nvec-2}, see below) beside a
+// thread-per-chunk level of the S vector: grid.z = vector - 1
+template <class F>
+__global__ void __launch_bounds__(128) k_sum_level(const XYZZ<F>* __restrict__ in, uint32_t n_in, uint32_t n_out, uint32_t L,
+                                                   size_t in_stride, XYZZ<F>* __restrict__ out, size_t out_stride) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_out) return;
+  const size_t job = blockIdx.y, v = blockIdx.z + 1;
+  const XYZZ<F>* s = in + job * in_stride + v * n_in + (size_t)t * L;
+  const uint32_t cnt = n_in - t * L < L ? n_in - t * L : L;
+  XYZZ<F> acc = s[0];
+  for (uint32_t i = 1; i < cnt; i++) acc = add_ool(acc, s[i]);
+  out[job * out_stride + v * n_out + t] = acc;
+}
+
+// ---- the hierarchy on quads (ec.cuh: qadd / qdbl) -- the default ----------------------------------------------------
+// With b = sum_k d_k W_k (mixed radix, W_0 = 1, W_{k+1} = W_k L_k):   R = sum_b (b+1) B_b = G + sum_k W_k D_k,
+// G = sum_b B_b,  D_k = sum_b d_k(b) B_b.  Level k cuts the running vector S^k (S^0 = B) into chunks of L_k = 8, one WARP
+// per chunk, one QUAD per element: a 3-step suffix scan gives Suf_i (so S^{k+1}_t = Suf_0) and a 3-step tree over
+// Suf_1..7 gives the chunk's share T_t = sum_i i X_i of D_k.  The T vectors are NOT folded into a weighted accumulator
+// (that costs log2 W_k dependent doublings at every level: 45 of the 87 chained operations at 2^16 buckets); they ride
+// along as plain vectors that later levels only tree-sum 8:1 (blockIdx.z = vector: 0 = S, v >= 1 = the partial sums of
+// D_{v-1}), and ONE warp evaluates G + D_0 + W_1 (D_1 + ...) by Horner at the end: log2(nb) doublings in all.
+// in: per job `nvec` vectors of n_in elements (job stride in_stride); out: per job nvec + 1 vectors of n_out elements
+// (S', D_0' .. D_{nvec-2}', and the new T), job stride (nvec + 1) * n_out.
+template <class F>
+__global__ void __launch_bounds__(128) k_level_quad(const XYZZ<F>* __restrict__ in, uint32_t n_in, uint32_t n_out, int nvec,
+                                                    size_t in_stride, XYZZ<F>* __restrict__ out) {
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_out) return;  // whole warps leave together
+  const int lane = threadIdx.x & 31, quad = lane >> 2;
+  const size_t job = blockIdx.y;
+  const int v = blockIdx.z;
+  const uint32_t e = t * 8 + quad;
+  const XYZZ<F>* src = in + job * in_stride + (size_t)v * n_in;
+  XYZZ<F>* dst = out + job * (size_t)(nvec + 1) * n_out;
+  XYZZ<F> x = e < n_in ? src[e] : XYZZ<F>::inf();
+  if (v == 0) {
+    for (int off = 1; off < 8; off <<= 1) {
+      XYZZ<F> y = shfl_down_xyzz(x, 4 * off);
+      if (quad + off >= 8) y = XYZZ<F>::inf();
+      x = qadd(x, y);
+    }
+    XYZZ<F> w = quad ? x : XYZZ<F>::inf();
+    for (int off = 4; off > 0; off >>= 1) {
+      XYZZ<F> y = shfl_down_xyzz(w, 4 * off);
+      if (quad + off >= 8) y = XYZZ<F>::inf();
+      w = qadd(w, y);
+    }
+    if (lane == 0) {
+      dst[t] = x;
+      dst[(size_t)nvec * n_out + t] = w;
+    }
+  } else {
+    for (int off = 4; off > 0; off >>= 1) {
+      XYZZ<F> y = shfl_down_xyzz(x, 4 * off);
+      if (quad + off >= 8) y = XYZZ<F>::inf();
+      x = qadd(x, y);
+    }
+    if (lane == 0) dst[(size_t)v * n_out + t] = x;
+  }
+}
+
+struct HornerPlan {
+  int nd;        // number of D vectors
+  int sh[16];    // sh[k] = log2(W_{k+1} / W_k): doublings between D_{k+1} and D_k
+};
+// R = G + D_0 + W_1 (D_1 + (W_2 / W_1) (D_2 + ...)): one warp per job, every quad computes the same
+template <class F>
+__global__ void __launch_bounds__(32) k_horner_final(const XYZZ<F>* __restrict__ in, size_t in_stride, HornerPlan hp, XYZZ<F>* __restrict__ out) {
+  const XYZZ<F>* v = in + blockIdx.x * in_stride;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int k = hp.nd - 1; k >= 0; k--) {
+    acc = qadd(acc, v[1 + k]);
+    if (k > 0)
+      for (int q = 0; q < hp.sh[k - 1]; q++) acc = qdbl(acc);
+  }
+  acc = qadd(acc, v[0]);
+  if (threadIdx.x == 0) out[blockIdx.x] = acc;
 }
 
 // The same level map with L = 32 and one WARP per chunk (lane i holds X_{32t+i}): a shuffle suffix
@@ -401,6 +577,13 @@ __global__ void __launch_bounds__(128) k_expand_table(Affine<F>* __restrict__ ta
 template <class F>
 static int launch_accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
                              size_t nacc, ChunkPlan ch, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind) {
+#if defined(ZKB_ACC_SM_VARIANT)
+  static const int sm_mode = getenv("ZKB_ACC_SM") ? atoi(getenv("ZKB_ACC_SM")) : ZKB_ACC_SM_VARIANT - 1;  // developer switch
+  if (sm_mode) {
+    ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks_sm<F>, cdiv(nacc, ZKB_ACC_THREADS), ZKB_ACC_THREADS, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
+    return ZKB_OK;
+  }
+#endif
   ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks<F>, cdiv(nacc, ZKB_ACC_THREADS), ZKB_ACC_THREADS, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
   return ZKB_OK;
 }
@@ -414,9 +597,54 @@ static int launch_fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, Ch
 // (16 when that still gives >= 32K threads, else 4), then warp levels (32 per warp)
 static inline uint32_t msm_first_L(uint32_t nb, int njobs) { return (size_t)nb * njobs / 16 >= 32768 ? 16 : 4; }
 
+// Quad plan.  While the vector is too long for the quad levels to run one warp per scheduler (they spend four lanes per
+// addition: 4x the multiplier work of a thread), levels with one THREAD per chunk of L (16 from 2^19 elements over all
+// jobs: throughput-bound there; else 4) -- their A output with shift 0 is exactly T, and k_sum_level folds the D vectors
+// alongside; then quad levels 8:1 down to one element; then Horner.  Developer switches: ZKB_TAIL=1 selects the previous
+// plan (launch_reduce_v1), ZKB_TAIL_QMAX the element count (all jobs) from which the quad levels take over.
 template <class F>
-static int launch_reduce(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int njobs, XYZZ<F>* lvlS, XYZZ<F>* lvlA, XYZZ<F>* d_out,
-                         cudaStream_t st) {
+static int launch_reduce_quad(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int njobs, XYZZ<F>* lvl, size_t lvl_cap, XYZZ<F>* d_out,
+                              cudaStream_t st, int tail) {
+  // measured (profiles/r02_tail_plans.txt): quads from 8192 elements give the shortest chain (2^16 single proof 2.77 ms
+  // vs 3.04 from 2048); with other proofs in flight 2048 costs less multiplier time (2^16 batch 2.06 vs 2.13 ms / proof)
+  static const size_t qmax_env = getenv("ZKB_TAIL_QMAX") ? (size_t)atoll(getenv("ZKB_TAIL_QMAX")) : 0;
+  const size_t qmax = qmax_env ? qmax_env : (tail == 2 ? 2048 : 8192);
+  HornerPlan hp;
+  hp.nd = 0;
+  const XYZZ<F>* in = buckets;
+  size_t in_stride = nb, used = 0;
+  uint32_t m = nb;
+  int nvec = 1;
+  XYZZ<F>* cur = lvl;
+  while (m > 1) {
+    const bool quad = (size_t)m * njobs <= qmax;
+    const uint32_t L = quad ? 8 : ((size_t)m * njobs >= ((size_t)1 << 19) ? 16 : 4);
+    const uint32_t mo = (m + L - 1) / L;
+    const size_t out_stride = (size_t)(nvec + 1) * mo, need = out_stride * njobs;
+    if (used + need > lvl_cap || hp.nd >= 16) return set_err(ctx, ZKB_ERR_ALLOC, "msm reduce: level scratch too small");
+    if (quad) {
+      dim3 grid(cdiv((size_t)mo * 32, 128), njobs, nvec);
+      ZKB_LAUNCH(ctx, k_level_quad<F>, grid, 128, 0, st, in, m, mo, nvec, in_stride, cur);
+    } else {
+      dim3 grid(cdiv(mo, 128), njobs);
+      ZKB_LAUNCH(ctx, k_bucket_level<F>, grid, 128, 0, st, in, (const XYZZ<F>*)nullptr, m, mo, L, 0, cur, cur + (size_t)nvec * mo, in_stride,
+                 out_stride);
+      if (nvec > 1) {
+        dim3 grid2(cdiv(mo, 128), njobs, nvec - 1);
+        ZKB_LAUNCH(ctx, k_sum_level<F>, grid2, 128, 0, st, in, m, mo, L, in_stride, cur, out_stride);
+      }
+    }
+    hp.sh[hp.nd++] = quad ? 3 : (L == 16 ? 4 : 2);
+    in = cur; in_stride = out_stride; nvec++; m = mo;
+    cur += need; used += need;
+  }
+  ZKB_LAUNCH(ctx, k_horner_final<F>, njobs, 32, 0, st, in, in_stride, hp, d_out);
+  return ZKB_OK;
+}
+
+template <class F>
+static int launch_reduce_v1(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int njobs, XYZZ<F>* lvlS, XYZZ<F>* lvlA, XYZZ<F>* d_out,
+                            cudaStream_t st) {
   const XYZZ<F>*Sin = buckets, *Ain = nullptr;
   XYZZ<F>*So = lvlS, *Ao = lvlA;
   int shift = 0;
@@ -425,7 +653,7 @@ static int launch_reduce(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int 
     const uint32_t L = msm_first_L(nb, njobs);
     uint32_t mo = (m + L - 1) / L;
     dim3 grid(cdiv(mo, 128), njobs);
-    ZKB_LAUNCH(ctx, k_bucket_level<F>, grid, 128, 0, st, Sin, Ain, m, mo, L, shift, So, Ao);
+    ZKB_LAUNCH(ctx, k_bucket_level<F>, grid, 128, 0, st, Sin, Ain, m, mo, L, shift, So, Ao, (size_t)m, (size_t)mo);
     Sin = So; Ain = Ao;
     So += (size_t)mo * njobs; Ao += (size_t)mo * njobs;
     shift += L == 16 ? 4 : 2;
@@ -442,6 +670,14 @@ static int launch_reduce(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int 
   }
   ZKB_LAUNCH(ctx, k_bucket_final<F>, 1, 32, 0, st, Sin, Ain, njobs, d_out);
   return ZKB_OK;
+}
+template <class F>
+static int launch_reduce(zkb_ctx* ctx, const XYZZ<F>* buckets, uint32_t nb, int njobs, XYZZ<F>* lvlS, XYZZ<F>* lvlA, XYZZ<F>* d_out,
+                         cudaStream_t st, int tail) {
+  static const int forced = getenv("ZKB_TAIL") ? atoi(getenv("ZKB_TAIL")) : -1;  // developer switch: 0 quad, 1 v1
+  if ((forced >= 0 ? forced : tail) == 1) return launch_reduce_v1<F>(ctx, buckets, nb, njobs, lvlS, lvlA, d_out, st);
+  // lvlS and lvlA are one contiguous region (msm_prepare_t)
+  return launch_reduce_quad<F>(ctx, buckets, nb, njobs, lvlS, 2 * msm_level_elems(nb, njobs), d_out, st, tail);
 }
 template <class F>
 static int launch_expand_table(zkb_ctx* ctx, Affine<F>* tab, size_t stride, size_t n, int c, cudaStream_t st) {

@@ -111,7 +111,7 @@ __global__ void k_fill_tw_tiles(uint4* __restrict__ out, const Fr* __restrict__ 
   out[(g * 2 + 1) * T + slot] = b;
 }
 
-template <bool DIT, bool TMA>
+template <bool DIT, bool TMA, bool SHF = false>
 __global__ void k_ntt_pass(Fr* __restrict__ d, const Fr* __restrict__ tw, const uint4* __restrict__ tiles, uint32_t log_n, uint32_t hi,
                            uint32_t lo, uint32_t logC);
 
@@ -236,7 +236,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 // TMA = true: `tiles` is this pass's tiled twiddle table (k_fill_tw_tiles); thread 0 issues one bulk copy of the
 // block's 32*T-byte tile into the upper half of shared memory before the data tile is loaded, every thread waits
 // on the mbarrier after the data barrier, and twiddles are LDS.128 pairs.  TMA = false: 32-byte gathers from `tw`.
-template <bool DIT, bool TMA>
+//
+// SHF = true (DIF, the contiguous 1024-element pass only; ZKB_NTT_SHFL=1): the warp-shuffle variant the north star names.
+// A thread keeps its radix-4 groups in registers over the last three rounds (stages 5..0); between rounds the four
+// threads that differ in two LANE bits (q bits [2r, 2r+1], r = 1, 0) exchange elements with a 4x4 transpose made of
+// XOR shuffles instead of the round trip through shared memory and its barrier.  (The earlier rounds regroup across
+// warps and cannot use shuffles.)  Bit-identical output.  Measured on B200 (profiles/r02_ntt_shuffle.txt) and NOT the
+// default: a 256-bit element is 8 SHFL plus the selects that emulate register indexing (64 instructions per exchanged
+// element, three per group and transition) against two STS.128 + two LDS.128, and the pass is bound by the integer
+// multiplier, not by shared memory or its barriers.
+template <bool DIT, bool TMA, bool SHF>
 __global__ void __launch_bounds__(128, ZKB_NTT_MIN_BLOCKS) k_ntt_pass(Fr* __restrict__ d, const Fr* __restrict__ tw,
                                                   const uint4* __restrict__ tiles, uint32_t log_n,
                                                   uint32_t hi, uint32_t lo, uint32_t logC) {
@@ -312,6 +321,59 @@ __global__ void __launch_bounds__(128, ZKB_NTT_MIN_BLOCKS) k_ntt_pass(Fr* __rest
       }
     } else {
       const uint32_t r = DIT ? step : (pairs - 1 - (odd ? step - 1 : step));
+      if (SHF && !DIT && r == 2 && lo == 0 && logC == 0 && B == 10 && nthr == 128) {
+        // rounds 2, 1, 0 in registers; thread t owns the groups q = t and q = t + 128 in every round
+        Fr v[2][4];
+        const uint32_t lane = t & 31;
+#pragma unroll
+        for (int rr = 2; rr >= 0; rr--) {
+          const uint32_t sh = 2 * rr, h = 1u << sh;
+#pragma unroll
+          for (int gidx = 0; gidx < 2; gidx++) {
+            const uint32_t q = t + 128 * gidx;
+            const uint32_t e0 = ((q >> sh) << (sh + 2)) | (q & (h - 1));
+            if (rr == 2) {
+#pragma unroll
+              for (int x = 0; x < 4; x++) v[gidx][x] = lds_fr(p0, p1, e0 + x * h);
+            }
+            const Fr wb = twiddle(e0, sh + 1), wc = twiddle(e0 + h, sh + 1);
+            Fr a0 = v[gidx][0] + v[gidx][2], a2 = (v[gidx][0] - v[gidx][2]) * wb;
+            Fr a1 = v[gidx][1] + v[gidx][3], a3 = (v[gidx][1] - v[gidx][3]) * wc;
+            v[gidx][0] = a0 + a1;
+            v[gidx][2] = a2 + a3;
+            if (rr == 0) {  // stage 0: every twiddle is 1
+              v[gidx][1] = a0 - a1;
+              v[gidx][3] = a2 - a3;
+            } else {
+              const Fr wa = twiddle(e0, sh);
+              v[gidx][1] = (a0 - a1) * wa;
+              v[gidx][3] = (a2 - a3) * wa;
+            }
+            if (rr > 0) {
+              // to round rr - 1: element (thread j, local x) -> (thread x, local j) among the four lanes that differ in
+              // lane bits [2 (rr - 1), 2 (rr - 1) + 1]
+              const int stride = 1 << (2 * (rr - 1));
+              const int j = (lane >> (2 * (rr - 1))) & 3;
+#pragma unroll
+              for (int k = 1; k < 4; k++) {
+                const int idx = j ^ k;
+                const Fr send = sel4(idx, v[gidx][0], v[gidx][1], v[gidx][2], v[gidx][3]);
+                Fr recv;
+#pragma unroll
+                for (int i = 0; i < 8; i++) recv.v[i] = __shfl_xor_sync(0xffffffffu, send.v[i], k * stride);
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+                  if (idx == x) v[gidx][x] = recv;
+              }
+            } else {
+#pragma unroll
+              for (int x = 0; x < 4; x++) sts_fr(p0, p1, e0 + x * h, v[gidx][x]);
+            }
+          }
+        }
+        __syncthreads();
+        break;
+      }
       const uint32_t ls = 2 * r;  // lower stage of the round
       const uint32_t sh = ls + logC;
       const uint32_t h = 1u << sh;
@@ -380,7 +442,11 @@ static int run_ntt(zkb_ctx* ctx, Fr* d, uint32_t log_n, bool inverse, cudaStream
     const uint4* tiles = pi < 4 ? ctx->twt[log_n][inverse ? 1 : 0][pi] : nullptr;  // null: this pass gathers from the flat table
     auto* k_ntt_pass_tiles = &k_ntt_pass<DIT, true>;     // named so that traces (zkb_trace_dump) tell the two apart
     auto* k_ntt_pass_gather = &k_ntt_pass<DIT, false>;
-    if (tiles) {
+    static const int env_shfl = getenv("ZKB_NTT_SHFL") ? atoi(getenv("ZKB_NTT_SHFL")) : 0;  // developer switch (A/B; see k_ntt_pass)
+    auto* k_ntt_pass_shuffle = &k_ntt_pass<false, false, true>;
+    if (env_shfl && !DIT && p.lo == 0 && p.hi == 10 && block == 128) {
+      ZKB_LAUNCH_K(ctx, PK_NTT, k_ntt_pass_shuffle, grid, block, smem, st, d, tw, tiles, log_n, p.hi, p.lo, p.logC);
+    } else if (tiles) {
       ZKB_LAUNCH_K(ctx, PK_NTT, k_ntt_pass_tiles, grid, block, 2 * smem, st, d, tw, tiles, log_n, p.hi, p.lo, p.logC);
     } else {
       ZKB_LAUNCH_K(ctx, PK_NTT, k_ntt_pass_gather, grid, block, smem, st, d, tw, tiles, log_n, p.hi, p.lo, p.logC);

@@ -503,8 +503,10 @@ static int prove_out(zkb_ctx* ctx, DevBuf* slots, ProveOut* o) {
 // comm != NULL: ONE proof over all ranks of `comm` (CRS in layout 1): the polynomial stage is sharded (shard.cu, three
 // exchanges over peer memory on channel `ch`), the partial sums are exchanged and folded on the device, and every rank
 // ends up with the complete proof.
+// batch: other proofs are in flight on other lanes (their accumulations hide this proof's bucket hierarchy, so the plan
+// with the least multiplier work wins); else the caller waits for THIS proof and the hierarchy runs on quads.
 static int prove_enqueue(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, const zkb_crs* c, const uint64_t* weights,
-                         int on_device, const uint64_t* r, const uint64_t* s, zkb_comm* comm = nullptr, int ch = 0) {
+                         int on_device, const uint64_t* r, const uint64_t* s, zkb_comm* comm = nullptr, int ch = 0, bool batch = false) {
   cudaStream_t hi = L->hi, lo = L->lo;
   // Every allocation, table and plan first, launches after: scratch growth synchronises the device and the first use of a
   // twiddle table synchronises a stream, and neither may happen behind a kernel that is waiting for a peer.
@@ -526,6 +528,9 @@ static int prove_enqueue(zkb_ctx* ctx, zkb_lane* L, const zkb_qap* q, const zkb_
   MsmPlan P2, P1;
   ZKB_TRY(msm_prepare(ctx, L->scratch, 3, 2, c->g2, c->g2_cnt, c->c2, &jb, 1, o.b, &P2));
   ZKB_TRY(msm_prepare(ctx, L->scratch, 0, 1, c->g1, c->g1_cnt, c->c1, j1, 2, o.ac, &P1));
+  // hierarchy plan: quads unless this is one of several proofs in flight AND the accumulations are long enough to hide
+  // the (then cheaper) thread-level hierarchy -- a rank of an 8-GPU proof at 2^20 has 6.8 M G1 records: quads
+  P1.tail = P2.tail = !batch ? 0 : (P1.max_recs >= ((size_t)1 << 24) ? 1 : 2);
   if (comm) ZKB_TRY(shard_prepare(ctx, comm, q->log_n));
   const Fr* d_w = (const Fr*)weights;
   if (!on_device) {
@@ -636,7 +641,7 @@ int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint
       done = i - nl + 1;
       if (rc != ZKB_OK) break;
     }
-    rc = prove_enqueue(ctx, L, q, c, weights[i], on_device, r + 4 * i, s + 4 * i);
+    rc = prove_enqueue(ctx, L, q, c, weights[i], on_device, r + 4 * i, s + 4 * i, nullptr, 0, count > 1);
   }
   for (size_t i = done; i < count && rc == ZKB_OK; i++) rc = prove_collect(ctx, &ctx->lanes[i % nl], &out[i]);
   if (rc != ZKB_OK) cudaDeviceSynchronize();  // leave no work in flight behind an error
@@ -696,7 +701,7 @@ int zkb_prove_shard_batch(zkb_ctx* ctx, zkb_comm* comm, const zkb_qap* q, const 
       done = i - nl + 1;
       if (rc != ZKB_OK) break;
     }
-    rc = prove_enqueue(ctx, &ctx->lanes[lane], q, c, weights[i], on_device, r + 4 * i, s + 4 * i, comm, lane);
+    rc = prove_enqueue(ctx, &ctx->lanes[lane], q, c, weights[i], on_device, r + 4 * i, s + 4 * i, comm, lane, count > 1);
   }
   for (size_t i = done; i < count && rc == ZKB_OK; i++) rc = prove_collect(ctx, &ctx->lanes[i % nl], &out[i], true);
   if (rc != ZKB_OK) cudaDeviceSynchronize();
