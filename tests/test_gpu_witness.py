@@ -85,10 +85,11 @@ def test_generated_witness_proves_and_verifies(ctx):
     ctx.dev_free(d_wit)
 
 
-@pytest.mark.parametrize("width,depth,fan_in", [(1, 40, 1), (8, 5, 3), (64, 64, 2), (513, 9, 2), (600, 3, 4), (1024, 64, 2)])
+@pytest.mark.parametrize("width,depth,fan_in", [(1, 40, 1), (8, 5, 3), (32, 20, 2), (33, 20, 2), (64, 64, 2), (513, 9, 2), (600, 3, 4),
+                                                (1024, 64, 2), (4096, 5, 2), (4097, 5, 2), (8192, 4, 2)])
 def test_layered_circuit_matches_oracle(ctx, width, depth, fan_in):
-    """Wide synthetic circuits (one launch per level above 512 gates, chained narrow levels below) against the
-    gate-by-gate walk on the CPU; the plan's levels are the circuit's layers."""
+    """Wide synthetic circuits against the gate-by-gate walk on the CPU; the plan's levels are the circuit's layers.  Levels
+    above 512 gates are one launch each (chained by programmatic dependent launch), runs of narrower levels one block."""
     n, m, n_input, rows, free = zg.layered_qap_rows(width, depth, fan_in=fan_in, seed=width + depth)
     n2 = max(2, 1 << (n - 1).bit_length())
     qap = zk.QAP(ctx, n2, m, n_input, rows)

@@ -11,9 +11,18 @@
 //     produce k's inputs (free wires and the unity wire: level 0); gates counting-sorted by level; the
 //     u / v entries of the gates copied into a level-ordered CSR on the device (one contiguous read per
 //     level instead of three dependent gathers per gate);
-//   generate (device, per witness): scatter the free values, then one launch per WIDE level (one thread
-//     per gate) and one single-block launch per RUN of consecutive narrow levels (block-wide barrier
-//     between levels: a depth-d chain costs d barriers instead of d launches).
+//   generate (device, per witness): scatter the free values, then
+//     - levels wider than 512 gates: one launch each (one thread per gate), chained with PROGRAMMATIC DEPENDENT LAUNCH:
+//       a level's grid is launched while its predecessor still runs, loads its gates' structure (offsets, wires,
+//       coefficients -- none of which depend on the witness) and only then waits for the predecessor's stores
+//       (griddepcontrol.wait), so the launch latency and the structure loads leave the chain (measured: 8.4 -> 6.5 us
+//       per level; 2^20 gates in 4 levels 0.245 -> 0.156 ms);
+//     - runs of consecutive narrower levels: ONE single-block launch, block barrier between levels: a depth-d stretch
+//       costs d barriers instead of d launches.
+//     Measured and NOT the default (ZKB_WIT_CLUSTER=1; profiles/r02_witness_v2_cluster_pdl.jsonl): runs of levels up to
+//     4096 gates on a thread-block CLUSTER of 8 CTAs with a cluster barrier per level.  A level is a dependent chain (three
+//     L2 accesses, five products of one thread), not multiplier throughput, so eight SMs do not shorten it and the cluster
+//     barrier + L2-coherent loads cost more than the block barrier: 8.5 vs 7.0 us per 256-gate level, 16 vs 8.4 at 4096.
 // Error behaviour mirrors the reference: assigning a wire twice, reading a wire no gate has produced
 // ("Under constrained expression"; with ZKB_WITNESS_PROGRAM_ORDER also a wire only a LATER gate produces,
 // which is what the sequential walk of circuit/mod.rs:598-621 rejects), a wire nothing assigns, the wrong
@@ -31,14 +40,26 @@ struct zkb_witness_plan {
   uint32_t* d_out = nullptr;    // n_gates: output wire
   zkb::Fr* d_winv = nullptr;    // n_gates: 1 / (w coefficient), only when some coefficient != 1
   uint32_t* d_lptr = nullptr;   // n_levels + 1: plan-gate range of every level
-  struct Seg { uint32_t l0, l1; bool wide; };
+  struct Seg { uint32_t l0, l1; int kind; };  // 0: chain (one block), 1: cluster, 2: one wide level
   std::vector<Seg> segs;        // launch schedule
   std::vector<uint32_t> h_lptr;
 };
 
 namespace zkb {
 
-static const uint32_t WIT_NARROW = 512;  // levels up to this many gates are chained inside one block
+static const uint32_t WIT_NARROW = 512;    // block size of the chain kernel
+static const uint32_t WIT_CHAIN_MAX = 32;  // runs whose levels all have at most this many gates stay in one block
+static const uint32_t WIT_CL = 8;          // CTAs per cluster (the portable maximum)
+static const uint32_t WIT_CL_THREADS = 256;
+static const uint32_t WIT_CL_MAX = 4096;   // levels up to this many gates run inside the cluster kernel
+
+__device__ __forceinline__ Fr ld_fr_l2(const Fr* p) {  // L2-coherent (no L1): the value may come from another SM of the cluster
+  Fr a;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  *reinterpret_cast<uint4*>(&a.v[0]) = __ldcg(q);
+  *reinterpret_cast<uint4*>(&a.v[4]) = __ldcg(q + 1);
+  return a;
+}
 
 __device__ __forceinline__ void wit_gate(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ wire,
                                          const Fr* __restrict__ coef, const uint32_t* __restrict__ out,
@@ -52,11 +73,57 @@ __device__ __forceinline__ void wit_gate(const uint32_t* __restrict__ ptr, const
   a[out[g]] = r;
 }
 
-// one wide level: plan gates [g0, g1), one thread each
-__global__ void k_wit_level(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ wire, const Fr* __restrict__ coef,
-                            const uint32_t* __restrict__ out, const Fr* __restrict__ winv, Fr* a, uint32_t g0, uint32_t g1) {
+// one wide level: plan gates [g0, g1), one thread each.  Launched with programmatic stream serialisation: everything
+// before griddepcontrol.wait overlaps the previous level's grid; the witness is only touched after it.
+__global__ void __launch_bounds__(128) k_wit_level(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ wire,
+                                                   const Fr* __restrict__ coef, const uint32_t* __restrict__ out,
+                                                   const Fr* __restrict__ winv, Fr* a, uint32_t g0, uint32_t g1) {
+  asm volatile("griddepcontrol.launch_dependents;");  // the next level may start launching (it waits for our completion below)
   const uint32_t g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < g1) wit_gate(ptr, wire, coef, out, winv, a, g);
+  uint32_t pu = 0, pv = 0, pe = 0, o = 0, w0 = 0;
+  Fr c0 = Fr::zero();
+  if (g < g1) {
+    pu = ptr[2 * g]; pv = ptr[2 * g + 1]; pe = ptr[2 * g + 2];
+    o = out[g];
+    if (pe > pu) { w0 = wire[pu]; c0 = coef[pu]; }  // first entry; the others follow from L2 while the first product runs
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (g >= g1) return;
+  Fr su = Fr::zero(), sv = Fr::zero();
+  for (uint32_t p = pu; p < pe; p++) {
+    const uint32_t w = p == pu ? w0 : wire[p];
+    const Fr c = p == pu ? c0 : coef[p];
+    const Fr t = c * ld_fr_l2(a + w);
+    if (p < pv) su = su + t; else sv = sv + t;
+  }
+  Fr r = su * sv;
+  if (winv) r = r * winv[g];
+  a[o] = r;
+}
+
+// a run of levels [l0, l1), each at most WIT_CL_MAX gates, on ONE cluster of WIT_CL CTAs
+__global__ void __cluster_dims__(WIT_CL, 1, 1) __launch_bounds__(WIT_CL_THREADS)
+    k_wit_cluster(const uint32_t* __restrict__ lptr, const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ wire,
+                  const Fr* __restrict__ coef, const uint32_t* __restrict__ out, const Fr* __restrict__ winv, Fr* a, uint32_t l0, uint32_t l1) {
+  const uint32_t tid = blockIdx.x * WIT_CL_THREADS + threadIdx.x, nthr = WIT_CL * WIT_CL_THREADS;
+  uint32_t lo = lptr[l0];
+  for (uint32_t l = l0; l < l1; l++) {
+    const uint32_t hi = lptr[l + 1];
+    for (uint32_t g = lo + tid; g < hi; g += nthr) {
+      const uint32_t pu = ptr[2 * g], pv = ptr[2 * g + 1], pe = ptr[2 * g + 2];
+      Fr su = Fr::zero(), sv = Fr::zero();
+      for (uint32_t p = pu; p < pe; p++) {
+        const Fr t = coef[p] * ld_fr_l2(a + wire[p]);
+        if (p < pv) su = su + t; else sv = sv + t;
+      }
+      Fr r = su * sv;
+      if (winv) r = r * winv[g];
+      a[out[g]] = r;
+    }
+    lo = hi;
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
 }
 
 // a run of narrow levels [l0, l1) in ONE block: the stores of level l are visible to the block after the barrier
@@ -239,12 +306,16 @@ int zkb_witness_plan_create(zkb_ctx* ctx, const zkb_qap* q, const uint32_t* free
   p->m = m; p->n_gates = n_gates; p->n_free = n_free; p->n_levels = n_levels; p->nnz = nnz;
   p->h_lptr = lptr;
   for (uint32_t l = 0; l < n_levels; l++) p->max_width = std::max<uint64_t>(p->max_width, lptr[l + 1] - lptr[l]);
-  // launch schedule: runs of narrow levels share one single-block launch
+  // launch schedule: a wide level is its own launch; a run of narrower levels (up to 512 gates each) shares one
+  // single-block launch.  ZKB_WIT_CLUSTER=1 (developer switch, A/B): runs of levels up to 4096 gates on the cluster kernel
+  // unless every level of the run is at most WIT_CHAIN_MAX gates.
+  static const bool use_cluster = getenv("ZKB_WIT_CLUSTER") && atoi(getenv("ZKB_WIT_CLUSTER")) != 0;
+  const uint32_t run_max = use_cluster ? WIT_CL_MAX : WIT_NARROW;
   for (uint32_t l = 0; l < n_levels;) {
-    if (lptr[l + 1] - lptr[l] > WIT_NARROW) { p->segs.push_back({l, l + 1, true}); l++; continue; }
-    uint32_t e = l;
-    while (e < n_levels && lptr[e + 1] - lptr[e] <= WIT_NARROW) e++;
-    p->segs.push_back({l, e, false});
+    if (lptr[l + 1] - lptr[l] > run_max) { p->segs.push_back({l, l + 1, 2}); l++; continue; }
+    uint32_t e = l, widest = 0;
+    while (e < n_levels && lptr[e + 1] - lptr[e] <= run_max) { widest = std::max(widest, lptr[e + 1] - lptr[e]); e++; }
+    p->segs.push_back({l, e, use_cluster && widest > WIT_CHAIN_MAX ? 1 : 0});
     l = e;
   }
   cudaStream_t st = ctx->stream;
@@ -318,9 +389,24 @@ int zkb_witness_generate(zkb_ctx* ctx, const zkb_witness_plan* p, const uint64_t
   ZKB_CUDA(ctx, cudaMemsetAsync(a, 0, m * sizeof(Fr), st));
   ZKB_LAUNCH(ctx, k_wit_init, cdiv(std::max<size_t>(p->n_free, 1), 256), 256, 0, st, a, m, p->d_free, d_vals, (size_t)p->n_free);
   for (const auto& s : p->segs) {
-    if (s.wide) {
+    if (s.kind == 2) {
       const uint32_t g0 = p->h_lptr[s.l0], g1 = p->h_lptr[s.l1];
-      ZKB_LAUNCH(ctx, k_wit_level, cdiv(g1 - g0, 128), 128, 0, st, p->d_ptr, p->d_wire, p->d_coef, p->d_out, p->d_winv, a, g0, g1);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cdiv(g1 - g0, 128));
+      cfg.blockDim = dim3(128);
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (ctx->trace) prof_begin(ctx, 0, st, "k_wit_level");
+      ZKB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_wit_level, (const uint32_t*)p->d_ptr, (const uint32_t*)p->d_wire, (const Fr*)p->d_coef,
+                                       (const uint32_t*)p->d_out, (const Fr*)p->d_winv, a, g0, g1));
+      if (ctx->trace) prof_end(ctx, st);
+      ctx->launches++;
+    } else if (s.kind == 1) {
+      ZKB_LAUNCH(ctx, k_wit_cluster, WIT_CL, WIT_CL_THREADS, 0, st, p->d_lptr, p->d_ptr, p->d_wire, p->d_coef, p->d_out, p->d_winv, a, s.l0, s.l1);
     } else {
       ZKB_LAUNCH(ctx, k_wit_run, 1, WIT_NARROW, 0, st, p->d_lptr, p->d_ptr, p->d_wire, p->d_coef, p->d_out, p->d_winv, a, s.l0, s.l1);
     }
