@@ -171,6 +171,16 @@ def test_fq2_ops_match_bigint(ctx):
     assert zg.field_op(ctx, 2, 1, a) == [mul(x, x) for x in a]
     inv = zg.field_op(ctx, 2, 2, a[25:125])
     assert [mul(x, y) for x, y in zip(a[25:125], inv)] == [(1, 0)] * 100
+    # a b - c d with two reductions (both Karatsuba products unreduced): the last step of the G2 mixed addition.
+    # Edge operands drive every intermediate to the ends of its range (all-(q-1): re = 0 mod q with the 2 q^2 offset).
+    c = [(y, x) for x, y in a[:25]] + [(rng.randrange(p), rng.randrange(p)) for _ in range(2048)]
+    d = [a[(7 * i) % 25] for i in range(25)] + [(rng.randrange(p), rng.randrange(p)) for _ in range(2048)]
+    sub = lambda x, y: ((x[0] - y[0]) % p, (x[1] - y[1]) % p)
+    assert zg.field_op(ctx, 2, 3, a, b, c, d) == [sub(mul(x, y), mul(z, w)) for x, y, z, w in zip(a, b, c, d)]
+    top = [(p - 1, p - 1)] * 8 + [(p - 1, 0), (0, p - 1), (0, 0), (1, p - 1)]
+    for rot in range(4):
+        ops = [top[rot:] + top[:rot], top, top[::-1], top[rot:] + top[:rot]]
+        assert zg.field_op(ctx, 2, 3, *ops) == [sub(mul(x, y), mul(z, w)) for x, y, z, w in zip(*ops)]
 
 
 # ------------------------------------------------------------------------------------------------

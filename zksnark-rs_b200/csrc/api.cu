@@ -526,15 +526,18 @@ __global__ void k_field_op(int op, const F* a, const F* b, const F* c, const F* 
   }
   out[i] = from_mont(r);
 }
-__global__ void k_fq2_op(int op, const Fq2* a, const Fq2* b, Fq2* out, size_t n) {
+__global__ void k_fq2_op(int op, const Fq2* a, const Fq2* b, const Fq2* c, const Fq2* d, Fq2* out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fq2 x, y, r;
+  Fq2 x, y, z, w, r;
   x.c0 = to_mont(a[i].c0); x.c1 = to_mont(a[i].c1);
   y.c0 = to_mont(b[i].c0); y.c1 = to_mont(b[i].c1);
+  z.c0 = to_mont(c[i].c0); z.c1 = to_mont(c[i].c1);
+  w.c0 = to_mont(d[i].c0); w.c1 = to_mont(d[i].c1);
   switch (op) {
     case 0: r = x * y; break;
     case 1: r = sqr(x); break;
+    case 3: r = mul_sub_mul_lazy(x, y, z, w); break;  // the two-reduction a b - c d of the G2 mixed addition
     default: r = inverse(x); break;
   }
   out[i].c0 = from_mont(r.c0);
@@ -562,7 +565,8 @@ extern "C" int zkb_field_op(zkb_ctx* ctx, int field, int op, const uint64_t* a, 
     ZKB_LAUNCH(ctx, k_field_op<Fq>, cdiv(n, 128), 128, 0, st, op, (Fq*)base, (Fq*)(base + n * esz), (Fq*)(base + 2 * n * esz),
                (Fq*)(base + 3 * n * esz), (Fq*)o, n);
   } else {
-    ZKB_LAUNCH(ctx, k_fq2_op, cdiv(n, 128), 128, 0, st, op, (Fq2*)base, (Fq2*)(base + n * esz), (Fq2*)o, n);
+    ZKB_LAUNCH(ctx, k_fq2_op, cdiv(n, 128), 128, 0, st, op, (Fq2*)base, (Fq2*)(base + n * esz), (Fq2*)(base + 2 * n * esz),
+               (Fq2*)(base + 3 * n * esz), (Fq2*)o, n);
   }
   ZKB_CUDA(ctx, cudaMemcpyAsync(out, o, n * esz, cudaMemcpyDeviceToHost, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));

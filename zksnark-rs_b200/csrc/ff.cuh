@@ -844,6 +844,41 @@ __device__ __forceinline__ Fq2 fq2_sqr(const Fq2& a) {
   r.c1 = add(t, t);
   return r;
 }
+// a * b - c * d over Fq2 with TWO reductions (two Karatsuba products unreduced, combined in 512 bits): the last step
+// of the mixed addition, rr (q - x3) - y1 ppp.  Ranges (q < 2^254, so 4 q^2 < q 2^256, the bound of redc):
+//   re = a0 b0 - a1 b1 - c0 d0 + c1 d1 + 2 q^2   in (0, 4 q^2)
+//   im = (a0 b1 + a1 b0) - (c0 d1 + c1 d0) + 2 q^2 in (0, 4 q^2); formed as [a0 b1 + a1 b0 + c0 d0 + c1 d1 + 2 q^2]
+//        (< 6 q^2 < 2^512) minus (c0 + c1)(d0 + d1), so no intermediate goes negative.
+__device__ __forceinline__ Fq2 fq2_msm_lazy(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) {
+  uint32_t re[16], im[16], t[16], s1[8], s2[8], q2[16];
+  psq<FqParams>(q2);
+  mul_wide(re, a.c0.v, b.c0.v);
+  mul_wide(t, a.c1.v, b.c1.v);
+  add_nored(s1, a.c0.v, a.c1.v);
+  add_nored(s2, b.c0.v, b.c1.v);
+  mul_wide(im, s1, s2);
+  wide_sub(im, im, re);
+  wide_sub(im, im, t);   // a0 b1 + a1 b0
+  wide_add(re, re, q2);
+  wide_sub(re, re, t);   // a0 b0 - a1 b1 + q^2
+  mul_wide(t, c.c0.v, d.c0.v);
+  wide_add(re, re, q2);
+  wide_sub(re, re, t);   // ... - c0 d0 + q^2
+  wide_add(im, im, t);
+  mul_wide(t, c.c1.v, d.c1.v);
+  wide_add(re, re, t);   // ... + c1 d1
+  wide_add(im, im, t);
+  add_nored(s1, c.c0.v, c.c1.v);
+  add_nored(s2, d.c0.v, d.c1.v);
+  mul_wide(t, s1, s2);
+  wide_add(im, im, q2);
+  wide_add(im, im, q2);
+  wide_sub(im, im, t);
+  Fq2 r;
+  redc<FqParams>(r.c0.v, re);
+  redc<FqParams>(r.c1.v, im);
+  return r;
+}
 }  // namespace dev_impl
 #if defined(ZKB_NO_LAZY)
 #define ZKB_FQ2_MUL_IMPL dev_impl::fq2_mul_plain
@@ -852,6 +887,7 @@ __device__ __forceinline__ Fq2 fq2_sqr(const Fq2& a) {
 #endif
 static __device__ __noinline__ Fq2 fq2_mul_ool(Fq2 a, Fq2 b) { return ZKB_FQ2_MUL_IMPL(a, b); }
 static __device__ __noinline__ Fq2 fq2_sqr_ool(Fq2 a) { return dev_impl::fq2_sqr(a); }
+static __device__ __noinline__ Fq2 fq2_msm_ool(Fq2 a, Fq2 b, Fq2 c, Fq2 d) { return dev_impl::fq2_msm_lazy(a, b, c, d); }
 #endif
 ZKB_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
 #if defined(__CUDA_ARCH__) && defined(ZKB_FQ2_OOL)
@@ -869,7 +905,24 @@ ZKB_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
 #endif
 }
 // a * b - c * d over Fq2
-ZKB_HD Fq2 mul_sub_mul(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) { return a * b - c * d; }
+// the two-reduction form by name (validation hook zkb_field_op; host: the plain definition)
+ZKB_HD Fq2 mul_sub_mul_lazy(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) {
+#if defined(__CUDA_ARCH__)
+  return dev_impl::fq2_msm_lazy(a, b, c, d);
+#else
+  return a * b - c * d;
+#endif
+}
+// ZKB_FQ2_MSM_LAZY: the two-reduction form (device, lazy build); 2 = out of line (the G2 accumulation kernel)
+ZKB_HD Fq2 mul_sub_mul(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) {
+#if defined(__CUDA_ARCH__) && !defined(ZKB_NO_LAZY) && defined(ZKB_FQ2_MSM_LAZY) && ZKB_FQ2_MSM_LAZY == 2
+  return fq2_msm_ool(a, b, c, d);
+#elif defined(__CUDA_ARCH__) && !defined(ZKB_NO_LAZY) && defined(ZKB_FQ2_MSM_LAZY)
+  return dev_impl::fq2_msm_lazy(a, b, c, d);
+#else
+  return a * b - c * d;
+#endif
+}
 ZKB_HD Fq2 sqr(const Fq2& a) {
 #if defined(__CUDA_ARCH__) && defined(ZKB_FQ2_OOL)
   return fq2_sqr_ool(a);

@@ -3,6 +3,10 @@
 // mixed addition is ~100 KB of code and ran instruction-fetch bound (ncu: no_instruction 1.2 per issue,
 // fmaheavy pipe 64 %); out of line it reaches 0.89 of the modmul peak (profiles/r01_*).
 #define ZKB_FQ2_OOL 1
+// -DZKB_FQ2_MSM_LAZY=2 builds rr (q - x3) - y1 ppp with two reductions instead of four (ff.cuh: fq2_msm_lazy, out of line).
+// Measured on B200 (profiles/r02_notes.md): 4.5 % fewer multiplier instructions per addition, but the kernel gets SLOWER
+// (2^20: 8.30 -> 8.67 ms; the six-product body is a third large out-of-line function and 64 registers of arguments per
+// call), so the default keeps two Fq2 products and a subtraction.
 #define ZKB_ACC_SM_VARIANT 1  // 1: built, off by default (ZKB_ACC_SM=1 selects it); 2: on by default
 #include "msm_impl.cuh"
 namespace zkb {
