@@ -233,7 +233,9 @@ int zkb_qap_h(zkb_ctx* ctx, const zkb_qap* qap, const uint64_t* weights, uint64_
  * gate produces, which is what the sequential walk rejects -- ("Under constrained expression", :608-616), a wire
  * nothing assigns ("Every variable should have an assignment", :630), "Wrong number of values supplied" (:553-558).
  * Without the flag any topological order is accepted (the builder's demand-driven evaluate).  A gate with several
- * wires in its w row is ZKB_ERR_UNSUPPORTED.  The plan borrows the QAP's device arrays: free it before the QAP. */
+ * wires in its w row is ZKB_ERR_UNSUPPORTED.  The plan copies what it needs (a level-ordered CSR of the gates' u / v
+ * entries): it stays valid after the QAP is freed.  Device buffers passed in (values, weights_out) must be 16-byte
+ * aligned (zkb_dev_alloc's are). */
 typedef struct zkb_witness_plan zkb_witness_plan;
 #define ZKB_WITNESS_PROGRAM_ORDER 1
 int zkb_witness_plan_create(zkb_ctx* ctx, const zkb_qap* qap, const uint32_t* free_wires, size_t n_free, int flags,

@@ -1061,7 +1061,7 @@ class WitnessPlan:
     circuit/mod.rs:598-621); False accepts any topological order (the builder's `evaluate`, builder/mod.rs:556-580)."""
 
     def __init__(self, ctx: Context, qap: QAP, free_wires, program_order: bool = True):
-        self.ctx, self.qap = ctx, qap  # the plan borrows the QAP's device arrays
+        self.ctx, self.qap = ctx, qap  # (the plan is self-contained; qap is kept for its row count)
         fw = np.ascontiguousarray(np.asarray(list(free_wires), dtype=np.int64).astype(np.uint32))
         self.n_free = int(fw.size)
         h = C.c_void_p()
