@@ -1,8 +1,8 @@
 """Workload for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): exercises the
 multi-pass NTT (2^13: three shared-memory passes incl. strided tiles), the MSM with graded chunks,
 head folding on both paths (skewed scalars -> one huge bucket -> warp-cooperative fold), the
-warp-level bucket hierarchy, batch proving on two lanes and the sharded fold, at sizes a sanitizer
-finishes in a minute.  Results are checked against the oracle's closed forms.
+bucket hierarchy (quad plan for single proofs, its small-batch variant in the batches), batch proving on two lanes, the
+sharded fold and witness generation, at sizes a sanitizer finishes in a minute.  Results are checked against the oracle's closed forms.
 Usage: compute-sanitizer --tool memcheck python tests/sanitize_case.py"""
 import importlib
 import os
@@ -57,6 +57,14 @@ def main():
     b = zk.Bases.generate(ctx, 1, ks[:256])
     sc = [rng.randrange(P) for _ in range(256)]
     assert zg.points_sum(ctx, 1, [zk.msm(ctx, b, sc, windows=(g, 3)) for g in range(3)]) == zk.msm(ctx, b, sc)
+    # witness generation: a chain (one block, barrier per level), wide levels (programmatic dependent launches), mixed
+    from oracle import circuit  # noqa: E402  (checker only)
+    for width, depth in ((1, 50), (40, 12), (700, 4)):
+        n, m, n_input, rows, free = zg.layered_qap_rows(width, depth, seed=width)
+        q2 = zk.QAP(ctx, max(2, 1 << (n - 1).bit_length()), m, n_input, rows)
+        plan = zk.WitnessPlan(ctx, q2, free)
+        vals = [rng.randrange(P) for _ in free]
+        assert zk.weights(ctx, plan, vals) == circuit.weights_from_rows(P, n, m, circuit.csr_by_gate(n, m, rows), free, vals)
     print(f"sanitize case ok: {ctx.launches} kernel launches")
     ctx.close()
 
