@@ -249,6 +249,11 @@ int zkb_witness_plan_info(const zkb_witness_plan* plan, uint64_t* n_gates, uint6
 int zkb_witness_generate(zkb_ctx* ctx, const zkb_witness_plan* plan, const uint64_t* values, size_t n_values,
                          int values_on_device, uint64_t* weights_out, int out_on_device);
 void zkb_witness_plan_free(zkb_ctx* ctx, zkb_witness_plan* plan);
+/* Host only (no device, no context; errors via zkb_last_error(NULL)): the level the planner assigns to every gate of a
+ * QAP in its upload form -- gate_level[k] in 1 .. *n_levels, 0 for gates that assign nothing -- with the same checks and
+ * error messages as zkb_witness_plan_create. */
+int zkb_witness_levels(const zkb_qap_host* qap, const uint32_t* free_wires, size_t n_free, int flags, uint32_t* gate_level,
+                       uint64_t* n_levels);
 
 /* ---- wire format: flat little-endian layout of QAP, CRS and Proof (host-only; no device is touched) -------------
  * The reference cannot serialise anything: QAP, SigmaG1, SigmaG2, Proof have private fields and no accessors

@@ -94,3 +94,78 @@ def test_layered_rows_shape_and_walk():
         su = sum(c * a[w] for w, c in bg[0][k]) % FR.p
         sv = sum(c * a[w] for w, c in bg[1][k]) % FR.p
         assert a[9 + k] == su * sv % FR.p
+
+
+# ---- the planner's host logic (libzkb200's zkb_witness_levels: no device needed) ------------------------------------------
+def _levels_ref(n, m, by_gate, free):
+    """level(gate) = 1 + the deepest producer among its u / v inputs; free wires and the unity wire are level 0."""
+    gu, gv, gw = by_gate
+    wl = {0: 0, **{w: 0 for w in free}}
+    prod = {gw[k][0][0]: k for k in range(n) if len(gw[k]) == 1}
+    lev = [0] * n
+
+    def level(k):
+        if lev[k]:
+            return lev[k]
+        lv = 0
+        for w, _ in gu[k] + gv[k]:
+            lv = max(lv, wl[w] if w in wl else level(prod[w]))
+        lev[k] = lv + 1
+        wl[gw[k][0][0]] = lv + 1
+        return lev[k]
+
+    for k in range(n):
+        if len(gw[k]) == 1:
+            level(k)
+    return lev
+
+
+def _rows_of(by_gate, m):
+    per = [[[] for _ in range(m)] for _ in range(3)]
+    for t in range(3):
+        for k, row in enumerate(by_gate[t]):
+            for w, c in row:
+                per[t][w].append((k, c))
+    return [zg._csr(per[t], m) for t in range(3)]
+
+
+@pytest.mark.parametrize("text,n_in", [(SIMPLE, 3), (QUAD, 4), (MIXED, 3), (synthetic.horner_program_text(16), 17)])
+def test_planner_levels_on_parser_circuits(text, n_in):
+    rep = circuit.try_parse(FR, text)
+    bg, fw = circuit.rep_by_gate(rep), circuit.input_wires(FR, text)
+    n, m = len(rep.roots), len(rep.u)
+    got = zg.witness_levels(n, m, rep.input, _rows_of(bg, m), fw)
+    assert got == _levels_ref(n, m, bg, fw) and min(got) >= 1
+    assert got == zg.witness_levels(n, m, rep.input, _rows_of(bg, m), fw, program_order=False)
+
+
+def test_planner_levels_layered_and_padding():
+    n, m, n_input, rows, free = zg.layered_qap_rows(16, 7, fan_in=3, seed=2)
+    got = zg.witness_levels(32 * 4, m, n_input, rows, free)  # 112 gates on a 128-gate domain: the padding gates assign nothing
+    assert got[:n] == [1 + k // 16 for k in range(n)] and got[n:] == [0] * (128 - n)
+
+
+def test_planner_error_messages():
+    rep, bg, fw, names = swapped_two_gates()
+    m = len(rep.u)
+    rows = _rows_of(bg, m)
+    with pytest.raises(zg.ZkbError, match="Under constrained expression.*later gate"):
+        zg.witness_levels(2, m, rep.input, rows, fw)
+    assert zg.witness_levels(2, m, rep.input, rows, fw, program_order=False) == [2, 1]
+    with pytest.raises(zg.ZkbError, match="already assigned variable"):
+        zg.witness_levels(2, m, rep.input, rows, fw + [names.index("y")], program_order=False)
+    with pytest.raises(zg.ZkbError, match="listed twice"):
+        zg.witness_levels(2, m, rep.input, rows, fw + fw[:1])
+    with pytest.raises(zg.ZkbError, match="Under constrained expression"):
+        zg.witness_levels(2, m, rep.input, rows, fw[:1], program_order=False)
+    with pytest.raises(zg.ZkbError, match="out of range"):
+        zg.witness_levels(2, m, rep.input, rows, [m])
+    rows2 = _rows_of(tuple(g + [] for g in bg), m + 1)  # one more wire that nothing reads or assigns
+    with pytest.raises(zg.ZkbError, match="Every variable should have an assignment"):
+        zg.witness_levels(2, m + 1, rep.input, rows2, fw, program_order=False)
+    cyc = ([[(1, 1)], [(2, 1)]], [[(0, 1)], [(0, 1)]], [[(2, 1)], [(1, 1)]])  # b = a * 1, a = b * 1
+    with pytest.raises(zg.ZkbError, match="depend on each other"):
+        zg.witness_levels(2, 3, 1, _rows_of(cyc, 3), [], program_order=False)
+    two = ([[(1, 1)], []], [[(1, 1)], []], [[(2, 1), (3, 1)], []])
+    with pytest.raises(zg.ZkbError, match="exactly one output"):
+        zg.witness_levels(2, 4, 1, _rows_of(two, 4), [1])

@@ -172,27 +172,13 @@ __global__ void k_wit_any_not_one(const Fr* __restrict__ c, size_t n, int* flag)
 
 using namespace zkb;
 
-extern "C" {
-
-void zkb_witness_plan_free(zkb_ctx* ctx, zkb_witness_plan* p) {
-  if (!p) return;
-  if (ctx) cudaSetDevice(ctx->device);
-  cudaFree(p->d_free); cudaFree(p->d_ptr); cudaFree(p->d_wire); cudaFree(p->d_coef);
-  cudaFree(p->d_out); cudaFree(p->d_winv); cudaFree(p->d_lptr);
-  delete p;
-}
-
-int zkb_witness_plan_create(zkb_ctx* ctx, const zkb_qap* q, const uint32_t* free_wires, size_t n_free, int flags,
-                            zkb_witness_plan** out) {
-  if (!ctx || !q || !out || (n_free && !free_wires)) return set_err(ctx, ZKB_ERR_ARG, "zkb_witness_plan_create: NULL argument");
-  *out = nullptr;
-  const uint64_t n = q->n, m = q->m;
-  const bool program_order = (flags & ZKB_WITNESS_PROGRAM_ORDER) != 0;
-  const std::vector<uint32_t>*gp = q->h_gptr, *gw = q->h_wire;
-  if (gp[0].size() != n + 1 || gp[1].size() != n + 1 || gp[2].size() != n + 1)
-    return set_err(ctx, ZKB_ERR_ARG, "zkb_witness_plan_create: the QAP carries no host copy of its by-gate rows");
+// Levelisation (host only): gp / gw = by-gate offsets and wires of u, v, w.  On success glevel[k] = level of gate k
+// (1-based; NONE for gates that assign nothing) and outw[k] = its output wire.
+static const uint32_t NONE = 0xffffffffu;
+static int wit_levelise(zkb_ctx* ctx, uint64_t n, uint64_t m, const std::vector<uint32_t>* gp, const std::vector<uint32_t>* gw,
+                        const uint32_t* free_wires, size_t n_free, bool program_order, std::vector<uint32_t>& glevel,
+                        std::vector<uint32_t>& outw, uint64_t* n_gates_out) {
   // wire state: NONE = nothing assigns it (yet); otherwise the level at which its value exists
-  const uint32_t NONE = 0xffffffffu;
   std::vector<uint32_t> wlevel(m, NONE), producer(m, NONE);
   wlevel[0] = 0;  // the unity wire (`once(F::one())`, circuit/mod.rs:634)
   for (size_t i = 0; i < n_free; i++) {
@@ -203,7 +189,7 @@ int zkb_witness_plan_create(zkb_ctx* ctx, const zkb_qap* q, const uint32_t* free
   }
   // output wire of every gate: the single entry of its w row.  Gates without a w entry assign nothing (padding gates
   // 0 * 0 = 0 of a re-indexed QAP, or pure constraints) and are skipped.
-  std::vector<uint32_t> outw(n, NONE);
+  outw.assign(n, NONE);
   uint64_t n_gates = 0;
   for (uint64_t k = 0; k < n; k++) {
     uint32_t cnt = gp[2][k + 1] - gp[2][k];
@@ -220,7 +206,7 @@ int zkb_witness_plan_create(zkb_ctx* ctx, const zkb_qap* q, const uint32_t* free
     n_gates++;
   }
   // levels
-  std::vector<uint32_t> glevel(n, NONE);
+  glevel.assign(n, NONE);
   auto input_level = [&](uint64_t k, uint32_t w, uint32_t* lv) -> int {  // level at which wire w exists, for gate k
     if (wlevel[w] != NONE) { *lv = wlevel[w]; return ZKB_OK; }
     return set_err(ctx, ZKB_ERR_ARG, "witness plan: gate %llu: Under constrained expression (wire %u has no value%s)",
@@ -276,6 +262,31 @@ int zkb_witness_plan_create(zkb_ctx* ctx, const zkb_qap* q, const uint32_t* free
   for (uint64_t w = 1; w < m; w++)
     if (wlevel[w] == NONE)  // `.expect("Every variable should have an assignment")`, circuit/mod.rs:630
       return set_err(ctx, ZKB_ERR_ARG, "witness plan: Every variable should have an assignment (wire %llu has none)", (unsigned long long)w);
+  *n_gates_out = n_gates;
+  return ZKB_OK;
+}
+
+extern "C" {
+
+void zkb_witness_plan_free(zkb_ctx* ctx, zkb_witness_plan* p) {
+  if (!p) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(p->d_free); cudaFree(p->d_ptr); cudaFree(p->d_wire); cudaFree(p->d_coef);
+  cudaFree(p->d_out); cudaFree(p->d_winv); cudaFree(p->d_lptr);
+  delete p;
+}
+
+int zkb_witness_plan_create(zkb_ctx* ctx, const zkb_qap* q, const uint32_t* free_wires, size_t n_free, int flags,
+                            zkb_witness_plan** out) {
+  if (!ctx || !q || !out || (n_free && !free_wires)) return set_err(ctx, ZKB_ERR_ARG, "zkb_witness_plan_create: NULL argument");
+  *out = nullptr;
+  const uint64_t n = q->n, m = q->m;
+  const std::vector<uint32_t>*gp = q->h_gptr, *gw = q->h_wire;
+  if (gp[0].size() != n + 1 || gp[1].size() != n + 1 || gp[2].size() != n + 1)
+    return set_err(ctx, ZKB_ERR_ARG, "zkb_witness_plan_create: the QAP carries no host copy of its by-gate rows");
+  std::vector<uint32_t> glevel, outw;
+  uint64_t n_gates = 0;
+  ZKB_TRY(wit_levelise(ctx, n, m, gp, gw, free_wires, n_free, (flags & ZKB_WITNESS_PROGRAM_ORDER) != 0, glevel, outw, &n_gates));
   // counting sort of the gates by level
   uint32_t n_levels = 0;
   for (uint64_t k = 0; k < n; k++)
@@ -355,6 +366,40 @@ int zkb_witness_plan_create(zkb_ctx* ctx, const zkb_qap* q, const uint32_t* free
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return fail(set_err(ctx, ZKB_ERR_CUDA, "witness plan gather: %s", cudaGetErrorString(e)));
   *out = p;
+  return ZKB_OK;
+}
+
+// Host only (no device is touched): the levels the planner would assign to the gates of `h` -- the seam the CPU tests
+// check the host logic through.  gate_level: n entries (0 = the gate assigns nothing).
+int zkb_witness_levels(const zkb_qap_host* h, const uint32_t* free_wires, size_t n_free, int flags, uint32_t* gate_level,
+                       uint64_t* n_levels) {
+  if (!h || !gate_level || (n_free && !free_wires)) return set_err(nullptr, ZKB_ERR_ARG, "zkb_witness_levels: NULL argument");
+  const uint64_t n = h->n, m = h->m;
+  if (n == 0 || m == 0 || m >= ((uint64_t)1 << 31)) return set_err(nullptr, ZKB_ERR_ARG, "zkb_witness_levels: bad dimensions");
+  std::vector<uint32_t> gp[3], gw[3];
+  for (int t = 0; t < 3; t++) {  // by-wire CSR -> by-gate (the transposition zkb_qap_upload does)
+    const uint64_t* rp = h->row_ptr[t];
+    if (!rp || (rp[m] && !h->gate[t])) return set_err(nullptr, ZKB_ERR_ARG, "zkb_witness_levels: NULL rows");
+    gp[t].assign(n + 1, 0);
+    gw[t].resize(rp[m]);
+    for (uint64_t e = 0; e < rp[m]; e++) {
+      if (h->gate[t][e] >= n) return set_err(nullptr, ZKB_ERR_ARG, "gate index out of range");
+      gp[t][h->gate[t][e] + 1]++;
+    }
+    for (uint64_t k = 0; k < n; k++) gp[t][k + 1] += gp[t][k];
+    std::vector<uint32_t> cur(gp[t].begin(), gp[t].end() - 1);
+    for (uint64_t i = 0; i < m; i++)
+      for (uint64_t e = rp[i]; e < rp[i + 1]; e++) gw[t][cur[h->gate[t][e]]++] = (uint32_t)i;
+  }
+  std::vector<uint32_t> glevel, outw;
+  uint64_t n_gates = 0;
+  ZKB_TRY(wit_levelise(nullptr, n, m, gp, gw, free_wires, n_free, (flags & ZKB_WITNESS_PROGRAM_ORDER) != 0, glevel, outw, &n_gates));
+  uint32_t top = 0;
+  for (uint64_t k = 0; k < n; k++) {
+    gate_level[k] = glevel[k] == NONE ? 0 : glevel[k];
+    top = std::max(top, gate_level[k]);
+  }
+  if (n_levels) *n_levels = top;
   return ZKB_OK;
 }
 

@@ -120,6 +120,7 @@ ABI = {
     "zkb_witness_plan_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "zkb_witness_generate": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int, _P, C.c_int]),
     "zkb_witness_plan_free": (None, [_P, _P]),
+    "zkb_witness_levels": (C.c_int, [C.POINTER(_QapHost), _P, C.c_size_t, C.c_int, _P, C.POINTER(C.c_uint64)]),
 }
 WITNESS_PROGRAM_ORDER = 1
 WIRE_PROOF_BYTES = 320
@@ -1141,3 +1142,16 @@ def layered_qap_rows(width: int, depth: int, fan_in: int = 2, seed: int = 1):
     one[:, 0] = 1
     rows.append((pw, np.arange(n, dtype=np.uint32), one))
     return n, m, width, rows, list(range(1, width + 1))
+
+
+def witness_levels(n: int, m: int, n_input: int, rows, free_wires, program_order: bool = True) -> list:
+    """Host only (works without a GPU): the level the witness planner gives every gate (0: assigns nothing)."""
+    lib = load_library()
+    host, keep = _qap_host(n, m, n_input, rows)
+    fw = np.ascontiguousarray(np.asarray(list(free_wires), dtype=np.int64).astype(np.uint32))
+    out = np.zeros(n, dtype=np.uint32)
+    nl = C.c_uint64()
+    _wire_check(lib.zkb_witness_levels(C.byref(host), fw.ctypes.data if fw.size else None, fw.size,
+                                       WITNESS_PROGRAM_ORDER if program_order else 0, out.ctypes.data, C.byref(nl)), "zkb_witness_levels")
+    assert int(out.max(initial=0)) == nl.value
+    return out.tolist()
