@@ -130,6 +130,9 @@ def test_w_coefficient_and_mixed_widths(ctx):
     y = t * (t + x) * pow(c5, -1, P) % P
     assert zk.weights(ctx, plan, [x]) == [1, x, y, t]
     assert plan.info()["n_levels"] == 2
+    entries[2] = [(3, 1, 0), (2, 0, c5)]  # 0 * t = ...: nothing to solve for
+    with pytest.raises(zk.ZkbError, match="coefficient 0"):
+        zk.WitnessPlan(ctx, zk.QAP(ctx, 2, 4, 2, _hand_rows(4, 2, entries)), [1], program_order=False)
 
 
 def test_error_behaviour(ctx):

@@ -153,14 +153,16 @@ __global__ void k_wit_gather(const uint32_t* __restrict__ order, const uint32_t*
                              const uint32_t* __restrict__ wire_u, const Fr* __restrict__ coef_u, const uint32_t* __restrict__ gptr_v,
                              const uint32_t* __restrict__ wire_v, const Fr* __restrict__ coef_v, const uint32_t* __restrict__ gptr_w,
                              const Fr* __restrict__ coef_w, uint32_t* __restrict__ wire, Fr* __restrict__ coef, Fr* __restrict__ winv,
-                             size_t n_gates) {
+                             int* __restrict__ zero_flag, size_t n_gates) {
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_gates) return;
   const uint32_t k = order[g];
   uint32_t o = ptr[2 * g];
   for (uint32_t p = gptr_u[k], e = gptr_u[k + 1]; p < e; p++, o++) { wire[o] = wire_u[p]; coef[o] = coef_u[p]; }
   for (uint32_t p = gptr_v[k], e = gptr_v[k + 1]; p < e; p++, o++) { wire[o] = wire_v[p]; coef[o] = coef_v[p]; }
-  if (winv) winv[g] = inverse(coef_w[gptr_w[k]]);
+  const Fr cw = coef_w[gptr_w[k]];
+  if (cw.is_zero()) *zero_flag = 1;  // 0 * out = U * V assigns nothing: the reference's evaluate has no such gate; refuse it
+  if (winv) winv[g] = inverse(cw);
 }
 
 __global__ void k_wit_any_not_one(const Fr* __restrict__ c, size_t n, int* flag) {
@@ -356,15 +358,19 @@ int zkb_witness_plan_create(zkb_ctx* ctx, const zkb_qap* q, const uint32_t* free
   cudaError_t e = cudaStreamSynchronize(st);  // host vectors go out of scope; flag decides the allocation below
   if (e != cudaSuccess) return fail(set_err(ctx, ZKB_ERR_CUDA, "witness plan upload: %s", cudaGetErrorString(e)));
   if (flag && cudaMalloc(&p->d_winv, (n_gates + 1) * 32)) return fail(set_err(ctx, ZKB_ERR_ALLOC, "witness plan: cudaMalloc failed"));
+  cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+  flag = 0;
   if (n_gates) {
     k_wit_gather<<<cdiv(n_gates, 128), 128, 0, st>>>(d_order, p->d_ptr, q->d_gptr[0], q->d_wire[0], q->d_coeff[0], q->d_gptr[1],
                                                      q->d_wire[1], q->d_coeff[1], q->d_gptr[2], q->d_coeff[2], p->d_wire, p->d_coef,
-                                                     p->d_winv, (size_t)n_gates);
+                                                     p->d_winv, d_flag, (size_t)n_gates);
     ctx->launches++;
   }
+  cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
   e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return fail(set_err(ctx, ZKB_ERR_CUDA, "witness plan gather: %s", cudaGetErrorString(e)));
+  if (flag) return fail(set_err(ctx, ZKB_ERR_DIV_ZERO, "witness plan: a gate's output wire has coefficient 0 in its w row"));
   *out = p;
   return ZKB_OK;
 }
