@@ -103,6 +103,20 @@ def test_layered_circuit_matches_oracle(ctx, width, depth, fan_in):
     assert got == circuit.weights_from_rows(P, n, m, circuit.csr_by_gate(n, m, rows), free, vals)
 
 
+def test_unit_coefficient_entries(ctx):
+    """Entries with coefficient 1 skip their product (flagged at plan time); mixed with weighted entries in one gate, on the
+    chain kernel (prefetched and non-prefetched entries: fan-in 6) and on wide levels."""
+    for width, depth, fan_in in ((8, 30, 6), (700, 3, 6)):
+        n, m, n_input, rows, free = zg.layered_qap_rows(width, depth, fan_in=fan_in, seed=99, unit_coeffs=True)
+        rng = random.Random(width)
+        for t in (0, 1):  # re-weight every third entry
+            rows[t][2][::3, 0] = np.asarray([rng.randrange(2, 1000) for _ in range(len(rows[t][2][::3]))], dtype=np.uint64)
+        qap = zk.QAP(ctx, max(2, 1 << (n - 1).bit_length()), m, n_input, rows)
+        plan = zk.WitnessPlan(ctx, qap, free)
+        vals = [rng.randrange(P) for _ in free]
+        assert zk.weights(ctx, plan, vals) == circuit.weights_from_rows(P, n, m, circuit.csr_by_gate(n, m, rows), free, vals)
+
+
 def _hand_rows(m, n, entries):
     """entries[t] = [(wire, gate, coeff)] -> CSR triples by wire"""
     rows = []

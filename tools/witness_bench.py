@@ -25,10 +25,11 @@ def main():
     ctx = zk.Context(0)
     rng = np.random.default_rng(1)
     cases = [("layered", 1 << 18, 4), ("layered", 1 << 16, 16), ("layered", 1 << 14, 64), ("layered", 1 << 12, 256), ("layered", 1 << 10, 1024),
-             ("layered", 1 << 8, 4096), ("horner", 1 << 16, None), ("horner", 1 << 20, None)]
+             ("layered", 1 << 8, 4096), ("layered-unit", 1 << 18, 4), ("layered-unit", 1 << 12, 256), ("layered-unit", 1 << 8, 4096),
+             ("horner", 1 << 16, None), ("horner", 1 << 20, None)]
     for kind, a, b in cases:
-        if kind == "layered":
-            n, m, n_input, rows, free = zg.layered_qap_rows(a, b, seed=3)
+        if kind.startswith("layered"):
+            n, m, n_input, rows, free = zg.layered_qap_rows(a, b, seed=3, unit_coeffs=kind.endswith("unit"))
             qap = zk.QAP(ctx, n, m, n_input, rows)
         else:
             n = a

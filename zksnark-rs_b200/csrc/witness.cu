@@ -53,6 +53,8 @@ static const uint32_t WIT_CL = 8;          // CTAs per cluster (the portable max
 static const uint32_t WIT_CL_THREADS = 256;
 static const uint32_t WIT_CL_MAX = 4096;   // levels up to this many gates run inside the cluster kernel
 
+static const uint32_t WIT_UNIT = 0x80000000u;  // wire-index flag: the entry's coefficient is 1
+
 __device__ __forceinline__ Fr ld_fr_l2(const Fr* p) {  // L2-coherent (no L1): the value may come from another SM of the cluster
   Fr a;
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -66,8 +68,12 @@ __device__ __forceinline__ void wit_gate(const uint32_t* __restrict__ ptr, const
                                          const Fr* __restrict__ winv, Fr* a, uint32_t g) {
   const uint32_t pu = ptr[2 * g], pv = ptr[2 * g + 1], pe = ptr[2 * g + 2];
   Fr su = Fr::zero(), sv = Fr::zero();
-  for (uint32_t p = pu; p < pv; p++) su = su + coef[p] * a[wire[p]];
-  for (uint32_t p = pv; p < pe; p++) sv = sv + coef[p] * a[wire[p]];
+  for (uint32_t p = pu; p < pe; p++) {
+    const uint32_t w = wire[p];
+    const Fr x = a[w & ~WIT_UNIT];
+    const Fr t = (w & WIT_UNIT) ? x : coef[p] * x;
+    if (p < pv) su = su + t; else sv = sv + t;
+  }
   Fr r = su * sv;
   if (winv) r = r * winv[g];
   a[out[g]] = r;
@@ -92,8 +98,8 @@ __global__ void __launch_bounds__(128) k_wit_level(const uint32_t* __restrict__ 
   Fr su = Fr::zero(), sv = Fr::zero();
   for (uint32_t p = pu; p < pe; p++) {
     const uint32_t w = p == pu ? w0 : wire[p];
-    const Fr c = p == pu ? c0 : coef[p];
-    const Fr t = c * ld_fr_l2(a + w);
+    const Fr x = ld_fr_l2(a + (w & ~WIT_UNIT));
+    const Fr t = (w & WIT_UNIT) ? x : (p == pu ? c0 : coef[p]) * x;
     if (p < pv) su = su + t; else sv = sv + t;
   }
   Fr r = su * sv;
@@ -113,7 +119,9 @@ __global__ void __cluster_dims__(WIT_CL, 1, 1) __launch_bounds__(WIT_CL_THREADS)
       const uint32_t pu = ptr[2 * g], pv = ptr[2 * g + 1], pe = ptr[2 * g + 2];
       Fr su = Fr::zero(), sv = Fr::zero();
       for (uint32_t p = pu; p < pe; p++) {
-        const Fr t = coef[p] * ld_fr_l2(a + wire[p]);
+        const uint32_t w = wire[p];
+        const Fr x = ld_fr_l2(a + (w & ~WIT_UNIT));
+        const Fr t = (w & WIT_UNIT) ? x : coef[p] * x;
         if (p < pv) su = su + t; else sv = sv + t;
       }
       Fr r = su * sv;
@@ -126,17 +134,61 @@ __global__ void __cluster_dims__(WIT_CL, 1, 1) __launch_bounds__(WIT_CL_THREADS)
   }
 }
 
-// a run of narrow levels [l0, l1) in ONE block: the stores of level l are visible to the block after the barrier
+// a run of narrow levels [l0, l1) in ONE block: the stores of level l are visible to the block after the barrier.
+// The structure of the NEXT level's gate (offsets, output wire, the first four wire indices) does not depend on the
+// witness: it is loaded before the barrier, so that after it only a[wire] -> products -> store remain on the chain
+// (per level of a depth-n chain: 3.0 -> 1.5 us with unit coefficients, profiles/r02_witness_v3.jsonl).
+struct WitGate {
+  uint32_t pu, pv, pe, o, w[4];
+};
+__device__ __forceinline__ WitGate wit_fetch(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ wire,
+                                             const uint32_t* __restrict__ out, uint32_t g) {
+  WitGate s;
+  s.pu = ptr[2 * g]; s.pv = ptr[2 * g + 1]; s.pe = ptr[2 * g + 2];
+  s.o = out[g];
+#pragma unroll
+  for (int i = 0; i < 4; i++) s.w[i] = s.pu + i < s.pe ? wire[s.pu + i] : 0u;
+  return s;
+}
 __global__ void __launch_bounds__(WIT_NARROW) k_wit_run(const uint32_t* __restrict__ lptr, const uint32_t* __restrict__ ptr,
                                                         const uint32_t* __restrict__ wire, const Fr* __restrict__ coef,
                                                         const uint32_t* __restrict__ out, const Fr* __restrict__ winv, Fr* a,
                                                         uint32_t l0, uint32_t l1) {
-  uint32_t lo = lptr[l0];
+  uint32_t lo = lptr[l0], hi = lptr[l0 + 1];
+  uint32_t g = lo + threadIdx.x;
+  bool have = g < hi;
+  WitGate s = {};
+  if (have) s = wit_fetch(ptr, wire, out, g);
   for (uint32_t l = l0; l < l1; l++) {
-    const uint32_t hi = lptr[l + 1];
-    const uint32_t g = lo + threadIdx.x;
-    if (g < hi) wit_gate(ptr, wire, coef, out, winv, a, g);
-    lo = hi;
+    if (have) {
+      Fr su = Fr::zero(), sv = Fr::zero();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {  // the prefetched entries (compile-time indices: s.w stays in registers)
+        const uint32_t p = s.pu + i;
+        if (p < s.pe) {
+          const uint32_t w = s.w[i];
+          const Fr x = a[w & ~WIT_UNIT];
+          const Fr t = (w & WIT_UNIT) ? x : coef[p] * x;
+          if (p < s.pv) su = su + t; else sv = sv + t;
+        }
+      }
+      for (uint32_t p = s.pu + 4; p < s.pe; p++) {
+        const uint32_t w = wire[p];
+        const Fr x = a[w & ~WIT_UNIT];
+        const Fr t = (w & WIT_UNIT) ? x : coef[p] * x;
+        if (p < s.pv) su = su + t; else sv = sv + t;
+      }
+      Fr r = su * sv;
+      if (winv) r = r * winv[g];
+      a[s.o] = r;
+    }
+    if (l + 1 < l1) {  // next level's structure, before the barrier
+      lo = hi;
+      hi = lptr[l + 2];
+      g = lo + threadIdx.x;
+      have = g < hi;
+      if (have) s = wit_fetch(ptr, wire, out, g);
+    }
     __syncthreads();
   }
 }
@@ -158,8 +210,18 @@ __global__ void k_wit_gather(const uint32_t* __restrict__ order, const uint32_t*
   if (g >= n_gates) return;
   const uint32_t k = order[g];
   uint32_t o = ptr[2 * g];
-  for (uint32_t p = gptr_u[k], e = gptr_u[k + 1]; p < e; p++, o++) { wire[o] = wire_u[p]; coef[o] = coef_u[p]; }
-  for (uint32_t p = gptr_v[k], e = gptr_v[k + 1]; p < e; p++, o++) { wire[o] = wire_v[p]; coef[o] = coef_v[p]; }
+  // bit 31 of the wire index marks a coefficient of 1 (variables and unweighted sums: most entries of a parsed program,
+  // circuit/mod.rs:300-480): the evaluation then skips the product
+  for (uint32_t p = gptr_u[k], e = gptr_u[k + 1]; p < e; p++, o++) {
+    const Fr c = coef_u[p];
+    wire[o] = wire_u[p] | (c == Fr::one() ? WIT_UNIT : 0u);
+    coef[o] = c;
+  }
+  for (uint32_t p = gptr_v[k], e = gptr_v[k + 1]; p < e; p++, o++) {
+    const Fr c = coef_v[p];
+    wire[o] = wire_v[p] | (c == Fr::one() ? WIT_UNIT : 0u);
+    coef[o] = c;
+  }
   const Fr cw = coef_w[gptr_w[k]];
   if (cw.is_zero()) *zero_flag = 1;  // 0 * out = U * V assigns nothing: the reference's evaluate has no such gate; refuse it
   if (winv) winv[g] = inverse(cw);

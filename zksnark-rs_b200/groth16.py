@@ -1108,10 +1108,11 @@ def witness_generate_dev(ctx: Context, plan: WitnessPlan, d_values: int, n_value
     ctx.check(ctx.lib.zkb_witness_generate(ctx.h, plan.h, d_values, n_values, 1, d_out, 1), "zkb_witness_generate")
 
 
-def layered_qap_rows(width: int, depth: int, fan_in: int = 2, seed: int = 1):
+def layered_qap_rows(width: int, depth: int, fan_in: int = 2, seed: int = 1, unit_coeffs: bool = False):
     """Synthetic WIDE circuit for witness generation (the Horner family is a depth-n chain): `depth` layers of `width`
     gates; gate j of layer l multiplies two sums of `fan_in` wires each, drawn (seeded) from the previous layer's
-    outputs -- layer 0 from the `width` free input wires -- with small literal weights.  Wire order: 0 unity,
+    outputs -- layer 0 from the `width` free input wires -- with small literal weights (``unit_coeffs``: all 1, the shape of
+    a parsed program, where variables and unweighted sums dominate).  Wire order: 0 unity,
     1..width inputs, then the gate outputs in gate order (gate k -> wire width + 1 + k); n = width * depth gates.
     Returns (n, m, n_input, rows, free_wires).  Vectorised: builds 2^20 gates in about a second."""
     rng = np.random.default_rng(seed)
@@ -1123,7 +1124,7 @@ def layered_qap_rows(width: int, depth: int, fan_in: int = 2, seed: int = 1):
     rows = []
     for _ in range(2):  # u, v
         wire = base + rng.integers(0, width, size=n * fan_in)
-        coef = rng.integers(1, 8, size=n * fan_in).astype(np.uint64)
+        coef = np.ones(n * fan_in, dtype=np.uint64) if unit_coeffs else rng.integers(1, 8, size=n * fan_in).astype(np.uint64)
         # merge duplicate (wire, gate) pairs: a by-wire row holds one entry per gate
         key = wire * n + gate
         uniq, inv = np.unique(key, return_inverse=True)
