@@ -341,7 +341,7 @@ int zkb_points_sum(zkb_ctx* ctx, int group, const uint64_t* h_points, size_t n, 
 /* Element-wise field operations on the device (validation hook for the field arithmetic the kernels
  * are built from: crate `bn`'s Fr / Fq / Fq2 ops reached through fr.rs:18-56).  field: 0 Fr, 1 Fq
  * (4 limbs per element), 2 Fq2 (8 limbs: c0, c1).  op for Fr/Fq: 0 a*b, 1 a^2, 2 a*b - c*d, 3 a+b,
- * 4 a-b, 5 1/a (0 -> 0); for Fq2: 0 a*b, 1 a^2, 2 1/a, 3 a*b - c*d (the two-reduction form the G2 mixed addition
+ * 4 a-b, 5 1/a (0 -> 0), 6 / 7 a*b as wide product + stand-alone reduction (7: Karatsuba wide product); for Fq2: 0 a*b, 1 a^2, 2 1/a, 3 a*b - c*d (the two-reduction form the G2 mixed addition
  * uses).  All arrays host, canonical, n elements. */
 int zkb_field_op(zkb_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, const uint64_t* c,
                  const uint64_t* d, uint64_t* out, size_t n);
@@ -349,7 +349,8 @@ int zkb_field_op(zkb_ctx* ctx, int field, int op, const uint64_t* a, const uint6
 /* Peak-rate micro-benchmark: every thread runs `iters` dependent-chain pairs of Fq Montgomery
  * multiplications (ILP 4); returns measured modmul/s in *rate (denominator of the point-add
  * roofline) and the launch duration in *ms. */
-int zkb_bench_modmul(zkb_ctx* ctx, int field /*0 Fr, 1 Fq*/, int iters, double* rate, double* ms);
+int zkb_bench_modmul(zkb_ctx* ctx, int field /*0 Fr, 1 Fq; 2 / 3: Fq as wide product + reduction, 3 with Karatsuba*/, int iters,
+                     double* rate, double* ms);
 
 #ifdef __cplusplus
 }

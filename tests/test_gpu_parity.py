@@ -157,6 +157,11 @@ def test_field_ops_match_bigint(ctx, field):
     assert zg.field_op(ctx, field, 3, a, b) == [(x + y) % p for x, y in zip(a, b)]
     assert zg.field_op(ctx, field, 4, a, b) == [(x - y) % p for x, y in zip(a, b)]
     assert zg.field_op(ctx, field, 5, a[:200]) == [pow(x, p - 2, p) for x in a[:200]]
+    # the product as wide product + stand-alone reduction (what the Fq2 arithmetic is built from) and its Karatsuba form
+    half = [(1 << 128) - 1, 1 << 128, ((1 << 125) - 1) << 128, (1 << 253) | ((1 << 128) - 1)]
+    aa, bb = a + [x % p for x in half for _ in half], b + [y % p for _ in half for y in half]
+    for op in (6, 7):
+        assert zg.field_op(ctx, field, op, aa, bb) == [x * y % p for x, y in zip(aa, bb)]
 
 
 def test_fq2_ops_match_bigint(ctx):

@@ -83,6 +83,69 @@ def mul_wide(a, b):
     return merge(E, O)
 
 
+def mul_half(A, B):
+    """4 x 4 limbs -> 8 limbs with the same even / odd carry chains (the three products of mul_wide_k)."""
+    E, O = [0] * 9, [0] * 8
+    chain(E, 0, A, (0, 2), B[0])
+    chain(O, 0, A, (1, 3), B[0])
+    chain(O, 0, A, (0, 2), B[1])
+    chain(E, 2, A, (1, 3), B[1])
+    chain(E, 2, A, (0, 2), B[2])
+    chain(O, 2, A, (1, 3), B[2])
+    chain(O, 2, A, (0, 2), B[3])
+    chain(E, 4, A, (1, 3), B[3])
+    assert E[8] == 0 and O[7] == 0
+    return merge(E[:8], O)
+
+
+def add_n(x, y, cin=0):
+    r, cf = [], cin
+    for a, b in zip(x, y):
+        t = a + b + cf
+        r.append(t & M32)
+        cf = t >> 32
+    return r, cf
+
+
+def sub_n(x, y, bin_=0):
+    r, bf = [], bin_
+    for a, b in zip(x, y):
+        t = a - b - bf
+        r.append(t & M32)
+        bf = 1 if t < 0 else 0
+    return r, bf
+
+
+def mul_wide_k(a, b):
+    """One level of Karatsuba: 48 limb products instead of 64.  a = a0 + a1 B, b = b0 + b1 B (B = 2^128):
+    z0 = a0 b0, z2 = a1 b1, zm = (a0 + a1)(b0 + b1) - z0 - z2 (9 limbs), r = z0 + zm B + z2 B^2."""
+    A, Bv = limbs(a), limbs(b)
+    z0 = mul_half(A[:4], Bv[:4])
+    z2 = mul_half(A[4:], Bv[4:])
+    sa, ca = add_n(A[:4], A[4:])
+    sb, cb = add_n(Bv[:4], Bv[4:])
+    zm = mul_half(sa, sb) + [0]
+    # + ca * sb * B + cb * sa * B + ca * cb * B^2
+    t = [x & (M32 if ca else 0) for x in sb]
+    u = [x & (M32 if cb else 0) for x in sa]
+    hi, c = add_n(zm[4:8], t)
+    top = zm[8] + c
+    hi, c = add_n(hi, u)
+    top += c + (ca & cb)
+    assert top <= 7
+    zm = zm[:4] + hi + [top]
+    zm, bf = sub_n(zm, z0 + [0])
+    assert bf == 0
+    zm, bf = sub_n(zm, z2 + [0])
+    assert bf == 0 and zm[8] <= 1
+    r = z0[:4]
+    mid, c1 = add_n(z0[4:], zm[:4])
+    hi2, c2 = add_n(z2[:4], zm[4:8], c1)
+    top2, c3 = add_n(z2[4:], [zm[8], 0, 0, 0], c2)
+    assert c3 == 0
+    return r + mid + hi2 + top2
+
+
 def sqr_wide(a):
     A = limbs(a)
     E, O = [0] * 16, [0] * 16
@@ -170,10 +233,12 @@ if __name__ == "__main__":
     for p in (r_mod, q_mod):
         inv = (-pow(p, -1, 1 << 32)) % (1 << 32)
         Rinv = pow(R, -1, p)
-        edge = [0, 1, p - 1, p - 2, (1 << 255) - 1, R - 1, (1 << 254), M32, R - (1 << 224)]
+        edge = [0, 1, p - 1, p - 2, (1 << 255) - 1, R - 1, (1 << 254), M32, R - (1 << 224), (1 << 128) - 1, ((1 << 128) - 1) << 128,
+                (1 << 128), R - (1 << 128) - 1, ((1 << 127) << 128) | (1 << 127)]
         cases = [(a, b) for a in edge for b in edge] + [(rng.randrange(R), rng.randrange(R)) for _ in range(3000)]
         for a, b in cases:
             assert unlimbs(mul_wide(a, b)) == a * b, (a, b)
+            assert unlimbs(mul_wide_k(a, b)) == a * b, (a, b)
             assert unlimbs(sqr_wide(a)) == a * a, a
         red = [0, 1, p - 1, p * R - 1, p * R - p, (p - 1) * (p - 1), 2 * (p - 1) * (p - 1), p * p + (p - 1) ** 2]
         red += [rng.randrange(p * R) for _ in range(20000)]

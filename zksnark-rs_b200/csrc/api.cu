@@ -522,6 +522,8 @@ __global__ void k_field_op(int op, const F* a, const F* b, const F* c, const F* 
     case 2: r = mul_sub_mul(x, y, z, w); break;
     case 3: r = x + y; break;
     case 4: r = x - y; break;
+    case 6: r = mul_wide_redc<false>(x, y); break;  // wide product + stand-alone reduction
+    case 7: r = mul_wide_redc<true>(x, y); break;   // Karatsuba wide product + reduction
     default: r = inverse(x); break;
   }
   out[i] = from_mont(r);
@@ -598,6 +600,30 @@ __global__ void __launch_bounds__(256) k_bench_modmul(F* out, int iters) {
   s = s + ((b[0] + b[1]) + (b[2] + b[3]));
   if (s.v[0] == 0xdeadbeefu && s.v[7] == 0x12345678u) out[t] = s;  // practically never; defeats DCE
 }
+// the same chain with the product as wide product + stand-alone reduction (KARA: Karatsuba wide product)
+template <bool KARA>
+__global__ void __launch_bounds__(256) k_bench_modmul_wide(Fq* out, int iters) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  Fq a[4], b[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    a[q] = Fq::one();
+    b[q] = Fq::r2();
+    a[q].v[0] += t + q;
+    b[q].v[1] ^= t * 2654435761u + q;
+    b[q].v[7] &= 0x0fffffffu;
+  }
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      a[q] = mul_wide_redc<KARA>(a[q], b[q]);
+      b[q] = mul_wide_redc<KARA>(b[q], a[q]);
+    }
+  }
+  Fq s = (a[0] + a[1]) + (a[2] + a[3]);
+  s = s + ((b[0] + b[1]) + (b[2] + b[3]));
+  if (s.v[0] == 0xdeadbeefu && s.v[7] == 0x12345678u) out[t] = s;
+}
 }  // namespace zkb
 
 extern "C" int zkb_bench_modmul(zkb_ctx* ctx, int field, int iters, double* rate, double* ms) {
@@ -614,6 +640,10 @@ extern "C" int zkb_bench_modmul(zkb_ctx* ctx, int field, int iters, double* rate
     cudaEventRecord(e0, ctx->stream);
     if (field == 0) {
       ZKB_LAUNCH(ctx, k_bench_modmul<Fr>, blocks, threads, 0, ctx->stream, (Fr*)p, iters);
+    } else if (field == 2) {
+      ZKB_LAUNCH(ctx, k_bench_modmul_wide<false>, blocks, threads, 0, ctx->stream, (Fq*)p, iters);
+    } else if (field == 3) {
+      ZKB_LAUNCH(ctx, k_bench_modmul_wide<true>, blocks, threads, 0, ctx->stream, (Fq*)p, iters);
     } else {
       ZKB_LAUNCH(ctx, k_bench_modmul<Fq>, blocks, threads, 0, ctx->stream, (Fq*)p, iters);
     }

@@ -389,6 +389,86 @@ __device__ __forceinline__ void mul_wide(uint32_t (&r)[16], const uint32_t (&a)[
   wide_merge(r, E, O);
 }
 
+// ---- one level of Karatsuba on the wide product: 48 limb products instead of 64 ------------------------------------
+// a = a0 + a1 B, b = b0 + b1 B (B = 2^128):  z0 = a0 b0,  z2 = a1 b1,  zm = (a0 + a1)(b0 + b1) - z0 - z2 = a0 b1 + a1 b0
+// (9 limbs),  a b = z0 + zm B + z2 B^2.  The idea: the accumulation kernels are bound by the multiplier pipe at ~40 % issue
+// utilisation, so 16 fewer IMAD.WIDE for ~70 more integer adds should pay.  MEASURED ON B200 (zkb_bench_modmul fields
+// 1 / 2 / 3, profiles/r02_notes.md): it does not -- CIOS 67.0 G modmul/s, wide product + reduction 56.5, Karatsuba wide
+// product + reduction 54.5-55.0: ptxas schedules a large share of the extra adds as IMAD forms on the same pipe (SASS per
+// product: 120 IMAD.WIDE + 16 IMAD + 82 other for CIOS; 102 + 58 + 202 here).  Kept as a validated primitive (field-op
+// hook 7, bench field 3; -DZKB_KARATSUBA routes the Fq2 products through it); not used by any kernel.  Bookkeeping
+// validated in tools/emul_wide.py (mul_wide_k).
+// r[0..7] = a[0..3] * b[0..3]
+__device__ __forceinline__ void mul_half(uint32_t (&r)[8], const uint32_t* a, const uint32_t* b) {
+  uint32_t E[9], O[8];
+#pragma unroll
+  for (int i = 0; i < 9; i++) E[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) O[i] = 0;
+  ZKB_WCHAIN2((E + 0), E[4], a[0], a[2], b[0]);
+  ZKB_WCHAIN2((O + 0), O[4], a[1], a[3], b[0]);
+  ZKB_WCHAIN2((O + 0), O[4], a[0], a[2], b[1]);
+  ZKB_WCHAIN2((E + 2), E[6], a[1], a[3], b[1]);
+  ZKB_WCHAIN2((E + 2), E[6], a[0], a[2], b[2]);
+  ZKB_WCHAIN2((O + 2), O[6], a[1], a[3], b[2]);
+  ZKB_WCHAIN2((O + 2), O[6], a[0], a[2], b[3]);
+  ZKB_WCHAIN2((E + 4), E[8], a[1], a[3], b[3]);  // E[8] and O[7] stay 0 (product < 2^256)
+  r[0] = E[0];
+  asm("add.cc.u32 %0, %7, %14;\n\t"
+      "addc.cc.u32 %1, %8, %15;\n\t"
+      "addc.cc.u32 %2, %9, %16;\n\t"
+      "addc.cc.u32 %3, %10, %17;\n\t"
+      "addc.cc.u32 %4, %11, %18;\n\t"
+      "addc.cc.u32 %5, %12, %19;\n\t"
+      "addc.u32 %6, %13, %20;"
+      : "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
+      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+        "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+}
+// r[0..3] = x + y (+ cin), cout
+#define ZKB_ADD4(r, x, y, cin, cout)                                                               \
+  asm("{\n\t.reg .u32 t;\n\t"                                                                    \
+      "add.cc.u32 t, %13, 0xffffffff;\n\t"                                                        \
+      "addc.cc.u32 %0, %5, %9;\n\t"                                                               \
+      "addc.cc.u32 %1, %6, %10;\n\t"                                                              \
+      "addc.cc.u32 %2, %7, %11;\n\t"                                                              \
+      "addc.cc.u32 %3, %8, %12;\n\t"                                                              \
+      "addc.u32 %4, 0, 0;\n\t}"                                                                   \
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(cout)                            \
+      : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(cin))
+__device__ __forceinline__ void mul_wide_k(uint32_t (&r)[16], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+  const uint32_t zero = 0;
+  uint32_t z0[8], z2[8], zm[8], sa[4], sb[4], ca, cb, top, c;
+  mul_half(z0, a, b);
+  mul_half(z2, a + 4, b + 4);
+  ZKB_ADD4(sa, a, (a + 4), zero, ca);
+  ZKB_ADD4(sb, b, (b + 4), zero, cb);
+  mul_half(zm, sa, sb);
+  // + ca sb B + cb sa B + ca cb B^2  (zm grows to 9 limbs: `top`)
+  uint32_t t[4], u[4], hi[4];
+  const uint32_t ma = 0u - ca, mb = 0u - cb;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { t[i] = sb[i] & ma; u[i] = sa[i] & mb; }
+  ZKB_ADD4(hi, (zm + 4), t, zero, c);
+  top = c + (ca & cb);
+  ZKB_ADD4((zm + 4), hi, u, zero, c);
+  top += c;
+  // zm -= z0, zm -= z2 (no borrow out of the 9 limbs)
+  uint32_t bw;
+  ZKB_SUB8(zm, zm, z0, zero, bw);
+  top -= bw;
+  ZKB_SUB8(zm, zm, z2, zero, bw);
+  top -= bw;
+  // r = z0 + zm B + z2 B^2
+#pragma unroll
+  for (int i = 0; i < 4; i++) r[i] = z0[i];
+  uint32_t X[8] = {z0[4], z0[5], z0[6], z0[7], z2[0], z2[1], z2[2], z2[3]};
+  ZKB_ADD8((r + 4), X, zm, zero, c);
+  uint32_t Y[4] = {top, 0, 0, 0};
+  uint32_t c2;
+  ZKB_ADD4((r + 12), (z2 + 4), Y, c, c2);
+}
+
 // r = a * a: 28 off-diagonal products, doubled, plus the 8 diagonal squares
 __device__ __forceinline__ void sqr_wide(uint32_t (&r)[16], const uint32_t (&a)[8]) {
   uint32_t E[17], O[16];
@@ -812,13 +892,18 @@ ZKB_HD Fq2 operator-(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 - b.c0; r.
 #if defined(__CUDA_ARCH__)
 namespace dev_impl {
 // Karatsuba on unreduced 512-bit products: 3 wide products, 2 Montgomery reductions
+#if defined(ZKB_KARATSUBA)
+#define ZKB_MULW mul_wide_k
+#else
+#define ZKB_MULW mul_wide
+#endif
 __device__ __forceinline__ Fq2 fq2_mul_lazy(const Fq2& a, const Fq2& b) {
   uint32_t v0[16], v1[16], v2[16], sa[8], sb[8], q2[16];
-  mul_wide(v0, a.c0.v, b.c0.v);
-  mul_wide(v1, a.c1.v, b.c1.v);
+  ZKB_MULW(v0, a.c0.v, b.c0.v);
+  ZKB_MULW(v1, a.c1.v, b.c1.v);
   add_nored(sa, a.c0.v, a.c1.v);
   add_nored(sb, b.c0.v, b.c1.v);
-  mul_wide(v2, sa, sb);
+  ZKB_MULW(v2, sa, sb);
   wide_sub(v2, v2, v0);
   wide_sub(v2, v2, v1);  // a0 b1 + a1 b0 < 2 q^2
   psq<FqParams>(q2);
@@ -905,6 +990,20 @@ ZKB_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
 #endif
 }
 // a * b - c * d over Fq2
+// a * b as a wide product followed by a stand-alone reduction; KARA: the wide product by one level of Karatsuba
+// (micro-benchmark and validation hooks; host: the plain product)
+template <bool KARA, class P>
+ZKB_HD Fp<P> mul_wide_redc(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t T[16];
+  if (KARA) dev_impl::mul_wide_k(T, a.v, b.v); else dev_impl::mul_wide(T, a.v, b.v);
+  Fp<P> r;
+  dev_impl::redc<P>(r.v, T);
+  return r;
+#else
+  return a * b;
+#endif
+}
 // the two-reduction form by name (validation hook zkb_field_op; host: the plain definition)
 ZKB_HD Fq2 mul_sub_mul_lazy(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) {
 #if defined(__CUDA_ARCH__)
