@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libzkb200.so")
 SOURCES = ["msm_g2_acc.cu", "msm_g2_red.cu", "msm_g2_tab.cu", "msm_g1.cu", "msm_g2.cu", "crs.cu", "prove.cu", "api.cu", "ntt.cu", "pairing.cu", "shard.cu", "wire.cu", "witness.cu"]
-HEADERS = ["ff.cuh", "ec.cuh", "constants.h", "common.cuh", "msm_impl.cuh", os.path.join("..", "..", "include", "zkb200.h")]
+HEADERS = ["ff.cuh", "ec.cuh", "constants.h", "common.cuh", "msm_impl.cuh", "affine_level.cuh", os.path.join("..", "..", "include", "zkb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -173,6 +173,7 @@ struct ChunkPlan {
     return max_recs <= r1 ? (max_recs + S1 - 1) / S1 : T1 + (max_recs - r1 + S2 - 1) / S2;
   }
 };
+static const int MSM_AFF_MAX_LEVELS = 8;
 struct MsmPlan {
   int group = 1;  // 1: G1 (Fq), 2: G2 (Fq2)
   const void* tab = nullptr;
@@ -187,6 +188,19 @@ struct MsmPlan {
   size_t nbk = 0, max_recs = 0, nacc = 0, lvl_elems = 0;
   uint32_t *hist = nullptr, *offs = nullptr, *cursor = nullptr, *sums = nullptr, *sorted = nullptr;
   void *buckets = nullptr, *heads = nullptr, *lvlS = nullptr, *lvlA = nullptr, *d_out = nullptr;
+  // batched-affine pair tree in front of the XYZZ chain (affine_level.cuh; 0 levels = off): level l = 1 .. aff_levels has
+  // the offsets aff_offs + (l - 1) * (nbk + 1) and at most aff_max[l] elements (aff_max[0] = max_recs), written to
+  // aff_buf[(l - 1) & 1]; the chain then runs over the last level with the chunk plan ch_fin (nacc_fin chunks)
+  int aff_levels = 0, aff_batch = 16;
+  size_t aff_max[MSM_AFF_MAX_LEVELS + 1] = {};
+  uint32_t *aff_offs = nullptr, *aff_sums = nullptr, *aff_counters = nullptr;
+  void* aff_buf[2] = {nullptr, nullptr};
+  void* aff_prefix = nullptr;
+  unsigned aff_blocks = 0, aff_k = 4;  // grid of the longest level (columns of the prefix scratch / 128); groups of 32 items per warp
+  ChunkPlan ch_fin;
+  size_t nacc_fin = 0;
+  const uint32_t* offs_fin() const { return aff_levels ? aff_offs + (size_t)(aff_levels - 1) * (nbk + 1) : offs; }
+  const ChunkPlan& ch_tail() const { return aff_levels ? ch_fin : ch; }
 };
 int msm_prepare(zkb_ctx* ctx, DevBuf* slots, int slot_base, int group, const void* tab, size_t stride, int c, const MsmJob* jobs,
                 int njobs, void* d_out, MsmPlan* plan);

@@ -5,6 +5,7 @@
 // but a longer dependency chain): 0.968 vs 0.957 of the modmul peak.
 #define ZKB_NO_LAZY 1
 #define ZKB_ACC_MIN_BLOCKS 5
+#define ZKB_AFF_MIN_BLOCKS 5  // k_affine_level<Fq>: 92 registers without spills
 #include "msm_impl.cuh"
 namespace zkb {
 
@@ -143,12 +144,96 @@ int msm_sort_records(zkb_ctx* ctx, const MsmJob* jobs, int njobs, size_t stride,
   return ZKB_OK;
 }
 
+// ---- offsets of the pair-tree levels (affine_level.cuh): level l >= 1 holds ceil(k_b / 2^l) elements of bucket b, so all
+// levels scan the level-0 offsets independently: the three scan kernels once, blockIdx.y = level - 1 -------------------
+__global__ void k_lvl_scan_block(const uint32_t* __restrict__ offs0, uint32_t* __restrict__ lvl_offs, uint32_t* __restrict__ lvl_sums,
+                                 size_t n, size_t nblocks) {
+  __shared__ uint32_t sh[256];
+  const int l = blockIdx.y + 1;
+  uint32_t* out = lvl_offs + (size_t)blockIdx.y * (n + 1);
+  uint32_t* sums = lvl_sums + (size_t)blockIdx.y * (nblocks + 1);
+  size_t base = (size_t)blockIdx.x * SCAN_B + threadIdx.x * 4;
+  uint32_t v[4], tot = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    v[q] = base + q < n ? affine_level_count(offs0[base + q + 1] - offs0[base + q], l) : 0;
+    tot += v[q];
+  }
+  sh[threadIdx.x] = tot;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {
+    uint32_t x = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += x;
+    __syncthreads();
+  }
+  uint32_t excl = sh[threadIdx.x] - tot;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    if (base + q < n) out[base + q] = excl;
+    excl += v[q];
+  }
+  if (threadIdx.x == 255) sums[blockIdx.x] = sh[255];
+}
+__global__ void __launch_bounds__(256) k_lvl_scan_sums(uint32_t* lvl_sums, size_t nblocks) {
+  __shared__ uint32_t sh[256];
+  __shared__ uint32_t carry;
+  uint32_t* sums = lvl_sums + (size_t)blockIdx.x * (nblocks + 1);
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < nblocks; base += 1024) {
+    const size_t i0 = base + threadIdx.x * 4;
+    uint32_t v[4], tot = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      v[q] = i0 + q < nblocks ? sums[i0 + q] : 0;
+      tot += v[q];
+    }
+    sh[threadIdx.x] = tot;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+      uint32_t x = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += x;
+      __syncthreads();
+    }
+    uint32_t excl = carry + sh[threadIdx.x] - tot;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (i0 + q < nblocks) sums[i0 + q] = excl;
+      excl += v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) carry += sh[255];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[nblocks] = carry;  // the level's element count
+}
+__global__ void k_lvl_scan_add(uint32_t* __restrict__ lvl_offs, const uint32_t* __restrict__ lvl_sums, size_t n, size_t nblocks) {
+  uint32_t* out = lvl_offs + (size_t)blockIdx.y * (n + 1);
+  const uint32_t* sums = lvl_sums + (size_t)blockIdx.y * (nblocks + 1);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += sums[i / SCAN_B];
+  if (i == n) out[n] = sums[nblocks];
+}
+static int msm_level_offsets(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
+  if (!P.aff_levels) return ZKB_OK;
+  const size_t nscan_blocks = (P.nbk + SCAN_B - 1) / SCAN_B;
+  ZKB_LAUNCH(ctx, k_lvl_scan_block, dim3((unsigned)nscan_blocks, P.aff_levels), 256, 0, st, P.offs, P.aff_offs, P.aff_sums, P.nbk, nscan_blocks);
+  ZKB_LAUNCH(ctx, k_lvl_scan_sums, P.aff_levels, 256, 0, st, P.aff_sums, nscan_blocks);
+  ZKB_LAUNCH(ctx, k_lvl_scan_add, dim3(cdiv(P.nbk + 1, 256), P.aff_levels), 256, 0, st, P.aff_offs, P.aff_sums, P.nbk, nscan_blocks);
+  return ZKB_OK;
+}
+
 int msm_pick_c(size_t n) { return pick_c(n); }
 
 template <> int MsmLaunch<Fq>::accumulate(zkb_ctx* ctx, const G1Affine* tab, const uint32_t* offs, const uint32_t* sorted,
                                           uint32_t nbk, size_t nacc, ChunkPlan ch, G1XYZZ* buckets, G1XYZZ* heads, cudaStream_t st,
                                           int pk) {
   return launch_accumulate<Fq>(ctx, tab, offs, sorted, nbk, nacc, ch, buckets, heads, st, pk);
+}
+template <> int MsmLaunch<Fq>::accumulate_affine(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st, int pk) {
+  return launch_accumulate_affine<Fq>(ctx, P, st, pk);
 }
 template <> int MsmLaunch<Fq>::fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, ChunkPlan ch, G1XYZZ* buckets,
                                          const G1XYZZ* heads, cudaStream_t st) {
@@ -168,7 +253,8 @@ int msm_sort(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
   DigitPlan pl = make_plan(P.c);
   pl.wr = P.win_rank;
   pl.ww = P.win_world;
-  return msm_sort_records(ctx, P.jobs, P.njobs, P.stride, pl, P.hist, P.offs, P.cursor, P.sums, P.sorted, st);
+  ZKB_TRY(msm_sort_records(ctx, P.jobs, P.njobs, P.stride, pl, P.hist, P.offs, P.cursor, P.sums, P.sorted, st));
+  return msm_level_offsets(ctx, P, st);
 }
 int msm_g1(zkb_ctx* ctx, const G1Affine* tab, size_t stride, int c, const MsmJob* jobs, int njobs, G1XYZZ* d_out, int slot,
            cudaStream_t st, int win_rank, int win_world) {

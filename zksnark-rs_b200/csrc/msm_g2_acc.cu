@@ -15,4 +15,7 @@ template <> int MsmLaunch<Fq2>::accumulate(zkb_ctx* ctx, const G2Affine* tab, co
                                            int pk) {
   return launch_accumulate<Fq2>(ctx, tab, offs, sorted, nbk, nacc, ch, buckets, heads, st, pk);
 }
+template <> int MsmLaunch<Fq2>::accumulate_affine(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st, int pk) {
+  return launch_accumulate_affine<Fq2>(ctx, P, st, pk);
+}
 }  // namespace zkb

@@ -29,6 +29,7 @@
 #pragma once
 #include <stdlib.h>
 #include "common.cuh"
+#include "affine_level.cuh"
 
 namespace zkb {
 
@@ -104,6 +105,8 @@ template <class F>
 struct MsmLaunch {
   static int accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t* offs, const uint32_t* sorted, uint32_t nbk,
                         size_t nacc, ChunkPlan ch, XYZZ<F>* buckets, XYZZ<F>* heads, cudaStream_t st, int prof_kind);
+  // the batched-affine pair tree (P.aff_levels levels) followed by the XYZZ chain over the last level
+  static int accumulate_affine(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st, int prof_kind);
   static int fix_heads(zkb_ctx* ctx, const uint32_t* offs, uint32_t nbk, ChunkPlan ch, XYZZ<F>* buckets, const XYZZ<F>* heads,
                        cudaStream_t st);
   // full hierarchy: buckets[njobs][nb] -> d_out[njobs]; lvlS / lvlA hold the intermediate levels
@@ -122,6 +125,37 @@ static inline size_t msm_level_elems(uint32_t nb, int njobs) {
   // < nb/3 (+ one per level) in each; the quad plan (launch_reduce_quad) at most 2 nb/4 + 3 nb/16 + 4 nb/64 + ... < 0.78 nb
   // (+ a few per level) in total, checked there.
   return ((size_t)nb / 2 + 128) * njobs;
+}
+
+// Levels of the batched-affine pair tree in front of the XYZZ chain (affine_level.cuh); 0 = the chain alone.
+// ZKB_AFF_G1 / ZKB_AFF_G2 = levels (0..8), ZKB_AFF_B = 16 | 32 (additions per inversion): developer switches.
+static inline int affine_levels_policy(int group, size_t max_recs, size_t nbk) {
+  int L = 0;
+  if (const char* e = getenv(group == 1 ? "ZKB_AFF_G1" : "ZKB_AFF_G2")) L = atoi(e);
+  if (L < 0) L = 0;
+  if (L > MSM_AFF_MAX_LEVELS) L = MSM_AFF_MAX_LEVELS;
+  if (max_recs >= ((size_t)1 << 31) - nbk) L = 0;  // source words keep bit 31 for the sign
+  while (L > 0 && (max_recs >> L) < nbk / 4) L--;  // a level is worth a launch while buckets still hold several elements
+  return L;
+}
+static inline int affine_batch_policy() {
+  if (const char* e = getenv("ZKB_AFF_B")) return atoi(e) == 32 ? 32 : 16;
+  return 16;
+}
+// Work items are handed out 32 at a time (one per lane); a warp takes up to K such groups and leaves, so that blocks
+// end every few hundred microseconds and the latency-class kernels of other proofs in flight find room (a persistent
+// grid would hold every SM for the whole level).  ZKB_AFF_K: developer switch.
+static inline unsigned affine_groups_per_warp() {
+  if (const char* e = getenv("ZKB_AFF_K")) {
+    int k = atoi(e);
+    if (k >= 1 && k <= (1 << 20)) return (unsigned)k;
+  }
+  return 4;
+}
+static inline unsigned affine_level_grid(size_t max_out, int batch, unsigned K) {
+  const size_t items = (max_out + batch - 1) / batch, groups = (items + 31) / 32;
+  const size_t blocks = (groups + 4 * (size_t)K - 1) / (4 * (size_t)K);
+  return blocks ? (unsigned)blocks : 1u;
 }
 
 // phases of one MSM call (see MsmPlan in common.cuh); F-typed views of the plan's buffers
@@ -149,22 +183,47 @@ static int msm_prepare_t(zkb_ctx* ctx, DevBuf* slots, int slot, const Affine<F>*
   P->ch = chunk_plan<F>(P->max_recs, ctx->sm_count);
   P->nacc = P->ch.count(P->max_recs);
   P->lvl_elems = msm_level_elems(pl.nb, njobs);
+  // pair tree: sizes of the levels (sum of ceil(k_b / 2) <= (sum k_b + nbk) / 2), chunk plan of the chain behind them
+  P->aff_levels = affine_levels_policy(P->group, P->max_recs, P->nbk);
+  P->aff_batch = affine_batch_policy();
+  size_t nheads = P->nacc, aff_bytes = 0;
+  if (P->aff_levels) {
+    P->aff_max[0] = P->max_recs;
+    for (int l = 1; l <= P->aff_levels; l++) P->aff_max[l] = (P->aff_max[l - 1] + P->nbk) / 2;
+    P->aff_k = affine_groups_per_warp();
+    P->aff_blocks = affine_level_grid(P->aff_max[1], P->aff_batch, P->aff_k);  // level 1 is the longest
+    P->ch_fin = chunk_plan<F>(P->aff_max[P->aff_levels], ctx->sm_count);
+    P->nacc_fin = P->ch_fin.count(P->aff_max[P->aff_levels]);
+    if (P->nacc_fin > nheads) nheads = P->nacc_fin;
+    aff_bytes = (P->aff_max[1] + (P->aff_levels >= 2 ? P->aff_max[2] : 0)) * sizeof(Affine<F>) +
+                (size_t)P->aff_blocks * 128 * P->aff_batch * sizeof(F);
+  }
   void* p;
-  // u32 scratch: hist[nbk] | offs[nbk+1] | cursor[nbk] | sums[nscan_blocks+1]
+  // u32 scratch: hist[nbk] | offs[nbk+1] | cursor[nbk] | sums[nscan_blocks+1] | pair tree: offsets[L][nbk+1] | sums[L][nscan_blocks+1] | counters[L]
   size_t u32_words = P->nbk * 3 + 1 + nscan_blocks + 8;
-  ZKB_TRY(scratch_get_in(ctx, slots, slot + 0, u32_words * 4, &p));
+  const size_t aff_words = (size_t)P->aff_levels * (P->nbk + 1 + nscan_blocks + 1) + MSM_AFF_MAX_LEVELS;
+  ZKB_TRY(scratch_get_in(ctx, slots, slot + 0, (u32_words + aff_words) * 4, &p));
   P->hist = (uint32_t*)p;
   P->offs = P->hist + P->nbk;
   P->cursor = P->offs + P->nbk + 1;
   P->sums = P->cursor + P->nbk;
+  P->aff_offs = P->hist + u32_words;
+  P->aff_sums = P->aff_offs + (size_t)P->aff_levels * (P->nbk + 1);
+  P->aff_counters = P->aff_sums + (size_t)P->aff_levels * (nscan_blocks + 1);
   ZKB_TRY(scratch_get_in(ctx, slots, slot + 1, P->max_recs * 4, &p));
   P->sorted = (uint32_t*)p;
-  ZKB_TRY(scratch_get_in(ctx, slots, slot + 2, (P->nbk + P->nacc + 2 * P->lvl_elems) * sizeof(XYZZ<F>), &p));
+  ZKB_TRY(scratch_get_in(ctx, slots, slot + 2, (P->nbk + nheads + 2 * P->lvl_elems) * sizeof(XYZZ<F>) + aff_bytes, &p));
   XYZZ<F>* buckets = (XYZZ<F>*)p;
   P->buckets = buckets;
   P->heads = buckets + P->nbk;
-  P->lvlS = buckets + P->nbk + P->nacc;
-  P->lvlA = buckets + P->nbk + P->nacc + P->lvl_elems;
+  P->lvlS = buckets + P->nbk + nheads;
+  P->lvlA = buckets + P->nbk + nheads + P->lvl_elems;
+  if (P->aff_levels) {
+    Affine<F>* a = reinterpret_cast<Affine<F>*>(buckets + P->nbk + nheads + 2 * P->lvl_elems);
+    P->aff_buf[0] = a;
+    P->aff_buf[1] = a + P->aff_max[1];
+    P->aff_prefix = a + P->aff_max[1] + (P->aff_levels >= 2 ? P->aff_max[2] : 0);
+  }
   return ZKB_OK;
 }
 
@@ -174,6 +233,10 @@ static int msm_accumulate_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
   const int prof_kind = P.group == 1 ? PK_ACC_G1 : PK_ACC_G2;
   ZKB_CUDA(ctx, cudaMemsetAsync(P.buckets, 0, P.nbk * sizeof(XYZZ<F>), st));  // all-zero XYZZ = identity
   if (ctx->profile) ctx->prof_units[prof_kind] += P.max_recs;
+  if (P.aff_levels) {
+    ZKB_CUDA(ctx, cudaMemsetAsync(P.aff_counters, 0, MSM_AFF_MAX_LEVELS * 4, st));
+    return MsmLaunch<F>::accumulate_affine(ctx, P, st, prof_kind);
+  }
   return MsmLaunch<F>::accumulate(ctx, (const Affine<F>*)P.tab, P.offs, P.sorted, (uint32_t)P.nbk, P.nacc, P.ch, (XYZZ<F>*)P.buckets,
                                   (XYZZ<F>*)P.heads, st, prof_kind);
 }
@@ -181,7 +244,7 @@ static int msm_accumulate_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
 template <class F>
 static int msm_tail_t(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st) {
   if (P.empty) return MsmLaunch<F>::set_inf(ctx, (XYZZ<F>*)P.d_out, P.njobs, st);
-  ZKB_TRY(MsmLaunch<F>::fix_heads(ctx, P.offs, (uint32_t)P.nbk, P.ch, (XYZZ<F>*)P.buckets, (const XYZZ<F>*)P.heads, st));
+  ZKB_TRY(MsmLaunch<F>::fix_heads(ctx, P.offs_fin(), (uint32_t)P.nbk, P.ch_tail(), (XYZZ<F>*)P.buckets, (const XYZZ<F>*)P.heads, st));
   return MsmLaunch<F>::reduce(ctx, (const XYZZ<F>*)P.buckets, make_plan(P.c).nb, P.njobs, (XYZZ<F>*)P.lvlS, (XYZZ<F>*)P.lvlA,
                               (XYZZ<F>*)P.d_out, st, P.tail);
 }
@@ -252,6 +315,65 @@ __global__ void __launch_bounds__(ZKB_ACC_THREADS, ZKB_ACC_MIN_BLOCKS) k_accumul
     Affine<F> P = ld_table_entry(pts + (rec & 0x7fffffffu));
     if (rec >> 31) P = neg(P);
     acc = madd(acc, P);
+  }
+  if (is_head) heads[t] = acc; else buckets[g] = acc;
+}
+
+// ---- the batched-affine pair tree in front of the chain (affine_level.cuh) -------------------------------------------
+// One level: every warp takes 32 consecutive work items at a time from an atomic counter, one item (B output elements, one
+// inversion) per lane, up to `groups` times.  The running products of a thread's item live in a global scratch laid out
+// [element][thread] (coalesced 32-byte / 64-byte rows; the rows of the resident blocks stay in the L2).
+#ifndef ZKB_AFF_MIN_BLOCKS
+#define ZKB_AFF_MIN_BLOCKS 1
+#endif
+template <class F, int B, bool FIRST>
+__global__ void __launch_bounds__(128, ZKB_AFF_MIN_BLOCKS) k_affine_level(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ sorted,
+                                                                          const uint32_t* __restrict__ offs_in, const uint32_t* __restrict__ offs_out,
+                                                                          uint32_t nbk, Affine<F>* __restrict__ out, F* __restrict__ prefix_base,
+                                                                          uint32_t* __restrict__ counter, unsigned groups) {
+  const uint32_t total = offs_out[nbk];
+  const uint32_t n_items = total / B + (total % B ? 1u : 0u);
+  const size_t pstride = (size_t)gridDim.x * blockDim.x;
+  F* prefix = prefix_base + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  for (unsigned k = 0; k < groups; k++) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(counter, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n_items) break;
+    if (base + lane < n_items)
+      affine_level_item<F, B, FIRST>(base + lane, pts, sorted, offs_in, offs_out, nbk, out, prefix, pstride);
+    __syncwarp();
+  }
+}
+// The chain over the elements of the last level: k_accumulate_chunks with the points read in place.
+template <class F>
+__global__ void __launch_bounds__(ZKB_ACC_THREADS, ZKB_ACC_MIN_BLOCKS) k_accumulate_points(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ offs,
+                                                                                           uint32_t nbk, size_t nchunks, ChunkPlan ch,
+                                                                                           XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  const uint32_t total = offs[nbk];
+  const uint32_t start = ch.start((uint32_t)t);
+  if (start >= total) return;
+  const uint32_t S = ch.len((uint32_t)t);
+  const uint32_t end = (total - start > S) ? start + S : total;
+  uint32_t lo = 0, hi = nbk;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (offs[mid] <= start) lo = mid + 1; else hi = mid;
+  }
+  uint32_t g = lo - 1;
+  bool is_head = offs[g] < start;
+  uint32_t bend = offs[g + 1];
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t p = start; p < end; p++) {
+    if (p == bend) {
+      if (is_head) { heads[t] = acc; is_head = false; } else buckets[g] = acc;
+      acc = XYZZ<F>::inf();
+      do { g++; bend = offs[g + 1]; } while (bend <= p);
+    }
+    acc = madd(acc, pts[p]);
   }
   if (is_head) heads[t] = acc; else buckets[g] = acc;
 }
@@ -585,6 +707,33 @@ static int launch_accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t*
   }
 #endif
   ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks<F>, cdiv(nacc, ZKB_ACC_THREADS), ZKB_ACC_THREADS, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
+  return ZKB_OK;
+}
+template <class F, int B>
+static int launch_affine_levels(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st, int prof_kind) {
+  const uint32_t nbk = (uint32_t)P.nbk;
+  for (int l = 0; l < P.aff_levels; l++) {  // level l + 1 from level l
+    const uint32_t* offs_in = l == 0 ? P.offs : P.aff_offs + (size_t)(l - 1) * (P.nbk + 1);
+    const uint32_t* offs_out = P.aff_offs + (size_t)l * (P.nbk + 1);
+    Affine<F>* out = (Affine<F>*)P.aff_buf[l & 1];
+    unsigned blocks = affine_level_grid(P.aff_max[l + 1], B, P.aff_k);
+    if (blocks > P.aff_blocks) blocks = P.aff_blocks;  // the prefix scratch has aff_blocks * 128 columns
+    if (l == 0)
+      ZKB_LAUNCH_K(ctx, prof_kind, (k_affine_level<F, B, true>), blocks, 128, 0, st, (const Affine<F>*)P.tab, P.sorted, offs_in, offs_out, nbk, out,
+                   (F*)P.aff_prefix, P.aff_counters + l, P.aff_k);
+    else
+      ZKB_LAUNCH_K(ctx, prof_kind, (k_affine_level<F, B, false>), blocks, 128, 0, st, (const Affine<F>*)P.aff_buf[(l - 1) & 1], (const uint32_t*)nullptr,
+                   offs_in, offs_out, nbk, out, (F*)P.aff_prefix, P.aff_counters + l, P.aff_k);
+  }
+  return ZKB_OK;
+}
+template <class F>
+static int launch_accumulate_affine(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st, int prof_kind) {
+  if (P.aff_batch == 32) ZKB_TRY((launch_affine_levels<F, 32>(ctx, P, st, prof_kind)));
+  else ZKB_TRY((launch_affine_levels<F, 16>(ctx, P, st, prof_kind)));
+  ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_points<F>, cdiv(P.nacc_fin, ZKB_ACC_THREADS), ZKB_ACC_THREADS, 0, st,
+               (const Affine<F>*)P.aff_buf[(P.aff_levels - 1) & 1], P.offs_fin(), (uint32_t)P.nbk, P.nacc_fin, P.ch_fin, (XYZZ<F>*)P.buckets,
+               (XYZZ<F>*)P.heads);
   return ZKB_OK;
 }
 template <class F>
