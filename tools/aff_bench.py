@@ -21,9 +21,27 @@ def rand_fr(rng, n):
     return a
 
 
-def mode(g1, g2, b=16, k=4):
+def mode(g1, g2, b=16, k=1, occ=0):
     os.environ["ZKB_AFF_G1"], os.environ["ZKB_AFF_G2"] = str(g1), str(g2)
-    os.environ["ZKB_AFF_B"], os.environ["ZKB_AFF_K"] = str(b), str(k)
+    os.environ["ZKB_AFF_B"], os.environ["ZKB_AFF_K"], os.environ["ZKB_AFF_OCC"] = str(b), str(k), str(occ)
+
+
+def trace_levels(ctx, fn):
+    """One call under the per-launch trace: [(kernel, ms)] of the accumulation kernels in launch order."""
+    import csv
+    path = "/tmp/aff_trace.csv"
+    ctx.profile(2)
+    fn()
+    ctx.trace_dump(path)
+    ctx.profile(0)
+    out = []
+    for r in list(csv.reader(open(path)))[1:]:
+        name = r[1]
+        for key, short in (("k_affine_level", "lvl"), ("k_accumulate_points", "chain"), ("k_accumulate_chunks", "chain0"),
+                           ("k_fix_heads", "heads"), ("k_lvl_scan", "scan")):
+            if key in name:
+                out.append((short, round(float(r[4]), 3)))
+    return out
 
 
 def main():
@@ -34,15 +52,15 @@ def main():
     rng = np.random.default_rng(1)
     out = []
     if "--prove-only" not in sys.argv:
-        for group, sweeps in ((2, [(0, 16, 4), (3, 16, 4), (4, 16, 4), (5, 16, 4), (6, 16, 4), (5, 32, 4), (5, 16, 16), (5, 16, 1 << 20)]),
-                              (1, [(0, 16, 4), (2, 16, 4), (3, 16, 4), (4, 16, 4), (4, 32, 4), (4, 16, 1 << 20)])):
+        for group, sweeps in ((2, [(0, 16, 1, 0), (3, 16, 1, 0), (5, 16, 1, 0), (6, 16, 1, 0), (5, 16, 1, 1), (5, 32, 1, 1), (5, 32, 1, 0), (5, 16, 2, 0)]),
+                              (1, [(0, 16, 1, 0), (2, 16, 1, 0), (4, 16, 1, 0), (4, 32, 1, 0), (4, 16, 2, 0)])):
             b = zk.Bases.generate(ctx, group, rand_fr(rng, n))
             s = rand_fr(rng, n)
             ds = ctx.dev_alloc(s.nbytes)
             ctx.h2d(ds, s)
             ref = None
-            for levels, batch, k in sweeps:
-                mode(levels if group == 1 else 0, levels if group == 2 else 0, batch, k)
+            for levels, batch, k, occ in sweeps:
+                mode(levels if group == 1 else 0, levels if group == 2 else 0, batch, k, occ)
                 for _ in range(2):
                     r = zk.msm(ctx, b, ds, on_device=True, n=n)
                 ref = ref or r
@@ -55,9 +73,10 @@ def main():
                 wall = (time.perf_counter() - t0) / reps
                 ms, cnt, units = ctx.profile_read(2 if group == 1 else 3)
                 ctx.profile(False)
-                rec = {"what": "msm", "group": group, "log_n": lg, "levels": levels, "batch": batch, "k": k,
+                rec = {"what": "msm", "group": group, "log_n": lg, "levels": levels, "batch": batch, "k": k, "occ": occ,
                        "call_ms": round(wall * 1e3, 3), "accumulate_ms": round(ms / reps, 3), "launches_per_call": cnt // reps,
-                       "records_M": round(units / reps / 1e6, 2)}
+                       "records_M": round(units / reps / 1e6, 2),
+                       "trace": trace_levels(ctx, lambda: zk.msm(ctx, b, ds, on_device=True, n=n))}
                 out.append(rec)
                 print(json.dumps(rec), flush=True)
             ctx.dev_free(ds)
@@ -70,8 +89,8 @@ def main():
         d_w = ctx.dev_alloc(w.nbytes)
         ctx.h2d(d_w, w)
         ref = None
-        for g1, g2, batch, k in ((0, 0, 16, 4), (0, 5, 16, 4), (0, 4, 16, 4), (0, 5, 32, 4), (0, 5, 16, 16), (3, 5, 16, 4), (4, 5, 16, 4), (4, 0, 16, 4)):
-            mode(g1, g2, batch, k)
+        for g1, g2, batch, k, occ in ((0, 0, 16, 1, 0), (0, 5, 16, 1, 0), (0, 5, 16, 1, 1), (0, 6, 16, 1, 0), (0, 5, 32, 1, 0), (4, 5, 16, 1, 0), (4, 0, 16, 1, 0)):
+            mode(g1, g2, batch, k, occ)
             for _ in range(2):
                 p = zg.prove_dev(ctx, q, crs, d_w, 17, 19)
             ref = ref or (p.a, p.b, p.c)
@@ -87,7 +106,7 @@ def main():
             pb = zk.prove_batch(ctx, q, crs, [d_w] * reps, [17] * reps, [19] * reps, on_device=True)
             tb = (time.perf_counter() - t0) / reps
             assert all((x.a, x.b, x.c) == ref for x in pb)
-            rec = {"what": "prove", "log_n": lg, "g1_levels": g1, "g2_levels": g2, "batch": batch, "k": k,
+            rec = {"what": "prove", "log_n": lg, "g1_levels": g1, "g2_levels": g2, "batch": batch, "k": k, "occ": occ,
                    "one_proof_ms": round(t1 * 1e3, 3), "batch_ms_per_proof": round(tb * 1e3, 3)}
             out.append(rec)
             print(json.dumps(rec), flush=True)

@@ -196,7 +196,7 @@ struct MsmPlan {
   uint32_t *aff_offs = nullptr, *aff_sums = nullptr, *aff_counters = nullptr;
   void* aff_buf[2] = {nullptr, nullptr};
   void* aff_prefix = nullptr;
-  unsigned aff_blocks = 0, aff_k = 4;  // grid of the longest level (columns of the prefix scratch / 128); groups of 32 items per warp
+  unsigned aff_blocks = 0, aff_k = 1;  // grid of the longest level (columns of the prefix scratch / 128); groups of 32 items per warp
   ChunkPlan ch_fin;
   size_t nacc_fin = 0;
   const uint32_t* offs_fin() const { return aff_levels ? aff_offs + (size_t)(aff_levels - 1) * (nbk + 1) : offs; }

@@ -142,15 +142,16 @@ static inline int affine_batch_policy() {
   if (const char* e = getenv("ZKB_AFF_B")) return atoi(e) == 32 ? 32 : 16;
   return 16;
 }
-// Work items are handed out 32 at a time (one per lane); a warp takes up to K such groups and leaves, so that blocks
-// end every few hundred microseconds and the latency-class kernels of other proofs in flight find room (a persistent
-// grid would hold every SM for the whole level).  ZKB_AFF_K: developer switch.
+// Work items are handed out 32 at a time (one per lane); a warp takes up to K such groups and leaves.  K = 1: a block lives
+// ~100 us, the grid is many waves long (no quantisation loss in the last wave, small levels still fill the machine) and
+// the latency-class kernels of other proofs in flight find room.  Measured: K = 4 leaves the G2 levels at 3.25 waves (the
+// last one a quarter full) and the late levels below one wave.  ZKB_AFF_K: developer switch.
 static inline unsigned affine_groups_per_warp() {
   if (const char* e = getenv("ZKB_AFF_K")) {
     int k = atoi(e);
     if (k >= 1 && k <= (1 << 20)) return (unsigned)k;
   }
-  return 4;
+  return 1;
 }
 static inline unsigned affine_level_grid(size_t max_out, int batch, unsigned K) {
   const size_t items = (max_out + batch - 1) / batch, groups = (items + 31) / 32;
@@ -192,8 +193,17 @@ static int msm_prepare_t(zkb_ctx* ctx, DevBuf* slots, int slot, const Affine<F>*
     for (int l = 1; l <= P->aff_levels; l++) P->aff_max[l] = (P->aff_max[l - 1] + P->nbk) / 2;
     P->aff_k = affine_groups_per_warp();
     P->aff_blocks = affine_level_grid(P->aff_max[1], P->aff_batch, P->aff_k);  // level 1 is the longest
-    P->ch_fin = chunk_plan<F>(P->aff_max[P->aff_levels], ctx->sm_count);
-    P->nacc_fin = P->ch_fin.count(P->aff_max[P->aff_levels]);
+    // chain behind the tree: few elements are left, so short chunks (a chunk is a serial chain of additions: what counts
+    // is that the grid still fills the machine a few times over, not the number of head pieces)
+    const size_t fin = P->aff_max[P->aff_levels];
+    P->ch_fin = chunk_plan<F>(fin, ctx->sm_count);
+    if (fin < ((size_t)1 << 23)) {
+      uint32_t S = 32;
+      while (S > 4 && fin / S < (size_t)ctx->sm_count * 1024) S >>= 1;
+      P->ch_fin.S1 = P->ch_fin.S2 = S;
+      P->ch_fin.T1 = (uint32_t)((fin + S - 1) / S);
+    }
+    P->nacc_fin = P->ch_fin.count(fin);
     if (P->nacc_fin > nheads) nheads = P->nacc_fin;
     aff_bytes = (P->aff_max[1] + (P->aff_levels >= 2 ? P->aff_max[2] : 0)) * sizeof(Affine<F>) +
                 (size_t)P->aff_blocks * 128 * P->aff_batch * sizeof(F);
@@ -326,8 +336,11 @@ __global__ void __launch_bounds__(ZKB_ACC_THREADS, ZKB_ACC_MIN_BLOCKS) k_accumul
 #ifndef ZKB_AFF_MIN_BLOCKS
 #define ZKB_AFF_MIN_BLOCKS 1
 #endif
-template <class F, int B, bool FIRST>
-__global__ void __launch_bounds__(128, ZKB_AFF_MIN_BLOCKS) k_affine_level(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ sorted,
+#ifndef ZKB_AFF_MIN_BLOCKS_ALT   // second build of the kernel with another register budget (ZKB_AFF_OCC=1 selects it)
+#define ZKB_AFF_MIN_BLOCKS_ALT ZKB_AFF_MIN_BLOCKS
+#endif
+template <class F, int B, bool FIRST, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_affine_level(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ sorted,
                                                                           const uint32_t* __restrict__ offs_in, const uint32_t* __restrict__ offs_out,
                                                                           uint32_t nbk, Affine<F>* __restrict__ out, F* __restrict__ prefix_base,
                                                                           uint32_t* __restrict__ counter, unsigned groups) {
@@ -709,7 +722,7 @@ static int launch_accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t*
   ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks<F>, cdiv(nacc, ZKB_ACC_THREADS), ZKB_ACC_THREADS, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
   return ZKB_OK;
 }
-template <class F, int B>
+template <class F, int B, int MINB>
 static int launch_affine_levels(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st, int prof_kind) {
   const uint32_t nbk = (uint32_t)P.nbk;
   for (int l = 0; l < P.aff_levels; l++) {  // level l + 1 from level l
@@ -719,18 +732,24 @@ static int launch_affine_levels(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st,
     unsigned blocks = affine_level_grid(P.aff_max[l + 1], B, P.aff_k);
     if (blocks > P.aff_blocks) blocks = P.aff_blocks;  // the prefix scratch has aff_blocks * 128 columns
     if (l == 0)
-      ZKB_LAUNCH_K(ctx, prof_kind, (k_affine_level<F, B, true>), blocks, 128, 0, st, (const Affine<F>*)P.tab, P.sorted, offs_in, offs_out, nbk, out,
+      ZKB_LAUNCH_K(ctx, prof_kind, (k_affine_level<F, B, true, MINB>), blocks, 128, 0, st, (const Affine<F>*)P.tab, P.sorted, offs_in, offs_out, nbk, out,
                    (F*)P.aff_prefix, P.aff_counters + l, P.aff_k);
     else
-      ZKB_LAUNCH_K(ctx, prof_kind, (k_affine_level<F, B, false>), blocks, 128, 0, st, (const Affine<F>*)P.aff_buf[(l - 1) & 1], (const uint32_t*)nullptr,
+      ZKB_LAUNCH_K(ctx, prof_kind, (k_affine_level<F, B, false, MINB>), blocks, 128, 0, st, (const Affine<F>*)P.aff_buf[(l - 1) & 1], (const uint32_t*)nullptr,
                    offs_in, offs_out, nbk, out, (F*)P.aff_prefix, P.aff_counters + l, P.aff_k);
   }
   return ZKB_OK;
 }
 template <class F>
 static int launch_accumulate_affine(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st, int prof_kind) {
-  if (P.aff_batch == 32) ZKB_TRY((launch_affine_levels<F, 32>(ctx, P, st, prof_kind)));
-  else ZKB_TRY((launch_affine_levels<F, 16>(ctx, P, st, prof_kind)));
+  const bool alt = ZKB_AFF_MIN_BLOCKS_ALT != ZKB_AFF_MIN_BLOCKS && getenv("ZKB_AFF_OCC") && atoi(getenv("ZKB_AFF_OCC")) == 1;
+  if (alt) {
+    if (P.aff_batch == 32) ZKB_TRY((launch_affine_levels<F, 32, ZKB_AFF_MIN_BLOCKS_ALT>(ctx, P, st, prof_kind)));
+    else ZKB_TRY((launch_affine_levels<F, 16, ZKB_AFF_MIN_BLOCKS_ALT>(ctx, P, st, prof_kind)));
+  } else {
+    if (P.aff_batch == 32) ZKB_TRY((launch_affine_levels<F, 32, ZKB_AFF_MIN_BLOCKS>(ctx, P, st, prof_kind)));
+    else ZKB_TRY((launch_affine_levels<F, 16, ZKB_AFF_MIN_BLOCKS>(ctx, P, st, prof_kind)));
+  }
   ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_points<F>, cdiv(P.nacc_fin, ZKB_ACC_THREADS), ZKB_ACC_THREADS, 0, st,
                (const Affine<F>*)P.aff_buf[(P.aff_levels - 1) & 1], P.offs_fin(), (uint32_t)P.nbk, P.nacc_fin, P.ch_fin, (XYZZ<F>*)P.buckets,
                (XYZZ<F>*)P.heads);
