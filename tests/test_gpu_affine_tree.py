@@ -1,5 +1,5 @@
 """GPU parity of the batched-affine pair tree in front of the XYZZ bucket chain (csrc/affine_level.cuh, k_affine_level,
-k_accumulate_points; switched per group with ZKB_AFF_G1 / ZKB_AFF_G2 = levels, ZKB_AFF_B = additions per inversion).
+k_accumulate_points; switched per group with ZKB_AFF_G1 / ZKB_AFF_G2 = levels; off by default: measured not faster).
 Group addition is exact, so every MSM and every proof must be bit-identical to the oracle and to the chain-only path,
 whatever the number of levels: the adversarial bases of test_msm_small_adversarial (identity, P / -P, repeated points,
 one bucket taking every record), the collapse property at sizes where several work items and levels run, skewed scalars,
@@ -33,16 +33,23 @@ def rand_fr(rng, nonzero=False):
     return rng.randrange(1 if nonzero else 0, P)
 
 
-def set_mode(mp, g1, g2, batch):
+@pytest.fixture(params=[0, 1], ids=["plain", "staged"])
+def var(request):
+    """Level body: 0 = the host/device body the CPU test runs (affine_level.cuh), 1 = the staged device body (operands through
+    cp.async and shared memory, msm_impl.cuh: affine_level_item_staged)."""
+    return request.param
+
+
+def set_mode(mp, g1, g2, var=0):
     mp.setenv("ZKB_AFF_G1", str(g1))
     mp.setenv("ZKB_AFF_G2", str(g2))
-    mp.setenv("ZKB_AFF_B", str(batch))
+    mp.setenv("ZKB_AFF_VAR", str(var))
 
 
 @pytest.mark.parametrize("group", [1, 2])
-@pytest.mark.parametrize("levels,batch", [(1, 16), (2, 16), (3, 32), (8, 16)])
-def test_msm_adversarial_with_pair_tree(ctx, monkeypatch, group, levels, batch):
-    set_mode(monkeypatch, levels, levels, batch)
+@pytest.mark.parametrize("levels", [1, 2, 3, 8])
+def test_msm_adversarial_with_pair_tree(ctx, monkeypatch, var, group, levels):
+    set_mode(monkeypatch, levels, levels, var)
     rng = random.Random(140 + group)
     base = bn.BASE_G1 if group == 1 else bn.BASE_G2
     mul = bn.g1_mul if group == 1 else bn.g2_mul
@@ -68,9 +75,8 @@ def test_msm_adversarial_with_pair_tree(ctx, monkeypatch, group, levels, batch):
     assert zk.msm(ctx, b3, [scal[11]] * 16, window_bits=4) is None
 
 
-@pytest.mark.parametrize("group,log_n,levels,batch", [(1, 8, 2, 16), (1, 12, 3, 16), (1, 12, 5, 32), (2, 10, 4, 16), (2, 10, 6, 32),
-                                                      (1, 16, 4, 16), (2, 14, 5, 16), (1, 16, 8, 32)])
-def test_msm_collapse_with_pair_tree(ctx, monkeypatch, group, log_n, levels, batch):
+@pytest.mark.parametrize("group,log_n,levels", [(1, 8, 2), (1, 12, 3), (1, 12, 5), (2, 10, 4), (2, 10, 6), (1, 16, 4), (2, 14, 5), (1, 16, 8)])
+def test_msm_collapse_with_pair_tree(ctx, monkeypatch, var, group, log_n, levels):
     """bases P_i = k_i * BASE  =>  sum s_i P_i = (sum s_i k_i) * BASE, with witness-like skew (zeros and ones: one huge
     bucket) among random scalars; the chain-only result must be the same point."""
     n = 1 << log_n
@@ -82,9 +88,9 @@ def test_msm_collapse_with_pair_tree(ctx, monkeypatch, group, log_n, levels, bat
     b = zk.Bases.generate(ctx, group, ks)
     e = sum(s * k for s, k in zip(ss, ks)) % P
     want = bn.g1_mul(bn.BASE_G1, e) if group == 1 else bn.g2_mul(bn.BASE_G2, e)
-    set_mode(monkeypatch, 0, 0, 16)
+    set_mode(monkeypatch, 0, 0)
     assert zk.msm(ctx, b, ss) == want
-    set_mode(monkeypatch, levels, levels, batch)
+    set_mode(monkeypatch, levels, levels, var)
     assert zk.msm(ctx, b, ss) == want
     # small scalars only: few buckets hold everything (deep trees, long pass-through tails)
     small = [rng.randrange(0, 9) for _ in range(n)]
@@ -93,7 +99,7 @@ def test_msm_collapse_with_pair_tree(ctx, monkeypatch, group, log_n, levels, bat
     assert zk.msm(ctx, b, small) == want
 
 
-def test_msm_2pow20_with_pair_tree(ctx, monkeypatch):
+def test_msm_2pow20_with_pair_tree(ctx, monkeypatch, var):
     n = 1 << 20
     rng = np.random.default_rng(20)
     k = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
@@ -103,7 +109,7 @@ def test_msm_2pow20_with_pair_tree(ctx, monkeypatch):
     ki, si = zg.limbs_to_ints(k), zg.limbs_to_ints(s)
     e = sum(x * y for x, y in zip(ki, si)) % P
     for group, levels in ((1, 4), (2, 5)):
-        set_mode(monkeypatch, levels, levels, 16)
+        set_mode(monkeypatch, levels, levels, var)
         b = zk.Bases.generate(ctx, group, k)
         want = bn.g1_mul(bn.BASE_G1, e) if group == 1 else bn.g2_mul(bn.BASE_G2, e)
         assert zk.msm(ctx, b, s) == want
@@ -118,8 +124,8 @@ def _rows_from_csr(rows):
     return out
 
 
-@pytest.mark.parametrize("log_n,g1,g2,batch", [(6, 2, 2, 16), (10, 3, 3, 16), (12, 0, 4, 16), (12, 4, 0, 32), (16, 4, 5, 16)])
-def test_prove_with_pair_tree(ctx, monkeypatch, log_n, g1, g2, batch):
+@pytest.mark.parametrize("log_n,g1,g2", [(6, 2, 2), (10, 3, 3), (12, 0, 4), (12, 4, 0), (16, 4, 5)])
+def test_prove_with_pair_tree(ctx, monkeypatch, var, log_n, g1, g2):
     """Setup + prove on the synthetic Horner QAP against the closed-form proof from the toxic waste (bit-exact), single
     proof and batch, valid and invalid witness (the invalid one against the chain-only proof)."""
     n = 1 << log_n
@@ -132,10 +138,10 @@ def test_prove_with_pair_tree(ctx, monkeypatch, log_n, g1, g2, batch):
     toxic = tuple(rand_fr(rng, True) for _ in range(5))
     r, s = rand_fr(rng, True), rand_fr(rng, True)
     q = zk.QAP(ctx, n, m, n_input, rows)
-    set_mode(monkeypatch, 0, 0, 16)
+    set_mode(monkeypatch, 0, 0)
     crs = zk.setup(ctx, q, toxic)
     plain_bad = zk.prove(ctx, q, crs, bad, r, s)
-    set_mode(monkeypatch, g1, g2, batch)
+    set_mode(monkeypatch, g1, g2, var)
     got = zk.prove(ctx, q, crs, wit, r, s)
     if log_n <= 12:
         ru, rv, rw = _rows_from_csr(rows)

@@ -1,4 +1,4 @@
-"""Developer probe: the batched-affine pair tree (ZKB_AFF_G1 / ZKB_AFF_G2 levels, ZKB_AFF_B, ZKB_AFF_K) against the
+"""Developer probe: the batched-affine pair tree (ZKB_AFF_G1 / ZKB_AFF_G2 levels, ZKB_AFF_VAR body, ZKB_AFF_K) against the
 XYZZ chain alone -- stand-alone MSMs at 2^log_n (accumulation phase from the library's event brackets) and whole proofs
 (one alone, batch).  The switches are read at every call, so one process sweeps them.
 Usage: python tools/aff_bench.py [log_n] [--msm-only] [--prove-only]"""
@@ -21,9 +21,10 @@ def rand_fr(rng, n):
     return a
 
 
-def mode(g1, g2, b=16, k=1, occ=0):
+def mode(g1, g2, b=16, k=1, var=1):
+    """levels per group; b is fixed at 16 in the library now (kept in the records of the earlier sweeps); var 0 plain / 1 staged"""
     os.environ["ZKB_AFF_G1"], os.environ["ZKB_AFF_G2"] = str(g1), str(g2)
-    os.environ["ZKB_AFF_B"], os.environ["ZKB_AFF_K"], os.environ["ZKB_AFF_OCC"] = str(b), str(k), str(occ)
+    os.environ["ZKB_AFF_K"], os.environ["ZKB_AFF_VAR"] = str(k), str(var)
 
 
 def trace_levels(ctx, fn):
@@ -52,8 +53,8 @@ def main():
     rng = np.random.default_rng(1)
     out = []
     if "--prove-only" not in sys.argv:
-        for group, sweeps in ((2, [(0, 16, 1, 0), (3, 16, 1, 0), (5, 16, 1, 0), (6, 16, 1, 0), (5, 16, 1, 1), (5, 32, 1, 1), (5, 32, 1, 0), (5, 16, 2, 0)]),
-                              (1, [(0, 16, 1, 0), (2, 16, 1, 0), (4, 16, 1, 0), (4, 32, 1, 0), (4, 16, 2, 0)])):
+        for group, sweeps in ((2, [(0, 16, 1, 0), (5, 16, 1, 0), (5, 16, 1, 1), (6, 16, 1, 1), (4, 16, 1, 1)]),
+                              (1, [(0, 16, 1, 0), (4, 16, 1, 0), (4, 16, 1, 1), (3, 16, 1, 1)])):
             b = zk.Bases.generate(ctx, group, rand_fr(rng, n))
             s = rand_fr(rng, n)
             ds = ctx.dev_alloc(s.nbytes)
@@ -73,7 +74,7 @@ def main():
                 wall = (time.perf_counter() - t0) / reps
                 ms, cnt, units = ctx.profile_read(2 if group == 1 else 3)
                 ctx.profile(False)
-                rec = {"what": "msm", "group": group, "log_n": lg, "levels": levels, "batch": batch, "k": k, "occ": occ,
+                rec = {"what": "msm", "group": group, "log_n": lg, "levels": levels, "batch": batch, "k": k, "var": occ,
                        "call_ms": round(wall * 1e3, 3), "accumulate_ms": round(ms / reps, 3), "launches_per_call": cnt // reps,
                        "records_M": round(units / reps / 1e6, 2),
                        "trace": trace_levels(ctx, lambda: zk.msm(ctx, b, ds, on_device=True, n=n))}
@@ -89,7 +90,7 @@ def main():
         d_w = ctx.dev_alloc(w.nbytes)
         ctx.h2d(d_w, w)
         ref = None
-        for g1, g2, batch, k, occ in ((0, 0, 16, 1, 0), (0, 5, 16, 1, 0), (0, 5, 16, 1, 1), (0, 6, 16, 1, 0), (0, 5, 32, 1, 0), (4, 5, 16, 1, 0), (4, 0, 16, 1, 0)):
+        for g1, g2, batch, k, occ in ((0, 0, 16, 1, 0), (0, 5, 16, 1, 1), (0, 6, 16, 1, 1), (0, 4, 16, 1, 1), (4, 5, 16, 1, 1)):
             mode(g1, g2, batch, k, occ)
             for _ in range(2):
                 p = zg.prove_dev(ctx, q, crs, d_w, 17, 19)
@@ -106,7 +107,7 @@ def main():
             pb = zk.prove_batch(ctx, q, crs, [d_w] * reps, [17] * reps, [19] * reps, on_device=True)
             tb = (time.perf_counter() - t0) / reps
             assert all((x.a, x.b, x.c) == ref for x in pb)
-            rec = {"what": "prove", "log_n": lg, "g1_levels": g1, "g2_levels": g2, "batch": batch, "k": k, "occ": occ,
+            rec = {"what": "prove", "log_n": lg, "g1_levels": g1, "g2_levels": g2, "batch": batch, "k": k, "var": occ,
                    "one_proof_ms": round(t1 * 1e3, 3), "batch_ms_per_proof": round(tb * 1e3, 3)}
             out.append(rec)
             print(json.dumps(rec), flush=True)

@@ -8,7 +8,6 @@
 // (2^20: 8.30 -> 8.67 ms; the six-product body is a third large out-of-line function and 64 registers of arguments per
 // call), so the default keeps two Fq2 products and a subtraction.
 #define ZKB_AFF_MIN_BLOCKS 2
-#define ZKB_AFF_MIN_BLOCKS_ALT 3  // 168 registers, ~220 bytes of spills, 12 warps per SM instead of 8
 #define ZKB_ACC_SM_VARIANT 1  // 1: built, off by default (ZKB_ACC_SM=1 selects it); 2: on by default
 #include "msm_impl.cuh"
 namespace zkb {

@@ -128,7 +128,9 @@ static inline size_t msm_level_elems(uint32_t nb, int njobs) {
 }
 
 // Levels of the batched-affine pair tree in front of the XYZZ chain (affine_level.cuh); 0 = the chain alone.
-// ZKB_AFF_G1 / ZKB_AFF_G2 = levels (0..8), ZKB_AFF_B = 16 | 32 (additions per inversion): developer switches.
+// ZKB_AFF_G1 / ZKB_AFF_G2 = levels (0..8): developer switches.  Measured on B200 (profiles/r02_affine_tree_v*.jsonl,
+// r02_notes.md): bit-exact, and NOT faster than the chain -- G2 at 2^20: 7.55 + 0.62 ms (chain + head folding) against
+// 7.99 + 0.21 ms with five levels; G1 slower (3.4 against 2.4 ms) -- so the default is 0 for both groups.
 static inline int affine_levels_policy(int group, size_t max_recs, size_t nbk) {
   int L = 0;
   if (const char* e = getenv(group == 1 ? "ZKB_AFF_G1" : "ZKB_AFF_G2")) L = atoi(e);
@@ -138,10 +140,7 @@ static inline int affine_levels_policy(int group, size_t max_recs, size_t nbk) {
   while (L > 0 && (max_recs >> L) < nbk / 4) L--;  // a level is worth a launch while buckets still hold several elements
   return L;
 }
-static inline int affine_batch_policy() {
-  if (const char* e = getenv("ZKB_AFF_B")) return atoi(e) == 32 ? 32 : 16;
-  return 16;
-}
+static const int MSM_AFF_BATCH = 16;  // additions per inversion (32 measured: within 2 %; the host test also runs 4 and 32)
 // Work items are handed out 32 at a time (one per lane); a warp takes up to K such groups and leaves.  K = 1: a block lives
 // ~100 us, the grid is many waves long (no quantisation loss in the last wave, small levels still fill the machine) and
 // the latency-class kernels of other proofs in flight find room.  Measured: K = 4 leaves the G2 levels at 3.25 waves (the
@@ -186,7 +185,7 @@ static int msm_prepare_t(zkb_ctx* ctx, DevBuf* slots, int slot, const Affine<F>*
   P->lvl_elems = msm_level_elems(pl.nb, njobs);
   // pair tree: sizes of the levels (sum of ceil(k_b / 2) <= (sum k_b + nbk) / 2), chunk plan of the chain behind them
   P->aff_levels = affine_levels_policy(P->group, P->max_recs, P->nbk);
-  P->aff_batch = affine_batch_policy();
+  P->aff_batch = MSM_AFF_BATCH;
   size_t nheads = P->nacc, aff_bytes = 0;
   if (P->aff_levels) {
     P->aff_max[0] = P->max_recs;
@@ -336,14 +335,170 @@ __global__ void __launch_bounds__(ZKB_ACC_THREADS, ZKB_ACC_MIN_BLOCKS) k_accumul
 #ifndef ZKB_AFF_MIN_BLOCKS
 #define ZKB_AFF_MIN_BLOCKS 1
 #endif
-#ifndef ZKB_AFF_MIN_BLOCKS_ALT   // second build of the kernel with another register budget (ZKB_AFF_OCC=1 selects it)
-#define ZKB_AFF_MIN_BLOCKS_ALT ZKB_AFF_MIN_BLOCKS
+#ifndef ZKB_AFF_DEFAULT_VAR
+#define ZKB_AFF_DEFAULT_VAR 1
 #endif
-template <class F, int B, bool FIRST, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_affine_level(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ sorted,
-                                                                          const uint32_t* __restrict__ offs_in, const uint32_t* __restrict__ offs_out,
-                                                                          uint32_t nbk, Affine<F>* __restrict__ out, F* __restrict__ prefix_base,
-                                                                          uint32_t* __restrict__ counter, unsigned groups) {
+// ---- staged variant of the level body (device only) -------------------------------------------------------------------
+// ncu of the plain body (profiles/r02_affine_level_g2_v2.json): the multiplier is 55 % busy, a third of the warp time is
+// long-scoreboard stalls -- operand loads and the local-memory source words -- which the two warps per scheduler the
+// 220 registers of the Fq2 instantiation leave cannot cover.  Here the operands of the NEXT additions are copied global
+// -> shared asynchronously (cp.async, no registers) while the current one is computed, and the source words live in
+// shared memory: per thread 2 B words + max(4 stages x (x0, x1), 2 stages x (P0, P1, prefix)), laid out [word][thread]
+// (conflict-free 16-byte accesses).  Every thread only reads what it copied itself: no block barrier anywhere.
+namespace affdev {
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, bool hint64) {
+  if (hint64) asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  else asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <class T> __device__ __forceinline__ T lds(const uint4* base, int word0) {  // sizeof(T) / 16 words, stride 128
+  T r;
+  uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int w = 0; w < (int)(sizeof(T) / 16); w++) d[w] = base[(word0 + w) * 128];
+  return r;
+}
+}  // namespace affdev
+template <class F, int B>
+constexpr size_t affine_staged_smem() {
+  // source words [2B][128] u32, then the stage words [NW][128] uint4
+  return (size_t)2 * B * 128 * 4 + (size_t)2 * (2 * sizeof(Affine<F>) / 16 + sizeof(F) / 16) * 128 * 16;
+}
+template <class F, int B, bool FIRST>
+__device__ __forceinline__ void affine_level_item_staged(uint32_t item, const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ sorted,
+                                                         const uint32_t* __restrict__ offs_in, const uint32_t* __restrict__ offs_out, uint32_t nbk,
+                                                         Affine<F>* __restrict__ out, F* __restrict__ prefix, size_t pstride, uint32_t* sw, uint4* stg) {
+  using namespace affdev;
+  constexpr int WP = sizeof(Affine<F>) / 16, WF = sizeof(F) / 16;
+  constexpr int SB = 2 * WP + WF;      // words of one backward stage: P0 | P1 | prefix
+  constexpr int NSF = 4, SF = 2 * WF;  // forward: 4 stages of x0 | x1  (4 * 2 WF <= 2 * SB)
+  constexpr bool H = FIRST && sizeof(Affine<F>) == 64;
+  const uint32_t total = offs_out[nbk];
+  const uint32_t start = item * (uint32_t)B;
+  if (start >= total) return;
+  const uint32_t cnt = total - start < (uint32_t)B ? total - start : (uint32_t)B;
+  uint32_t lo = 0, hi = nbk;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (offs_out[mid] <= start) lo = mid + 1; else hi = mid;
+  }
+  uint32_t g = lo - 1;
+  uint32_t o_lo = offs_out[g], o_hi = offs_out[g + 1], i_lo = offs_in[g], i_hi = offs_in[g + 1];
+  uint32_t pairmask = 0;
+  // sw[j * 128] = s0[j], sw[(B + j) * 128] = s1[j]   (sw, stg already point at this thread's column)
+  for (uint32_t j = 0; j < cnt; j++) {
+    const uint32_t p = start + j;
+    while (p >= o_hi) {
+      g++;
+      o_lo = o_hi; o_hi = offs_out[g + 1];
+      i_lo = offs_in[g]; i_hi = offs_in[g + 1];
+    }
+    const uint32_t i0 = i_lo + 2 * (p - o_lo);
+    const bool pair = i0 + 1 < i_hi;
+    if (FIRST) {
+      sw[j * 128] = sorted[i0];
+      sw[(B + j) * 128] = pair ? sorted[i0 + 1] : 0;
+    } else {
+      sw[j * 128] = i0;
+      sw[(B + j) * 128] = i0 + 1;
+    }
+    if (pair) pairmask |= 1u << j;
+  }
+  const uint32_t stg_addr = (uint32_t)__cvta_generic_to_shared(stg);
+  // ---- forward: x0, x1 of element j in stage j % NSF, one commit group per element ---------------------------------
+  auto issue_f = [&](uint32_t j) {
+    if ((pairmask >> j) & 1u) {
+      const char* a0 = reinterpret_cast<const char*>(pts + (sw[j * 128] & aff::IDX));
+      const char* a1 = reinterpret_cast<const char*>(pts + (sw[(B + j) * 128] & aff::IDX));
+      const uint32_t d = stg_addr + (uint32_t)((j % NSF) * SF) * 128 * 16;
+#pragma unroll
+      for (int w = 0; w < WF; w++) {
+        cp16(d + w * 128 * 16, a0 + 16 * w, H);
+        cp16(d + (WF + w) * 128 * 16, a1 + 16 * w, H);
+      }
+    }
+    commit();
+  };
+  for (uint32_t j = 0; j < (uint32_t)(NSF - 1); j++) {
+    if (j < cnt) issue_f(j); else commit();
+  }
+  F acc = F::one();
+  for (uint32_t j = 0; j < cnt; j++) {
+    if (j + NSF - 1 < cnt) issue_f(j + NSF - 1); else commit();
+    wait<NSF - 1>();  // groups 0 .. j have landed
+    if (!((pairmask >> j) & 1u)) continue;
+    const int st = (int)(j % NSF) * SF;
+    const F x0 = lds<F>(stg, st), x1 = lds<F>(stg, st + WF);
+    F d = x1 - x0;
+    if (d.is_zero() || x0.is_zero() || x1.is_zero()) {  // rare: identity operand, P + P, P - P
+      const Affine<F> P0 = aff::load_point<F, H>(pts, sw[j * 128]), P1 = aff::load_point<F, H>(pts, sw[(B + j) * 128]);
+      if (pair_kind(P0, P1, d) >= 2) continue;
+    }
+    prefix[j * pstride] = acc;
+    acc = acc * d;
+  }
+  wait<0>();
+  // ---- backward: P0 | P1 | prefix of element j in stage j & 1 ---------------------------------------------------------
+  auto issue_b = [&](uint32_t j) {
+    const uint32_t d = stg_addr + (uint32_t)((j & 1u) * SB) * 128 * 16;
+    const char* a0 = reinterpret_cast<const char*>(pts + (sw[j * 128] & aff::IDX));
+#pragma unroll
+    for (int w = 0; w < WP; w++) cp16(d + w * 128 * 16, a0 + 16 * w, H);
+    if ((pairmask >> j) & 1u) {
+      const char* a1 = reinterpret_cast<const char*>(pts + (sw[(B + j) * 128] & aff::IDX));
+      const char* pf = reinterpret_cast<const char*>(prefix + j * pstride);
+#pragma unroll
+      for (int w = 0; w < WP; w++) cp16(d + (WP + w) * 128 * 16, a1 + 16 * w, H);
+#pragma unroll
+      for (int w = 0; w < WF; w++) cp16(d + (2 * WP + w) * 128 * 16, pf + 16 * w, false);
+    }
+    commit();
+  };
+  issue_b(cnt - 1);  // lands during the inversion
+  F inv = inverse(acc);
+  for (uint32_t j = cnt; j-- > 0;) {
+    if (j > 0) { issue_b(j - 1); wait<1>(); } else wait<0>();
+    const int st = (int)(j & 1u) * SB;
+    Affine<F> P0 = lds<Affine<F>>(stg, st);
+    if (sw[j * 128] >> 31) P0 = neg(P0);
+    if (!((pairmask >> j) & 1u)) {
+      out[start + j] = P0;
+      continue;
+    }
+    Affine<F> P1 = lds<Affine<F>>(stg, st + WP);
+    if (sw[(B + j) * 128] >> 31) P1 = neg(P1);
+    F d;
+    const int kind = pair_kind(P0, P1, d);
+    Affine<F> R;
+    if (kind >= 2) {
+      R = kind == 2 ? P1 : (kind == 3 ? P0 : Affine<F>::inf());
+    } else {
+      const F dinv = inv * lds<F>(stg, st + 2 * WP);
+      inv = inv * d;
+      F num;
+      if (kind == 0) {
+        num = P1.y - P0.y;
+      } else {
+        const F xx = sqr(P0.x);
+        num = dbl(xx) + xx;
+      }
+      const F lam = num * dinv;
+      R.x = sqr(lam) - P0.x - P1.x;
+      R.y = lam * (P0.x - R.x) - P0.y;
+    }
+    out[start + j] = R;
+  }
+}
+
+// VAR 0: plain body (affine_level.cuh, the one the CPU test runs); 1: staged body.  (A 168-register build of the plain Fq2
+// body -- three blocks per SM instead of two, ~220 bytes of spills -- was 4 % faster than the 220-register one and is gone.)
+template <class F, int B, bool FIRST, int VAR>
+__global__ void __launch_bounds__(128, ZKB_AFF_MIN_BLOCKS)
+    k_affine_level(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offs_in,
+                   const uint32_t* __restrict__ offs_out, uint32_t nbk, Affine<F>* __restrict__ out, F* __restrict__ prefix_base,
+                   uint32_t* __restrict__ counter, unsigned groups) {
+  extern __shared__ uint4 aff_smem[];
   const uint32_t total = offs_out[nbk];
   const uint32_t n_items = total / B + (total % B ? 1u : 0u);
   const size_t pstride = (size_t)gridDim.x * blockDim.x;
@@ -354,8 +509,13 @@ __global__ void __launch_bounds__(128, MINB) k_affine_level(const Affine<F>* __r
     if (lane == 0) base = atomicAdd(counter, 32u);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= n_items) break;
-    if (base + lane < n_items)
-      affine_level_item<F, B, FIRST>(base + lane, pts, sorted, offs_in, offs_out, nbk, out, prefix, pstride);
+    if (base + lane < n_items) {
+      if (VAR == 1)
+        affine_level_item_staged<F, B, FIRST>(base + lane, pts, sorted, offs_in, offs_out, nbk, out, prefix, pstride,
+                                              reinterpret_cast<uint32_t*>(aff_smem) + threadIdx.x, aff_smem + 2 * B * 128 / 4 + threadIdx.x);
+      else
+        affine_level_item<F, B, FIRST>(base + lane, pts, sorted, offs_in, offs_out, nbk, out, prefix, pstride);
+    }
     __syncwarp();
   }
 }
@@ -722,9 +882,18 @@ static int launch_accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t*
   ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks<F>, cdiv(nacc, ZKB_ACC_THREADS), ZKB_ACC_THREADS, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
   return ZKB_OK;
 }
-template <class F, int B, int MINB>
+template <class F, int B, int VAR>
 static int launch_affine_levels(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st, int prof_kind) {
   const uint32_t nbk = (uint32_t)P.nbk;
+  const size_t smem = VAR == 1 ? affine_staged_smem<F, B>() : 0;
+  if (VAR == 1) {
+    static bool once = false;  // > 48 KB of dynamic shared memory needs the opt-in, once per kernel
+    if (!once) {
+      ZKB_CUDA(ctx, cudaFuncSetAttribute(k_affine_level<F, B, true, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ZKB_CUDA(ctx, cudaFuncSetAttribute(k_affine_level<F, B, false, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      once = true;
+    }
+  }
   for (int l = 0; l < P.aff_levels; l++) {  // level l + 1 from level l
     const uint32_t* offs_in = l == 0 ? P.offs : P.aff_offs + (size_t)(l - 1) * (P.nbk + 1);
     const uint32_t* offs_out = P.aff_offs + (size_t)l * (P.nbk + 1);
@@ -732,24 +901,21 @@ static int launch_affine_levels(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st,
     unsigned blocks = affine_level_grid(P.aff_max[l + 1], B, P.aff_k);
     if (blocks > P.aff_blocks) blocks = P.aff_blocks;  // the prefix scratch has aff_blocks * 128 columns
     if (l == 0)
-      ZKB_LAUNCH_K(ctx, prof_kind, (k_affine_level<F, B, true, MINB>), blocks, 128, 0, st, (const Affine<F>*)P.tab, P.sorted, offs_in, offs_out, nbk, out,
+      ZKB_LAUNCH_K(ctx, prof_kind, (k_affine_level<F, B, true, VAR>), blocks, 128, smem, st, (const Affine<F>*)P.tab, P.sorted, offs_in, offs_out, nbk, out,
                    (F*)P.aff_prefix, P.aff_counters + l, P.aff_k);
     else
-      ZKB_LAUNCH_K(ctx, prof_kind, (k_affine_level<F, B, false, MINB>), blocks, 128, 0, st, (const Affine<F>*)P.aff_buf[(l - 1) & 1], (const uint32_t*)nullptr,
+      ZKB_LAUNCH_K(ctx, prof_kind, (k_affine_level<F, B, false, VAR>), blocks, 128, smem, st, (const Affine<F>*)P.aff_buf[(l - 1) & 1], (const uint32_t*)nullptr,
                    offs_in, offs_out, nbk, out, (F*)P.aff_prefix, P.aff_counters + l, P.aff_k);
   }
   return ZKB_OK;
 }
+// ZKB_AFF_VAR: 0 plain level body, 1 staged (cp.async + shared memory; the default); developer switch
 template <class F>
 static int launch_accumulate_affine(zkb_ctx* ctx, const MsmPlan& P, cudaStream_t st, int prof_kind) {
-  const bool alt = ZKB_AFF_MIN_BLOCKS_ALT != ZKB_AFF_MIN_BLOCKS && getenv("ZKB_AFF_OCC") && atoi(getenv("ZKB_AFF_OCC")) == 1;
-  if (alt) {
-    if (P.aff_batch == 32) ZKB_TRY((launch_affine_levels<F, 32, ZKB_AFF_MIN_BLOCKS_ALT>(ctx, P, st, prof_kind)));
-    else ZKB_TRY((launch_affine_levels<F, 16, ZKB_AFF_MIN_BLOCKS_ALT>(ctx, P, st, prof_kind)));
-  } else {
-    if (P.aff_batch == 32) ZKB_TRY((launch_affine_levels<F, 32, ZKB_AFF_MIN_BLOCKS>(ctx, P, st, prof_kind)));
-    else ZKB_TRY((launch_affine_levels<F, 16, ZKB_AFF_MIN_BLOCKS>(ctx, P, st, prof_kind)));
-  }
+  int var = ZKB_AFF_DEFAULT_VAR;
+  if (const char* e = getenv("ZKB_AFF_VAR")) var = atoi(e) ? 1 : 0;
+  if (var) ZKB_TRY((launch_affine_levels<F, MSM_AFF_BATCH, 1>(ctx, P, st, prof_kind)));
+  else ZKB_TRY((launch_affine_levels<F, MSM_AFF_BATCH, 0>(ctx, P, st, prof_kind)));
   ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_points<F>, cdiv(P.nacc_fin, ZKB_ACC_THREADS), ZKB_ACC_THREADS, 0, st,
                (const Affine<F>*)P.aff_buf[(P.aff_levels - 1) & 1], P.offs_fin(), (uint32_t)P.nbk, P.nacc_fin, P.ch_fin, (XYZZ<F>*)P.buckets,
                (XYZZ<F>*)P.heads);
