@@ -673,6 +673,9 @@ def test_error_paths(ctx):
         zk.QAP(ctx, 6, 4, 1, [(np.zeros(5, dtype=np.uint64), np.zeros(0, dtype=np.uint32), np.zeros((0, 4), dtype=np.uint64))] * 3)
     n = 4
     m, n_input, rows = zg.horner_qap_rows(n)
+    shifted = [(ptr + np.uint64(1), gate, coeff) for ptr, gate, coeff in rows]
+    with pytest.raises(zk.ZkbError):
+        zk.QAP(ctx, n, m, n_input, shifted)  # row offsets that do not start at 0
     q = zk.QAP(ctx, n, m, n_input, rows)
     with pytest.raises(zk.ZkbError):
         zk.setup(ctx, q, (1, 2, 0, 4, 5))  # zero secret: the reference's random_elem never yields 0

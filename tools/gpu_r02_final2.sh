@@ -13,3 +13,5 @@ import json
 d = json.loads(open("gpurun_out/${tag}_bench.json").read().strip().splitlines()[-1])
 print({k: d.get(k) for k in ("value", "ms_per_step", "gpu_launches", "clocks")}, d["e2e"], d["roofline"]["frac"], d["config"].get("single_proof_latency_ms"), (d.get("sustained") or {}).get("value"))
 PY
+# occupancy pad for the G1 accumulation (4 instead of 5 blocks per SM): does the pipeline of a batch gain what the kernel loses?
+for pad in 0 47000; do ZKB_ACC_PAD_G1=$pad timeout 200 python tools/quick_prove.py 20 12 2>&1 | tail -2; done > gpurun_out/${tag}_pad.log; cat gpurun_out/${tag}_pad.log

@@ -879,7 +879,10 @@ static int launch_accumulate(zkb_ctx* ctx, const Affine<F>* tab, const uint32_t*
     return ZKB_OK;
   }
 #endif
-  ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks<F>, cdiv(nacc, ZKB_ACC_THREADS), ZKB_ACC_THREADS, 0, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
+  // ZKB_ACC_PAD_G1 / _G2 (bytes, <= 48 K): unused dynamic shared memory per block, i.e. fewer accumulation blocks per SM, so
+  // that blocks of the latency-class kernels of other proofs in flight can be resident beside them (developer switch)
+  static const size_t pad = [] { const char* e = getenv(sizeof(F) == sizeof(Fq) ? "ZKB_ACC_PAD_G1" : "ZKB_ACC_PAD_G2"); long v = e ? atol(e) : 0; return (size_t)(v > 0 && v <= 49152 ? v : 0); }();
+  ZKB_LAUNCH_K(ctx, prof_kind, k_accumulate_chunks<F>, cdiv(nacc, ZKB_ACC_THREADS), ZKB_ACC_THREADS, pad, st, tab, offs, sorted, nbk, nacc, ch, buckets, heads);
   return ZKB_OK;
 }
 template <class F, int B, int VAR>

@@ -332,6 +332,7 @@ int zkb_qap_upload(zkb_ctx* ctx, const zkb_qap_host* h, zkb_qap** out) {
     uint64_t nnz = rp[m];
     q->nnz[t] = nnz;
     if (nnz >= ((uint64_t)1 << 32)) return fail(set_err(ctx, ZKB_ERR_ARG, "nnz too large"));
+    if (rp[0] != 0) return fail(set_err(ctx, ZKB_ERR_ARG, "row_ptr[0] must be 0"));
     for (uint64_t i = 0; i < m; i++)
       if (rp[i] > rp[i + 1]) return fail(set_err(ctx, ZKB_ERR_ARG, "row_ptr not monotone"));
     // by-gate transpose (counting sort on the host: one-time format conversion at upload)
