@@ -10,6 +10,8 @@ import random
 import subprocess
 
 import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
 
 from oracle import bn254 as bn
 
@@ -165,3 +167,28 @@ def test_pair_tree_random_sizes(hc):
         for b, elems, w in zip(buckets, got, want):
             assert len(elems) == (len(b) + (1 << levels) - 1) >> levels
             assert fold(G1, elems) == w
+
+
+_TABLE = None
+
+
+def _table():
+    global _TABLE
+    if _TABLE is None:
+        _TABLE = [None] + G1.points(random.Random(5), 7)
+    return _TABLE
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(sizes=st.lists(st.integers(min_value=0, max_value=37), min_size=1, max_size=12),
+       levels=st.integers(min_value=1, max_value=7), batch=st.sampled_from([4, 16, 32]), seed=st.integers(min_value=0, max_value=2**31))
+def test_pair_tree_property(hc, sizes, levels, batch, seed):
+    """Any bucket shape, any number of levels, any batch size: every bucket keeps its sum and has ceil(k / 2^levels) elements
+    (entries drawn from an 8-point table with the identity in it, so equal, opposite and identity operands are common)."""
+    rng = random.Random(seed)
+    table = _table()
+    buckets = [[(rng.randrange(len(table)), rng.randrange(2)) for _ in range(k)] for k in sizes]
+    got = run_tree(hc, G1, table, buckets, levels, batch)
+    for b, elems in zip(buckets, got):
+        assert len(elems) == (len(b) + (1 << levels) - 1) >> levels
+        assert fold(G1, elems) == bucket_sum(G1, table, b)
