@@ -7,8 +7,13 @@ import importlib
 import os
 import random
 
+import ctypes as C
+import struct
+
 import numpy as np
 import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
 
 from oracle.fields import FR
 
@@ -85,6 +90,66 @@ def test_damaged_records_are_rejected():
         zg.crs_raw_from_bytes(bytes(data))
     with pytest.raises(zk.ZkbError, match="shorter"):
         zg.proof_from_bytes(b"\0" * 16)
+
+
+def _fnv1a(b):
+    h = 0xcbf29ce484222325
+    for x in b:
+        h = ((h ^ x) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _reseal(buf):
+    """Recompute the checksum of a (tampered) record so that the reader gets past it and has to judge the structure."""
+    total = struct.unpack_from("<Q", buf, 16)[0]
+    if 64 <= total <= len(buf):
+        struct.pack_into("<Q", buf, 56, _fnv1a(bytes(buf[64:total])))
+    return buf
+
+
+_BASE_QAP = None
+
+
+def _base_qap():
+    global _BASE_QAP
+    if _BASE_QAP is None:
+        rng = random.Random(11)
+        _BASE_QAP = zg.qap_to_bytes(5, 9, 2, _rand_rows(rng, 5, 9), [rng.randrange(P) for _ in range(5)])
+    return _BASE_QAP
+
+
+@settings(max_examples=300, deadline=None)
+@given(edits=st.lists(st.tuples(st.integers(min_value=16, max_value=400), st.integers(min_value=0, max_value=2**64 - 1)), min_size=1, max_size=4),
+       small=st.booleans(), cut=st.integers(min_value=0, max_value=64))
+def test_tampered_qap_records_with_valid_checksums_stay_in_bounds(edits, small, cut):
+    """A record whose sizes, offsets or row counts were rewritten and whose checksum was recomputed (an adversary, not line
+    noise) is either refused or yields views that lie inside the caller's buffer: the reader trusts no length field."""
+    lib = zk.load_library()
+    data = bytearray(_base_qap())
+    for off, val in edits:
+        off = (off // 8) * 8
+        if off + 8 <= len(data) and not 56 <= off < 64:
+            struct.pack_into("<Q", data, off, val % 64 if small else val)
+    data = _reseal(data)
+    if cut:
+        data = _reseal(data[: max(0, len(data) - 8 * cut)])
+    buf = zg._aligned_copy(bytes(data))
+    host = zg._QapHost()
+    rc = lib.zkb_wire_read_qap(zg._ptr(buf), len(data), C.byref(host))
+    if rc != 0:
+        return
+    base = zg._ptr(buf).value
+    end = base + len(data)
+    m = int(host.m)
+    for t in range(3):
+        rp = C.cast(host.row_ptr[t], C.c_void_p).value
+        assert base <= rp and rp + (m + 1) * 8 <= end
+        nnz = int(np.ctypeslib.as_array(C.cast(host.row_ptr[t], C.POINTER(C.c_uint64)), shape=(m + 1,))[m])
+        g, c = C.cast(host.gate[t], C.c_void_p).value, C.cast(host.coeff[t], C.c_void_p).value
+        assert base <= g and g + nnz * 4 <= end and base <= c and c + nnz * 32 <= end
+    if host.roots:
+        r = C.cast(host.roots, C.c_void_p).value
+        assert base <= r and r + int(host.n) * 32 <= end
 
 
 @pytest.mark.gpu
