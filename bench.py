@@ -428,7 +428,7 @@ def run_ours(args):
             "scaling": "strong" if sw > 1 else "weak", "vs_baseline": None, "dtype": "u32x8 (256-bit modular integers)",
             "data": "synthetic",
             "config": {"workload": workload_name(args.log_n),
-                       "parallelism": (f"1 GPU, zkb_prove_batch ({4 if args.log_n <= 17 else 3 if args.log_n <= 19 else 2} proofs in flight)" if world == 1 else
+                       "parallelism": (f"1 GPU, zkb_prove_batch ({4 if args.log_n <= 17 else 3 if args.log_n <= 19 else 2} proofs in flight" + (", 3 in the e2e pass: a third proof hides the host-to-device copy of the witness)" if 20 <= args.log_n <= 22 else ")") if world == 1 else
                                        (f"one proof per step over all {world} ranks: NTT outer dimension + MSM points sharded, 4 exchanges per proof by kernel "
                                         f"stores into peer HBM over NVLink (in-library, per proof, no host bounce), several proofs in flight" if sw > 1 else
                                         f"replicas x{world}: one proof per step on EVERY rank")),

@@ -146,7 +146,8 @@ int zkb_prove_dev(zkb_ctx* ctx, const zkb_qap* qap, const zkb_crs* crs, const ui
                   const uint64_t r[4], const uint64_t s[4], zkb_proof* out);
 /* Throughput mode: `count` independent proofs over the same QAP and CRS (weights[i]: m x 4 limbs each,
  * all host or all device pointers; r, s: count x 4 limbs).  Several proofs are kept in flight (two at
- * 2^20 gates, three up to 2^19, four up to 2^17) on as many internal stream sets so that the short /
+ * 2^20 gates -- three when the weights come from host memory, whose copy a third proof hides --, three up to 2^19, four
+ * up to 2^17) on as many internal stream sets so that the short /
  * low-occupancy stages of one proof (polynomial stage, record sort, bucket reduction) overlap the
  * SM-filling bucket accumulation of another.  Results
  * are identical to `count` calls of zkb_prove (over a sharded CRS: of zkb_prove_partial, `out` then holds

@@ -619,9 +619,14 @@ int zkb_prove_dev(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64
 // Proofs in flight.  Measured on B200 (profiles/r01_lanes_by_size.txt, ms per proof for 1 / 2 / 3 / 4 lanes):
 // 2^16 4.27 / 2.82 / 2.34 / 2.19, 2^18 8.66 / 7.22 / 7.06 / 7.23, 2^20 23.8 / 23.2 / 23.2 / -- : small proofs are
 // dominated by the latency-bound tails (bucket hierarchy, head folding), which more proofs in flight hide.
-static size_t batch_lane_count(const zkb_ctx* ctx, const zkb_qap* q) {
+// Witnesses that come from HOST memory add a copy stage in front of every proof: at 2^20 a third proof in flight hides it
+// (ms per proof with 2 / 3 / 4 lanes, device-resident witnesses 23.24 / 23.33 / 23.94, host witnesses 23.65 / 23.32 / 23.54:
+// profiles/r02_lanes_host_witness.txt), so host witnesses get three lanes up to 2^22 (per-lane scratch: ~1.3 GB at 2^20).
+static size_t batch_lane_count(const zkb_ctx* ctx, const zkb_qap* q, bool host_witness) {
   if (ctx->batch_lanes >= 1 && ctx->batch_lanes <= 4) return (size_t)ctx->batch_lanes;
-  return q->n <= ((uint64_t)1 << 17) ? 4 : (q->n <= ((uint64_t)1 << 19) ? 3 : 2);
+  if (q->n <= ((uint64_t)1 << 17)) return 4;
+  if (q->n <= ((uint64_t)1 << 19)) return 3;
+  return host_witness && q->n <= ((uint64_t)1 << 22) ? 3 : 2;
 }
 
 int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint64_t* const* weights, int on_device,
@@ -633,7 +638,7 @@ int zkb_prove_batch(zkb_ctx* ctx, const zkb_qap* q, const zkb_crs* c, const uint
     if (!weights[i]) return set_err(ctx, ZKB_ERR_ARG, "zkb_prove_batch: weights[%zu] is NULL", i);
   int rc = ZKB_OK;
   size_t done = 0;
-  const size_t nl = batch_lane_count(ctx, q);
+  const size_t nl = batch_lane_count(ctx, q, !on_device);
   for (size_t l = 0; l < nl && l < count; l++) ZKB_TRY(lane_get(ctx, (int)l, nullptr));
   for (size_t i = 0; i < count && rc == ZKB_OK; i++) {
     zkb_lane* L = &ctx->lanes[i % nl];
